@@ -1,0 +1,162 @@
+/*
+ * sdod_kernels.h — flat C ABI of libsdod_b200.so, kernel level.
+ *
+ * Plain pointers and sizes only (device pointers unless stated otherwise); every call
+ * enqueues hand-written sm_100a kernels on `stream` and returns 0 on success or a
+ * negative status (sdod_last_error() holds the message).  There is no CPU fallback:
+ * without a CUDA device every compute entry point returns an error.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repo vaenyr/stable-diffusion-on-device).
+ */
+#ifndef SDOD_KERNELS_H
+#define SDOD_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef SDOD_API
+#define SDOD_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sdod_stream_t; /* cudaStream_t */
+
+enum sdod_dtype { SDOD_F32 = 0, SDOD_BF16 = 1 };
+enum sdod_layout { SDOD_NCHW = 0, SDOD_NHWC = 1 };
+enum sdod_act { SDOD_ACT_NONE = 0, SDOD_ACT_SILU = 1, SDOD_ACT_GELU = 2, SDOD_ACT_GEGLU = 3 };
+/* GEMM/conv output placement */
+enum sdod_out_mode {
+    SDOD_OUT_BF16 = 0,      /* C[m*ldc + n] bf16                                                     */
+    SDOD_OUT_F32 = 1,       /* C[m*ldc + n] fp32                                                     */
+    SDOD_OUT_HEADS = 2,     /* bf16 [B*heads, tokens, dpad]  : attention Q / K operand layout        */
+    SDOD_OUT_HEADS_T = 3,   /* bf16 [B*heads, dpad, tok_pad] : attention V^T operand layout          */
+    SDOD_OUT_QKV = 4        /* N = 3*heads*head_dim: Q,K -> HEADS (C, C2), V -> HEADS_T (C3)         */
+};
+
+SDOD_API const char* sdod_last_error(void);
+SDOD_API int sdod_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+SDOD_API unsigned long long sdod_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) (+per-(n,c) additive term, i.e. the timestep-embedding add).
+ * Replaces: sdod/efficient_gn.py:9-12 (EfficientGNFun.forward == F.group_norm), :29-30, :61-70 and
+ * the op contract of csrc/sdod_ops/config/group_norm.xml:16-107 / group_norm.json:6-21
+ * (inputs input/weight/bias, attrs num_groups, eps; NCHW per the XML, NHWC per the UDO JSON).
+ *   y = act( ((x + add[n,c]) - mu_g) * rsqrt(var_g + eps) * weight[c] + bias[c] )
+ * x,y: [N,C,HW] (NCHW) or [N,HW,C] (NHWC), dtype f32 or bf16; weight/bias/add fp32 or NULL.
+ * workspace: >= sdod_group_norm_workspace() bytes (NHWC path only; may be NULL for NCHW).
+ * ------------------------------------------------------------------------------------------- */
+SDOD_API size_t sdod_group_norm_workspace(int N, int C, int HW, int num_groups, int layout);
+SDOD_API int sdod_group_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias,
+                             const float* add_nc, int N, int C, int HW, int num_groups, float eps, int dtype,
+                             int layout, int fuse_silu, void* workspace, size_t workspace_bytes);
+
+/* LayerNorm over the last dim (SpatialTransformer norm1/2/3). x,y bf16 [rows, width]. */
+SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias,
+                             int rows, int width, float eps);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused classifier-free-guidance combine + eps->x0 + DPM-Solver++(2M) update (one kernel).
+ * Replaces: csrc/libsdod/src/context.cpp:359-378 (CFG via QnnTensor::get_data scale/accum,
+ * qnn_context.cpp:1065-1081) and DPMSolver::update, dpm_solver.cpp:136-181.
+ *   e  = (g == 1) ? eps_c : g*eps_c + (1-g)*eps_u          (separate roundings, as the host loops)
+ *   y0 = (x + (-sigma_s)*e) / alpha_s
+ *   x  = c_x*x  [+ c_prev*y_prev]  + c_y0*y0 ;  y_prev = y0
+ * x, y_prev fp32 (updated in place); eps_* f32 or bf16; x_bf16_out optional bf16 copy of the new x
+ * (next UNet input).  order 1 ignores y_prev on input.  Bit-exact vs the reference in fp32.
+ * ------------------------------------------------------------------------------------------- */
+SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, const void* eps_c, const void* eps_u,
+                               int eps_dtype, size_t n, float guidance, float sigma_s, float alpha_s, float c_x,
+                               float c_prev, float c_y0, int order, void* x_bf16_out);
+
+/* Host-side schedule tables. Replaces DPMSolver::DPMSolver / ::prepare, dpm_solver.cpp:84-131.
+ * Each out array has steps+1 floats (may be NULL). Returns 0 or a negative status. */
+SDOD_API int sdod_dpm_schedule(unsigned timesteps, float lin_start, float lin_end, unsigned steps, float* ts,
+                               float* log_alphas, float* lambdas, float* sigmas, float* alphas, float* phis, float* i2rs,
+                               float* model_ts);
+/* Per-step update coefficients derived from the tables exactly as dpm_solver.cpp:137,153-154,168-170. */
+SDOD_API int sdod_dpm_coeffs(unsigned timesteps, float lin_start, float lin_end, unsigned steps, unsigned step,
+                             float* sigma_s, float* alpha_s, float* c_x, float* c_prev, float* c_y0, int* order);
+
+/* Sinusoidal timestep features, cos first (context.cpp:257-275). out: fp32 [n_t, dim] on device. */
+SDOD_API int sdod_timestep_sinusoid(sdod_stream_t stream, const float* t_dev, int n_t, int dim, float max_period, float* out);
+
+/* Initial noise x_T ~ N(0,1) (context.cpp:333-334); Philox4x32-10 + Box-Muller on device. */
+SDOD_API int sdod_randn(sdod_stream_t stream, float* out, size_t n, unsigned long long seed, unsigned long long offset);
+
+/* Image quantise: out[i] = uint8(clamp(255*f,0,255)), truncating (context.cpp:392-395).
+ * img: [N,HW,C] f32 or bf16 (NHWC == the reference's [H,W,C] output order, libsdod.h:89). */
+SDOD_API int sdod_image_to_u8(sdod_stream_t stream, const void* img, int dtype, uint8_t* out, size_t n);
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05/TMEM GEMM:  C[M,N] = epilogue( alpha * A[M,K] * W[N,K]^T )   (bf16 in, fp32 accumulate)
+ * The reference runs these layers inside its opaque `unet`/`decoder` graphs
+ * (context.cpp:352,366,387); layer list: analyze_results.py:25-87.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sdod_epilogue {
+    void* C;                 /* output                                                             */
+    void* C2;                /* SDOD_OUT_QKV: K destination                                        */
+    void* C3;                /* SDOD_OUT_QKV: V^T destination                                      */
+    long long ldc;           /* row stride (elements) for BF16/F32 modes                           */
+    long long strideC;       /* batch stride (elements)                                            */
+    const float* bias;       /* [N] or NULL                                                        */
+    const float* row_bias;   /* [M/rows_per_group, N] fp32 or NULL (timestep-embedding add)        */
+    int rows_per_group;
+    const void* residual;    /* bf16 [M,N] row-major or NULL, added last                           */
+    long long ldr;
+    long long strideR;
+    float alpha;
+    int act;                 /* sdod_act; GEGLU: tile columns [0,BN/2) = value, [BN/2,BN) = gate    */
+    int out_mode;            /* sdod_out_mode                                                      */
+    int heads, head_dim, tokens, dpad, tok_pad;   /* HEADS / HEADS_T / QKV modes                   */
+} sdod_epilogue;
+
+typedef struct sdod_gemm_desc {
+    const void* A; long long lda; long long strideA;   /* bf16 [batch][M,K], K contiguous           */
+    const void* W; long long ldw; long long strideW;   /* bf16 [batch|1][N,K]; strideW==0: shared   */
+    int M, N, K, batch;
+    int block_n;             /* 0 = auto                                                           */
+    sdod_epilogue epi;
+} sdod_gemm_desc;
+SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d);
+
+/* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC:  Y[B,H,W,Cout] = epilogue( X (*) Wt )
+ * X bf16 [B,H,W,Cin] (Cin % 64 == 0), Wt bf16 [Cout, 9*Cin] with k = (ky*3+kx)*Cin + c.
+ * upsample2x != 0: X is [B,H/2,W/2,Cin] and is read through a nearest-2x gather. */
+typedef struct sdod_conv_desc {
+    const void* X; const void* Wt;
+    int B, H, W, Cin, Cout;
+    int block_n;
+    sdod_epilogue epi;       /* M = B*H*W rows, N = Cout                                            */
+} sdod_conv_desc;
+SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d);
+
+/* Fused flash-style attention on tcgen05 (S/P/O in TMEM, online softmax).
+ * Qh [BH, Nq, dpad], Kh [BH, Nkv, dpad] (HEADS layout), Vt [BH, dv_pad, kv_pad] (HEADS_T layout).
+ * O bf16 [B, Nq, heads*head_dim] (token-major, heads concatenated). scale applied to S. */
+SDOD_API int sdod_attention_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O,
+                                 int B, int heads, int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale);
+
+/* Row softmax (unfused attention for the VAE mid block, d=512). x,y bf16 [rows, cols], ld in elements. */
+SDOD_API int sdod_softmax_rows(sdod_stream_t stream, const void* x, void* y, long long rows, int cols, long long ld, float scale);
+
+/* Layout / data-movement helpers of the hot path (all bf16 NHWC unless stated). */
+SDOD_API int sdod_nchw_f32_to_nhwc_bf16(sdod_stream_t stream, const float* x, void* y, int N, int C, int HW);
+SDOD_API int sdod_nhwc_to_nchw_f32(sdod_stream_t stream, const void* x, int dtype, float* y, int N, int C, int HW);
+SDOD_API int sdod_upsample2x_nhwc(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C);
+SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, const void* b, int Cb, void* y, long long rows);
+SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C, int stride, int Kpad);
+SDOD_API int sdod_cast_f32_to_bf16(sdod_stream_t stream, const float* x, void* y, size_t n);
+SDOD_API int sdod_silu_bf16(sdod_stream_t stream, const void* x, void* y, size_t n);
+/* weight packing (device): OIHW fp32 -> [O][ky][kx][I] bf16 ; GEGLU row interleave per block_n tile */
+SDOD_API int sdod_pack_conv3x3_weight(sdod_stream_t stream, const float* w_oihw, void* out, int Cout, int Cin, int Kpad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDOD_KERNELS_H */

@@ -1,0 +1,316 @@
+// Memory-bound helpers of the hot path: LayerNorm, row softmax, layout conversion, nearest-2x
+// upsample, channel concat, im2col (conv_in / stride-2 downsample), casts, weight packing.
+// All bf16 tensors are channels-last; every kernel moves 16-byte vectors where alignment allows.
+#include "../common.cuh"
+#include "../host_common.h"
+#include "../launch_count.h"
+#include "sdod_kernels.h"
+
+namespace sdod {
+
+static inline int ew_grid(size_t work_items, int block) {
+    size_t g = (work_items + block - 1) / block;
+    const size_t cap = 148 * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+SDOD_DEVICE void unpack8(const uint4& u, float* f) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+SDOD_DEVICE uint4 pack8(const float* f) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+
+// ---------------------------------------------------------------- LayerNorm: one warp per row
+constexpr int kLnMaxVecPerLane = 8;   // width <= 32*8*8 = 2048
+__global__ void __launch_bounds__(256) layer_norm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int rows, int width, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nvec = width >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * width);
+    float v[kLnMaxVecPerLane][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVecPerLane; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+            unpack8(xr[i], v[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[k][j];
+        }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(width);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVecPerLane; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(width) + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(warp) * width);
+#pragma unroll
+    for (int k = 0; k < kLnMaxVecPerLane; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = i * 8 + j;
+                o[j] = (v[k][j] - mean) * rstd * (w ? w[c] : 1.f) + (b ? b[c] : 0.f);
+            }
+            yr[i] = pack8(o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- row softmax (bf16 in/out, fp32 math)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long rows, int cols,
+                                                           long long ld, float scale) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const bf16* xr = x + r * ld;
+        bf16* yr = y + r * ld;
+        float m = -INFINITY;
+        for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, __bfloat162float(xr[c]) * scale);
+        m = warp_max(m);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) { float t = red[0]; for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]); bc = t; }
+        __syncthreads();
+        m = bc;
+        float s = 0.f;
+        for (int c = threadIdx.x; c < cols; c += 256) s += __expf(__bfloat162float(xr[c]) * scale - m);
+        s = warp_sum(s);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bc = t; }
+        __syncthreads();
+        const float inv = 1.0f / bc;
+        for (int c = threadIdx.x; c < cols; c += 256) yr[c] = __float2bfloat16(__expf(__bfloat162float(xr[c]) * scale - m) * inv);
+    }
+}
+
+// ---------------------------------------------------------------- layout conversion (latents / images)
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int N, int C, int HW) {
+    const size_t total = static_cast<size_t>(N) * C * HW;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = o % C;
+        const size_t p = o / C;
+        const int hw = p % HW;
+        const int n = p / HW;
+        y[o] = __float2bfloat16(x[(static_cast<size_t>(n) * C + c) * HW + hw]);
+    }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int HW) {
+    const size_t total = static_cast<size_t>(N) * C * HW;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int hw = o % HW;
+        const size_t p = o / HW;
+        const int c = p % C;
+        const int n = p / C;
+        const T v = x[(static_cast<size_t>(n) * HW + hw) * C + c];
+        if constexpr (sizeof(T) == 4) y[o] = v; else y[o] = __bfloat162float(v);
+    }
+}
+
+// ---------------------------------------------------------------- nearest 2x upsample, NHWC, 16-B vectors
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cvec) {
+    const size_t total = static_cast<size_t>(N) * (2 * H) * (2 * W) * cvec;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = o % cvec;
+        size_t p = o / cvec;
+        const int ox = p % (2 * W); p /= (2 * W);
+        const int oy = p % (2 * H);
+        const int n = p / (2 * H);
+        y[o] = x[((static_cast<size_t>(n) * H + (oy >> 1)) * W + (ox >> 1)) * cvec + cv];
+    }
+}
+
+// ---------------------------------------------------------------- channel concat [rows,Ca] ++ [rows,Cb]
+__global__ void concat_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb, uint4* __restrict__ y, long long rows) {
+    const int vt = va + vb;
+    const size_t total = static_cast<size_t>(rows) * vt;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int v = o % vt;
+        const size_t r = o / vt;
+        y[o] = v < va ? a[r * va + v] : b[r * vb + (v - va)];
+    }
+}
+
+// ---------------------------------------------------------------- im2col 3x3 pad 1 (stride 1|2), k = (ky*3+kx)*C + c
+__global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int stride, int Kpad) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * Kpad;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = o % Kpad;
+        size_t p = o / Kpad;
+        const int ox = p % Wo; p /= Wo;
+        const int oy = p % Ho;
+        const int n = p / Ho;
+        bf16 v = __float2bfloat16(0.f);
+        if (k < 9 * C) {
+            const int tap = k / C, c = k - tap * C;
+            const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<size_t>(n) * H + iy) * W + ix) * C + c];
+        }
+        y[o] = v;
+    }
+}
+// vectorised variant (C % 8 == 0, Kpad == 9*C)
+__global__ void im2col3x3_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cvec, int stride) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * 9 * cvec;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = o % cvec;
+        size_t p = o / cvec;
+        const int tap = p % 9; p /= 9;
+        const int ox = p % Wo; p /= Wo;
+        const int oy = p % Ho;
+        const int n = p / Ho;
+        const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<size_t>(n) * H + iy) * W + ix) * cvec + cv];
+        y[o] = v;
+    }
+}
+
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        y[i] = __float2bfloat16(x[i]);
+}
+__global__ void silu_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t n) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
+}
+
+// OIHW fp32 -> [O][ky][kx][I] bf16, row length Kpad (zero padded)
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int Kpad) {
+    const size_t total = static_cast<size_t>(Cout) * Kpad;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = o % Kpad;
+        const int co = o / Kpad;
+        float v = 0.f;
+        if (k < 9 * Cin) {
+            const int tap = k / Cin, ci = k - tap * Cin;
+            v = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap];
+        }
+        out[o] = __float2bfloat16(v);
+    }
+}
+
+}  // namespace sdod
+
+using namespace sdod;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias, int rows, int width, float eps) {
+    if (!x || !y || rows <= 0 || width <= 0) return fail(kInvalidArgument, "layer_norm: bad arguments");
+    if (width % 8 != 0 || width > 32 * 8 * kLnMaxVecPerLane) return fail(kUnsupported, "layer_norm: width must be a multiple of 8 and <= 2048");
+    const int warps_per_block = 8;
+    layer_norm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
+                                                                                              weight, bias, rows, width, eps);
+    count_launch();
+    return check_launch("layer_norm_kernel");
+}
+
+SDOD_API int sdod_softmax_rows(sdod_stream_t stream, const void* x, void* y, long long rows, int cols, long long ld, float scale) {
+    if (!x || !y || rows <= 0 || cols <= 0) return fail(kInvalidArgument, "softmax_rows: bad arguments");
+    const long long grid = rows < 148 * 16 ? rows : 148 * 16;
+    softmax_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), rows, cols, ld, scale);
+    count_launch();
+    return check_launch("softmax_rows_kernel");
+}
+
+SDOD_API int sdod_nchw_f32_to_nhwc_bf16(sdod_stream_t stream, const float* x, void* y, int N, int C, int HW) {
+    if (!x || !y) return fail(kInvalidArgument, "nchw_f32_to_nhwc_bf16: NULL tensor");
+    const size_t n = static_cast<size_t>(N) * C * HW;
+    nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(x, static_cast<bf16*>(y), N, C, HW);
+    count_launch();
+    return check_launch("nchw_f32_to_nhwc_bf16_kernel");
+}
+
+SDOD_API int sdod_nhwc_to_nchw_f32(sdod_stream_t stream, const void* x, int dtype, float* y, int N, int C, int HW) {
+    if (!x || !y) return fail(kInvalidArgument, "nhwc_to_nchw_f32: NULL tensor");
+    const size_t n = static_cast<size_t>(N) * C * HW;
+    if (dtype == SDOD_F32) nhwc_to_nchw_f32_kernel<float><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(x), y, N, C, HW);
+    else nhwc_to_nchw_f32_kernel<bf16><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), y, N, C, HW);
+    count_launch();
+    return check_launch("nhwc_to_nchw_f32_kernel");
+}
+
+SDOD_API int sdod_upsample2x_nhwc(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C) {
+    if (!x || !y || C % 8 != 0) return fail(kInvalidArgument, "upsample2x: NULL tensor or C % 8 != 0");
+    const size_t n = static_cast<size_t>(N) * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
+    count_launch();
+    return check_launch("upsample2x_kernel");
+}
+
+SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, const void* b, int Cb, void* y, long long rows) {
+    if (!a || !b || !y || Ca % 8 != 0 || Cb % 8 != 0) return fail(kInvalidArgument, "concat_channels: NULL tensor or C % 8 != 0");
+    const size_t n = static_cast<size_t>(rows) * ((Ca + Cb) / 8);
+    concat_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8,
+                                                           static_cast<uint4*>(y), rows);
+    count_launch();
+    return check_launch("concat_kernel");
+}
+
+SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C, int stride, int Kpad) {
+    if (!x || !y || (stride != 1 && stride != 2) || Kpad < 9 * C) return fail(kInvalidArgument, "im2col3x3: bad arguments");
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    if (C % 8 == 0 && Kpad == 9 * C) {
+        const size_t n = static_cast<size_t>(N) * Ho * Wo * 9 * (C / 8);
+        im2col3x3_vec_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, stride);
+    } else {
+        const size_t n = static_cast<size_t>(N) * Ho * Wo * Kpad;
+        im2col3x3_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C, stride, Kpad);
+    }
+    count_launch();
+    return check_launch("im2col3x3_kernel");
+}
+
+SDOD_API int sdod_cast_f32_to_bf16(sdod_stream_t stream, const float* x, void* y, size_t n) {
+    if (!x || !y) return fail(kInvalidArgument, "cast_f32_to_bf16: NULL tensor");
+    if (n == 0) return kOk;
+    cast_f32_to_bf16_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(x, static_cast<bf16*>(y), n);
+    count_launch();
+    return check_launch("cast_f32_to_bf16_kernel");
+}
+
+SDOD_API int sdod_silu_bf16(sdod_stream_t stream, const void* x, void* y, size_t n) {
+    if (!x || !y) return fail(kInvalidArgument, "silu_bf16: NULL tensor");
+    if (n == 0) return kOk;
+    silu_bf16_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), n);
+    count_launch();
+    return check_launch("silu_bf16_kernel");
+}
+
+SDOD_API int sdod_pack_conv3x3_weight(sdod_stream_t stream, const float* w_oihw, void* out, int Cout, int Cin, int Kpad) {
+    if (!w_oihw || !out || Kpad < 9 * Cin) return fail(kInvalidArgument, "pack_conv3x3_weight: bad arguments");
+    const size_t n = static_cast<size_t>(Cout) * Kpad;
+    pack_conv3x3_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(w_oihw, static_cast<bf16*>(out), Cout, Cin, Kpad);
+    count_launch();
+    return check_launch("pack_conv3x3_kernel");
+}
+
+}  // extern "C"

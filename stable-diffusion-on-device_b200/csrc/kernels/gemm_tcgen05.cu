@@ -1,0 +1,441 @@
+// tcgen05/TMEM GEMM and implicit-GEMM conv3x3 for sm_100a.
+//
+//   C[M,N] = epilogue( alpha * A[M,K] * W[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1      : MMA issuer    (one thread issues tcgen05.mma 128xBNx16, commits to mbarriers)
+//   warps 2..5  : epilogue      (tcgen05.ld 32x32b -> bias / temb row-bias / SiLU / GELU / GEGLU /
+//                                residual -> bf16|fp32 stores, incl. attention head-split layouts)
+// Conv mode feeds the same mainloop: the A tile for tap (ky,kx) and channel block c is one 4-D TMA
+// box {64 ch, bw, bh, bb} of the NHWC activation at (c, x0+kx-1, y0+ky-1, b0); TMA's out-of-bounds
+// zero fill supplies the padding, so no im2col buffer exists in HBM.
+//
+// Layer list served (reference evidence: analyze_results.py:25-87; executed by the opaque
+// unet/decoder graphs at csrc/libsdod/src/context.cpp:352,366,387).
+#include "../common.cuh"
+#include "../host_common.h"
+#include "../launch_count.h"
+#include "sdod_kernels.h"
+
+namespace sdod {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                    // 64 bf16 = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kGemmThreads = 192;
+
+struct MainloopParams {
+    int M, N;          // logical extents (masking)
+    int k_blocks;      // K / 64
+    int conv;          // 0: A is a 3-D map (K, M, batch); 1: A is a 4-D map (C, W, H, B)
+    int cin_blocks;    // conv: Cin / 64
+    int H, W;          // conv: output spatial size
+    int bw, bh, bb;    // conv: TMA box (pixels); bw*bh*bb == 128
+    int up;            // conv: 1 = input is half resolution, nearest-2x gather (not via TMA; see host)
+    int w_batched;     // W has a batch dimension
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    // 2 CTAs/SM when they fit (epilogue of one overlaps the mainloop of the other)
+    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+SDOD_DEVICE float apply_act(float v, int act) {
+    if (act == SDOD_ACT_SILU) return silu_f(v);
+    if (act == SDOD_ACT_GELU) return gelu_f(v);
+    return v;
+}
+
+// Store 8 consecutive output columns [n, n+8) of row m (values already activated).
+SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zoff_r, int m, int n, int N, float (&v)[8]) {
+    if (ep.residual) {
+        const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + zoff_r + static_cast<long long>(m) * ep.ldr + n;
+        if (n + 8 <= N && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+            uint4 u = *reinterpret_cast<const uint4*>(r);
+            float2 f;
+            f = unpack_bf16x2(u.x); v[0] += f.x; v[1] += f.y;
+            f = unpack_bf16x2(u.y); v[2] += f.x; v[3] += f.y;
+            f = unpack_bf16x2(u.z); v[4] += f.x; v[5] += f.y;
+            f = unpack_bf16x2(u.w); v[6] += f.x; v[7] += f.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (n + i < N) v[i] += __bfloat162float(r[i]);
+        }
+    }
+    int mode = ep.out_mode;
+    void* base = ep.C;
+    int nn = n;
+    if (mode == SDOD_OUT_QKV) {
+        int Cw = ep.heads * ep.head_dim;
+        int which = n / Cw;
+        nn = n - which * Cw;
+        base = which == 0 ? ep.C : (which == 1 ? ep.C2 : ep.C3);
+        mode = which == 2 ? SDOD_OUT_HEADS_T : SDOD_OUT_HEADS;
+    }
+    if (mode == SDOD_OUT_BF16) {
+        bf16* c = reinterpret_cast<bf16*>(base) + zoff_c + static_cast<long long>(m) * ep.ldc + nn;
+        if (n + 8 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+            uint4 u;
+            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(c) = u;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (n + i < N) c[i] = __float2bfloat16(v[i]);
+        }
+    } else if (mode == SDOD_OUT_F32) {
+        float* c = reinterpret_cast<float*>(base) + zoff_c + static_cast<long long>(m) * ep.ldc + nn;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (n + i < N) c[i] = v[i];
+    } else if (mode == SDOD_OUT_HEADS) {
+        int b = m / ep.tokens, t = m - b * ep.tokens;
+        int h = nn / ep.head_dim, d = nn - h * ep.head_dim;
+        bf16* c = reinterpret_cast<bf16*>(base) + ((static_cast<long long>(b) * ep.heads + h) * ep.tokens + t) * ep.dpad + d;
+        if (n + 8 <= N && d + 8 <= ep.head_dim) {
+            uint4 u;
+            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(c) = u;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (n + i < N) {
+                    int hh = (nn + i) / ep.head_dim, dd = (nn + i) - hh * ep.head_dim;
+                    reinterpret_cast<bf16*>(base)[((static_cast<long long>(b) * ep.heads + hh) * ep.tokens + t) * ep.dpad + dd] = __float2bfloat16(v[i]);
+                }
+            }
+        }
+    } else {  // SDOD_OUT_HEADS_T: [B*heads, dpad, tok_pad], token contiguous (lanes = consecutive tokens)
+        int b = m / ep.tokens, t = m - b * ep.tokens;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (n + i < N) {
+                int hh = (nn + i) / ep.head_dim, dd = (nn + i) - hh * ep.head_dim;
+                reinterpret_cast<bf16*>(base)[((static_cast<long long>(b) * ep.heads + hh) * ep.dpad + dd) * ep.tok_pad + t] = __float2bfloat16(v[i]);
+            }
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmW,
+                                                                      const MainloopParams mp, const sdod_epilogue ep) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y, bz = blockIdx.z;
+    const int m0 = m_tile * kBlockM, n0 = n_tile * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            int b0 = 0, y0 = 0, x0 = 0;
+            if (mp.conv) {
+                const int hw = mp.H * mp.W;
+                if (mp.bb > 1) {
+                    b0 = m_tile * mp.bb;
+                } else {
+                    b0 = m0 / hw;
+                    int rem = m0 - b0 * hw;
+                    y0 = rem / mp.W;
+                    x0 = rem - y0 * mp.W;
+                }
+            }
+            for (int kb = 0; kb < mp.k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                if (mp.conv) {
+                    const int tap = kb / mp.cin_blocks;
+                    const int cb = kb - tap * mp.cin_blocks;
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    tma_load_4d(sA + s * kABytes, &tmA, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+                } else {
+                    tma_load_3d(sA + s * kABytes, &tmA, &full_bar[s], kb * kBlockK, m0, bz);
+                }
+                tma_load_3d(sB + s * Cfg::kBBytes, &tmW, &full_bar[s], kb * kBlockK, n0, mp.w_batched ? bz : 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+            for (int kb = 0; kb < mp.k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * kABytes);
+                const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    tc_mma_bf16(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                                idesc, (kb | k) != 0);
+                }
+                tc_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
+            }
+            tc_commit(tmem_full_bar);       // accumulator complete
+        }
+    } else {
+        // -------------------------------------------------------------------- epilogue
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const bool row_ok = m < mp.M;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const long long zc = static_cast<long long>(bz) * ep.strideC;
+        const long long zr = static_cast<long long>(bz) * ep.strideR;
+        const float* rb = nullptr;
+        if (ep.row_bias && row_ok) rb = ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * mp.N;
+
+        if (ep.act == SDOD_ACT_GEGLU) {
+            constexpr int HALF = BN / 2;
+            const int n_out_total = mp.N / 2;
+#pragma unroll 1
+            for (int j = 0; j < HALF; j += 16) {
+                uint32_t a[16], g[16];
+                tmem_ld16(taddr + j, a);
+                tmem_ld16(taddr + HALF + j, g);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        float v[8];
+                        const int no = n_tile * HALF + j + h8 * 8;   // output column
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int na = n0 + j + h8 * 8 + i;
+                            const int ng = na + HALF;
+                            float av = __uint_as_float(a[h8 * 8 + i]) * ep.alpha;
+                            float gv = __uint_as_float(g[h8 * 8 + i]) * ep.alpha;
+                            if (ep.bias && ng < mp.N) { av += ep.bias[na]; gv += ep.bias[ng]; }
+                            v[i] = av * gelu_f(gv);
+                        }
+                        if (no < n_out_total) store8(ep, zc, zr, m, no, n_out_total, v);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < BN; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        const int n = n0 + j + h8 * 8;
+                        if (n < mp.N) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float x = __uint_as_float(acc[h8 * 8 + i]) * ep.alpha;
+                                if (n + i < mp.N) {
+                                    if (ep.bias) x += ep.bias[n + i];
+                                    if (rb) x += rb[n + i];
+                                }
+                                v[i] = apply_act(x, ep.act);
+                            }
+                            store8(ep, zc, zr, m, n, mp.N, v);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+template <int BN>
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
+                       const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+                            "cudaFuncSetAttribute(gemm)"));
+        configured = true;
+    }
+    dim3 grid(n_tiles, m_tiles, batch);
+    gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, mp, ep);
+    count_launch();
+    return check_launch("gemm_tcgen05_kernel");
+}
+
+static int dispatch_gemm(int bn, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
+                         const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
+    switch (bn) {
+        case 32: return launch_gemm<32>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
+        case 64: return launch_gemm<64>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
+        case 128: return launch_gemm<128>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
+        case 160: return launch_gemm<160>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
+        case 256: return launch_gemm<256>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
+    }
+    return fail(kInvalidArgument, "unsupported block_n " + std::to_string(bn));
+}
+
+// Tile-width heuristic: fewest padded columns first, then enough CTAs to fill the chip.
+int pick_block_n(int M, int N, int batch, int act) {
+    if (act == SDOD_ACT_GEGLU) return 256;
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    const int m_tiles = (M + kBlockM - 1) / kBlockM;
+    const int cands[4] = {256, 160, 128, 64};
+    int best = 128;
+    double best_cost = 1e30;
+    const int sms = 148;
+    for (int c = 0; c < 4; ++c) {
+        const int bn = cands[c];
+        const int n_tiles = (N + bn - 1) / bn;
+        const long long tiles = static_cast<long long>(m_tiles) * n_tiles * batch;
+        const int per_sm = bn >= 256 ? 1 : 2;
+        const long long waves = (tiles + sms * per_sm - 1) / (sms * per_sm);
+        // per-tile time ~ max(MMA issue (bn), smem feed floor) + fixed overhead; 2 co-resident CTAs share the pipe
+        const double tile_t = (bn < 128 ? 128.0 : static_cast<double>(bn)) * per_sm + 24.0;
+        const double cost = static_cast<double>(waves) * tile_t;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+static int validate_epilogue(const sdod_epilogue& ep, int N) {
+    if (!ep.C) return fail(kInvalidArgument, "epilogue: C is NULL");
+    if (ep.row_bias && ep.rows_per_group <= 0) return fail(kInvalidArgument, "epilogue: rows_per_group must be > 0 with row_bias");
+    if (ep.out_mode >= SDOD_OUT_HEADS) {
+        if (ep.heads <= 0 || ep.head_dim <= 0 || ep.tokens <= 0 || ep.dpad <= 0)
+            return fail(kInvalidArgument, "epilogue: heads/head_dim/tokens/dpad required for head layouts");
+        if (ep.out_mode == SDOD_OUT_QKV && (!ep.C2 || !ep.C3 || N != 3 * ep.heads * ep.head_dim))
+            return fail(kInvalidArgument, "epilogue: QKV mode needs C2, C3 and N == 3*heads*head_dim");
+        if ((ep.out_mode == SDOD_OUT_HEADS_T || ep.out_mode == SDOD_OUT_QKV) && ep.tok_pad <= 0)
+            return fail(kInvalidArgument, "epilogue: tok_pad required for V^T layout");
+    }
+    if (ep.act == SDOD_ACT_GEGLU && (N % 2 != 0)) return fail(kInvalidArgument, "epilogue: GEGLU needs even N");
+    return kOk;
+}
+
+int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
+    if (!d.A || !d.W) return fail(kInvalidArgument, "gemm: NULL operand");
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.batch <= 0) return fail(kInvalidArgument, "gemm: non-positive extent");
+    if (d.K % kBlockK != 0) return fail(kInvalidArgument, "gemm: K must be a multiple of 64 (pad the operand)");
+    if (d.lda % 8 != 0 || d.ldw % 8 != 0) return fail(kInvalidArgument, "gemm: lda/ldw must be multiples of 8 elements");
+    SDOD_TRY(validate_epilogue(d.epi, d.N));
+    int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, d.batch, d.epi.act);
+    if (d.epi.act == SDOD_ACT_GEGLU && bn != 256 && d.block_n == 0) bn = 256;
+
+    CUtensorMap tmA, tmW;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.M), static_cast<uint64_t>(d.batch)};
+        uint64_t strides[2] = {static_cast<uint64_t>(d.lda) * 2, static_cast<uint64_t>(d.batch > 1 ? d.strideA : static_cast<long long>(d.M) * d.lda) * 2};
+        uint32_t box[3] = {kBlockK, kBlockM, 1};
+        SDOD_TRY(encode_tmap_bf16(&tmA, d.A, 3, dims, strides, box, true));
+    }
+    const bool wb = d.batch > 1 && d.strideW != 0;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N), static_cast<uint64_t>(wb ? d.batch : 1)};
+        uint64_t strides[2] = {static_cast<uint64_t>(d.ldw) * 2, static_cast<uint64_t>(wb ? d.strideW : static_cast<long long>(d.N) * d.ldw) * 2};
+        uint32_t box[3] = {kBlockK, static_cast<uint32_t>(bn), 1};
+        SDOD_TRY(encode_tmap_bf16(&tmW, d.W, 3, dims, strides, box, true));
+    }
+    MainloopParams mp{};
+    mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
+    const int m_tiles = (d.M + kBlockM - 1) / kBlockM;
+    const int n_tiles = (d.N + bn - 1) / bn;
+    return dispatch_gemm(bn, stream, tmA, tmW, mp, d.epi, m_tiles, n_tiles, d.batch);
+}
+
+int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d) {
+    if (!d.X || !d.Wt) return fail(kInvalidArgument, "conv3x3: NULL operand");
+    if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.Cin <= 0 || d.Cout <= 0) return fail(kInvalidArgument, "conv3x3: non-positive extent");
+    if (d.Cin % kBlockK != 0) return fail(kInvalidArgument, "conv3x3: Cin must be a multiple of 64 (use im2col + gemm otherwise)");
+    const int bw = d.W < 128 ? d.W : 128;
+    if (128 % bw != 0 || d.W % bw != 0) return fail(kInvalidArgument, "conv3x3: W must be a power of two (or a multiple of 128)");
+    int bh = 128 / bw;
+    if (bh > d.H) bh = d.H;
+    if (d.H % bh != 0 || 128 % (bw * bh) != 0) return fail(kInvalidArgument, "conv3x3: H*W must tile into 128-pixel boxes");
+    const int bb = 128 / (bw * bh);
+    const int M = d.B * d.H * d.W;
+    SDOD_TRY(validate_epilogue(d.epi, d.Cout));
+    const int bn = d.block_n ? d.block_n : pick_block_n(M, d.Cout, 1, d.epi.act);
+
+    CUtensorMap tmA, tmW;
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(d.Cin), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+        uint64_t strides[3] = {static_cast<uint64_t>(d.Cin) * 2, static_cast<uint64_t>(d.W) * d.Cin * 2,
+                               static_cast<uint64_t>(d.H) * d.W * d.Cin * 2};
+        uint32_t box[4] = {kBlockK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+        SDOD_TRY(encode_tmap_bf16(&tmA, d.X, 4, dims, strides, box, true));
+    }
+    const int K = 9 * d.Cin;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(d.Cout), 1};
+        uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * d.Cout * 2};
+        uint32_t box[3] = {kBlockK, static_cast<uint32_t>(bn), 1};
+        SDOD_TRY(encode_tmap_bf16(&tmW, d.Wt, 3, dims, strides, box, true));
+    }
+    MainloopParams mp{};
+    mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
+    mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
+    const int m_tiles = (M + kBlockM - 1) / kBlockM;
+    const int n_tiles = (d.Cout + bn - 1) / bn;
+    return dispatch_gemm(bn, stream, tmA, tmW, mp, d.epi, m_tiles, n_tiles, 1);
+}
+
+}  // namespace sdod
+
+extern "C" {
+SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d) {
+    if (!d) return sdod::fail(sdod::kInvalidArgument, "sdod_gemm_bf16: desc is NULL");
+    return sdod::gemm_bf16(static_cast<cudaStream_t>(stream), *d);
+}
+SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d) {
+    if (!d) return sdod::fail(sdod::kInvalidArgument, "sdod_conv3x3_bf16: desc is NULL");
+    return sdod::conv3x3_bf16(static_cast<cudaStream_t>(stream), *d);
+}
+}

@@ -1,0 +1,465 @@
+// GroupNorm (+SiLU, + per-(n,c) timestep-embedding add) for sm_100a.
+//
+// Contract restated from the reference operator surface: sdod/efficient_gn.py:9-12 (forward ==
+// F.group_norm), :29-30, :61-70 and the op schema csrc/sdod_ops/config/group_norm.xml:16-107
+// (NCHW) / group_norm.json:6-21 (NHWC):  biased variance over (C/G)*HW per (n,g), affine per channel.
+//
+// Three kernels:
+//  * gn_nchw_cluster_kernel  — single pass over HBM.  A thread-block cluster owns one (n,g) group
+//    (contiguous in NCHW); each CTA stages its slab in shared memory with TMA bulk copies
+//    (cp.async.bulk + mbarrier, 4 chunks in flight), accumulates pivot-shifted moments with 128-bit
+//    smem reads + warp shuffles, converts them to (count, mean, M2) and merges across the cluster
+//    with Chan/Welford updates over distributed shared memory, then normalises out of smem.
+//    Algorithmic traffic = read x once + write y once.
+//  * gn_nhwc_stats_kernel + gn_nhwc_apply_kernel — channels-last path used inside the UNet/VAE.
+//    Stats are pivot-shifted sums (pivot = first element of the group, shared by all CTAs, so partial
+//    sums add exactly like Welford partials with a common origin); the last CTA of each image folds
+//    the partials in fixed order (deterministic) and publishes mean / rstd.
+//  * gn_nchw_generic_kernel  — any shape/alignment (two reads), used when the TMA path's
+//    alignment or capacity preconditions do not hold.
+#include "../common.cuh"
+#include "../host_common.h"
+#include "../launch_count.h"
+#include "sdod_kernels.h"
+
+#include <algorithm>
+
+namespace sdod {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int N = 4; };
+template <> struct VecOf<bf16> { static constexpr int N = 8; };
+
+template <typename T> SDOD_DEVICE void load_vec(const T* p, float* out);
+template <> SDOD_DEVICE void load_vec<float>(const float* p, float* out) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <> SDOD_DEVICE void load_vec<bf16>(const bf16* p, float* out) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 f;
+    f = unpack_bf16x2(u.x); out[0] = f.x; out[1] = f.y;
+    f = unpack_bf16x2(u.y); out[2] = f.x; out[3] = f.y;
+    f = unpack_bf16x2(u.z); out[4] = f.x; out[5] = f.y;
+    f = unpack_bf16x2(u.w); out[6] = f.x; out[7] = f.y;
+}
+template <typename T> SDOD_DEVICE void store_vec(T* p, const float* v);
+template <> SDOD_DEVICE void store_vec<float>(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> SDOD_DEVICE void store_vec<bf16>(bf16* p, const float* v) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+template <typename T> SDOD_DEVICE float to_f(T v);
+template <> SDOD_DEVICE float to_f<float>(float v) { return v; }
+template <> SDOD_DEVICE float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> SDOD_DEVICE T from_f(float v);
+template <> SDOD_DEVICE float from_f<float>(float v) { return v; }
+template <> SDOD_DEVICE bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+SDOD_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+SDOD_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+SDOD_DEVICE void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+SDOD_DEVICE float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+    uint32_t a = smem_u32(local_ptr), ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// Chan et al. parallel Welford merge of (n, mean, M2)
+SDOD_DEVICE void welford_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
+    if (nb == 0.f) return;
+    float nt = n + nb;
+    float delta = meanb - mean;
+    float f = nb / nt;
+    mean += delta * f;
+    m2 += m2b + delta * delta * n * f;
+    n = nt;
+}
+
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxChunks = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                      const float* __restrict__ weight, const float* __restrict__ bias,
+                                                                      const float* __restrict__ add_nc, int C, int HW, int G, float eps,
+                                                                      int fuse_silu, int slab_elems) {
+    constexpr int VEC = VecOf<T>::N;
+    extern __shared__ __align__(128) uint8_t gn_smem[];
+    T* slab = reinterpret_cast<T*>(gn_smem);
+    __shared__ __align__(8) uint64_t bars[kGnMaxChunks];
+    __shared__ float red_s[kGnThreads / 32], red_ss[kGnThreads / 32];
+    __shared__ float cta_stats[4];   // n, mean, M2
+    __shared__ float pivot_sh;
+
+    const uint32_t cs = cluster_nctarank(), rank = cluster_ctarank();
+    const int group = blockIdx.x / cs;
+    const int n = group / G, g = group - n * G;
+    const int cpg = C / G;
+    const long long L = static_cast<long long>(cpg) * HW;
+    const long long gbase = (static_cast<long long>(n) * C + static_cast<long long>(g) * cpg) * HW;
+    const long long my_off = static_cast<long long>(rank) * slab_elems;
+    const T* src = x + gbase + my_off;
+    const uint32_t slab_bytes = static_cast<uint32_t>(slab_elems) * sizeof(T);
+    const int nch = slab_bytes >= 16384 ? kGnMaxChunks : 1;
+    const uint32_t chunk_bytes = ((slab_bytes / nch) + 15) & ~15u;
+    const float* addp = add_nc ? add_nc + static_cast<long long>(n) * C + g * cpg : nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < nch; ++c) mbar_init(&bars[c], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < nch; ++c) {
+            uint32_t off = c * chunk_bytes;
+            uint32_t bytes = (c == nch - 1) ? slab_bytes - off : chunk_bytes;
+            mbar_arrive_expect_tx(&bars[c], bytes);
+            bulk_load_1d(reinterpret_cast<uint8_t*>(slab) + off, reinterpret_cast<const uint8_t*>(src) + off, bytes, &bars[c]);
+        }
+    }
+    // ---- pass A (smem): pivot-shifted moments
+    mbar_wait(&bars[0], 0);
+    if (threadIdx.x == 0) pivot_sh = to_f<T>(slab[0]) + (addp ? addp[static_cast<int>(my_off / HW)] : 0.f);
+    __syncthreads();
+    const float K = pivot_sh;
+    float s = 0.f, ss = 0.f;
+    const int nvec = slab_elems / VEC;
+    const int chunk_vecs = chunk_bytes / 16;
+    int ready = 1;
+    for (int v = threadIdx.x; v < nvec; v += kGnThreads) {
+        int need = v / chunk_vecs;
+        if (need >= nch) need = nch - 1;
+        while (ready <= need) { mbar_wait(&bars[ready], 0); ++ready; }
+        float e[VEC];
+        load_vec<T>(slab + v * VEC, e);
+        if (addp) {
+            const long long gi = my_off + static_cast<long long>(v) * VEC;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) e[i] += addp[static_cast<int>((gi + i) / HW)];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { float d = e[i] - K; s += d; ss += d * d; }
+    }
+    while (ready < nch) { mbar_wait(&bars[ready], 0); ++ready; }
+    s = warp_sum(s); ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = s; red_ss[threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float S = 0.f, SS = 0.f;
+        for (int w = 0; w < kGnThreads / 32; ++w) { S += red_s[w]; SS += red_ss[w]; }
+        const float cnt = static_cast<float>(slab_elems);
+        cta_stats[0] = cnt;
+        cta_stats[1] = K + S / cnt;
+        cta_stats[2] = fmaxf(SS - S * S / cnt, 0.f);
+    }
+    // ---- cluster merge over DSMEM (fixed rank order => identical result in every CTA)
+    cluster_sync_all();
+    float cn = 0.f, cmean = 0.f, cm2 = 0.f;
+    for (uint32_t r = 0; r < cs; ++r) {
+        float nb = ld_dsmem_f32(&cta_stats[0], r), mb = ld_dsmem_f32(&cta_stats[1], r), qb = ld_dsmem_f32(&cta_stats[2], r);
+        if (r == 0) { cn = nb; cmean = mb; cm2 = qb; }
+        else welford_merge(cn, cmean, cm2, nb, mb, qb);
+    }
+    cluster_sync_all();   // peers have finished reading my cta_stats
+    const float mean = cmean;
+    const float rstd = rsqrtf(cm2 / static_cast<float>(L) + eps);
+
+    // ---- pass B (smem -> HBM): normalise, affine, SiLU
+    T* dst = y + gbase + my_off;
+    for (int v = threadIdx.x; v < nvec; v += kGnThreads) {
+        float e[VEC];
+        load_vec<T>(slab + v * VEC, e);
+        const long long gi = my_off + static_cast<long long>(v) * VEC;
+        const int ch0 = static_cast<int>(gi / HW);
+        const bool one_ch = (gi - static_cast<long long>(ch0) * HW) + VEC <= HW;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int ch = one_ch ? ch0 : static_cast<int>((gi + i) / HW);
+            const int c = g * cpg + ch;
+            float xv = e[i] + (addp ? addp[ch] : 0.f);
+            float o = (xv - mean) * rstd;
+            if (weight) o *= weight[c];
+            if (bias) o += bias[c];
+            e[i] = fuse_silu ? silu_f(o) : o;
+        }
+        store_vec<T>(dst + v * VEC, e);
+    }
+}
+
+// Any shape: one CTA per (n,g), exact two-pass statistics straight from global memory.
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads) gn_nchw_generic_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                      const float* __restrict__ weight, const float* __restrict__ bias,
+                                                                      const float* __restrict__ add_nc, int C, int HW, int G, float eps,
+                                                                      int fuse_silu) {
+    __shared__ float red[kGnThreads / 32];
+    __shared__ float bc;
+    const int n = blockIdx.x / G, g = blockIdx.x - n * G;
+    const int cpg = C / G;
+    const long long L = static_cast<long long>(cpg) * HW;
+    const long long gbase = (static_cast<long long>(n) * C + static_cast<long long>(g) * cpg) * HW;
+    const float* addp = add_nc ? add_nc + static_cast<long long>(n) * C + g * cpg : nullptr;
+    auto block_sum = [&](float v) -> float {
+        v = warp_sum(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < kGnThreads / 32; ++w) t += red[w]; bc = t; }
+        __syncthreads();
+        return bc;
+    };
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < L; i += kGnThreads) s += to_f<T>(x[gbase + i]) + (addp ? addp[static_cast<int>(i / HW)] : 0.f);
+    const float mean = block_sum(s) / static_cast<float>(L);
+    float q = 0.f;
+    for (long long i = threadIdx.x; i < L; i += kGnThreads) {
+        float d = to_f<T>(x[gbase + i]) + (addp ? addp[static_cast<int>(i / HW)] : 0.f) - mean;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(block_sum(q) / static_cast<float>(L) + eps);
+    for (long long i = threadIdx.x; i < L; i += kGnThreads) {
+        const int ch = static_cast<int>(i / HW), c = g * cpg + ch;
+        float o = (to_f<T>(x[gbase + i]) + (addp ? addp[ch] : 0.f) - mean) * rstd;
+        if (weight) o *= weight[c];
+        if (bias) o += bias[c];
+        y[gbase + i] = from_f<T>(fuse_silu ? silu_f(o) : o);
+    }
+}
+
+// ------------------------------------------------------------------------------------ NHWC
+// workspace layout: [counters: 256 ints][stats: N*G*2 floats][partials: N*S*G*2 floats]
+constexpr int kGnCounterInts = 256;
+constexpr int kGnMaxSlabs = 512;
+
+template <typename T>
+__global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __restrict__ add_nc, float* __restrict__ partials,
+                                     unsigned int* __restrict__ counters, float* __restrict__ stats, int C, int HW, int G,
+                                     int rows_per_slab, float eps) {
+    constexpr int VEC = VecOf<T>::N;
+    extern __shared__ float gsm[];          // [r][C][2] then reused
+    __shared__ float pivots[64];
+    __shared__ int is_last;
+    const int n = blockIdx.y, slab = blockIdx.x, S = gridDim.x;
+    const int cvec = C / VEC;
+    const int r = blockDim.x / cvec;
+    const int col = threadIdx.x % cvec, rr = threadIdx.x / cvec;
+    const bool active = rr < r;
+    const int cpg = C / G;
+    const T* xn = x + static_cast<long long>(n) * HW * C;
+    const float* addp = add_nc ? add_nc + static_cast<long long>(n) * C : nullptr;
+    for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+        const int c = gg * cpg;
+        pivots[gg] = to_f<T>(xn[c]) + (addp ? addp[c] : 0.f);
+    }
+    __syncthreads();
+    float K[VEC], ad[VEC], s[VEC], ss[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = col * VEC + i;
+        K[i] = pivots[c / cpg];
+        ad[i] = addp ? addp[c] : 0.f;
+        s[i] = 0.f; ss[i] = 0.f;
+    }
+    const int p0 = slab * rows_per_slab;
+    const int p1 = min(HW, p0 + rows_per_slab);
+    if (active) {
+        for (int p = p0 + rr; p < p1; p += r) {
+            float e[VEC];
+            load_vec<T>(xn + static_cast<long long>(p) * C + col * VEC, e);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { float d = e[i] + ad[i] - K[i]; s[i] += d; ss[i] += d * d; }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            gsm[(rr * C + col * VEC + i) * 2 + 0] = s[i];
+            gsm[(rr * C + col * VEC + i) * 2 + 1] = ss[i];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int q = 0; q < r; ++q) { a += gsm[(q * C + c) * 2]; b += gsm[(q * C + c) * 2 + 1]; }
+        gsm[c * 2] = a; gsm[c * 2 + 1] = b;     // row 0 doubles as the per-channel totals (q==0 read first)
+    }
+    __syncthreads();
+    for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = gg * cpg; c < (gg + 1) * cpg; ++c) { a += gsm[c * 2]; b += gsm[c * 2 + 1]; }
+        float* dst = partials + ((static_cast<long long>(n) * S + slab) * G + gg) * 2;
+        dst[0] = a; dst[1] = b;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&counters[n], 1u) == static_cast<unsigned>(S - 1));
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+            float a = 0.f, b = 0.f;
+            const float* src = partials + (static_cast<long long>(n) * S * G + gg) * 2;
+            for (int q = 0; q < S; ++q) { a += __ldcg(src + static_cast<long long>(q) * G * 2); b += __ldcg(src + static_cast<long long>(q) * G * 2 + 1); }
+            const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+            const float m = a / cnt;
+            const float var = fmaxf(b / cnt - m * m, 0.f);
+            stats[(n * G + gg) * 2 + 0] = pivots[gg] + m;
+            stats[(n * G + gg) * 2 + 1] = rsqrtf(var + eps);
+        }
+        if (threadIdx.x == 0) counters[n] = 0;   // self-cleaning: workspace stays reusable
+    }
+}
+
+template <typename T>
+__global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ weight,
+                                     const float* __restrict__ bias, const float* __restrict__ add_nc,
+                                     const float* __restrict__ stats, int C, int HW, int G, int rows_per_slab, int fuse_silu) {
+    constexpr int VEC = VecOf<T>::N;
+    const int n = blockIdx.y, slab = blockIdx.x;
+    const int cvec = C / VEC;
+    const int r = blockDim.x / cvec;
+    const int col = threadIdx.x % cvec, rr = threadIdx.x / cvec;
+    if (rr >= r) return;
+    const int cpg = C / G;
+    float A[VEC], B[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = col * VEC + i;
+        const int g = c / cpg;
+        const float mean = stats[(n * G + g) * 2], rstd = stats[(n * G + g) * 2 + 1];
+        const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
+        const float ad = add_nc ? add_nc[static_cast<long long>(n) * C + c] : 0.f;
+        A[i] = rstd * w;
+        B[i] = (ad - mean) * rstd * w + b;
+    }
+    const int p0 = slab * rows_per_slab;
+    const int p1 = min(HW, p0 + rows_per_slab);
+    const T* xn = x + static_cast<long long>(n) * HW * C;
+    T* yn = y + static_cast<long long>(n) * HW * C;
+    for (int p = p0 + rr; p < p1; p += r) {
+        float e[VEC];
+        load_vec<T>(xn + static_cast<long long>(p) * C + col * VEC, e);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float o = fmaf(e[i], A[i], B[i]);
+            e[i] = fuse_silu ? silu_f(o) : o;
+        }
+        store_vec<T>(yn + static_cast<long long>(p) * C + col * VEC, e);
+    }
+}
+
+static void nhwc_geometry(int N, int C, int HW, int vec, int* threads, int* slabs, int* rows_per_slab) {
+    const int cvec = C / vec;
+    int r = cvec >= 256 ? 1 : 256 / cvec;
+    if (r > HW) r = HW;
+    if (r < 1) r = 1;
+    *threads = cvec * r;
+    int S = (2 * 148 + N - 1) / N;
+    int max_s = HW / (r * 2);
+    if (max_s < 1) max_s = 1;
+    S = std::max(1, std::min(std::min(S, max_s), kGnMaxSlabs));
+    int rps = (HW + S - 1) / S;
+    *rows_per_slab = rps;
+    *slabs = (HW + rps - 1) / rps;
+}
+
+template <typename T>
+static int group_norm_typed(cudaStream_t stream, const T* x, T* y, const float* weight, const float* bias, const float* add_nc,
+                            int N, int C, int HW, int G, float eps, int layout, int fuse_silu, void* ws, size_t ws_bytes) {
+    constexpr int VEC = VecOf<T>::N;
+    const int cpg = C / G;
+    if (layout == SDOD_NCHW) {
+        const long long L = static_cast<long long>(cpg) * HW;
+        const long long Lb = L * sizeof(T);
+        const bool aligned = (Lb % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+        int cs = 1;
+        while (Lb / cs > 49152 && cs < 8) cs *= 2;
+        while (static_cast<long long>(N) * G * cs < 2 * 148 && cs < 8 && Lb / (cs * 2) >= 8192) cs *= 2;
+        while (cs > 1 && ((L % cs) != 0 || ((Lb / cs) % 16) != 0)) cs /= 2;
+        const long long slab_bytes = Lb / cs;
+        if (aligned && slab_bytes <= 200 * 1024 && slab_bytes >= 16 && (L / cs) % VEC == 0) {
+            static bool configured = false;
+            if (!configured) {
+                SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nchw_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                    "cudaFuncSetAttribute(gn)"));
+                configured = true;
+            }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(static_cast<unsigned>(N) * G * cs);
+            cfg.blockDim = dim3(kGnThreads);
+            cfg.dynamicSmemBytes = static_cast<size_t>(slab_bytes);
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int slab_elems = static_cast<int>(L / cs);
+            SDOD_TRY(check_cuda(cudaLaunchKernelEx(&cfg, gn_nchw_cluster_kernel<T>, x, y, weight, bias, add_nc, C, HW, G, eps, fuse_silu, slab_elems),
+                                "gn_nchw_cluster_kernel"));
+            count_launch();
+            return kOk;
+        }
+        gn_nchw_generic_kernel<T><<<N * G, kGnThreads, 0, stream>>>(x, y, weight, bias, add_nc, C, HW, G, eps, fuse_silu);
+        count_launch();
+        return check_launch("gn_nchw_generic_kernel");
+    }
+    // NHWC
+    if (C % VEC != 0) return fail(kUnsupported, "group_norm NHWC: C must be a multiple of 16 bytes worth of elements");
+    if (C / VEC > 1024) return fail(kUnsupported, "group_norm NHWC: C too large");
+    if (G > 64) return fail(kUnsupported, "group_norm NHWC: num_groups > 64");
+    if (N > kGnCounterInts) return fail(kUnsupported, "group_norm NHWC: batch > 256");
+    int threads, S, rps;
+    nhwc_geometry(N, C, HW, VEC, &threads, &S, &rps);
+    const size_t need = sdod_group_norm_workspace(N, C, HW, G, SDOD_NHWC);
+    if (!ws || ws_bytes < need) return fail(kInvalidArgument, "group_norm NHWC: workspace too small (need " + std::to_string(need) + " bytes)");
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    float* stats = reinterpret_cast<float*>(counters + kGnCounterInts);
+    float* partials = stats + static_cast<size_t>(N) * G * 2;
+    const int r = threads / (C / VEC);
+    const size_t smem = static_cast<size_t>(r) * C * 2 * sizeof(float);
+    if (smem > 48 * 1024) {
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                            "cudaFuncSetAttribute(gn stats)"));
+    }
+    gn_nhwc_stats_kernel<T><<<dim3(S, N), threads, smem, stream>>>(x, add_nc, partials, counters, stats, C, HW, G, rps, eps);
+    SDOD_TRY(check_launch("gn_nhwc_stats_kernel"));
+    gn_nhwc_apply_kernel<T><<<dim3(S, N), threads, 0, stream>>>(x, y, weight, bias, add_nc, stats, C, HW, G, rps, fuse_silu);
+    count_launch(2);
+    return check_launch("gn_nhwc_apply_kernel");
+}
+
+int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc, int N, int C,
+               int HW, int G, float eps, int dtype, int layout, int fuse_silu, void* ws, size_t ws_bytes) {
+    if (!x || !y) return fail(kInvalidArgument, "group_norm: NULL tensor");
+    if (N <= 0 || C <= 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");
+    if (C % G != 0) return fail(kInvalidArgument, "num_channels must be divisible by num_groups");   // efficient_gn.py:37-38
+    if ((weight == nullptr) != (bias == nullptr)) return fail(kInvalidArgument, "group_norm: weight and bias must both be given or both be NULL");  // efficient_gn.py:17-22
+    if (dtype == SDOD_F32)
+        return group_norm_typed<float>(stream, static_cast<const float*>(x), static_cast<float*>(y), weight, bias, add_nc, N, C, HW, G, eps, layout, fuse_silu, ws, ws_bytes);
+    if (dtype == SDOD_BF16)
+        return group_norm_typed<bf16>(stream, static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, add_nc, N, C, HW, G, eps, layout, fuse_silu, ws, ws_bytes);
+    return fail(kInvalidArgument, "group_norm: unknown dtype");
+}
+
+}  // namespace sdod
+
+extern "C" {
+SDOD_API size_t sdod_group_norm_workspace(int N, int C, int HW, int num_groups, int layout) {
+    (void)C; (void)HW;
+    if (layout != SDOD_NHWC) return 0;
+    return sdod::kGnCounterInts * sizeof(unsigned int) + static_cast<size_t>(N) * num_groups * 2 * sizeof(float) * (1 + sdod::kGnMaxSlabs);
+}
+SDOD_API int sdod_group_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc,
+                             int N, int C, int HW, int num_groups, float eps, int dtype, int layout, int fuse_silu, void* workspace,
+                             size_t workspace_bytes) {
+    return sdod::group_norm(static_cast<cudaStream_t>(stream), x, y, weight, bias, add_nc, N, C, HW, num_groups, eps, dtype, layout, fuse_silu,
+                            workspace, workspace_bytes);
+}
+}

@@ -1,0 +1,189 @@
+// Sampler-side device kernels: fused CFG combine + eps->x0 + DPM-Solver++(2M) update, sinusoidal
+// timestep features, Gaussian noise init, image quantisation.
+//
+// Reference behaviour restated (csrc/libsdod/src/):
+//   CFG     context.cpp:359-373 via QnnTensor::get_data(scale, accum) -> qnn_context.cpp:1065-1081
+//   update  dpm_solver.cpp:136-181 (normalize / scale / accumulate helpers :58-75)
+//   temb    context.cpp:257-275   noise context.cpp:333-334   uint8 map context.cpp:392-395
+// The host code performs ~6 separate passes with one float rounding per operation; the fused kernel
+// keeps every one of those roundings (__fmul_rn/__fadd_rn/__fdiv_rn forbid FMA contraction), so the
+// fp32 result is bit-identical to the reference for the same eps inputs.
+#include "../common.cuh"
+#include "../host_common.h"
+#include "../launch_count.h"
+#include "sdod_kernels.h"
+
+namespace sdod {
+
+struct StepCoef {
+    float g, one_minus_g, neg_sigma, alpha, c_x, c_prev, c_y0;
+    int order, cfg;
+};
+
+template <typename E> SDOD_DEVICE float eps_load(const E* p, size_t i);
+template <> SDOD_DEVICE float eps_load<float>(const float* p, size_t i) { return p[i]; }
+template <> SDOD_DEVICE float eps_load<bf16>(const bf16* p, size_t i) { return __bfloat162float(p[i]); }
+
+SDOD_DEVICE float dpm_one(float x, float ec, float eu, float& yprev, const StepCoef& k) {
+    float e;
+    if (k.cfg) {
+        e = __fmul_rn(ec, k.g);                                  // e = g*eps_c            (context.cpp:362)
+        e = __fadd_rn(e, __fmul_rn(eu, k.one_minus_g));          // e += (1-g)*eps_u       (context.cpp:373)
+    } else {
+        e = ec;                                                  // g == 1: uncond skipped (context.cpp:359-360)
+    }
+    const float y0 = __fdiv_rn(__fadd_rn(x, __fmul_rn(k.neg_sigma, e)), k.alpha);   // dpm_solver.cpp:139
+    float xn = __fmul_rn(x, k.c_x);                              // scale                  (:153 / :168)
+    if (k.order == 2) xn = __fadd_rn(xn, __fmul_rn(k.c_prev, yprev));               // :169
+    xn = __fadd_rn(xn, __fmul_rn(k.c_y0, y0));                   // :154 / :170
+    yprev = y0;                                                  // :177-180
+    return xn;
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) cfg_dpm_step_kernel(float* __restrict__ x, float* __restrict__ y_prev, const E* __restrict__ eps_c,
+                                                           const E* __restrict__ eps_u, size_t n, StepCoef k, bf16* __restrict__ x_bf16) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float yp = (k.order == 2) ? y_prev[i] : 0.f;
+        const float ec = eps_load<E>(eps_c, i);
+        const float eu = k.cfg ? eps_load<E>(eps_u, i) : 0.f;
+        const float xn = dpm_one(x[i], ec, eu, yp, k);
+        x[i] = xn;
+        y_prev[i] = yp;
+        if (x_bf16) x_bf16[i] = __float2bfloat16(xn);
+    }
+}
+
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, int n_t, int dim, float log_period, float* __restrict__ out) {
+    const int half = dim / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_t * half) return;
+    const int i = idx / half, j = idx - i * half;
+    // arg = t * exp(log_period * j / half)   (context.cpp:271), cos first (:272-273)
+    const float arg = __fmul_rn(t[i], expf(__fdiv_rn(__fmul_rn(log_period, static_cast<float>(j)), static_cast<float>(half))));
+    out[static_cast<size_t>(i) * dim + j] = cosf(arg);
+    out[static_cast<size_t>(i) * dim + half + j] = sinf(arg);
+}
+
+// Philox4x32-10 counter RNG + Box-Muller.  (The reference draws from std::mt19937 /
+// std::normal_distribution, context.cpp:16,333-334 — implementation-defined bit stream, so parity
+// is distributional; tests inject identical latents into both paths. SURVEY App. C.)
+SDOD_DEVICE void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__global__ void randn_kernel(float* __restrict__ out, size_t n, unsigned long long seed, unsigned long long offset) {
+    const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // one Philox block = 4 normals
+    if (q * 4 >= n) return;
+    const unsigned long long ctr = offset + q;
+    uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = (static_cast<float>(c[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);       // (0,1)
+        const float u2 = (static_cast<float>(c[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        z[2 * h] = r * cs;
+        z[2 * h + 1] = r * sn;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (q * 4 + i < n) out[q * 4 + i] = z[i];
+}
+
+template <typename T>
+__global__ void image_to_u8_kernel(const T* __restrict__ img, uint8_t* __restrict__ out, size_t n) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float f;
+        if constexpr (sizeof(T) == 4) f = img[i]; else f = __bfloat162float(img[i]);
+        float v = __fmul_rn(255.0f, f);
+        v = fminf(fmaxf(v, 0.0f), 255.0f);       // std::clamp(255*f, 0, 255)
+        out[i] = static_cast<uint8_t>(v);        // truncation, not rounding (context.cpp:394)
+    }
+}
+
+static inline int grid_for(size_t n, int block, int per_thread = 1) {
+    size_t g = (n + static_cast<size_t>(block) * per_thread - 1) / (static_cast<size_t>(block) * per_thread);
+    const size_t cap = 148 * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace sdod
+
+using namespace sdod;
+
+extern "C" {
+
+SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, const void* eps_c, const void* eps_u, int eps_dtype,
+                               size_t n, float guidance, float sigma_s, float alpha_s, float c_x, float c_prev, float c_y0, int order,
+                               void* x_bf16_out) {
+    if (!x || !y_prev || !eps_c) return fail(kInvalidArgument, "cfg_dpm_step: NULL tensor");
+    if (order != 1 && order != 2) return fail(kInvalidArgument, "cfg_dpm_step: order must be 1 or 2");
+    StepCoef k;
+    k.g = guidance;
+    k.one_minus_g = 1 - guidance;            // float, as `1-guidance` at context.cpp:373
+    k.neg_sigma = -sigma_s;
+    k.alpha = alpha_s;
+    k.c_x = c_x; k.c_prev = c_prev; k.c_y0 = c_y0;
+    k.order = order;
+    k.cfg = (guidance == 1.0f) ? 0 : 1;      // exact compare, context.cpp:359
+    if (k.cfg && !eps_u) return fail(kInvalidArgument, "cfg_dpm_step: eps_u required when guidance != 1");
+    if (n == 0) return kOk;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(n, 256);
+    if (eps_dtype == SDOD_F32)
+        cfg_dpm_step_kernel<float><<<grid, 256, 0, s>>>(x, y_prev, static_cast<const float*>(eps_c), static_cast<const float*>(eps_u), n, k,
+                                                        static_cast<bf16*>(x_bf16_out));
+    else if (eps_dtype == SDOD_BF16)
+        cfg_dpm_step_kernel<bf16><<<grid, 256, 0, s>>>(x, y_prev, static_cast<const bf16*>(eps_c), static_cast<const bf16*>(eps_u), n, k,
+                                                       static_cast<bf16*>(x_bf16_out));
+    else
+        return fail(kInvalidArgument, "cfg_dpm_step: unknown eps dtype");
+    count_launch();
+    return check_launch("cfg_dpm_step_kernel");
+}
+
+SDOD_API int sdod_timestep_sinusoid(sdod_stream_t stream, const float* t_dev, int n_t, int dim, float max_period, float* out) {
+    if (!t_dev || !out || n_t <= 0 || dim <= 0 || (dim & 1)) return fail(kInvalidArgument, "timestep_sinusoid: bad arguments (dim must be even)");
+    const float log_period = -logf(max_period);   // context.cpp:261
+    const int total = n_t * (dim / 2);
+    timestep_sinusoid_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t_dev, n_t, dim, log_period, out);
+    count_launch();
+    return check_launch("timestep_sinusoid_kernel");
+}
+
+SDOD_API int sdod_randn(sdod_stream_t stream, float* out, size_t n, unsigned long long seed, unsigned long long offset) {
+    if (!out) return fail(kInvalidArgument, "randn: NULL output");
+    if (n == 0) return kOk;
+    const size_t blocks = (n + 3) / 4;
+    randn_kernel<<<static_cast<unsigned>((blocks + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset);
+    count_launch();
+    return check_launch("randn_kernel");
+}
+
+SDOD_API int sdod_image_to_u8(sdod_stream_t stream, const void* img, int dtype, uint8_t* out, size_t n) {
+    if (!img || !out) return fail(kInvalidArgument, "image_to_u8: NULL tensor");
+    if (n == 0) return kOk;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == SDOD_F32) image_to_u8_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const float*>(img), out, n);
+    else if (dtype == SDOD_BF16) image_to_u8_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const bf16*>(img), out, n);
+    else return fail(kInvalidArgument, "image_to_u8: unknown dtype");
+    count_launch();
+    return check_launch("image_to_u8_kernel");
+}
+
+}  // extern "C"

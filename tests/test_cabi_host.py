@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and its host-side logic matches the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from sdod import _cabi
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"\b((?:sdod|libsdod)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    missing = [s for h in ("sdod_kernels.h", "libsdod.h", "sdod_model.h") if os.path.exists(os.path.join(ROOT, "include", h))
+               for s in _declared(h) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.sdod_abi_version() >= 1
+
+
+def test_binding_table_covers_header():
+    assert set(_declared("sdod_kernels.h")) <= set(_cabi.exported_symbols())
+
+
+@pytest.mark.parametrize("steps", [20, 10, 50])
+def test_product_schedule_bit_exact_vs_reference_golden(golden_dir, steps):
+    from sdod import ops
+    g = np.load(os.path.join(golden_dir, "dpm_golden.npz"))
+    t = ops.dpm_schedule(steps)
+    for k, v in t.items():
+        assert np.array_equal(v.view(np.uint32), g["s%d_%s" % (steps, k)].view(np.uint32)), k
+
+
+def test_product_coeffs_follow_reference_order_rule(golden_dir):
+    from sdod import ops
+    g = np.load(os.path.join(golden_dir, "dpm_golden.npz"))
+    a, p, r, s = g["s20_alphas"], g["s20_phis"], g["s20_i2rs"], g["s20_sigmas"]
+    for step in range(20):
+        k = ops.dpm_coeffs(step)
+        assert k["order"] == (1 if step == 0 else 2)                                # dpm_solver.cpp:137
+        assert np.float32(k["c_x"]) == s[step + 1] / s[step]
+        if step == 0:
+            assert np.float32(k["c_y0"]) == -a[1] * p[1] and k["c_prev"] == 0.0
+        else:
+            assert np.float32(k["c_prev"]) == a[step + 1] * p[step + 1] * r[step + 1]
+            assert np.float32(k["c_y0"]) == -a[step + 1] * p[step + 1] * (np.float32(1) + r[step + 1])
+
+
+def test_efficient_gn_host_contract():
+    import torch.nn as nn
+    from sdod import EfficientGN
+    with pytest.raises(ValueError):
+        EfficientGN(3, 8)                                    # efficient_gn.py:37-38
+    with pytest.raises(ValueError):
+        EfficientGN(2, 8, impl="fast")                       # :39-40
+    m = EfficientGN(2, 8, impl="eff")
+    assert torch.equal(m.weight, torch.ones(8)) and torch.equal(m.bias, torch.zeros(8))
+    ref = nn.GroupNorm(2, 8)
+    with torch.no_grad():
+        ref.weight.normal_(), ref.bias.normal_()
+    m.load_state_dict(ref.state_dict())                      # tests/gn_to_ln.py:26
+    assert torch.equal(m.weight, ref.weight)
+    assert EfficientGN(2, 8, affine=False).weight is None
+    assert "eps=1e-05" in repr(m)
+    with pytest.raises(_cabi.SdodError):                     # no CPU fallback
+        m(torch.randn(1, 8, 2, 2))
+    with pytest.raises(NotImplementedError):
+        EfficientGN(2, 8, impl="ln")(torch.randn(1, 8, 2, 2))
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _cabi.lib()
+    st = lib.sdod_randn(None, ctypes.c_void_p(16), 16, 0, 0)
+    assert st != 0 and lib.sdod_last_error()

@@ -1,0 +1,288 @@
+"""GPU parity tests, through the torch custom ops -> C ABI -> sm_100a kernels.
+
+Tolerances are BASELINE.json's: per-op max relative error 1e-3 (fp32) / 2e-2 (bf16); the sampler is
+bit-exact.  "relative" = max|got-want| / max|want| (per-op), as the north star states it.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from sdod import EfficientGN, ops
+    from sdod import _cabi as C
+from oracle import ldm_oracle as L
+from oracle import sampler as S
+
+DEV = "cuda"
+TOL_F32, TOL_BF16 = 1e-3, 2e-2
+
+
+def rel_err(got, want):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-12)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------ GroupNorm
+def test_gn_reference_golden_vectors(golden_dir):
+    """sdod.EfficientGN on CUDA vs outputs of the reference's own EfficientGN (tests/golden/gn_golden.npz)."""
+    gn = np.load(os.path.join(golden_dir, "gn_golden.npz"))
+    for k in sorted(k[:-2] for k in gn.files if k.endswith("_x")):
+        G, eps, affine = gn[k + "_meta"]
+        impl = "eff" if k.endswith("_eff") else None
+        x = torch.from_numpy(gn[k + "_x"]).to(DEV)
+        m = EfficientGN(int(G), x.shape[1], eps=float(eps), affine=bool(affine), impl=impl).to(DEV)
+        if affine:
+            m.load_state_dict({"weight": torch.from_numpy(gn[k + "_w"]), "bias": torch.from_numpy(gn[k + "_b"])})
+        with torch.no_grad():
+            y = m(x)
+        assert rel_err(y, torch.from_numpy(gn[k + "_y"])) < TOL_F32, k
+
+
+@pytest.mark.parametrize("silu", [False, True])
+def test_gn_config1_fp32_nchw(silu):
+    """BASELINE config 1: GN(32)+SiLU on [2,320,64,64] fp32 vs torch.nn.GroupNorm on CPU."""
+    torch.manual_seed(0)
+    x = torch.randn(2, 320, 64, 64) * 2 + 0.5
+    w, b = torch.randn(320), torch.randn(320)
+    want = F.group_norm(x, 32, w, b, 1e-5)
+    want = F.silu(want) if silu else want
+    got = torch.ops.sdod.group_norm(x.to(DEV), 32, w.to(DEV), b.to(DEV), 1e-5, silu, None)
+    assert rel_err(got, want) < TOL_F32
+
+
+@pytest.mark.parametrize("shape,G", [((2, 320, 64, 64), 32), ((2, 640, 32, 32), 32), ((1, 2560, 8, 8), 32), ((2, 1920, 16, 16), 32),
+                                      ((1, 128, 64, 64), 32), ((3, 960, 16, 16), 32), ((1, 32, 4, 4), 8)])
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_gn_nhwc_and_nchw_all_dtypes(shape, G, dtype):
+    torch.manual_seed(1)
+    x = torch.randn(shape) * 1.5 + 0.3
+    w, b = torch.randn(shape[1]), torch.randn(shape[1])
+    td = torch.bfloat16 if dtype == "bf16" else torch.float32
+    xq = x.to(td)
+    want = F.silu(L.group_norm_f64(xq, G, w, b, 1e-6).float())
+    tol = TOL_BF16 if dtype == "bf16" else TOL_F32
+    got_nchw = torch.ops.sdod.group_norm(xq.to(DEV), G, w.to(DEV), b.to(DEV), 1e-6, True, None)
+    assert rel_err(got_nchw, want) < tol
+    x_cl = xq.to(DEV).contiguous(memory_format=torch.channels_last)
+    got_nhwc = torch.ops.sdod.group_norm(x_cl, G, w.to(DEV), b.to(DEV), 1e-6, True, None)
+    assert got_nhwc.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(got_nhwc, want) < tol
+    # repeated call reuses the self-cleaning workspace
+    assert torch.equal(torch.ops.sdod.group_norm(x_cl, G, w.to(DEV), b.to(DEV), 1e-6, True, None), got_nhwc)
+
+
+def test_gn_fused_temb_add_and_parameterless():
+    torch.manual_seed(2)
+    x = torch.randn(2, 640, 32, 32)
+    add = torch.randn(2, 640)
+    w, b = torch.randn(640), torch.randn(640)
+    want = F.silu(F.group_norm(x + add[:, :, None, None], 32, w, b, 1e-5))
+    got = torch.ops.sdod.group_norm(x.to(DEV), 32, w.to(DEV), b.to(DEV), 1e-5, True, add.to(DEV))
+    assert rel_err(got, want) < TOL_F32
+    x_cl = bf(x).to(DEV).contiguous(memory_format=torch.channels_last)
+    got = torch.ops.sdod.group_norm(x_cl, 32, w.to(DEV), b.to(DEV), 1e-5, True, add.to(DEV))
+    want = F.silu(F.group_norm(bf(x).float() + add[:, :, None, None], 32, w, b, 1e-5))
+    assert rel_err(got, want) < TOL_BF16
+    got = torch.ops.sdod.group_norm(x.to(DEV), 32, None, None, 1e-5, False, None)       # sdod::ParameterlessGroupNorm
+    assert rel_err(got, F.group_norm(x, 32, None, None, 1e-5)) < TOL_F32
+    with pytest.raises(ValueError):
+        torch.ops.sdod.group_norm(x.to(DEV), 7, None, None, 1e-5, False, None)
+
+
+def test_gn_large_offset_numerics():
+    """mean >> std: the shifted single-pass statistics must not cancel catastrophically."""
+    torch.manual_seed(3)
+    x = torch.randn(2, 64, 32, 32) * 0.05 + 300.0
+    want = L.group_norm_f64(x, 32, None, None, 1e-5).float()
+    assert rel_err(torch.ops.sdod.group_norm(x.to(DEV), 32, None, None, 1e-5, False, None), want) < 5e-3
+    x_cl = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert rel_err(torch.ops.sdod.group_norm(x_cl, 32, None, None, 1e-5, False, None), want) < 5e-3
+
+
+def test_layer_norm():
+    torch.manual_seed(4)
+    for width in (320, 640, 1280):
+        x = bf(torch.randn(300, width) * 2 + 1)
+        w, b = torch.randn(width), torch.randn(width)
+        want = F.layer_norm(x.float(), (width,), w, b, 1e-5)
+        assert rel_err(torch.ops.sdod.layer_norm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5), want) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("guidance", [7.5, 1.0])
+def test_cfg_dpm_sampler_bit_exact_20_steps(guidance):
+    """Fused CFG + DPM-Solver++(2M) kernel vs the oracle (itself bit-exact vs the compiled reference)."""
+    rng = np.random.default_rng(5)
+    n = 2 * 4 * 64 * 64
+    o = S.OracleSolver()
+    o.prepare(20)
+    x_cpu = rng.standard_normal(n).astype(np.float32)
+    x = torch.from_numpy(x_cpu.copy()).to(DEV)
+    yprev = torch.zeros(n, device=DEV)
+    for s in range(20):
+        ec, eu = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+        e = S.cfg_combine(ec, eu, guidance)
+        o.update(s, x_cpu, e)
+        k = ops.dpm_coeffs(s)
+        torch.ops.sdod.cfg_dpm_step(x, yprev, torch.from_numpy(ec).to(DEV), torch.from_numpy(eu).to(DEV), guidance, k["sigma_s"],
+                                    k["alpha_s"], k["c_x"], k["c_prev"], k["c_y0"], k["order"])
+        assert np.array_equal(x.cpu().numpy().view(np.uint32), x_cpu.view(np.uint32)), "step %d" % s
+
+
+def test_sampler_golden_trajectory(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dpm_golden.npz"))
+    x = torch.tensor(0.25 * (np.arange(8) - 3.5), dtype=torch.float32, device=DEV)
+    yprev = torch.zeros(8, device=DEV)
+    for s in range(20):
+        e = torch.tensor((0.1 * (((7 * np.arange(8) + 3 * s) % 11) - 5)).astype(np.float32), device=DEV)
+        k = ops.dpm_coeffs(s)
+        torch.ops.sdod.cfg_dpm_step(x, yprev, e, None, 1.0, k["sigma_s"], k["alpha_s"], k["c_x"], k["c_prev"], k["c_y0"], k["order"])
+        assert np.array_equal(x.cpu().numpy().view(np.uint32), g["s20_traj"][s].view(np.uint32))
+
+
+def test_sinusoid_noise_u8():
+    t = torch.tensor(ops.dpm_schedule(20)["model_ts"][:20], device=DEV)
+    got = ops.timestep_sinusoid(t).cpu().numpy()
+    want = np.stack([S.sinusoid(float(v)) for v in t.cpu().numpy()])
+    assert np.abs(got - want).max() < 2e-4
+    z = ops.randn(1 << 20, seed=1234).cpu()
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3 and torch.isfinite(z).all()
+    assert abs((z ** 4).mean().item() - 3.0) < 0.05
+    assert torch.equal(ops.randn(1000, seed=7).cpu(), ops.randn(1000, seed=7).cpu())
+    assert not torch.equal(ops.randn(1000, seed=7).cpu(), ops.randn(1000, seed=8).cpu())
+    img = torch.rand(3, 64, 64) * 1.4 - 0.2
+    assert np.array_equal(ops.image_to_u8(img.to(DEV)).cpu().numpy(), S.to_u8(img.numpy()))
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [(128, 128, 64), (256, 320, 320), (8192, 320, 320), (100, 1280, 320), (2, 1280, 1280), (512, 640, 2560),
+               (4096, 2560, 320), (130, 72, 128), (1000, 4, 64), (8192, 960, 320)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(M, N, K):
+    torch.manual_seed(M + N + K)
+    a, w = bf(torch.randn(M, K)), bf(torch.randn(N, K) / K ** 0.5)
+    want = a.to(DEV).float() @ w.to(DEV).float().t()
+    got32 = torch.ops.sdod.linear(a.to(DEV), w.to(DEV), None, None, 0, 1.0, True)
+    assert rel_err(got32, want) < TOL_F32
+    got16 = torch.ops.sdod.linear(a.to(DEV), w.to(DEV))
+    assert got16.dtype == torch.bfloat16 and rel_err(got16, want) < TOL_BF16
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 160, 256])
+def test_gemm_every_tile_width(bn):
+    torch.manual_seed(bn)
+    a, w = bf(torch.randn(384, 256)), bf(torch.randn(640, 256) / 16)
+    want = a.to(DEV).float() @ w.to(DEV).float().t()
+    got = torch.ops.sdod.linear(a.to(DEV), w.to(DEV), None, None, 0, 1.0, True, None, 0, bn)
+    assert rel_err(got, want) < TOL_F32
+
+
+def test_gemm_epilogues():
+    torch.manual_seed(11)
+    M, N, K = 512, 640, 320
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias, res = torch.randn(N, device=DEV), bf(torch.randn(M, N)).to(DEV)
+    rowb = torch.randn(2, N, device=DEV)
+    base = a.float() @ w.float().t()
+    assert rel_err(torch.ops.sdod.linear(a, w, bias), base + bias) < TOL_BF16
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, res), base + bias + res.float()) < TOL_BF16
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, None, C.ACT_SILU), F.silu(base + bias)) < TOL_BF16
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, None, C.ACT_GELU), F.gelu(base + bias)) < TOL_BF16
+    assert rel_err(torch.ops.sdod.linear(a, w, None, None, 0, 0.125), base * 0.125) < TOL_BF16
+    want = base + bias + rowb.repeat_interleave(M // 2, dim=0)
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, None, 0, 1.0, False, rowb, M // 2), want) < TOL_BF16
+
+
+def test_gemm_geglu_packed():
+    torch.manual_seed(12)
+    M, Cc = 256, 320
+    a = bf(torch.randn(M, Cc)).to(DEV)
+    w = bf(torch.randn(8 * Cc, Cc) / Cc ** 0.5).to(DEV)
+    bias = torch.randn(8 * Cc, device=DEV)
+    h = a.float() @ w.float().t() + bias
+    want = h[:, :4 * Cc] * F.gelu(h[:, 4 * Cc:])
+    wp, bp = ops.pack_geglu_weight(w, bias, 256)
+    got = torch.ops.sdod.linear(a, wp, bp, None, C.ACT_GEGLU)
+    assert got.shape == (M, 4 * Cc) and rel_err(got, want) < TOL_BF16
+
+
+def test_gemm_batched():
+    torch.manual_seed(13)
+    a, w = bf(torch.randn(6, 200, 128)).to(DEV), bf(torch.randn(6, 328, 128) / 11).to(DEV)
+    want = torch.bmm(a.float(), w.float().transpose(1, 2))
+    assert rel_err(torch.ops.sdod.linear(a, w, None, None, 0, 1.0, True), want) < TOL_F32
+    w1 = w[0].contiguous()
+    want = a.float() @ w1.float().t()
+    assert rel_err(torch.ops.sdod.linear(a, w1, None, None, 0, 1.0, True), want) < TOL_F32
+
+
+# ------------------------------------------------------------------------------------------ conv3x3
+CONV_CASES = [(2, 16, 16, 64, 64), (1, 8, 8, 128, 320), (3, 8, 8, 64, 128), (2, 64, 64, 320, 320), (2, 32, 32, 640, 640),
+              (1, 16, 16, 1280, 1280), (1, 128, 128, 128, 128), (1, 256, 256, 64, 64), (2, 4, 4, 64, 96), (1, 64, 64, 320, 4)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_CASES)
+def test_conv3x3_implicit_gemm(B, H, W, Cin, Cout):
+    torch.manual_seed(B * H + Cin + Cout)
+    x = bf(torch.randn(B, Cin, H, W)).to(DEV)
+    w = bf(torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    bias = torch.randn(Cout, device=DEV)
+    want = F.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    wt = ops.pack_conv3x3_weight(w.float())
+    assert torch.equal(wt.view(Cout, 3, 3, Cin), w.permute(0, 2, 3, 1).contiguous())
+    got = torch.ops.sdod.conv3x3(x.permute(0, 2, 3, 1).contiguous(), wt, bias)
+    assert got.shape == (B, H, W, Cout) and rel_err(got, want) < TOL_BF16
+
+
+def test_conv3x3_fused_temb_and_residual():
+    torch.manual_seed(21)
+    B, H, W, Cin, Cout = 2, 32, 32, 320, 640
+    x = bf(torch.randn(B, H, W, Cin)).to(DEV)
+    w = bf(torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    bias, temb = torch.randn(Cout, device=DEV), torch.randn(B, Cout, device=DEV)
+    res = bf(torch.randn(B, H, W, Cout)).to(DEV)
+    base = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    wt = ops.pack_conv3x3_weight(w.float())
+    assert rel_err(torch.ops.sdod.conv3x3(x, wt, bias, None, temb), base + temb[:, None, None, :]) < TOL_BF16
+    assert rel_err(torch.ops.sdod.conv3x3(x, wt, bias, res), base + res.float()) < TOL_BF16
+
+
+def test_conv_via_im2col_stride2_and_narrow_input():
+    torch.manual_seed(22)
+    x = bf(torch.randn(2, 32, 32, 320)).to(DEV)
+    w = bf(torch.randn(320, 320, 3, 3) / 54).to(DEV)
+    want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), None, stride=2, padding=1).permute(0, 2, 3, 1)
+    cols = ops.im2col3x3(x, stride=2)
+    got = torch.ops.sdod.linear(cols, ops.pack_conv3x3_weight(w.float())).view(2, 16, 16, 320)
+    assert rel_err(got, want) < TOL_BF16
+    x4 = bf(torch.randn(2, 64, 64, 4)).to(DEV)                                        # conv_in: Cin = 4 -> K padded to 64
+    w4 = bf(torch.randn(320, 4, 3, 3) / 6).to(DEV)
+    want = F.conv2d(x4.permute(0, 3, 1, 2).float(), w4.float(), None, padding=1).permute(0, 2, 3, 1)
+    got = torch.ops.sdod.linear(ops.im2col3x3(x4, 1, 64), ops.pack_conv3x3_weight(w4.float(), 64)).view(2, 64, 64, 320)
+    assert rel_err(got, want) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------ data movement
+def test_layout_helpers():
+    torch.manual_seed(30)
+    x = torch.randn(2, 4, 64, 64, device=DEV)
+    y = ops.nchw_f32_to_nhwc_bf16(x)
+    assert torch.equal(y, bf(x).permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw_f32(y), bf(x).float())
+    a, b = bf(torch.randn(2, 8, 8, 64)).to(DEV), bf(torch.randn(2, 8, 8, 320)).to(DEV)
+    assert torch.equal(ops.concat_channels(a, b), torch.cat([a, b], dim=-1))
+    up = ops.upsample2x(a)
+    assert torch.equal(up, F.interpolate(a.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).to(torch.bfloat16))
+    s = bf(torch.randn(64, 4096)).to(DEV)
+    assert rel_err(ops.softmax_rows(s, 0.5), F.softmax(s.float() * 0.5, dim=-1)) < TOL_BF16
