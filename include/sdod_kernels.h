@@ -114,6 +114,7 @@ typedef struct sdod_epilogue {
     int act;                 /* sdod_act; GEGLU: tile columns [0,BN/2) = value, [BN/2,BN) = gate    */
     int out_mode;            /* sdod_out_mode                                                      */
     int heads, head_dim, tokens, dpad, tok_pad;   /* HEADS / HEADS_T / QKV modes                   */
+    int vt_rows;             /* HEADS_T / QKV: rows allocated per head in the V^T buffer           */
 } sdod_epilogue;
 
 typedef struct sdod_gemm_desc {
@@ -136,9 +137,11 @@ typedef struct sdod_conv_desc {
 } sdod_conv_desc;
 SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d);
 
-/* Fused flash-style attention on tcgen05 (S/P/O in TMEM, online softmax).
- * Qh [BH, Nq, dpad], Kh [BH, Nkv, dpad] (HEADS layout), Vt [BH, dv_pad, kv_pad] (HEADS_T layout).
- * O bf16 [B, Nq, heads*head_dim] (token-major, heads concatenated). scale applied to S. */
+/* Fused flash-style attention on tcgen05 (S and O accumulators in TMEM, online softmax, P through
+ * swizzled shared memory).  SpatialTransformer attn1/attn2 (analyze_results.py:60-75).
+ * Qh [BH, Nq, dpad], Kh [BH, Nkv, dpad] (HEADS layout, dpad = 64*ceil(head_dim/64), zero padded),
+ * Vt [BH, vt_rows, kv_pad] (HEADS_T layout, vt_rows = 16*ceil(head_dim/16), kv_pad % 8 == 0, zero padded).
+ * O bf16 [B, Nq, heads*head_dim] (token-major, heads concatenated).  softmax(scale * Q K^T) V. */
 SDOD_API int sdod_attention_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O,
                                  int B, int heads, int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale);
 

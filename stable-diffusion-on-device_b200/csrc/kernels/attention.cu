@@ -1,0 +1,309 @@
+// Fused flash-style attention for sm_100a (SpatialTransformer attn1 / attn2).
+//
+//   O = softmax(scale * Q K^T) V      per (batch*head), 128 query rows per CTA, KV tiles of 128.
+//
+// Warp roles (192 threads):
+//   warp 0     : TMA producer — Q once, then K / V^T tiles through an mbarrier ring
+//   warp 1     : MMA issuer   — S = Q K^T and O += P V on tcgen05, accumulators in TMEM
+//   warps 2..5 : softmax      — one thread per query row: tcgen05.ld S, online max/sum in the exp2
+//                domain, O rescale in TMEM (tcgen05.ld/st) only when some row's max moved,
+//                P (bf16) written into 128B-swizzled smem as the A operand of the PV MMA;
+//                final O / l -> bf16 [B, Nq, heads*head_dim]
+// TMEM columns: S at [0,128), O at [128, 128+dv).  Everything is K-major + SWIZZLE_128B: K^T comes
+// for free from the HEADS layout, V is stored transposed (HEADS_T) by the producing GEMM epilogue.
+#include "../common.cuh"
+#include "../host_common.h"
+#include "../launch_count.h"
+#include "sdod_kernels.h"
+
+namespace sdod {
+
+constexpr int kAttThreads = 192;
+constexpr int kBQ = 128;    // query rows per CTA
+constexpr int kBKV = 128;   // keys per tile
+
+template <int DH>
+struct AttCfg {
+    static constexpr int kNK = (DH + 63) / 64;            // 64-wide d chunks of Q / K
+    static constexpr int kKSteps = (DH + 15) / 16;        // UMMA K steps for S = Q K^T
+    static constexpr int kDV = ((DH + 15) / 16) * 16;     // N of the PV MMA (rows of V^T tile)
+    static constexpr int kStages = DH > 80 ? 1 : 2;
+    static constexpr int kQBytes = kNK * kBQ * 128;
+    static constexpr int kKBytes = kNK * kBKV * 128;
+    static constexpr int kVBytes = 2 * kDV * 128;         // two 64-key chunks, kDV rows of 128 B
+    static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;   // keep chunk bases 1024-B aligned
+    static constexpr int kStageBytes = kKBytes + 2 * kVChunk;
+    static constexpr int kPBytes = 2 * kBQ * 128;
+    static constexpr int kTmemCols = (128 + kDV) <= 256 ? 256 : 512;
+    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 1024 + 256;
+};
+
+SDOD_DEVICE float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                 const __grid_constant__ CUtensorMap tmK,
+                                                                 const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O,
+                                                                 int heads, int Nq, int Nkv, float scale_log2) {
+    using Cfg = AttCfg<DH>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + Cfg::kQBytes;
+    uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;                 // [STAGES]
+    uint64_t* kv_empty = kv_full + STAGES;        // [STAGES]
+    uint64_t* s_full = kv_empty + STAGES;
+    uint64_t* s_free = s_full + 1;
+    uint64_t* p_full = s_free + 1;
+    uint64_t* o_ready = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x, bh = blockIdx.y;
+    const int q0 = q_tile * kBQ;
+    const int n_tiles = (Nkv + kBKV - 1) / kBKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 128);
+        mbar_init(p_full, 128);
+        mbar_init(o_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+            for (int c = 0; c < Cfg::kNK; ++c) tma_load_3d(sQ + c * (kBQ * 128), &tmQ, q_full, c * 64, q0, bh);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], Cfg::kKBytes + Cfg::kVBytes);
+                uint8_t* sK = sKV + st * Cfg::kStageBytes;
+                uint8_t* sV = sK + Cfg::kKBytes;
+                for (int c = 0; c < Cfg::kNK; ++c) tma_load_3d(sK + c * (kBKV * 128), &tmK, &kv_full[st], c * 64, j * kBKV, bh);
+                for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * Cfg::kVChunk, &tmV, &kv_full[st], j * kBKV + c * 64, 0, bh);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, kBKV);
+            constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, Cfg::kDV);
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
+                const uint32_t v_addr = k_addr + Cfg::kKBytes;
+                mbar_wait(&kv_full[st], ph);
+                if (j > 0) mbar_wait(s_free, (j - 1) & 1);       // softmax has drained S of the previous tile
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < Cfg::kKSteps; ++k) {
+                    const uint32_t off = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                    tc_mma_bf16(tmem_S, make_kmajor_sw128_desc(q_addr + off), make_kmajor_sw128_desc(k_addr + off), idesc_s, k != 0);
+                }
+                tc_commit(s_full);
+                mbar_wait(p_full, j & 1);                        // P_j in smem, O rescaled
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < kBKV / 16; ++k) {
+                    const uint32_t poff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                    const uint32_t voff = (k >> 2) * Cfg::kVChunk + (k & 3) * 32;
+                    tc_mma_bf16(tmem_O, make_kmajor_sw128_desc(p_addr + poff), make_kmajor_sw128_desc(v_addr + voff), idesc_o,
+                                (j | k) != 0);
+                }
+                tc_commit(&kv_empty[st]);
+                tc_commit(o_ready);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- softmax / correction / epilogue
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        uint8_t* p_row0 = sP + row * 128;           // chunk 0; chunk 1 at + kBQ*128
+        const int sw = row & 7;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int kv_valid = min(kBKV, Nkv - j * kBKV);
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            // pass A: row max (scaled into the exp2 domain)
+            float mx = m_run;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]) * scale_log2);
+            }
+            const float alpha = ex2(m_run - mx);     // 0 on the first tile (m_run = -inf)
+            // O of the previous tile must be complete before it is rescaled and before P is overwritten
+            if (j > 0) {
+                mbar_wait(o_ready, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                    for (int c = 0; c < Cfg::kDV / 16; ++c) {
+                        uint32_t o[16];
+                        tmem_ld16(tmem_O + lane_off + c * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(tmem_O + lane_off + c * 16, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // pass B: P = exp2(s*scale - max), row sum, bf16 -> swizzled smem
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+                uint8_t* prow = p_row0 + (c >> 1) * (kBQ * 128);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int col = c * 32 + u * 8 + i;
+                        const float e = ex2(__uint_as_float(v[u * 8 + i]) * scale_log2 - mx);
+                        p[i] = col < kv_valid ? e : 0.f;
+                        lsum += p[i];
+                    }
+                    uint4 w;
+                    w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
+                    w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
+                    const int unit = (c & 1) * 4 + u;                // 16-B unit within the 128-B row
+                    *reinterpret_cast<uint4*>(prow + ((unit ^ sw) << 4)) = w;
+                }
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = mx;
+            tc_fence_before();
+            mbar_arrive(s_free);                 // S may be overwritten by the next QK^T
+            fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the UMMA async proxy
+            mbar_arrive(p_full);
+        }
+        // epilogue: O / l
+        mbar_wait(o_ready, (n_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        const int b = bh / heads, h = bh - b * heads;
+        const int qi = q0 + row;
+        bf16* orow = O + (static_cast<long long>(b) * Nq + qi) * (heads * DH) + h * DH;
+#pragma unroll 1
+        for (int c = 0; c < Cfg::kDV / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_off + c * 16, o);
+            tmem_ld_wait();
+            if (qi < Nq) {
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    const int d0 = c * 16 + h8 * 8;
+                    if (d0 < DH) {     // DH % 8 == 0
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l);
+                        w.y = pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l);
+                        w.z = pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l);
+                        w.w = pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + d0) = w;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+template <int DH>
+static int launch_attention(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq,
+                            int Nkv, int dpad, int kv_pad, float scale) {
+    using Cfg = AttCfg<DH>;
+    if (dpad != Cfg::kNK * 64) return fail(kInvalidArgument, "attention: dpad must be 64*ceil(head_dim/64)");
+    if (kv_pad % 8 != 0 || kv_pad < Nkv) return fail(kInvalidArgument, "attention: kv_pad must be a multiple of 8 and >= Nkv");
+    const int BH = B * heads;
+    CUtensorMap tmQ, tmK, tmV;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(dpad), static_cast<uint64_t>(Nq), static_cast<uint64_t>(BH)};
+        uint64_t strides[2] = {static_cast<uint64_t>(dpad) * 2, static_cast<uint64_t>(Nq) * dpad * 2};
+        uint32_t box[3] = {64, kBQ, 1};
+        SDOD_TRY(encode_tmap_bf16(&tmQ, Qh, 3, dims, strides, box, true));
+    }
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(dpad), static_cast<uint64_t>(Nkv), static_cast<uint64_t>(BH)};
+        uint64_t strides[2] = {static_cast<uint64_t>(dpad) * 2, static_cast<uint64_t>(Nkv) * dpad * 2};
+        uint32_t box[3] = {64, kBKV, 1};
+        SDOD_TRY(encode_tmap_bf16(&tmK, Kh, 3, dims, strides, box, true));
+    }
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(kv_pad), static_cast<uint64_t>(Cfg::kDV), static_cast<uint64_t>(BH)};
+        uint64_t strides[2] = {static_cast<uint64_t>(kv_pad) * 2, static_cast<uint64_t>(Cfg::kDV) * kv_pad * 2};
+        uint32_t box[3] = {64, static_cast<uint32_t>(Cfg::kDV), 1};
+        SDOD_TRY(encode_tmap_bf16(&tmV, Vt, 3, dims, strides, box, true));
+    }
+    static bool configured = false;
+    if (!configured) {
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+                            "cudaFuncSetAttribute(attention)"));
+        configured = true;
+    }
+    dim3 grid((Nq + kBQ - 1) / kBQ, BH);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    attention_kernel<DH><<<grid, kAttThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, static_cast<bf16*>(O), heads, Nq, Nkv, scale_log2);
+    count_launch();
+    return check_launch("attention_kernel");
+}
+
+int attention_bf16(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
+                   int head_dim, int dpad, int kv_pad, float scale) {
+    if (!Qh || !Kh || !Vt || !O) return fail(kInvalidArgument, "attention: NULL tensor");
+    if (B <= 0 || heads <= 0 || Nq <= 0 || Nkv <= 0) return fail(kInvalidArgument, "attention: non-positive extent");
+    switch (head_dim) {
+        case 40: return launch_attention<40>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 64: return launch_attention<64>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 80: return launch_attention<80>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 160: return launch_attention<160>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+    }
+    return fail(kUnsupported, "attention: head_dim must be one of 40, 64, 80, 160 (SD v1.x)");
+}
+
+}  // namespace sdod
+
+extern "C" SDOD_API int sdod_attention_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads,
+                                            int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale) {
+    return sdod::attention_bf16(static_cast<cudaStream_t>(stream), Qh, Kh, Vt, O, B, heads, Nq, Nkv, head_dim, dpad, kv_pad, scale);
+}

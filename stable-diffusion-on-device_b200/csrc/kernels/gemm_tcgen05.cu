@@ -120,7 +120,7 @@ SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zof
         for (int i = 0; i < 8; ++i) {
             if (n + i < N) {
                 int hh = (nn + i) / ep.head_dim, dd = (nn + i) - hh * ep.head_dim;
-                reinterpret_cast<bf16*>(base)[((static_cast<long long>(b) * ep.heads + hh) * ep.dpad + dd) * ep.tok_pad + t] = __float2bfloat16(v[i]);
+                reinterpret_cast<bf16*>(base)[((static_cast<long long>(b) * ep.heads + hh) * ep.vt_rows + dd) * ep.tok_pad + t] = __float2bfloat16(v[i]);
             }
         }
     }
@@ -349,12 +349,12 @@ static int validate_epilogue(const sdod_epilogue& ep, int N) {
     if (!ep.C) return fail(kInvalidArgument, "epilogue: C is NULL");
     if (ep.row_bias && ep.rows_per_group <= 0) return fail(kInvalidArgument, "epilogue: rows_per_group must be > 0 with row_bias");
     if (ep.out_mode >= SDOD_OUT_HEADS) {
-        if (ep.heads <= 0 || ep.head_dim <= 0 || ep.tokens <= 0 || ep.dpad <= 0)
+        if (ep.heads <= 0 || ep.head_dim <= 0 || ep.tokens <= 0 || (ep.dpad <= 0 && ep.out_mode != SDOD_OUT_HEADS_T))
             return fail(kInvalidArgument, "epilogue: heads/head_dim/tokens/dpad required for head layouts");
         if (ep.out_mode == SDOD_OUT_QKV && (!ep.C2 || !ep.C3 || N != 3 * ep.heads * ep.head_dim))
             return fail(kInvalidArgument, "epilogue: QKV mode needs C2, C3 and N == 3*heads*head_dim");
-        if ((ep.out_mode == SDOD_OUT_HEADS_T || ep.out_mode == SDOD_OUT_QKV) && ep.tok_pad <= 0)
-            return fail(kInvalidArgument, "epilogue: tok_pad required for V^T layout");
+        if ((ep.out_mode == SDOD_OUT_HEADS_T || ep.out_mode == SDOD_OUT_QKV) && (ep.tok_pad <= 0 || ep.vt_rows < ep.head_dim))
+            return fail(kInvalidArgument, "epilogue: tok_pad and vt_rows >= head_dim required for V^T layout");
     }
     if (ep.act == SDOD_ACT_GEGLU && (N % 2 != 0)) return fail(kInvalidArgument, "epilogue: GEGLU needs even N");
     return kOk;

@@ -26,7 +26,7 @@ class SdodError(RuntimeError):
 class Epilogue(ctypes.Structure):
     _fields_ = [("C", c_vp), ("C2", c_vp), ("C3", c_vp), ("ldc", c_ll), ("strideC", c_ll), ("bias", c_vp), ("row_bias", c_vp),
                 ("rows_per_group", c_int), ("residual", c_vp), ("ldr", c_ll), ("strideR", c_ll), ("alpha", c_f), ("act", c_int),
-                ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int)]
+                ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int), ("vt_rows", c_int)]
 
 
 class GemmDesc(ctypes.Structure):

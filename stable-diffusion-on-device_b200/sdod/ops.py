@@ -165,7 +165,7 @@ def image_to_u8(img):
 
 
 def _epilogue(out, bias=None, row_bias=None, rows_per_group=0, residual=None, alpha=1.0, act=C.ACT_NONE, out_mode=None,
-              c2=None, c3=None, heads=0, head_dim=0, tokens=0, dpad=0, tok_pad=0, keep=None):
+              c2=None, c3=None, heads=0, head_dim=0, tokens=0, dpad=0, tok_pad=0, vt_rows=0):
     e = C.Epilogue()
     e.C, e.C2, e.C3 = _p(out), _p(c2), _p(c3)
     e.ldc = out.stride(-2) if out.dim() >= 2 else 0
@@ -177,7 +177,7 @@ def _epilogue(out, bias=None, row_bias=None, rows_per_group=0, residual=None, al
         e.strideR = residual.stride(0) if residual.dim() == 3 else 0
     e.alpha, e.act = alpha, act
     e.out_mode = out_mode if out_mode is not None else (C.OUT_F32 if out.dtype == torch.float32 else C.OUT_BF16)
-    e.heads, e.head_dim, e.tokens, e.dpad, e.tok_pad = heads, head_dim, tokens, dpad, tok_pad
+    e.heads, e.head_dim, e.tokens, e.dpad, e.tok_pad, e.vt_rows = heads, head_dim, tokens, dpad, tok_pad, vt_rows
     return e
 
 
@@ -325,3 +325,63 @@ def nhwc_to_nchw_f32(x):
 
 def launch_count():
     return int(C.lib().sdod_launch_count())
+
+
+# ------------------------------------------------------------------------------------------ attention
+def head_geometry(head_dim, n_kv):
+    """(dpad, vt_rows, kv_pad) of the attention operand layouts (include/sdod_kernels.h)."""
+    return 64 * ((head_dim + 63) // 64), 16 * ((head_dim + 15) // 16), 8 * ((n_kv + 7) // 8)
+
+
+def qkv_project(x, w_qkv, heads, head_dim, tokens):
+    """x [B*tokens, Cin] bf16, w_qkv [3*heads*head_dim, Cin] -> (Qh, Kh, Vt) written directly in the attention
+    operand layouts by the GEMM epilogue (SDOD_OUT_QKV)."""
+    _need_cuda(x, w_qkv)
+    x, w_qkv = x.contiguous(), w_qkv.contiguous()
+    M, K = x.shape
+    B = M // tokens
+    dpad, vt_rows, kv_pad = head_geometry(head_dim, tokens)
+    qh = torch.zeros(B * heads, tokens, dpad, dtype=torch.bfloat16, device=x.device)
+    kh = torch.zeros(B * heads, tokens, dpad, dtype=torch.bfloat16, device=x.device)
+    vt = torch.zeros(B * heads, vt_rows, kv_pad, dtype=torch.bfloat16, device=x.device)
+    d = C.GemmDesc()
+    d.A, d.lda, d.strideA = _p(x), K, M * K
+    d.W, d.ldw, d.strideW = _p(w_qkv), K, 0
+    d.M, d.N, d.K, d.batch, d.block_n = M, w_qkv.shape[0], K, 1, 0
+    d.epi = _epilogue(qh, out_mode=C.OUT_QKV, c2=kh, c3=vt, heads=heads, head_dim=head_dim, tokens=tokens, dpad=dpad,
+                      tok_pad=kv_pad, vt_rows=vt_rows)
+    C.check(C.lib().sdod_gemm_bf16(_stream(), d), "sdod_gemm_bf16")
+    return qh, kh, vt
+
+
+def pack_heads(t, heads, head_dim, transpose=False):
+    """[B, N, heads*head_dim] -> HEADS [B*heads, N, dpad] or HEADS_T [B*heads, vt_rows, kv_pad] (torch-side packing)."""
+    B, N, _ = t.shape
+    dpad, vt_rows, kv_pad = head_geometry(head_dim, N)
+    th = t.reshape(B, N, heads, head_dim).permute(0, 2, 1, 3).reshape(B * heads, N, head_dim)
+    if not transpose:
+        out = torch.zeros(B * heads, N, dpad, dtype=t.dtype, device=t.device)
+        out[:, :, :head_dim] = th
+    else:
+        out = torch.zeros(B * heads, vt_rows, kv_pad, dtype=t.dtype, device=t.device)
+        out[:, :head_dim, :N] = th.transpose(1, 2)
+    return out
+
+
+@torch.library.custom_op("sdod::attention", mutates_args=(), device_types="cuda")
+def attention(qh: torch.Tensor, kh: torch.Tensor, vt: torch.Tensor, batch: int, heads: int, head_dim: int, n_kv: int,
+              scale: float) -> torch.Tensor:
+    """Fused flash-style attention.  qh [B*heads,Nq,dpad], kh [B*heads,Nkv,dpad], vt [B*heads,vt_rows,kv_pad]
+    -> [B, Nq, heads*head_dim] bf16."""
+    _need_cuda(qh, kh, vt)
+    qh, kh, vt = qh.contiguous(), kh.contiguous(), vt.contiguous()
+    nq, dpad = qh.shape[1], qh.shape[2]
+    out = torch.empty(batch, nq, heads * head_dim, dtype=torch.bfloat16, device=qh.device)
+    C.check(C.lib().sdod_attention_bf16(_stream(), _p(qh), _p(kh), _p(vt), _p(out), batch, heads, nq, n_kv, head_dim, dpad,
+                                        vt.shape[2], scale), "sdod_attention_bf16")
+    return out
+
+
+@attention.register_fake
+def _(qh, kh, vt, batch, heads, head_dim, n_kv, scale):
+    return qh.new_empty(batch, qh.shape[1], heads * head_dim)

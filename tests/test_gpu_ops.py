@@ -286,3 +286,55 @@ def test_layout_helpers():
     assert torch.equal(up, F.interpolate(a.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).to(torch.bfloat16))
     s = bf(torch.randn(64, 4096)).to(DEV)
     assert rel_err(ops.softmax_rows(s, 0.5), F.softmax(s.float() * 0.5, dim=-1)) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, heads):
+    B, N, Cc = q.shape
+    dh = Cc // heads
+    qh, kh, vh = (t.float().reshape(B, t.shape[1], heads, dh).permute(0, 2, 1, 3) for t in (q, k, v))
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * dh ** -0.5, dim=-1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(B, N, Cc)
+
+
+ATTN_CASES = [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (2, 8, 160, 64, 64),
+              (2, 8, 40, 4096, 77), (1, 8, 80, 1024, 77), (2, 8, 160, 64, 77), (1, 4, 64, 200, 333), (1, 8, 40, 256, 256)]
+
+
+@pytest.mark.parametrize("B,heads,dh,Nq,Nkv", ATTN_CASES)
+def test_fused_attention(B, heads, dh, Nq, Nkv):
+    torch.manual_seed(Nq + Nkv + dh)
+    Cc = heads * dh
+    q, k, v = (bf(torch.randn(B, n, Cc) * s).to(DEV) for n, s in ((Nq, 1.5), (Nkv, 1.5), (Nkv, 1.0)))
+    want = _attn_ref(q, k, v, heads)
+    got = torch.ops.sdod.attention(ops.pack_heads(q, heads, dh), ops.pack_heads(k, heads, dh), ops.pack_heads(v, heads, dh, True),
+                                   B, heads, dh, Nkv, dh ** -0.5)
+    assert got.shape == (B, Nq, Cc) and torch.isfinite(got.float()).all()
+    assert rel_err(got, want) < TOL_BF16
+
+
+def test_attention_peaked_softmax_rescale_path():
+    """Row maxima that keep growing along the key axis force the in-TMEM O rescale on every tile."""
+    torch.manual_seed(77)
+    B, heads, dh, N = 1, 8, 40, 1024
+    q = bf(torch.randn(B, N, heads * dh)).to(DEV)
+    k = bf(torch.randn(B, N, heads * dh) * torch.linspace(0.2, 6.0, N)[None, :, None]).to(DEV)
+    v = bf(torch.randn(B, N, heads * dh)).to(DEV)
+    got = torch.ops.sdod.attention(ops.pack_heads(q, heads, dh), ops.pack_heads(k, heads, dh), ops.pack_heads(v, heads, dh, True),
+                                   B, heads, dh, N, dh ** -0.5)
+    assert rel_err(got, _attn_ref(q, k, v, heads)) < TOL_BF16
+
+
+@pytest.mark.parametrize("heads,dh,tokens", [(8, 40, 256), (8, 80, 64), (8, 160, 64), (8, 40, 77)])
+def test_qkv_projection_writes_attention_layouts(heads, dh, tokens):
+    torch.manual_seed(dh + tokens)
+    B, Cc = 2, heads * dh
+    x = bf(torch.randn(B * tokens, Cc)).to(DEV)
+    w = bf(torch.randn(3 * Cc, Cc) / Cc ** 0.5).to(DEV)
+    qkv = bf(x.float() @ w.float().t()).view(B, tokens, 3, Cc)
+    qh, kh, vt = ops.qkv_project(x, w, heads, dh, tokens)
+    for got, want in ((qh, ops.pack_heads(qkv[:, :, 0], heads, dh)), (kh, ops.pack_heads(qkv[:, :, 1], heads, dh)),
+                      (vt, ops.pack_heads(qkv[:, :, 2], heads, dh, True))):
+        assert got.shape == want.shape and rel_err(got, want) < TOL_BF16
+    out = torch.ops.sdod.attention(qh, kh, vt, B, heads, dh, tokens, dh ** -0.5)
+    assert rel_err(out, _attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], heads)) < TOL_BF16
