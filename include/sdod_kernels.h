@@ -105,8 +105,9 @@ typedef struct sdod_epilogue {
     long long ldc;           /* row stride (elements) for BF16/F32 modes                           */
     long long strideC;       /* batch stride (elements)                                            */
     const float* bias;       /* [N] or NULL                                                        */
-    const float* row_bias;   /* [M/rows_per_group, N] fp32 or NULL (timestep-embedding add)        */
+    const float* row_bias;   /* [M/rows_per_group, ld_row_bias] fp32 or NULL (timestep-embedding add) */
     int rows_per_group;
+    long long ld_row_bias;   /* row stride of row_bias in elements; 0 = N                           */
     const void* residual;    /* bf16 [M,N] row-major or NULL, added last                           */
     long long ldr;
     long long strideR;

@@ -14,6 +14,7 @@
 #include "../common.cuh"
 #include "../host_common.h"
 #include "../launch_count.h"
+#include "launchers.h"
 #include "sdod_kernels.h"
 
 namespace sdod {
@@ -250,13 +251,15 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
 }
 
 template <int DH>
-static int launch_attention(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq,
-                            int Nkv, int dpad, int kv_pad, float scale) {
+static int prepare_attention(AttnLaunch* out, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq,
+                             int Nkv, int dpad, int kv_pad, float scale) {
     using Cfg = AttCfg<DH>;
     if (dpad != Cfg::kNK * 64) return fail(kInvalidArgument, "attention: dpad must be 64*ceil(head_dim/64)");
     if (kv_pad % 8 != 0 || kv_pad < Nkv) return fail(kInvalidArgument, "attention: kv_pad must be a multiple of 8 and >= Nkv");
     const int BH = B * heads;
-    CUtensorMap tmQ, tmK, tmV;
+    CUtensorMap& tmQ = out->tmQ;
+    CUtensorMap& tmK = out->tmK;
+    CUtensorMap& tmV = out->tmV;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(dpad), static_cast<uint64_t>(Nq), static_cast<uint64_t>(BH)};
         uint64_t strides[2] = {static_cast<uint64_t>(dpad) * 2, static_cast<uint64_t>(Nq) * dpad * 2};
@@ -275,30 +278,55 @@ static int launch_attention(cudaStream_t stream, const void* Qh, const void* Kh,
         uint32_t box[3] = {64, static_cast<uint32_t>(Cfg::kDV), 1};
         SDOD_TRY(encode_tmap_bf16(&tmV, Vt, 3, dims, strides, box, true));
     }
+    out->O = O; out->heads = heads; out->Nq = Nq; out->Nkv = Nkv; out->head_dim = DH; out->BH = BH;
+    out->scale_log2 = scale * 1.4426950408889634f;
+    return kOk;
+}
+
+template <int DH>
+static int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
+    using Cfg = AttCfg<DH>;
     static bool configured = false;
     if (!configured) {
         SDOD_TRY(check_cuda(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
                             "cudaFuncSetAttribute(attention)"));
         configured = true;
     }
-    dim3 grid((Nq + kBQ - 1) / kBQ, BH);
-    const float scale_log2 = scale * 1.4426950408889634f;
-    attention_kernel<DH><<<grid, kAttThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, static_cast<bf16*>(O), heads, Nq, Nkv, scale_log2);
+    dim3 grid((a.Nq + kBQ - 1) / kBQ, a.BH);
+    attention_kernel<DH><<<grid, kAttThreads, Cfg::kSmemBytes, stream>>>(a.tmQ, a.tmK, a.tmV, static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv,
+                                                                         a.scale_log2);
     count_launch();
     return check_launch("attention_kernel");
 }
 
-int attention_bf16(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
-                   int head_dim, int dpad, int kv_pad, float scale) {
+int attention_prepare(AttnLaunch* out, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
+                      int head_dim, int dpad, int kv_pad, float scale) {
     if (!Qh || !Kh || !Vt || !O) return fail(kInvalidArgument, "attention: NULL tensor");
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nkv <= 0) return fail(kInvalidArgument, "attention: non-positive extent");
     switch (head_dim) {
-        case 40: return launch_attention<40>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
-        case 64: return launch_attention<64>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
-        case 80: return launch_attention<80>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
-        case 160: return launch_attention<160>(stream, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 40: return prepare_attention<40>(out, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 64: return prepare_attention<64>(out, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 80: return prepare_attention<80>(out, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
+        case 160: return prepare_attention<160>(out, Qh, Kh, Vt, O, B, heads, Nq, Nkv, dpad, kv_pad, scale);
     }
     return fail(kUnsupported, "attention: head_dim must be one of 40, 64, 80, 160 (SD v1.x)");
+}
+
+int attention_launch(const AttnLaunch& a, cudaStream_t stream) {
+    switch (a.head_dim) {
+        case 40: return launch_attention<40>(a, stream);
+        case 64: return launch_attention<64>(a, stream);
+        case 80: return launch_attention<80>(a, stream);
+        case 160: return launch_attention<160>(a, stream);
+    }
+    return fail(kUnsupported, "attention: bad plan");
+}
+
+int attention_bf16(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
+                   int head_dim, int dpad, int kv_pad, float scale) {
+    AttnLaunch a;
+    SDOD_TRY(attention_prepare(&a, Qh, Kh, Vt, O, B, heads, Nq, Nkv, head_dim, dpad, kv_pad, scale));
+    return attention_launch(a, stream);
 }
 
 }  // namespace sdod

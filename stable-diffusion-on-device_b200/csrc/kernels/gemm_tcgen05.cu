@@ -16,6 +16,7 @@
 #include "../common.cuh"
 #include "../host_common.h"
 #include "../launch_count.h"
+#include "launchers.h"
 #include "sdod_kernels.h"
 
 namespace sdod {
@@ -24,17 +25,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                    // 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kGemmThreads = 192;
-
-struct MainloopParams {
-    int M, N;          // logical extents (masking)
-    int k_blocks;      // K / 64
-    int conv;          // 0: A is a 3-D map (K, M, batch); 1: A is a 4-D map (C, W, H, B)
-    int cin_blocks;    // conv: Cin / 64
-    int H, W;          // conv: output spatial size
-    int bw, bh, bb;    // conv: TMA box (pixels); bw*bh*bb == 128
-    int up;            // conv: 1 = input is half resolution, nearest-2x gather (not via TMA; see host)
-    int w_batched;     // W has a batch dimension
-};
 
 template <int BN>
 struct GemmCfg {
@@ -227,7 +217,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         const long long zc = static_cast<long long>(bz) * ep.strideC;
         const long long zr = static_cast<long long>(bz) * ep.strideR;
         const float* rb = nullptr;
-        if (ep.row_bias && row_ok) rb = ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * mp.N;
+        if (ep.row_bias && row_ok) rb = ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N);
 
         if (ep.act == SDOD_ACT_GEGLU) {
             constexpr int HALF = BN / 2;
@@ -360,7 +350,7 @@ static int validate_epilogue(const sdod_epilogue& ep, int N) {
     return kOk;
 }
 
-int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
+int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     if (!d.A || !d.W) return fail(kInvalidArgument, "gemm: NULL operand");
     if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.batch <= 0) return fail(kInvalidArgument, "gemm: non-positive extent");
     if (d.K % kBlockK != 0) return fail(kInvalidArgument, "gemm: K must be a multiple of 64 (pad the operand)");
@@ -369,7 +359,8 @@ int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
     int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, d.batch, d.epi.act);
     if (d.epi.act == SDOD_ACT_GEGLU && bn != 256 && d.block_n == 0) bn = 256;
 
-    CUtensorMap tmA, tmW;
+    CUtensorMap& tmA = out->tmA;
+    CUtensorMap& tmW = out->tmW;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.M), static_cast<uint64_t>(d.batch)};
         uint64_t strides[2] = {static_cast<uint64_t>(d.lda) * 2, static_cast<uint64_t>(d.batch > 1 ? d.strideA : static_cast<long long>(d.M) * d.lda) * 2};
@@ -385,12 +376,24 @@ int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
     }
     MainloopParams mp{};
     mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
-    const int m_tiles = (d.M + kBlockM - 1) / kBlockM;
-    const int n_tiles = (d.N + bn - 1) / bn;
-    return dispatch_gemm(bn, stream, tmA, tmW, mp, d.epi, m_tiles, n_tiles, d.batch);
+    out->mp = mp; out->ep = d.epi; out->bn = bn;
+    out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
+    out->n_tiles = (d.N + bn - 1) / bn;
+    out->batch = d.batch;
+    return kOk;
 }
 
-int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d) {
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
+    return dispatch_gemm(g.bn, stream, g.tmA, g.tmW, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+}
+
+int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
+    GemmLaunch g;
+    SDOD_TRY(gemm_prepare(d, &g));
+    return gemm_launch(g, stream);
+}
+
+int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     if (!d.X || !d.Wt) return fail(kInvalidArgument, "conv3x3: NULL operand");
     if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.Cin <= 0 || d.Cout <= 0) return fail(kInvalidArgument, "conv3x3: non-positive extent");
     if (d.Cin % kBlockK != 0) return fail(kInvalidArgument, "conv3x3: Cin must be a multiple of 64 (use im2col + gemm otherwise)");
@@ -404,7 +407,8 @@ int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d) {
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
     const int bn = d.block_n ? d.block_n : pick_block_n(M, d.Cout, 1, d.epi.act);
 
-    CUtensorMap tmA, tmW;
+    CUtensorMap& tmA = out->tmA;
+    CUtensorMap& tmW = out->tmW;
     {
         uint64_t dims[4] = {static_cast<uint64_t>(d.Cin), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
         uint64_t strides[3] = {static_cast<uint64_t>(d.Cin) * 2, static_cast<uint64_t>(d.W) * d.Cin * 2,
@@ -422,9 +426,17 @@ int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d) {
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
-    const int m_tiles = (M + kBlockM - 1) / kBlockM;
-    const int n_tiles = (d.Cout + bn - 1) / bn;
-    return dispatch_gemm(bn, stream, tmA, tmW, mp, d.epi, m_tiles, n_tiles, 1);
+    out->mp = mp; out->ep = d.epi; out->bn = bn;
+    out->m_tiles = (M + kBlockM - 1) / kBlockM;
+    out->n_tiles = (d.Cout + bn - 1) / bn;
+    out->batch = 1;
+    return kOk;
+}
+
+int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d) {
+    GemmLaunch g;
+    SDOD_TRY(conv3x3_prepare(d, &g));
+    return gemm_launch(g, stream);
 }
 
 }  // namespace sdod

@@ -1,0 +1,13 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+namespace sdod {
+int pack_rows(cudaStream_t s, const float* src, void* dst_bf16, int N, int K, int Kpad, const int* rowmap);
+int gather_f32(cudaStream_t s, const float* src, float* dst, int n, const int* map);
+int silu_f32_to_bf16(cudaStream_t s, const float* x, void* y_bf16, size_t n, int apply_silu);
+int latent_prequant(cudaStream_t s, const float* z, void* y_bf16, size_t rows, const float* w, const float* b, float inv_scale);
+int vae_post(cudaStream_t s, const float* x, uint8_t* u8, float* img, size_t n);
+int fill_f32(cudaStream_t s, float* x, size_t n, float v);
+int scale_f32(cudaStream_t s, float* x, size_t n, float v);
+}  // namespace sdod

@@ -1,0 +1,49 @@
+// Prepared launches: tensor maps + parameters are encoded once (plan build time) and replayed
+// every step, so the hot loop does no host-side encoding and is CUDA-graph capturable.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "sdod_kernels.h"
+
+namespace sdod {
+
+struct MainloopParams {
+    int M, N;          // logical extents (masking)
+    int k_blocks;      // K / 64
+    int conv;          // 0: A is a 3-D map (K, M, batch); 1: A is a 4-D map (C, W, H, B)
+    int cin_blocks;    // conv: Cin / 64
+    int H, W;          // conv: output spatial size
+    int bw, bh, bb;    // conv: TMA box (pixels); bw*bh*bb == 128
+    int w_batched;     // W has a batch dimension
+};
+
+struct GemmLaunch {
+    CUtensorMap tmA, tmW;
+    MainloopParams mp;
+    sdod_epilogue ep;
+    int bn, m_tiles, n_tiles, batch;
+};
+
+struct AttnLaunch {
+    CUtensorMap tmQ, tmK, tmV;
+    void* O;
+    int heads, Nq, Nkv, head_dim, BH;
+    float scale_log2;
+};
+
+int pick_block_n(int M, int N, int batch, int act);
+int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out);
+int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out);
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d);
+int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d);
+
+int attention_prepare(AttnLaunch* out, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
+                      int head_dim, int dpad, int kv_pad, float scale);
+int attention_launch(const AttnLaunch& a, cudaStream_t stream);
+
+int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc, int N, int C,
+               int HW, int G, float eps, int dtype, int layout, int fuse_silu, void* ws, size_t ws_bytes);
+
+}  // namespace sdod

@@ -1,0 +1,108 @@
+// Weight packing and small glue kernels used by the model runtime (run once at load, or once per step
+// on tiny tensors): row gather + fp32->bf16 cast, SiLU+cast of the time embedding, the VAE's latent
+// pre-scale + post_quant_conv, and the VAE output map to [0,1] / uint8.
+#include "../common.cuh"
+#include "../host_common.h"
+#include "../launch_count.h"
+#include "glue.h"
+
+namespace sdod {
+
+__global__ void pack_rows_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int K, int Kpad, const int* __restrict__ rowmap) {
+    const size_t total = static_cast<size_t>(N) * Kpad;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = o % Kpad;
+        const int n = o / Kpad;
+        const int r = rowmap ? rowmap[n] : n;
+        dst[o] = __float2bfloat16(k < K ? src[static_cast<size_t>(r) * K + k] : 0.f);
+    }
+}
+__global__ void gather_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, const int* __restrict__ map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[map ? map[i] : i];
+}
+__global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n, int apply_silu) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        y[i] = __float2bfloat16(apply_silu ? silu_f(v) : v);
+    }
+}
+// z [rows,4] fp32 -> (z * inv_scale) * Wpq^T + bpq -> bf16 [rows,4]   (AutoencoderKL.decode: post_quant_conv(z / 0.18215))
+__global__ void latent_prequant_kernel(const float* __restrict__ z, bf16* __restrict__ y, size_t rows, const float* __restrict__ w,
+                                       const float* __restrict__ b, float inv_scale) {
+    for (size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4*>(z + r * 4);
+        const float in[4] = {v.x * inv_scale, v.y * inv_scale, v.z * inv_scale, v.w * inv_scale};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float acc = b ? b[o] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc += w[o * 4 + i] * in[i];
+            y[r * 4 + o] = __float2bfloat16(acc);
+        }
+    }
+}
+// conv_out fp32 [n] -> img = clamp((x+1)/2, 0, 1); u8 = uint8(clamp(255*img, 0, 255))  (truncation; context.cpp:392-395)
+__global__ void vae_post_kernel(const float* __restrict__ x, uint8_t* __restrict__ u8, float* __restrict__ img, size_t n) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float f = __fdiv_rn(__fadd_rn(x[i], 1.0f), 2.0f);
+        f = fminf(fmaxf(f, 0.0f), 1.0f);
+        if (img) img[i] = f;
+        if (u8) {
+            float v = __fmul_rn(255.0f, f);
+            v = fminf(fmaxf(v, 0.0f), 255.0f);
+            u8[i] = static_cast<uint8_t>(v);
+        }
+    }
+}
+__global__ void fill_f32_kernel(float* __restrict__ x, size_t n, float v) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) x[i] = v;
+}
+__global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float s) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) x[i] *= s;
+}
+
+static inline int g1(size_t n) {
+    size_t g = (n + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+int pack_rows(cudaStream_t s, const float* src, void* dst, int N, int K, int Kpad, const int* rowmap) {
+    pack_rows_kernel<<<g1(static_cast<size_t>(N) * Kpad), 256, 0, s>>>(src, static_cast<bf16*>(dst), N, K, Kpad, rowmap);
+    count_launch();
+    return check_launch("pack_rows_kernel");
+}
+int gather_f32(cudaStream_t s, const float* src, float* dst, int n, const int* map) {
+    gather_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, dst, n, map);
+    count_launch();
+    return check_launch("gather_f32_kernel");
+}
+int silu_f32_to_bf16(cudaStream_t s, const float* x, void* y, size_t n, int apply_silu) {
+    silu_f32_to_bf16_kernel<<<g1(n), 256, 0, s>>>(x, static_cast<bf16*>(y), n, apply_silu);
+    count_launch();
+    return check_launch("silu_f32_to_bf16_kernel");
+}
+int latent_prequant(cudaStream_t s, const float* z, void* y, size_t rows, const float* w, const float* b, float inv_scale) {
+    latent_prequant_kernel<<<g1(rows), 256, 0, s>>>(z, static_cast<bf16*>(y), rows, w, b, inv_scale);
+    count_launch();
+    return check_launch("latent_prequant_kernel");
+}
+int vae_post(cudaStream_t s, const float* x, uint8_t* u8, float* img, size_t n) {
+    vae_post_kernel<<<g1(n), 256, 0, s>>>(x, u8, img, n);
+    count_launch();
+    return check_launch("vae_post_kernel");
+}
+int fill_f32(cudaStream_t s, float* x, size_t n, float v) {
+    fill_f32_kernel<<<g1(n), 256, 0, s>>>(x, n, v);
+    count_launch();
+    return check_launch("fill_f32_kernel");
+}
+int scale_f32(cudaStream_t s, float* x, size_t n, float v) {
+    scale_f32_kernel<<<g1(n), 256, 0, s>>>(x, n, v);
+    count_launch();
+    return check_launch("scale_f32_kernel");
+}
+
+}  // namespace sdod

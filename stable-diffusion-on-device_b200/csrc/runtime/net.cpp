@@ -1,0 +1,384 @@
+#include "net.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "../kernels/glue.h"
+#include "../launch_count.h"
+
+namespace sdod {
+
+// ------------------------------------------------------------------------------------------ WeightStore
+WeightStore::~WeightStore() {
+    for (auto& kv : t_) cudaFree(kv.second.p);
+}
+
+int WeightStore::set(const std::string& name, const float* host, const std::vector<long long>& shape) {
+    size_t n = 1;
+    for (long long s : shape) {
+        if (s <= 0) return fail(kInvalidArgument, "weights: non-positive dimension for " + name);
+        n *= static_cast<size_t>(s);
+    }
+    DevTensor& d = t_[name];
+    if (d.p && d.numel != n) { cudaFree(d.p); d.p = nullptr; }
+    if (!d.p) SDOD_TRY(check_cuda(cudaMalloc(reinterpret_cast<void**>(&d.p), n * sizeof(float)), "cudaMalloc(weight)"));
+    d.shape = shape;
+    d.numel = n;
+    return check_cuda(cudaMemcpy(d.p, host, n * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(weight)");
+}
+
+int WeightStore::load_file(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return fail(kInvalidArgument, "weights: cannot open " + path);
+    auto bail = [&](const std::string& m) { std::fclose(f); return fail(kInvalidArgument, "weights: " + m + " in " + path); };
+    char magic[8];
+    uint32_t count = 0;
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "SDODW001", 8) != 0) return bail("bad magic");
+    if (std::fread(&count, 4, 1, f) != 1) return bail("truncated header");
+    std::vector<float> buf;
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t nl = 0, nd = 0;
+        if (std::fread(&nl, 4, 1, f) != 1 || nl == 0 || nl > 4096) return bail("bad name length");
+        std::string name(nl, '\0');
+        if (std::fread(&name[0], 1, nl, f) != nl) return bail("truncated name");
+        if (std::fread(&nd, 4, 1, f) != 1 || nd > 8) return bail("bad rank");
+        std::vector<long long> shape(nd);
+        if (nd && std::fread(shape.data(), 8, nd, f) != nd) return bail("truncated shape");
+        size_t n = 1;
+        for (long long s : shape) n *= static_cast<size_t>(s);
+        buf.resize(n);
+        if (std::fread(buf.data(), 4, n, f) != n) return bail("truncated data for " + name);
+        int st = set(name, buf.data(), shape);
+        if (st != kOk) { std::fclose(f); return st; }
+    }
+    std::fclose(f);
+    return kOk;
+}
+
+const DevTensor* WeightStore::find(const std::string& name) const {
+    auto it = t_.find(name);
+    return it == t_.end() ? nullptr : &it->second;
+}
+
+// ------------------------------------------------------------------------------------------ Pool
+Pool::~Pool() {
+    for (auto& b : blks_) cudaFree(b.p);
+}
+
+void* Pool::get(size_t bytes) {
+    bytes = (bytes + 1023) & ~static_cast<size_t>(1023);
+    int best = -1;
+    for (size_t i = 0; i < blks_.size(); ++i) {
+        if (blks_[i].free_ && blks_[i].sz >= bytes && blks_[i].sz <= bytes + bytes / 2 + 4096) {
+            if (best < 0 || blks_[i].sz < blks_[best].sz) best = static_cast<int>(i);
+        }
+    }
+    if (best >= 0) {
+        blks_[best].free_ = false;
+        return blks_[best].p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        throw std::runtime_error("device pool: cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    }
+    blks_.push_back({p, bytes, false});
+    total_ += bytes;
+    return p;
+}
+
+void Pool::put(void* p) {
+    for (auto& b : blks_)
+        if (b.p == p) { b.free_ = true; return; }
+}
+
+// ------------------------------------------------------------------------------------------ Plan
+Plan::~Plan() {
+    if (exec_) cudaGraphExecDestroy(exec_);
+}
+
+int Plan::run_eager(cudaStream_t s) {
+    for (auto& f : ops_) SDOD_TRY(f(s));
+    return kOk;
+}
+
+int Plan::run(cudaStream_t s, bool use_graph) {
+    if (!use_graph || s == nullptr) return run_eager(s);    // legacy default stream cannot be captured
+    if (!warmed_) {                                         // first pass eager: sets kernel attributes, validates launches
+        warmed_ = true;
+        return run_eager(s);
+    }
+    if (!exec_) {
+        cudaGraph_t g = nullptr;
+        SDOD_TRY(check_cuda(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture"));
+        const unsigned long long before = g_launch_count.load();
+        int st = run_eager(s);
+        g_launch_count.store(before);                       // captured, not launched
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (st != kOk) { if (g) cudaGraphDestroy(g); return st; }
+        SDOD_TRY(check_cuda(e, "cudaStreamEndCapture"));
+        e = cudaGraphInstantiate(&exec_, g, 0);
+        cudaGraphDestroy(g);
+        SDOD_TRY(check_cuda(e, "cudaGraphInstantiate"));
+    }
+    SDOD_TRY(check_cuda(cudaGraphLaunch(exec_, s), "cudaGraphLaunch"));
+    count_launch(launches_);
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------------------ NetBase
+NetBase::NetBase(const WeightStore* ws, unsigned long long seed) : ws_(ws), random_(ws == nullptr), seed_(seed) {
+    gn_ws_bytes_ = sdod_group_norm_workspace(256, 1, 1, 64, SDOD_NHWC);
+    gn_ws_ = dev_alloc(gn_ws_bytes_, true);
+}
+
+NetBase::~NetBase() {
+    for (void* p : owned_) cudaFree(p);
+}
+
+void NetBase::check(int status) {
+    if (status != kOk) throw std::runtime_error(last_error());
+}
+
+void* NetBase::dev_alloc(size_t bytes, bool zero) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        throw std::runtime_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    }
+    if (zero) cudaMemset(p, 0, bytes);
+    owned_.push_back(p);
+    return p;
+}
+
+const float* NetBase::w32(const std::string& name, const std::vector<long long>& shape, InitKind kind) {
+    size_t n = 1;
+    for (long long s : shape) n *= static_cast<size_t>(s);
+    if (!random_) {
+        const DevTensor* t = ws_->find(name);
+        if (!t) throw std::runtime_error("missing weight tensor '" + name + "'");
+        if (t->numel != n) throw std::runtime_error("weight tensor '" + name + "' has " + std::to_string(t->numel) + " elements, expected " + std::to_string(n));
+        return t->p;
+    }
+    auto hit = cache_.find("r|" + name);
+    if (hit != cache_.end()) return static_cast<const float*>(hit->second);
+    float* p = static_cast<float*>(dev_alloc(n * sizeof(float), false));
+    cache_["r|" + name] = p;
+    if (kind == kInitOnes || kind == kInitZeros) {
+        check(fill_f32(nullptr, p, n, kind == kInitOnes ? 1.f : 0.f));
+    } else {
+        const size_t fan_in = shape.empty() ? 1 : n / static_cast<size_t>(shape[0]);
+        const float std_ = kind == kInitWeight ? 1.0f / std::sqrt(static_cast<float>(fan_in ? fan_in : 1)) : 0.02f;
+        check(sdod_randn(nullptr, p, n, seed_, rng_ctr_));
+        rng_ctr_ += (n + 3) / 4;
+        check(scale_f32(nullptr, p, n, std_));
+    }
+    return p;
+}
+
+void* NetBase::pack_linear(const std::string& wname, int N, int K, int Kpad, const std::vector<int>* rowmap) {
+    if (Kpad == 0) Kpad = K;
+    const std::string key = "l|" + wname + "|" + std::to_string(Kpad) + (rowmap ? "|g" : "");
+    auto hit = cache_.find(key);
+    if (hit != cache_.end()) return hit->second;
+    const float* src = w32(wname, {N, K}, kInitWeight);
+    void* dst = dev_alloc(static_cast<size_t>(N) * Kpad * 2, false);
+    cache_[key] = dst;
+    int* dmap = nullptr;
+    if (rowmap) {
+        check(check_cuda(cudaMalloc(reinterpret_cast<void**>(&dmap), rowmap->size() * sizeof(int)), "cudaMalloc(rowmap)"));
+        check(check_cuda(cudaMemcpy(dmap, rowmap->data(), rowmap->size() * sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(rowmap)"));
+    }
+    check(pack_rows(nullptr, src, dst, N, K, Kpad, dmap));
+    if (dmap) { cudaDeviceSynchronize(); cudaFree(dmap); }
+    return dst;
+}
+
+void* NetBase::pack_conv3(const std::string& wname, int Cout, int Cin, int Kpad) {
+    if (Kpad == 0) Kpad = 9 * Cin;
+    const std::string key = "c|" + wname + "|" + std::to_string(Kpad);
+    auto hit = cache_.find(key);
+    if (hit != cache_.end()) return hit->second;
+    const float* src = w32(wname, {Cout, Cin, 3, 3}, kInitWeight);
+    void* dst = dev_alloc(static_cast<size_t>(Cout) * Kpad * 2, false);
+    cache_[key] = dst;
+    check(sdod_pack_conv3x3_weight(nullptr, src, dst, Cout, Cin, Kpad));
+    return dst;
+}
+
+void* NetBase::pack_concat(const std::string& key, const std::vector<std::string>& wnames, const std::vector<int>& Ns, int K) {
+    auto hit = cache_.find("k|" + key);
+    if (hit != cache_.end()) return hit->second;
+    size_t total = 0;
+    for (int n : Ns) total += n;
+    char* dst = static_cast<char*>(dev_alloc(total * K * 2, false));
+    cache_["k|" + key] = dst;
+    size_t off = 0;
+    for (size_t i = 0; i < wnames.size(); ++i) {
+        const float* src = w32(wnames[i], {Ns[i], K}, kInitWeight);
+        check(pack_rows(nullptr, src, dst + off * K * 2, Ns[i], K, K, nullptr));
+        off += Ns[i];
+    }
+    return dst;
+}
+
+const float* NetBase::concat_bias(const std::string& key, const std::vector<std::string>& bnames, const std::vector<int>& Ns) {
+    auto hit = cache_.find("kb|" + key);
+    if (hit != cache_.end()) return static_cast<const float*>(hit->second);
+    size_t total = 0;
+    for (int n : Ns) total += n;
+    float* dst = static_cast<float*>(dev_alloc(total * sizeof(float), false));
+    cache_["kb|" + key] = dst;
+    size_t off = 0;
+    for (size_t i = 0; i < bnames.size(); ++i) {
+        const float* src = w32(bnames[i], {Ns[i]}, kInitBias);
+        check(check_cuda(cudaMemcpy(dst + off, src, Ns[i] * sizeof(float), cudaMemcpyDeviceToDevice), "cudaMemcpy(bias concat)"));
+        off += Ns[i];
+    }
+    return dst;
+}
+
+const float* NetBase::gather_bias(const std::string& bname, int N, const std::vector<int>& rowmap) {
+    auto hit = cache_.find("gb|" + bname);
+    if (hit != cache_.end()) return static_cast<const float*>(hit->second);
+    const float* src = w32(bname, {N}, kInitBias);
+    float* dst = static_cast<float*>(dev_alloc(N * sizeof(float), false));
+    cache_["gb|" + bname] = dst;
+    int* dmap = nullptr;
+    check(check_cuda(cudaMalloc(reinterpret_cast<void**>(&dmap), N * sizeof(int)), "cudaMalloc(rowmap)"));
+    check(check_cuda(cudaMemcpy(dmap, rowmap.data(), N * sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(rowmap)"));
+    check(gather_f32(nullptr, src, dst, N, dmap));
+    cudaDeviceSynchronize();
+    cudaFree(dmap);
+    return dst;
+}
+
+Act NetBase::new_act(int B, int H, int W, int C) {
+    Act a;
+    a.B = B; a.H = H; a.W = W; a.C = C;
+    a.p = pool_.get(a.bytes());
+    return a;
+}
+
+void NetBase::release(Act& a) {
+    if (a.p) pool_.put(a.p);
+    a.p = nullptr;
+}
+
+Act NetBase::gn(const Act& x, const std::string& prefix, float eps, bool silu) {
+    const float* w = w32(prefix + ".weight", {x.C}, kInitOnes);
+    const float* b = w32(prefix + ".bias", {x.C}, kInitZeros);
+    Act y = new_act(x.B, x.H, x.W, x.C);
+    void* ws = gn_ws_;
+    const size_t wsb = gn_ws_bytes_;
+    const void* xp = x.p;
+    void* yp = y.p;
+    const int B = x.B, C = x.C, HW = x.H * x.W, s = silu ? 1 : 0;
+    plan_->push([=](cudaStream_t st) { return group_norm(st, xp, yp, w, b, nullptr, B, C, HW, 32, eps, SDOD_BF16, SDOD_NHWC, s, ws, wsb); }, 2);
+    return y;
+}
+
+Act NetBase::ln(const Act& x, const std::string& prefix) {
+    const float* w = w32(prefix + ".weight", {x.C}, kInitOnes);
+    const float* b = w32(prefix + ".bias", {x.C}, kInitZeros);
+    Act y = new_act(x.B, x.H, x.W, x.C);
+    const void* xp = x.p;
+    void* yp = y.p;
+    const int rows = x.M(), C = x.C;
+    plan_->push([=](cudaStream_t st) { return sdod_layer_norm(st, xp, yp, w, b, rows, C, 1e-5f); });
+    return y;
+}
+
+int NetBase::gemm_into(const sdod_gemm_desc& d) {
+    auto g = std::make_shared<GemmLaunch>();
+    check(gemm_prepare(d, g.get()));
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
+    return kOk;
+}
+
+Act NetBase::linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o) {
+    const int n_out = o.act == SDOD_ACT_GEGLU ? N / 2 : N;
+    Act y = new_act(x.B, x.H, x.W, n_out);
+    sdod_gemm_desc d{};
+    d.A = x.p; d.lda = x.C; d.strideA = 0;
+    d.W = w_bf16; d.ldw = x.C; d.strideW = 0;
+    d.M = x.M(); d.N = N; d.K = x.C; d.batch = 1; d.block_n = o.block_n;
+    d.epi.C = y.p; d.epi.ldc = n_out;
+    d.epi.bias = o.bias;
+    if (o.residual) { d.epi.residual = o.residual->p; d.epi.ldr = o.residual->C; }
+    d.epi.alpha = o.alpha; d.epi.act = o.act; d.epi.out_mode = SDOD_OUT_BF16;
+    gemm_into(d);
+    return y;
+}
+
+Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const float* row_bias, long long ld_row_bias, const Act* residual,
+                   float* out_f32) {
+    void* wt = pack_conv3(prefix + ".weight", cout, x.C);
+    const float* bias = w32(prefix + ".bias", {cout}, kInitBias);
+    Act y;
+    if (!out_f32) y = new_act(x.B, x.H, x.W, cout);
+    sdod_conv_desc d{};
+    d.X = x.p; d.Wt = wt; d.B = x.B; d.H = x.H; d.W = x.W; d.Cin = x.C; d.Cout = cout;
+    d.epi.C = out_f32 ? static_cast<void*>(out_f32) : y.p;
+    d.epi.ldc = cout;
+    d.epi.bias = bias;
+    d.epi.row_bias = row_bias; d.epi.rows_per_group = x.H * x.W; d.epi.ld_row_bias = ld_row_bias;
+    if (residual) { d.epi.residual = residual->p; d.epi.ldr = residual->C; }
+    d.epi.alpha = 1.0f; d.epi.out_mode = out_f32 ? SDOD_OUT_F32 : SDOD_OUT_BF16;
+    auto g = std::make_shared<GemmLaunch>();
+    check(conv3x3_prepare(d, g.get()));
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
+    return y;
+}
+
+Act NetBase::conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride) {
+    const int K = 9 * x.C;
+    const int Kpad = (K + 63) / 64 * 64;
+    void* wt = pack_conv3(prefix + ".weight", cout, x.C, Kpad);
+    const float* bias = w32(prefix + ".bias", {cout}, kInitBias);
+    const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
+    Act cols = new_act(x.B, Ho, Wo, Kpad);
+    {
+        const void* xp = x.p;
+        void* cp = cols.p;
+        const int B = x.B, H = x.H, W = x.W, C = x.C;
+        plan_->push([=](cudaStream_t st) { return sdod_im2col3x3(st, xp, cp, B, H, W, C, stride, Kpad); });
+    }
+    LinearOpts o;
+    o.bias = bias;
+    Act y = linear(cols, wt, cout, o);
+    release(cols);
+    return y;
+}
+
+Act NetBase::conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual) {
+    void* w = pack_linear(prefix + ".weight", cout, x.C);
+    LinearOpts o;
+    o.bias = w32(prefix + ".bias", {cout}, kInitBias);
+    o.residual = residual;
+    return linear(x, w, cout, o);
+}
+
+Act NetBase::upsample(const Act& x) {
+    Act y = new_act(x.B, 2 * x.H, 2 * x.W, x.C);
+    const void* xp = x.p;
+    void* yp = y.p;
+    const int B = x.B, H = x.H, W = x.W, C = x.C;
+    plan_->push([=](cudaStream_t st) { return sdod_upsample2x_nhwc(st, xp, yp, B, H, W, C); });
+    return y;
+}
+
+Act NetBase::concat(const Act& a, const Act& b) {
+    Act y = new_act(a.B, a.H, a.W, a.C + b.C);
+    const void *ap = a.p, *bp = b.p;
+    void* yp = y.p;
+    const int Ca = a.C, Cb = b.C;
+    const long long rows = a.M();
+    plan_->push([=](cudaStream_t st) { return sdod_concat_channels(st, ap, Ca, bp, Cb, yp, rows); });
+    return y;
+}
+
+}  // namespace sdod

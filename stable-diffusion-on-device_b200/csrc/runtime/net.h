@@ -1,0 +1,127 @@
+// Runtime plumbing shared by the UNet and VAE executors: named device weights, a device buffer pool,
+// pre-planned launch sequences (optionally replayed as a CUDA graph) and the layer builders that
+// turn ldm layer names into prepared kernel launches.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../host_common.h"
+#include "../kernels/launchers.h"
+#include "sdod_kernels.h"
+
+namespace sdod {
+
+struct DevTensor {
+    float* p = nullptr;
+    std::vector<long long> shape;
+    size_t numel = 0;
+};
+
+class WeightStore {
+public:
+    ~WeightStore();
+    int set(const std::string& name, const float* host, const std::vector<long long>& shape);
+    int load_file(const std::string& path);
+    const DevTensor* find(const std::string& name) const;
+    size_t size() const { return t_.size(); }
+
+private:
+    std::unordered_map<std::string, DevTensor> t_;
+};
+
+// Caching pool of device buffers; plan-build-time alloc/release gives buffer reuse across layers
+// (stream order makes reuse safe), which keeps the step's working set L2-friendly.
+class Pool {
+public:
+    ~Pool();
+    void* get(size_t bytes);
+    void put(void* p);
+    size_t total_bytes() const { return total_; }
+
+private:
+    struct Blk { void* p; size_t sz; bool free_; };
+    std::vector<Blk> blks_;
+    size_t total_ = 0;
+};
+
+struct Act {
+    void* p = nullptr;
+    int B = 0, H = 0, W = 0, C = 0;
+    int M() const { return B * H * W; }
+    size_t bytes() const { return static_cast<size_t>(M()) * C * 2; }
+};
+
+class Plan {
+public:
+    ~Plan();
+    void push(std::function<int(cudaStream_t)> f, unsigned launches = 1) { ops_.push_back(std::move(f)); launches_ += launches; }
+    int run(cudaStream_t s, bool use_graph);
+    unsigned long long launches() const { return launches_; }
+    size_t size() const { return ops_.size(); }
+
+private:
+    int run_eager(cudaStream_t s);
+    std::vector<std::function<int(cudaStream_t)>> ops_;
+    unsigned long long launches_ = 0;
+    bool warmed_ = false;
+    cudaGraphExec_t exec_ = nullptr;
+};
+
+enum InitKind { kInitWeight = 0, kInitBias = 1, kInitOnes = 2, kInitZeros = 3 };
+
+class NetBase {
+public:
+    NetBase(const WeightStore* ws, unsigned long long seed);
+    virtual ~NetBase();
+
+protected:
+    // ---- weights
+    const float* w32(const std::string& name, const std::vector<long long>& shape, InitKind kind);
+    void* pack_linear(const std::string& wname, int N, int K, int Kpad = 0, const std::vector<int>* rowmap = nullptr);
+    void* pack_conv3(const std::string& wname, int Cout, int Cin, int Kpad = 0);
+    // rows of several [N_i, K] matrices stacked into one bf16 [sum N_i, K] matrix (fused QKV, all emb_layers)
+    void* pack_concat(const std::string& key, const std::vector<std::string>& wnames, const std::vector<int>& Ns, int K);
+    const float* concat_bias(const std::string& key, const std::vector<std::string>& bnames, const std::vector<int>& Ns);
+    const float* gather_bias(const std::string& bname, int N, const std::vector<int>& rowmap);
+    void* dev_alloc(size_t bytes, bool zero);           // owned by the net, freed in the destructor
+    // ---- activations
+    Act new_act(int B, int H, int W, int C);
+    void release(Act& a);
+    // ---- layer builders (append prepared launches to *plan_)
+    Act gn(const Act& x, const std::string& prefix, float eps, bool silu);
+    Act ln(const Act& x, const std::string& prefix);
+    struct LinearOpts {
+        const float* bias = nullptr;
+        const Act* residual = nullptr;
+        int act = SDOD_ACT_NONE;
+        float alpha = 1.0f;
+        int block_n = 0;
+    };
+    Act linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o);          // out [M, N or N/2 (GEGLU)]
+    int gemm_into(const sdod_gemm_desc& d);                                           // fully custom epilogue
+    Act conv3(const Act& x, const std::string& prefix, int cout, const float* row_bias, long long ld_row_bias, const Act* residual,
+              float* out_f32 = nullptr);
+    Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride);
+    Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual);
+    Act upsample(const Act& x);
+    Act concat(const Act& a, const Act& b);
+    void check(int status);                              // throws std::runtime_error with sdod last error
+
+    const WeightStore* ws_;
+    bool random_;
+    unsigned long long seed_, rng_ctr_ = 0;
+    std::vector<void*> owned_;
+    std::unordered_map<std::string, void*> cache_;       // packed / random-init tensors, shared by all plans
+    Pool pool_;
+    Plan* plan_ = nullptr;
+    void* gn_ws_ = nullptr;
+    size_t gn_ws_bytes_ = 0;
+};
+
+}  // namespace sdod

@@ -25,7 +25,7 @@ class SdodError(RuntimeError):
 
 class Epilogue(ctypes.Structure):
     _fields_ = [("C", c_vp), ("C2", c_vp), ("C3", c_vp), ("ldc", c_ll), ("strideC", c_ll), ("bias", c_vp), ("row_bias", c_vp),
-                ("rows_per_group", c_int), ("residual", c_vp), ("ldr", c_ll), ("strideR", c_ll), ("alpha", c_f), ("act", c_int),
+                ("rows_per_group", c_int), ("ld_row_bias", c_ll), ("residual", c_vp), ("ldr", c_ll), ("strideR", c_ll), ("alpha", c_f), ("act", c_int),
                 ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int), ("vt_rows", c_int)]
 
 
@@ -64,6 +64,21 @@ _SIGS = {
     "sdod_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_vp, c_sz]),
     "sdod_silu_bf16": (c_int, [c_vp, c_vp, c_vp, c_sz]),
     "sdod_pack_conv3x3_weight": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),
+    # include/sdod_model.h
+    "sdod_weights_create": (c_int, [ctypes.POINTER(c_vp)]),
+    "sdod_weights_set_f32": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_int, ctypes.POINTER(c_ll)]),
+    "sdod_weights_load_file": (c_int, [c_vp, ctypes.c_char_p]),
+    "sdod_weights_count": (c_ll, [c_vp]),
+    "sdod_weights_destroy": (None, [c_vp]),
+    "sdod_unet_create": (c_int, [ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_int, c_int]),
+    "sdod_unet_destroy": (None, [c_vp]),
+    "sdod_unet_time_embed": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
+    "sdod_unet_set_context": (c_int, [c_vp, c_vp, c_vp, c_int, c_int]),
+    "sdod_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
+    "sdod_unet_launches_per_forward": (ctypes.c_ulonglong, [c_vp, c_int]),
+    "sdod_vae_create": (c_int, [ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_int, c_int]),
+    "sdod_vae_destroy": (None, [c_vp]),
+    "sdod_vae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
 }
 
 _lib = None
