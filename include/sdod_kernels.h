@@ -55,9 +55,13 @@ SDOD_API size_t sdod_group_norm_workspace(int N, int C, int HW, int num_groups, 
 SDOD_API int sdod_group_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias,
                              const float* add_nc, int N, int C, int HW, int num_groups, float eps, int dtype,
                              int layout, int fuse_silu, void* workspace, size_t workspace_bytes);
+/* NHWC only: input and output dtypes may differ (fp32 residual stream in, bf16 GEMM operand out). */
+SDOD_API int sdod_group_norm_nhwc(sdod_stream_t stream, const void* x, int in_dtype, void* y, int out_dtype, const float* weight,
+                                  const float* bias, const float* add_nc, int N, int C, int HW, int num_groups, float eps,
+                                  int fuse_silu, void* workspace, size_t workspace_bytes);
 
-/* LayerNorm over the last dim (SpatialTransformer norm1/2/3). x,y bf16 [rows, width]. */
-SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias,
+/* LayerNorm over the last dim (SpatialTransformer norm1/2/3). x [rows, width] f32|bf16 -> y bf16. */
+SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, void* y, const float* weight, const float* bias,
                              int rows, int width, float eps);
 
 /* ---------------------------------------------------------------------------------------------
@@ -116,6 +120,7 @@ typedef struct sdod_epilogue {
     int out_mode;            /* sdod_out_mode                                                      */
     int heads, head_dim, tokens, dpad, tok_pad;   /* HEADS / HEADS_T / QKV modes                   */
     int vt_rows;             /* HEADS_T / QKV: rows allocated per head in the V^T buffer           */
+    int residual_f32;        /* residual is fp32 (fp32 residual stream) instead of bf16            */
 } sdod_epilogue;
 
 typedef struct sdod_gemm_desc {
@@ -152,9 +157,12 @@ SDOD_API int sdod_softmax_rows(sdod_stream_t stream, const void* x, void* y, lon
 /* Layout / data-movement helpers of the hot path (all bf16 NHWC unless stated). */
 SDOD_API int sdod_nchw_f32_to_nhwc_bf16(sdod_stream_t stream, const float* x, void* y, int N, int C, int HW);
 SDOD_API int sdod_nhwc_to_nchw_f32(sdod_stream_t stream, const void* x, int dtype, float* y, int N, int C, int HW);
-SDOD_API int sdod_upsample2x_nhwc(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C);
-SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, const void* b, int Cb, void* y, long long rows);
-SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C, int stride, int Kpad);
+/* x f32|bf16 -> y bf16 */
+SDOD_API int sdod_upsample2x_nhwc(sdod_stream_t stream, const void* x, int in_dtype, void* y, int N, int H, int W, int C);
+/* a, b, y share one dtype (f32|bf16) */
+SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, const void* b, int Cb, void* y, long long rows, int dtype);
+/* x f32|bf16 -> y bf16 [N*Ho*Wo, Kpad] */
+SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, int in_dtype, void* y, int N, int H, int W, int C, int stride, int Kpad);
 SDOD_API int sdod_cast_f32_to_bf16(sdod_stream_t stream, const float* x, void* y, size_t n);
 SDOD_API int sdod_silu_bf16(sdod_stream_t stream, const void* x, void* y, size_t n);
 /* weight packing (device): OIHW fp32 -> [O][ky][kx][I] bf16 ; GEGLU row interleave per block_n tile */

@@ -32,20 +32,28 @@ SDOD_DEVICE uint4 pack8(const float* f) {
 
 // ---------------------------------------------------------------- LayerNorm: one warp per row
 constexpr int kLnMaxVecPerLane = 8;   // width <= 32*8*8 = 2048
-__global__ void __launch_bounds__(256) layer_norm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
+template <typename T> SDOD_DEVICE void ld8(const T* p, float* f);
+template <> SDOD_DEVICE void ld8<bf16>(const bf16* p, float* f) { unpack8(*reinterpret_cast<const uint4*>(p), f); }
+template <> SDOD_DEVICE void ld8<float>(const float* p, float* f) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
                                                          const float* __restrict__ b, int rows, int width, float eps) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const int nvec = width >> 3;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * width);
+    const T* xr = x + static_cast<size_t>(warp) * width;
     float v[kLnMaxVecPerLane][8];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < kLnMaxVecPerLane; ++k) {
         const int i = lane + k * 32;
         if (i < nvec) {
-            unpack8(xr[i], v[k]);
+            ld8<T>(xr + i * 8, v[k]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += v[k][j];
         }
@@ -132,7 +140,8 @@ __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restri
 }
 
 // ---------------------------------------------------------------- nearest 2x upsample, NHWC, 16-B vectors
-__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cvec) {
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cvec) {
     const size_t total = static_cast<size_t>(N) * (2 * H) * (2 * W) * cvec;
     for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int cv = o % cvec;
@@ -140,7 +149,9 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
         const int ox = p % (2 * W); p /= (2 * W);
         const int oy = p % (2 * H);
         const int n = p / (2 * H);
-        y[o] = x[((static_cast<size_t>(n) * H + (oy >> 1)) * W + (ox >> 1)) * cvec + cv];
+        float f[8];
+        ld8<T>(x + (((static_cast<size_t>(n) * H + (oy >> 1)) * W + (ox >> 1)) * cvec + cv) * 8, f);
+        y[o] = pack8(f);
     }
 }
 
@@ -156,7 +167,8 @@ __global__ void concat_kernel(const uint4* __restrict__ a, int va, const uint4* 
 }
 
 // ---------------------------------------------------------------- im2col 3x3 pad 1 (stride 1|2), k = (ky*3+kx)*C + c
-__global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int stride, int Kpad) {
+template <typename T>
+__global__ void im2col3x3_kernel(const T* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int stride, int Kpad) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const size_t total = static_cast<size_t>(N) * Ho * Wo * Kpad;
     for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -169,13 +181,17 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
         if (k < 9 * C) {
             const int tap = k / C, c = k - tap * C;
             const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<size_t>(n) * H + iy) * W + ix) * C + c];
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                const T e = x[((static_cast<size_t>(n) * H + iy) * W + ix) * C + c];
+                if constexpr (sizeof(T) == 4) v = __float2bfloat16(e); else v = e;
+            }
         }
         y[o] = v;
     }
 }
 // vectorised variant (C % 8 == 0, Kpad == 9*C)
-__global__ void im2col3x3_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cvec, int stride) {
+template <typename T>
+__global__ void im2col3x3_vec_kernel(const T* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cvec, int stride) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const size_t total = static_cast<size_t>(N) * Ho * Wo * 9 * cvec;
     for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -187,7 +203,11 @@ __global__ void im2col3x3_vec_kernel(const uint4* __restrict__ x, uint4* __restr
         const int n = p / Ho;
         const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<size_t>(n) * H + iy) * W + ix) * cvec + cv];
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            float f[8];
+            ld8<T>(x + (((static_cast<size_t>(n) * H + iy) * W + ix) * cvec + cv) * 8, f);
+            v = pack8(f);
+        }
         y[o] = v;
     }
 }
@@ -223,12 +243,15 @@ using namespace sdod;
 
 extern "C" {
 
-SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias, int rows, int width, float eps) {
+SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, void* y, const float* weight, const float* bias, int rows, int width, float eps) {
     if (!x || !y || rows <= 0 || width <= 0) return fail(kInvalidArgument, "layer_norm: bad arguments");
     if (width % 8 != 0 || width > 32 * 8 * kLnMaxVecPerLane) return fail(kUnsupported, "layer_norm: width must be a multiple of 8 and <= 2048");
     const int warps_per_block = 8;
-    layer_norm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
-                                                                                              weight, bias, rows, width, eps);
+    const int grid = (rows + warps_per_block - 1) / warps_per_block;
+    if (in_dtype == SDOD_F32)
+        layer_norm_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);
+    else
+        layer_norm_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);
     count_launch();
     return check_launch("layer_norm_kernel");
 }
@@ -258,32 +281,42 @@ SDOD_API int sdod_nhwc_to_nchw_f32(sdod_stream_t stream, const void* x, int dtyp
     return check_launch("nhwc_to_nchw_f32_kernel");
 }
 
-SDOD_API int sdod_upsample2x_nhwc(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C) {
+SDOD_API int sdod_upsample2x_nhwc(sdod_stream_t stream, const void* x, int in_dtype, void* y, int N, int H, int W, int C) {
     if (!x || !y || C % 8 != 0) return fail(kInvalidArgument, "upsample2x: NULL tensor or C % 8 != 0");
     const size_t n = static_cast<size_t>(N) * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
+    if (in_dtype == SDOD_F32)
+        upsample2x_kernel<float><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
+    else
+        upsample2x_kernel<bf16><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
     count_launch();
     return check_launch("upsample2x_kernel");
 }
 
-SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, const void* b, int Cb, void* y, long long rows) {
+SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, const void* b, int Cb, void* y, long long rows, int dtype) {
     if (!a || !b || !y || Ca % 8 != 0 || Cb % 8 != 0) return fail(kInvalidArgument, "concat_channels: NULL tensor or C % 8 != 0");
-    const size_t n = static_cast<size_t>(rows) * ((Ca + Cb) / 8);
-    concat_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8,
+    const int per = dtype == SDOD_F32 ? 4 : 8;     // elements per 16-byte unit
+    const size_t n = static_cast<size_t>(rows) * ((Ca + Cb) / per);
+    concat_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(a), Ca / per, static_cast<const uint4*>(b), Cb / per,
                                                            static_cast<uint4*>(y), rows);
     count_launch();
     return check_launch("concat_kernel");
 }
 
-SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, void* y, int N, int H, int W, int C, int stride, int Kpad) {
+SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, int in_dtype, void* y, int N, int H, int W, int C, int stride, int Kpad) {
     if (!x || !y || (stride != 1 && stride != 2) || Kpad < 9 * C) return fail(kInvalidArgument, "im2col3x3: bad arguments");
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     if (C % 8 == 0 && Kpad == 9 * C) {
         const size_t n = static_cast<size_t>(N) * Ho * Wo * 9 * (C / 8);
-        im2col3x3_vec_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, stride);
+        if (in_dtype == SDOD_F32)
+            im2col3x3_vec_kernel<float><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<uint4*>(y), N, H, W, C / 8, stride);
+        else
+            im2col3x3_vec_kernel<bf16><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<uint4*>(y), N, H, W, C / 8, stride);
     } else {
         const size_t n = static_cast<size_t>(N) * Ho * Wo * Kpad;
-        im2col3x3_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C, stride, Kpad);
+        if (in_dtype == SDOD_F32)
+            im2col3x3_kernel<float><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), N, H, W, C, stride, Kpad);
+        else
+            im2col3x3_kernel<bf16><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C, stride, Kpad);
     }
     count_launch();
     return check_launch("im2col3x3_kernel");

@@ -44,7 +44,17 @@ SDOD_DEVICE float apply_act(float v, int act) {
 
 // Store 8 consecutive output columns [n, n+8) of row m (values already activated).
 SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zoff_r, int m, int n, int N, float (&v)[8]) {
-    if (ep.residual) {
+    if (ep.residual && ep.residual_f32) {
+        const float* r = reinterpret_cast<const float*>(ep.residual) + zoff_r + static_cast<long long>(m) * ep.ldr + n;
+        if (n + 8 <= N && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+            const float4 a = *reinterpret_cast<const float4*>(r), b = *reinterpret_cast<const float4*>(r + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (n + i < N) v[i] += r[i];
+        }
+    } else if (ep.residual) {
         const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + zoff_r + static_cast<long long>(m) * ep.ldr + n;
         if (n + 8 <= N && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
             uint4 u = *reinterpret_cast<const uint4*>(r);
@@ -83,9 +93,14 @@ SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zof
         }
     } else if (mode == SDOD_OUT_F32) {
         float* c = reinterpret_cast<float*>(base) + zoff_c + static_cast<long long>(m) * ep.ldc + nn;
+        if (n + 8 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+            *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (n + i < N) c[i] = v[i];
+            for (int i = 0; i < 8; ++i)
+                if (n + i < N) c[i] = v[i];
+        }
     } else if (mode == SDOD_OUT_HEADS) {
         int b = m / ep.tokens, t = m - b * ep.tokens;
         int h = nn / ep.head_dim, d = nn - h * ep.head_dim;

@@ -239,12 +239,26 @@ __global__ void __launch_bounds__(kGnThreads) gn_nchw_generic_kernel(const T* __
 // workspace layout: [counters: 256 ints][stats: N*G*2 floats][partials: N*S*G*2 floats]
 constexpr int kGnCounterInts = 256;
 constexpr int kGnMaxSlabs = 512;
+constexpr int kNhwcVec = 8;      // channels per thread (16 B of bf16, 32 B of fp32)
+
+template <typename T> SDOD_DEVICE void load8(const T* p, float* out);
+template <> SDOD_DEVICE void load8<float>(const float* p, float* out) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
+template <> SDOD_DEVICE void load8<bf16>(const bf16* p, float* out) { load_vec<bf16>(p, out); }
+template <typename T> SDOD_DEVICE void store8v(T* p, const float* v);
+template <> SDOD_DEVICE void store8v<float>(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> SDOD_DEVICE void store8v<bf16>(bf16* p, const float* v) { store_vec<bf16>(p, v); }
 
 template <typename T>
 __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __restrict__ add_nc, float* __restrict__ partials,
                                      unsigned int* __restrict__ counters, float* __restrict__ stats, int C, int HW, int G,
                                      int rows_per_slab, float eps) {
-    constexpr int VEC = VecOf<T>::N;
+    constexpr int VEC = kNhwcVec;
     extern __shared__ float gsm[];          // [r][C][2] then reused
     __shared__ float pivots[64];
     __shared__ int is_last;
@@ -274,7 +288,7 @@ __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __res
     if (active) {
         for (int p = p0 + rr; p < p1; p += r) {
             float e[VEC];
-            load_vec<T>(xn + static_cast<long long>(p) * C + col * VEC, e);
+            load8<T>(xn + static_cast<long long>(p) * C + col * VEC, e);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { float d = e[i] + ad[i] - K[i]; s[i] += d; ss[i] += d * d; }
         }
@@ -317,11 +331,11 @@ __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __res
     }
 }
 
-template <typename T>
-__global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ weight,
+template <typename TI, typename TO>
+__global__ void gn_nhwc_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ weight,
                                      const float* __restrict__ bias, const float* __restrict__ add_nc,
                                      const float* __restrict__ stats, int C, int HW, int G, int rows_per_slab, int fuse_silu) {
-    constexpr int VEC = VecOf<T>::N;
+    constexpr int VEC = kNhwcVec;
     const int n = blockIdx.y, slab = blockIdx.x;
     const int cvec = C / VEC;
     const int r = blockDim.x / cvec;
@@ -341,17 +355,17 @@ __global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
     }
     const int p0 = slab * rows_per_slab;
     const int p1 = min(HW, p0 + rows_per_slab);
-    const T* xn = x + static_cast<long long>(n) * HW * C;
-    T* yn = y + static_cast<long long>(n) * HW * C;
+    const TI* xn = x + static_cast<long long>(n) * HW * C;
+    TO* yn = y + static_cast<long long>(n) * HW * C;
     for (int p = p0 + rr; p < p1; p += r) {
         float e[VEC];
-        load_vec<T>(xn + static_cast<long long>(p) * C + col * VEC, e);
+        load8<TI>(xn + static_cast<long long>(p) * C + col * VEC, e);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float o = fmaf(e[i], A[i], B[i]);
             e[i] = fuse_silu ? silu_f(o) : o;
         }
-        store_vec<T>(yn + static_cast<long long>(p) * C + col * VEC, e);
+        store8v<TO>(yn + static_cast<long long>(p) * C + col * VEC, e);
     }
 }
 
@@ -368,6 +382,50 @@ static void nhwc_geometry(int N, int C, int HW, int vec, int* threads, int* slab
     int rps = (HW + S - 1) / S;
     *rows_per_slab = rps;
     *slabs = (HW + rps - 1) / rps;
+}
+
+template <typename TI, typename TO>
+static int group_norm_nhwc_typed(cudaStream_t stream, const TI* x, TO* y, const float* weight, const float* bias, const float* add_nc,
+                                 int N, int C, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
+    constexpr int VEC = kNhwcVec;
+    if (C % VEC != 0) return fail(kUnsupported, "group_norm NHWC: C must be a multiple of 8");
+    if (C / VEC > 1024) return fail(kUnsupported, "group_norm NHWC: C too large");
+    if (G > 64) return fail(kUnsupported, "group_norm NHWC: num_groups > 64");
+    if (N > kGnCounterInts) return fail(kUnsupported, "group_norm NHWC: batch > 256");
+    int threads, S, rps;
+    nhwc_geometry(N, C, HW, VEC, &threads, &S, &rps);
+    const size_t need = sdod_group_norm_workspace(N, C, HW, G, SDOD_NHWC);
+    if (!ws || ws_bytes < need) return fail(kInvalidArgument, "group_norm NHWC: workspace too small (need " + std::to_string(need) + " bytes)");
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    float* stats = reinterpret_cast<float*>(counters + kGnCounterInts);
+    float* partials = stats + static_cast<size_t>(N) * G * 2;
+    const int r = threads / (C / VEC);
+    const size_t smem = static_cast<size_t>(r) * C * 2 * sizeof(float);
+    if (smem > 48 * 1024) {
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_stats_kernel<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                            "cudaFuncSetAttribute(gn stats)"));
+    }
+    gn_nhwc_stats_kernel<TI><<<dim3(S, N), threads, smem, stream>>>(x, add_nc, partials, counters, stats, C, HW, G, rps, eps);
+    SDOD_TRY(check_launch("gn_nhwc_stats_kernel"));
+    gn_nhwc_apply_kernel<TI, TO><<<dim3(S, N), threads, 0, stream>>>(x, y, weight, bias, add_nc, stats, C, HW, G, rps, fuse_silu);
+    count_launch(2);
+    return check_launch("gn_nhwc_apply_kernel");
+}
+
+int group_norm_nhwc(cudaStream_t stream, const void* x, int in_dtype, void* y, int out_dtype, const float* weight, const float* bias,
+                    const float* add_nc, int N, int C, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
+    if (!x || !y) return fail(kInvalidArgument, "group_norm: NULL tensor");
+    if (N <= 0 || C <= 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");
+    if (C % G != 0) return fail(kInvalidArgument, "num_channels must be divisible by num_groups");
+    if ((weight == nullptr) != (bias == nullptr)) return fail(kInvalidArgument, "group_norm: weight and bias must both be given or both be NULL");
+#define SDOD_GN_CASE(TI, TO) \
+    return group_norm_nhwc_typed<TI, TO>(stream, static_cast<const TI*>(x), static_cast<TO*>(y), weight, bias, add_nc, N, C, HW, G, eps, fuse_silu, ws, ws_bytes)
+    if (in_dtype == SDOD_F32 && out_dtype == SDOD_F32) SDOD_GN_CASE(float, float);
+    if (in_dtype == SDOD_F32 && out_dtype == SDOD_BF16) SDOD_GN_CASE(float, bf16);
+    if (in_dtype == SDOD_BF16 && out_dtype == SDOD_BF16) SDOD_GN_CASE(bf16, bf16);
+    if (in_dtype == SDOD_BF16 && out_dtype == SDOD_F32) SDOD_GN_CASE(bf16, float);
+#undef SDOD_GN_CASE
+    return fail(kInvalidArgument, "group_norm: unknown dtype");
 }
 
 template <typename T>
@@ -410,29 +468,7 @@ static int group_norm_typed(cudaStream_t stream, const T* x, T* y, const float* 
         count_launch();
         return check_launch("gn_nchw_generic_kernel");
     }
-    // NHWC
-    if (C % VEC != 0) return fail(kUnsupported, "group_norm NHWC: C must be a multiple of 16 bytes worth of elements");
-    if (C / VEC > 1024) return fail(kUnsupported, "group_norm NHWC: C too large");
-    if (G > 64) return fail(kUnsupported, "group_norm NHWC: num_groups > 64");
-    if (N > kGnCounterInts) return fail(kUnsupported, "group_norm NHWC: batch > 256");
-    int threads, S, rps;
-    nhwc_geometry(N, C, HW, VEC, &threads, &S, &rps);
-    const size_t need = sdod_group_norm_workspace(N, C, HW, G, SDOD_NHWC);
-    if (!ws || ws_bytes < need) return fail(kInvalidArgument, "group_norm NHWC: workspace too small (need " + std::to_string(need) + " bytes)");
-    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
-    float* stats = reinterpret_cast<float*>(counters + kGnCounterInts);
-    float* partials = stats + static_cast<size_t>(N) * G * 2;
-    const int r = threads / (C / VEC);
-    const size_t smem = static_cast<size_t>(r) * C * 2 * sizeof(float);
-    if (smem > 48 * 1024) {
-        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
-                            "cudaFuncSetAttribute(gn stats)"));
-    }
-    gn_nhwc_stats_kernel<T><<<dim3(S, N), threads, smem, stream>>>(x, add_nc, partials, counters, stats, C, HW, G, rps, eps);
-    SDOD_TRY(check_launch("gn_nhwc_stats_kernel"));
-    gn_nhwc_apply_kernel<T><<<dim3(S, N), threads, 0, stream>>>(x, y, weight, bias, add_nc, stats, C, HW, G, rps, fuse_silu);
-    count_launch(2);
-    return check_launch("gn_nhwc_apply_kernel");
+    return fail(kInvalidArgument, "group_norm: unknown layout");
 }
 
 int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc, int N, int C,
@@ -441,6 +477,7 @@ int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight,
     if (N <= 0 || C <= 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");
     if (C % G != 0) return fail(kInvalidArgument, "num_channels must be divisible by num_groups");   // efficient_gn.py:37-38
     if ((weight == nullptr) != (bias == nullptr)) return fail(kInvalidArgument, "group_norm: weight and bias must both be given or both be NULL");  // efficient_gn.py:17-22
+    if (layout == SDOD_NHWC) return group_norm_nhwc(stream, x, dtype, y, dtype, weight, bias, add_nc, N, C, HW, G, eps, fuse_silu, ws, ws_bytes);
     if (dtype == SDOD_F32)
         return group_norm_typed<float>(stream, static_cast<const float*>(x), static_cast<float*>(y), weight, bias, add_nc, N, C, HW, G, eps, layout, fuse_silu, ws, ws_bytes);
     if (dtype == SDOD_BF16)
@@ -455,6 +492,12 @@ SDOD_API size_t sdod_group_norm_workspace(int N, int C, int HW, int num_groups, 
     (void)C; (void)HW;
     if (layout != SDOD_NHWC) return 0;
     return sdod::kGnCounterInts * sizeof(unsigned int) + static_cast<size_t>(N) * num_groups * 2 * sizeof(float) * (1 + sdod::kGnMaxSlabs);
+}
+SDOD_API int sdod_group_norm_nhwc(sdod_stream_t stream, const void* x, int in_dtype, void* y, int out_dtype, const float* weight,
+                                  const float* bias, const float* add_nc, int N, int C, int HW, int num_groups, float eps, int fuse_silu,
+                                  void* workspace, size_t workspace_bytes) {
+    return sdod::group_norm_nhwc(static_cast<cudaStream_t>(stream), x, in_dtype, y, out_dtype, weight, bias, add_nc, N, C, HW, num_groups, eps,
+                                 fuse_silu, workspace, workspace_bytes);
 }
 SDOD_API int sdod_group_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc,
                              int N, int C, int HW, int num_groups, float eps, int dtype, int layout, int fuse_silu, void* workspace,

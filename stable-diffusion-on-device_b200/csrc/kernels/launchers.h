@@ -46,4 +46,7 @@ int attention_launch(const AttnLaunch& a, cudaStream_t stream);
 int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc, int N, int C,
                int HW, int G, float eps, int dtype, int layout, int fuse_silu, void* ws, size_t ws_bytes);
 
+int group_norm_nhwc(cudaStream_t stream, const void* x, int in_dtype, void* y, int out_dtype, const float* weight, const float* bias,
+                    const float* add_nc, int N, int C, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes);
+
 }  // namespace sdod

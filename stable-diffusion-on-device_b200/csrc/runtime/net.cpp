@@ -256,9 +256,9 @@ const float* NetBase::gather_bias(const std::string& bname, int N, const std::ve
     return dst;
 }
 
-Act NetBase::new_act(int B, int H, int W, int C) {
+Act NetBase::new_act(int B, int H, int W, int C, bool f32) {
     Act a;
-    a.B = B; a.H = H; a.W = W; a.C = C;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.f32 = f32;
     a.p = pool_.get(a.bytes());
     return a;
 }
@@ -276,8 +276,8 @@ Act NetBase::gn(const Act& x, const std::string& prefix, float eps, bool silu) {
     const size_t wsb = gn_ws_bytes_;
     const void* xp = x.p;
     void* yp = y.p;
-    const int B = x.B, C = x.C, HW = x.H * x.W, s = silu ? 1 : 0;
-    plan_->push([=](cudaStream_t st) { return group_norm(st, xp, yp, w, b, nullptr, B, C, HW, 32, eps, SDOD_BF16, SDOD_NHWC, s, ws, wsb); }, 2);
+    const int B = x.B, C = x.C, HW = x.H * x.W, s = silu ? 1 : 0, idt = x.dtype();
+    plan_->push([=](cudaStream_t st) { return group_norm_nhwc(st, xp, idt, yp, SDOD_BF16, w, b, nullptr, B, C, HW, 32, eps, s, ws, wsb); }, 2);
     return y;
 }
 
@@ -287,8 +287,8 @@ Act NetBase::ln(const Act& x, const std::string& prefix) {
     Act y = new_act(x.B, x.H, x.W, x.C);
     const void* xp = x.p;
     void* yp = y.p;
-    const int rows = x.M(), C = x.C;
-    plan_->push([=](cudaStream_t st) { return sdod_layer_norm(st, xp, yp, w, b, rows, C, 1e-5f); });
+    const int rows = x.M(), C = x.C, idt = x.dtype();
+    plan_->push([=](cudaStream_t st) { return sdod_layer_norm(st, xp, idt, yp, w, b, rows, C, 1e-5f); });
     return y;
 }
 
@@ -301,40 +301,52 @@ int NetBase::gemm_into(const sdod_gemm_desc& d) {
 
 Act NetBase::linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o) {
     const int n_out = o.act == SDOD_ACT_GEGLU ? N / 2 : N;
-    Act y = new_act(x.B, x.H, x.W, n_out);
+    if (x.f32) throw std::runtime_error("linear: GEMM operand must be bf16");
+    Act y = new_act(x.B, x.H, x.W, n_out, o.out_f32);
     sdod_gemm_desc d{};
     d.A = x.p; d.lda = x.C; d.strideA = 0;
     d.W = w_bf16; d.ldw = x.C; d.strideW = 0;
     d.M = x.M(); d.N = N; d.K = x.C; d.batch = 1; d.block_n = o.block_n;
     d.epi.C = y.p; d.epi.ldc = n_out;
     d.epi.bias = o.bias;
-    if (o.residual) { d.epi.residual = o.residual->p; d.epi.ldr = o.residual->C; }
-    d.epi.alpha = o.alpha; d.epi.act = o.act; d.epi.out_mode = SDOD_OUT_BF16;
+    if (o.residual) { d.epi.residual = o.residual->p; d.epi.ldr = o.residual->C; d.epi.residual_f32 = o.residual->f32 ? 1 : 0; }
+    d.epi.alpha = o.alpha; d.epi.act = o.act; d.epi.out_mode = o.out_f32 ? SDOD_OUT_F32 : SDOD_OUT_BF16;
     gemm_into(d);
     return y;
 }
 
 Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const float* row_bias, long long ld_row_bias, const Act* residual,
-                   float* out_f32) {
+                   bool stream_out, float* out_f32) {
+    if (x.f32) throw std::runtime_error("conv3: operand must be bf16");
     void* wt = pack_conv3(prefix + ".weight", cout, x.C);
     const float* bias = w32(prefix + ".bias", {cout}, kInitBias);
     Act y;
-    if (!out_f32) y = new_act(x.B, x.H, x.W, cout);
+    if (!out_f32) y = new_act(x.B, x.H, x.W, cout, stream_out);
     sdod_conv_desc d{};
     d.X = x.p; d.Wt = wt; d.B = x.B; d.H = x.H; d.W = x.W; d.Cin = x.C; d.Cout = cout;
     d.epi.C = out_f32 ? static_cast<void*>(out_f32) : y.p;
     d.epi.ldc = cout;
     d.epi.bias = bias;
     d.epi.row_bias = row_bias; d.epi.rows_per_group = x.H * x.W; d.epi.ld_row_bias = ld_row_bias;
-    if (residual) { d.epi.residual = residual->p; d.epi.ldr = residual->C; }
-    d.epi.alpha = 1.0f; d.epi.out_mode = out_f32 ? SDOD_OUT_F32 : SDOD_OUT_BF16;
+    if (residual) { d.epi.residual = residual->p; d.epi.ldr = residual->C; d.epi.residual_f32 = residual->f32 ? 1 : 0; }
+    d.epi.alpha = 1.0f; d.epi.out_mode = (out_f32 || stream_out) ? SDOD_OUT_F32 : SDOD_OUT_BF16;
     auto g = std::make_shared<GemmLaunch>();
     check(conv3x3_prepare(d, g.get()));
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
     return y;
 }
 
-Act NetBase::conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride) {
+Act NetBase::to_bf16(const Act& x) {
+    if (!x.f32) throw std::runtime_error("to_bf16: already bf16");
+    Act y = new_act(x.B, x.H, x.W, x.C, false);
+    const float* xp = static_cast<const float*>(x.p);
+    void* yp = y.p;
+    const size_t n = static_cast<size_t>(x.M()) * x.C;
+    plan_->push([=](cudaStream_t st) { return sdod_cast_f32_to_bf16(st, xp, yp, n); });
+    return y;
+}
+
+Act NetBase::conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride, bool stream_out) {
     const int K = 9 * x.C;
     const int Kpad = (K + 63) / 64 * 64;
     void* wt = pack_conv3(prefix + ".weight", cout, x.C, Kpad);
@@ -344,40 +356,43 @@ Act NetBase::conv3_im2col(const Act& x, const std::string& prefix, int cout, int
     {
         const void* xp = x.p;
         void* cp = cols.p;
-        const int B = x.B, H = x.H, W = x.W, C = x.C;
-        plan_->push([=](cudaStream_t st) { return sdod_im2col3x3(st, xp, cp, B, H, W, C, stride, Kpad); });
+        const int B = x.B, H = x.H, W = x.W, C = x.C, idt = x.dtype();
+        plan_->push([=](cudaStream_t st) { return sdod_im2col3x3(st, xp, idt, cp, B, H, W, C, stride, Kpad); });
     }
     LinearOpts o;
     o.bias = bias;
+    o.out_f32 = stream_out;
     Act y = linear(cols, wt, cout, o);
     release(cols);
     return y;
 }
 
-Act NetBase::conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual) {
+Act NetBase::conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out) {
     void* w = pack_linear(prefix + ".weight", cout, x.C);
     LinearOpts o;
     o.bias = w32(prefix + ".bias", {cout}, kInitBias);
     o.residual = residual;
+    o.out_f32 = stream_out;
     return linear(x, w, cout, o);
 }
 
 Act NetBase::upsample(const Act& x) {
-    Act y = new_act(x.B, 2 * x.H, 2 * x.W, x.C);
+    Act y = new_act(x.B, 2 * x.H, 2 * x.W, x.C, false);
     const void* xp = x.p;
     void* yp = y.p;
-    const int B = x.B, H = x.H, W = x.W, C = x.C;
-    plan_->push([=](cudaStream_t st) { return sdod_upsample2x_nhwc(st, xp, yp, B, H, W, C); });
+    const int B = x.B, H = x.H, W = x.W, C = x.C, idt = x.dtype();
+    plan_->push([=](cudaStream_t st) { return sdod_upsample2x_nhwc(st, xp, idt, yp, B, H, W, C); });
     return y;
 }
 
 Act NetBase::concat(const Act& a, const Act& b) {
-    Act y = new_act(a.B, a.H, a.W, a.C + b.C);
+    if (a.f32 != b.f32) throw std::runtime_error("concat: dtype mismatch");
+    Act y = new_act(a.B, a.H, a.W, a.C + b.C, a.f32);
     const void *ap = a.p, *bp = b.p;
     void* yp = y.p;
-    const int Ca = a.C, Cb = b.C;
+    const int Ca = a.C, Cb = b.C, dt = a.dtype();
     const long long rows = a.M();
-    plan_->push([=](cudaStream_t st) { return sdod_concat_channels(st, ap, Ca, bp, Cb, yp, rows); });
+    plan_->push([=](cudaStream_t st) { return sdod_concat_channels(st, ap, Ca, bp, Cb, yp, rows, dt); });
     return y;
 }
 

@@ -53,8 +53,10 @@ private:
 struct Act {
     void* p = nullptr;
     int B = 0, H = 0, W = 0, C = 0;
+    bool f32 = false;            // fp32 residual-stream tensor (otherwise bf16 GEMM operand)
     int M() const { return B * H * W; }
-    size_t bytes() const { return static_cast<size_t>(M()) * C * 2; }
+    size_t bytes() const { return static_cast<size_t>(M()) * C * (f32 ? 4 : 2); }
+    int dtype() const { return f32 ? SDOD_F32 : SDOD_BF16; }
 };
 
 class Plan {
@@ -91,7 +93,7 @@ protected:
     const float* gather_bias(const std::string& bname, int N, const std::vector<int>& rowmap);
     void* dev_alloc(size_t bytes, bool zero);           // owned by the net, freed in the destructor
     // ---- activations
-    Act new_act(int B, int H, int W, int C);
+    Act new_act(int B, int H, int W, int C, bool f32 = false);
     void release(Act& a);
     // ---- layer builders (append prepared launches to *plan_)
     Act gn(const Act& x, const std::string& prefix, float eps, bool silu);
@@ -102,13 +104,15 @@ protected:
         int act = SDOD_ACT_NONE;
         float alpha = 1.0f;
         int block_n = 0;
+        bool out_f32 = false;    // write the fp32 residual stream
     };
     Act linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o);          // out [M, N or N/2 (GEGLU)]
     int gemm_into(const sdod_gemm_desc& d);                                           // fully custom epilogue
     Act conv3(const Act& x, const std::string& prefix, int cout, const float* row_bias, long long ld_row_bias, const Act* residual,
-              float* out_f32 = nullptr);
-    Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride);
-    Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual);
+              bool stream_out = false, float* out_f32 = nullptr);
+    Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride, bool stream_out = false);
+    Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out = false);
+    Act to_bf16(const Act& x);
     Act upsample(const Act& x);
     Act concat(const Act& a, const Act& b);
     void check(int status);                              // throws std::runtime_error with sdod last error

@@ -101,11 +101,13 @@ Act UNet::res_block(const Act& x, const std::string& prefix, int cout, int emb_i
     release(h2);
     Act out;
     if (x.C != cout) {
-        Act s = conv1x1(x, prefix + ".skip_connection", cout, nullptr);
-        out = conv3(h3, prefix + ".out_layers.3", cout, nullptr, 0, &s);
+        Act xb = to_bf16(x);
+        Act s = conv1x1(xb, prefix + ".skip_connection", cout, nullptr, true);
+        release(xb);
+        out = conv3(h3, prefix + ".out_layers.3", cout, nullptr, 0, &s, true);
         release(s);
     } else {
-        out = conv3(h3, prefix + ".out_layers.3", cout, nullptr, 0, &x);
+        out = conv3(h3, prefix + ".out_layers.3", cout, nullptr, 0, &x, true);
     }
     release(h3);
     return out;
@@ -123,7 +125,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     const HeadGeom g = head_geom(C);
     const LevelBufs& lb = level_bufs_[level];
     Act hn = gn(x, prefix + ".norm", 1e-6f, false);
-    Act h = conv1x1(hn, prefix + ".proj_in", C, nullptr);
+    Act h = conv1x1(hn, prefix + ".proj_in", C, nullptr, true);     // fp32 token stream
     release(hn);
     const std::string tb = prefix + ".transformer_blocks.0";
 
@@ -144,6 +146,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     LinearOpts o1;
     o1.bias = w32(tb + ".attn1.to_out.0.bias", {C}, kInitBias);
     o1.residual = &h;
+    o1.out_f32 = true;
     Act h2 = linear(a1, pack_linear(tb + ".attn1.to_out.0.weight", C, C), C, o1);
     release(a1);
     release(h);
@@ -164,6 +167,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     LinearOpts o2;
     o2.bias = w32(tb + ".attn2.to_out.0.bias", {C}, kInitBias);
     o2.residual = &h2;
+    o2.out_f32 = true;
     Act h3 = linear(a2, pack_linear(tb + ".attn2.to_out.0.weight", C, C), C, o2);
     release(a2);
     release(h2);
@@ -192,7 +196,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     release(gg);
     release(h3);
 
-    Act out = conv1x1(h4, prefix + ".proj_out", C, &x);
+    Act out = conv1x1(h4, prefix + ".proj_out", C, &x, true);
     release(h4);
     return out;
 }
@@ -228,7 +232,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
         plan_->push([=](cudaStream_t st) { return sdod_cast_f32_to_bf16(st, xin, xp, n); });
     }
     std::vector<Act> hs;
-    Act h = conv3_im2col(x0, "input_blocks.0.0", kMc, 1);
+    Act h = conv3_im2col(x0, "input_blocks.0.0", kMc, 1, true);
     release(x0);
     hs.push_back(h);
     int k = 1;
@@ -247,7 +251,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
         }
         if (level != 3) {
             const std::string p = "input_blocks." + std::to_string(k++);
-            h = conv3_im2col(h, p + ".0.op", h.C, 2);
+            h = conv3_im2col(h, p + ".0.op", h.C, 2, true);
             hs.push_back(h);
         }
     }
@@ -281,7 +285,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
             if (level > 0 && i == 2) {
                 Act u = upsample(r);
                 release(r);
-                Act c = conv3(u, p + "." + std::to_string(sub) + ".conv", u.C, nullptr, 0, nullptr);
+                Act c = conv3(u, p + "." + std::to_string(sub) + ".conv", u.C, nullptr, 0, nullptr, true);
                 release(u);
                 r = c;
             }
@@ -291,7 +295,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
     }
     Act hn = gn(h, "out.0", 1e-5f, true);
     release(h);
-    conv3(hn, "out.2", 4, nullptr, 0, nullptr, eps_out_);
+    conv3(hn, "out.2", 4, nullptr, 0, nullptr, false, eps_out_);
     release(hn);
     plan_ = nullptr;
     return plan;

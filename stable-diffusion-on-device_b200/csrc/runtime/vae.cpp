@@ -140,7 +140,7 @@ std::unique_ptr<Plan> VaeDecoder::build(int B) {
     }
     Act hn = gn(h, "decoder.norm_out", 1e-6f, true);
     release(h);
-    conv3(hn, "decoder.conv_out", 3, nullptr, 0, nullptr, conv_out_);
+    conv3(hn, "decoder.conv_out", 3, nullptr, 0, nullptr, false, conv_out_);
     release(hn);
     {
         const float* co = conv_out_;

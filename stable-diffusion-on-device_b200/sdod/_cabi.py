@@ -26,7 +26,7 @@ class SdodError(RuntimeError):
 class Epilogue(ctypes.Structure):
     _fields_ = [("C", c_vp), ("C2", c_vp), ("C3", c_vp), ("ldc", c_ll), ("strideC", c_ll), ("bias", c_vp), ("row_bias", c_vp),
                 ("rows_per_group", c_int), ("ld_row_bias", c_ll), ("residual", c_vp), ("ldr", c_ll), ("strideR", c_ll), ("alpha", c_f), ("act", c_int),
-                ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int), ("vt_rows", c_int)]
+                ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int), ("vt_rows", c_int), ("residual_f32", c_int)]
 
 
 class GemmDesc(ctypes.Structure):
@@ -45,7 +45,8 @@ _SIGS = {
     "sdod_launch_count": (ctypes.c_ulonglong, []),
     "sdod_group_norm_workspace": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
     "sdod_group_norm": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_vp, c_sz]),
-    "sdod_layer_norm": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f]),
+    "sdod_group_norm_nhwc": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_sz]),
+    "sdod_layer_norm": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f]),
     "sdod_cfg_dpm_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_sz, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_vp]),
     "sdod_dpm_schedule": (c_int, [c_u, c_f, c_f, c_u] + [c_vp] * 8),
     "sdod_dpm_coeffs": (c_int, [c_u, c_f, c_f, c_u, c_u] + [c_vp] * 6),
@@ -58,9 +59,9 @@ _SIGS = {
     "sdod_softmax_rows": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_ll, c_f]),
     "sdod_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),
     "sdod_nhwc_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int]),
-    "sdod_upsample2x_nhwc": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int]),
-    "sdod_concat_channels": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_ll]),
-    "sdod_im2col3x3": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "sdod_upsample2x_nhwc": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int]),
+    "sdod_concat_channels": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_ll, c_int]),
+    "sdod_im2col3x3": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int]),
     "sdod_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_vp, c_sz]),
     "sdod_silu_bf16": (c_int, [c_vp, c_vp, c_vp, c_sz]),
     "sdod_pack_conv3x3_weight": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),

@@ -81,16 +81,17 @@ def _(x, num_groups, weight, bias, eps, silu=False, add_nc=None):
     return torch.empty_like(x)
 
 
-def group_norm_nhwc(x, num_groups, weight, bias, eps, silu=False, add_nc=None):
-    """x: [N, HW, C] (tokens x channels) bf16/f32 contiguous — the layout used inside the UNet/VAE."""
+def group_norm_nhwc(x, num_groups, weight, bias, eps, silu=False, add_nc=None, out_dtype=None):
+    """x: [N, HW, C] (tokens x channels) bf16/f32 contiguous — the layout used inside the UNet/VAE.
+    out_dtype may differ from x.dtype (fp32 residual stream in, bf16 GEMM operand out)."""
     _need_cuda(x)
     n, hw, c = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x, dtype=out_dtype or x.dtype)
     w, b, a = _f32(weight), _f32(bias), _f32(add_nc)
     ws_n = C.lib().sdod_group_norm_workspace(n, c, hw, num_groups, C.NHWC)
     ws = _gn_workspace(x.device, ws_n)
-    C.check(C.lib().sdod_group_norm(_stream(), _p(x), _p(y), _p(w), _p(b), _p(a), n, c, hw, num_groups, eps, _dt(x), C.NHWC,
-                                    int(silu), _p(ws), ws.numel()), "sdod_group_norm")
+    C.check(C.lib().sdod_group_norm_nhwc(_stream(), _p(x), _dt(x), _p(y), _dt(y), _p(w), _p(b), _p(a), n, c, hw, num_groups, eps,
+                                         int(silu), _p(ws), ws.numel()), "sdod_group_norm_nhwc")
     return y
 
 
@@ -98,16 +99,16 @@ def group_norm_nhwc(x, num_groups, weight, bias, eps, silu=False, add_nc=None):
 def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
     _need_cuda(x)
     x = x.contiguous()
-    y = torch.empty_like(x)
+    y = torch.empty_like(x, dtype=torch.bfloat16)
     w, b = _f32(weight), _f32(bias)
     rows = x.numel() // x.shape[-1]
-    C.check(C.lib().sdod_layer_norm(_stream(), _p(x), _p(y), _p(w), _p(b), rows, x.shape[-1], eps), "sdod_layer_norm")
+    C.check(C.lib().sdod_layer_norm(_stream(), _p(x), _dt(x), _p(y), _p(w), _p(b), rows, x.shape[-1], eps), "sdod_layer_norm")
     return y
 
 
 @layer_norm.register_fake
 def _(x, weight, bias, eps):
-    return torch.empty_like(x)
+    return torch.empty_like(x, dtype=torch.bfloat16)
 
 
 def dpm_schedule(steps=20, timesteps=1000, lin_start=0.00085, lin_end=0.0120):
@@ -172,6 +173,7 @@ def _epilogue(out, bias=None, row_bias=None, rows_per_group=0, residual=None, al
     e.strideC = out.stride(0) if out.dim() == 3 else 0
     e.bias, e.row_bias, e.rows_per_group = _p(bias), _p(row_bias), rows_per_group
     e.residual = _p(residual)
+    e.residual_f32 = int(residual is not None and residual.dtype == torch.float32)
     if residual is not None:
         e.ldr = residual.stride(-2)
         e.strideR = residual.stride(0) if residual.dim() == 3 else 0
@@ -230,7 +232,7 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = No
     d.X, d.Wt, d.B, d.H, d.W, d.Cin, d.Cout, d.block_n = _p(x), _p(wt), B, H, W, Cin, Cout, block_n
     e = _epilogue(out.view(B * H * W, Cout), bias, row_bias, H * W, None, 1.0, act)
     if residual is not None:
-        e.residual, e.ldr, e.strideR = _p(residual), Cout, 0
+        e.residual, e.ldr, e.strideR, e.residual_f32 = _p(residual), Cout, 0, int(residual.dtype == torch.float32)
     d.epi = e
     C.check(C.lib().sdod_conv3x3_bf16(_stream(), d), "sdod_conv3x3_bf16")
     return out
@@ -272,7 +274,7 @@ def im2col3x3(x, stride=1, kpad=None):
     kpad = kpad or 9 * Cc
     Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
     out = torch.empty(B * Ho * Wo, kpad, dtype=torch.bfloat16, device=x.device)
-    C.check(C.lib().sdod_im2col3x3(_stream(), _p(x), _p(out), B, H, W, Cc, stride, kpad), "sdod_im2col3x3")
+    C.check(C.lib().sdod_im2col3x3(_stream(), _p(x), _dt(x), _p(out), B, H, W, Cc, stride, kpad), "sdod_im2col3x3")
     return out
 
 
@@ -280,8 +282,8 @@ def upsample2x(x):
     _need_cuda(x)
     x = x.contiguous()
     B, H, W, Cc = x.shape
-    out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)
-    C.check(C.lib().sdod_upsample2x_nhwc(_stream(), _p(x), _p(out), B, H, W, Cc), "sdod_upsample2x_nhwc")
+    out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=torch.bfloat16, device=x.device)
+    C.check(C.lib().sdod_upsample2x_nhwc(_stream(), _p(x), _dt(x), _p(out), B, H, W, Cc), "sdod_upsample2x_nhwc")
     return out
 
 
@@ -290,7 +292,8 @@ def concat_channels(a, b):
     a, b = a.contiguous(), b.contiguous()
     rows = a.numel() // a.shape[-1]
     out = torch.empty(a.shape[:-1] + (a.shape[-1] + b.shape[-1],), dtype=a.dtype, device=a.device)
-    C.check(C.lib().sdod_concat_channels(_stream(), _p(a), a.shape[-1], _p(b), b.shape[-1], _p(out), rows), "sdod_concat_channels")
+    assert a.dtype == b.dtype
+    C.check(C.lib().sdod_concat_channels(_stream(), _p(a), a.shape[-1], _p(b), b.shape[-1], _p(out), rows, _dt(a)), "sdod_concat_channels")
     return out
 
 

@@ -338,3 +338,22 @@ def test_qkv_projection_writes_attention_layouts(heads, dh, tokens):
         assert got.shape == want.shape and rel_err(got, want) < TOL_BF16
     out = torch.ops.sdod.attention(qh, kh, vt, B, heads, dh, tokens, dh ** -0.5)
     assert rel_err(out, _attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], heads)) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------ fp32 residual stream variants
+def test_fp32_stream_variants():
+    torch.manual_seed(40)
+    x = (torch.randn(2, 1024, 640) * 1.5 + 0.3).to(DEV)                                # [N, HW, C] fp32 stream
+    w, b = torch.randn(640, device=DEV), torch.randn(640, device=DEV)
+    want = F.silu(F.group_norm(x.permute(0, 2, 1).reshape(2, 640, 32, 32), 32, w, b, 1e-5)).reshape(2, 640, 1024).permute(0, 2, 1)
+    got = ops.group_norm_nhwc(x, 32, w, b, 1e-5, True, None, torch.bfloat16)
+    assert got.dtype == torch.bfloat16 and rel_err(got, want) < TOL_BF16
+    got = torch.ops.sdod.layer_norm(x.view(2048, 640), w, b, 1e-5)
+    assert got.dtype == torch.bfloat16 and rel_err(got, F.layer_norm(x.view(2048, 640), (640,), w, b, 1e-5)) < TOL_BF16
+    a, wt = bf(torch.randn(2048, 640)).to(DEV), bf(torch.randn(640, 640) / 25).to(DEV)
+    got = torch.ops.sdod.linear(a, wt, b, x.view(2048, 640), 0, 1.0, True)             # fp32 residual, fp32 out
+    assert got.dtype == torch.float32 and rel_err(got, a.float() @ wt.float().t() + b + x.view(2048, 640)) < TOL_F32
+    xi = torch.randn(2, 16, 16, 64, device=DEV)
+    assert torch.equal(ops.upsample2x(xi), ops.upsample2x(bf(xi)))
+    assert torch.equal(ops.im2col3x3(xi, 2), ops.im2col3x3(bf(xi), 2))
+    assert torch.equal(ops.concat_channels(xi, xi * 2), torch.cat([xi, xi * 2], -1))
