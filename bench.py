@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path on B200: SD v1.5 512x512, 20-step DPM-Solver++(2M) txt2img with
+classifier-free guidance (UNet batch 2 per image: cond + uncond) + VAE decode, random-init weights, synthetic prompts.
+
+  python bench.py --gpus N --steps K --warmup W [--images-per-step I] [--impl reference]
+
+One "step" = one call of the generate loop for I images per GPU (20 UNet steps + decode each).  Sample-parallel over
+GPUs (one process per GPU, no data-path collective; weak scaling).  Prints ONE JSON line (rank 0).
+  value    : images/s, device-event timed, inputs/outputs resident in HBM (libsdod_b200_generate_device)
+  e2e      : images/s through the reference-facing C API with HOST buffers (libsdod_b200_generate: pinned H2D of
+             conditioning + latents, D2H of the uint8 images inside the timed region)
+  roofline : the UNet denoising step (one CUDA-graph replay = all its kernels) against the measured bf16 peak
+  cpu_baseline : the oracle (fp32 PyTorch restatement + C sampler) on the host cores, bounded sample
+--impl reference times that CPU path as its own arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-on-device_b200"))
+
+METRIC = "SD1.5 512x512 20-step CFG txt2img throughput"
+UNIT = "images/s"
+UNET_STEP_TFLOP = 1.6065            # batch-2 step, SURVEY §8(d) / Appendix B (803.3 GMAC)
+WORKLOAD = "SD v1.5 txt2img 512x512: 20-step DPM-Solver++(2M), CFG 7.5 (UNet batch 2 per image), VAE decode; random-init weights"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_oracle_times(n_unet_steps=1):
+    """Bounded CPU sample of the same workload: one CFG UNet step (cond + uncond, as context.cpp:352,366) and one VAE
+    decode at full size, fp32, all host threads -> extrapolated images/s = 1 / (20 * t_step + t_vae)."""
+    import torch
+    from oracle import ldm_oracle as L
+    from oracle import sampler as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    unet, vae = L.make_unet(0), L.make_vae(0)
+    x = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(1))
+    g = torch.Generator().manual_seed(2)
+    cond, uncond = torch.randn(1, 77, 768, generator=g), torch.randn(1, 77, 768, generator=g)
+    solver = S.OracleSolver()
+    solver.prepare(20)
+    ts = []
+    with torch.no_grad():
+        emb = unet.embed_time(torch.tensor(solver.table("model_ts")[:1]))
+        xs = x.numpy().copy().ravel()
+        for i in range(n_unet_steps):
+            t0 = time.perf_counter()
+            e_c = unet(x, emb, cond).numpy().ravel()
+            e_u = unet(x, emb, uncond).numpy().ravel()
+            e = S.cfg_combine(e_c, e_u, 7.5)
+            solver.update(0 if i == 0 else 1, xs, e)
+            ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        vae(x * 0.18215)
+        t_vae = time.perf_counter() - t0
+    return ts, t_vae, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ts, t_vae, cores = cpu_oracle_times(n_unet_steps=args.warmup + args.steps)
+    ts = ts[args.warmup:]
+    t_step = statistics.mean(ts)
+    v = 1.0 / (20 * t_step + t_vae)
+    sample = "%d timed CFG UNet steps (cond+uncond, 64x64 latent) + 1 VAE decode, fp32 PyTorch oracle; images/s = 1/(20*t_step + t_vae)" % len(ts)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * (20 * t_step + t_vae), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sampled": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "unet_cfg_step_s": t_step, "vae_decode_s": t_vae},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sdod import libsdod as A
+    from sdod import model as M
+    from sdod import ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.images_per_step
+    pk = peaks()
+
+    ctx = A.Context("random-init:0", latent_spatial=64, steps=20, log_level=A.LOG_ERROR, max_images=n, device=local_rank)
+    g = torch.Generator().manual_seed(2)
+    cond_h, uncond_h = torch.randn(n, 77, 768, generator=g), torch.randn(n, 77, 768, generator=g)
+    lat_h = torch.randn(n, 4, 64, 64, generator=torch.Generator().manual_seed(1))
+    cond_d, uncond_d = cond_h.to(dev), uncond_h.to(dev)
+    lat_d = lat_h.permute(0, 2, 3, 1).contiguous().to(dev)
+    img_d = torch.empty(n, 512, 512, 3, dtype=torch.uint8, device=dev)
+    cond_np, uncond_np, lat_np = cond_h.numpy(), uncond_h.numpy(), lat_h.numpy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > L2 (126 MB)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up (builds plans, captures graphs)
+    for _ in range(max(args.warmup, 3)):
+        ctx.generate_device(cond_d, uncond_d, lat_d, 7.5, img_d)
+    ctx.generate(cond_np, uncond_np, lat_np, 7.5)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: HBM-resident leg (device events inside the library bracket each call)
+    launches0 = ops.launch_count()
+    dev_ms, iter_ms = [], []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        ctx.generate_device(cond_d, uncond_d, lat_d, 7.5, img_d)
+        t = ctx.last_timings()
+        dev_ms.append(t["total_ms"])
+        iter_ms.append(t["iteration_ms"])
+    barrier()
+    wall_dev = time.perf_counter() - t0
+    launches = ops.launch_count() - launches0
+    # ---- timed: end-to-end leg through the host-pointer C API
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.generate(cond_np, uncond_np, lat_np, 7.5)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- UNet step p50 (batch 2, CUDA-graph replay) on its own stream, L2 flushed between replays
+    unet = M.UNet(None, seed=0, latent_hw=64, max_batch=2)
+    s = torch.cuda.Stream(device=dev)
+    x2 = torch.randn(2, 64, 64, 4, device=dev)
+    emb2 = torch.randn(2, 1280, device=dev)
+    unet.set_context(torch.randn(2, 77, 768, device=dev))
+    step_ms = []
+    with torch.cuda.stream(s):
+        for _ in range(4):
+            unet.forward_nhwc(x2, emb2, use_graph=True)
+        for _ in range(max(20, args.steps)):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            unet.forward_nhwc(x2, emb2, use_graph=True)
+            b.record(s)
+            s.synchronize()
+            step_ms.append(a.elapsed_time(b))
+    unet_p50 = statistics.median(step_ms)
+    unet_launches = unet.launches_per_forward(2)
+
+    tot_dev_s = sum(dev_ms) / 1000.0
+    t_dev = torch.tensor([tot_dev_s, wall_e2e, wall_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    tot_dev_s, wall_e2e, wall_dev = t_dev.tolist()
+    images = args.steps * n * world
+    if rank == 0:
+        achieved = UNET_STEP_TFLOP / (unet_p50 / 1000.0)
+        line = {
+            "metric": METRIC, "value": images / tot_dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1000.0 * tot_dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step_per_gpu": n, "latent": "4x64x64", "parallelism": "sample-parallel x%d" % world,
+                       "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events inside the library around each generate call; max over ranks"},
+            "unet_step_p50_ms": unet_p50, "unet_step_batch": 2, "iteration_ms_in_loop": statistics.median(iter_ms),
+            "wall_s_device_leg": wall_dev,
+            "e2e": {"value": images / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * (2 * 77 * 768 * 4 + 4 * 64 * 64 * 4)),
+                    "d2h_bytes_per_step": int(n * 512 * 512 * 3), "timing": "wall clock around libsdod_b200_generate with host buffers; max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "UNet denoising step, batch 2 (one CUDA-graph replay of %d kernels)" % unet_launches,
+                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                         "frac_of_burst_peak": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " (sustained: timed inside a long step)",
+                         "algorithmic_tflop_per_launch": UNET_STEP_TFLOP, "traffic": None},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            ts, t_vae, cores = cpu_oracle_times(1)
+            v = 1.0 / (20 * ts[0] + t_vae)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 CFG UNet step (cond+uncond) + 1 VAE decode, fp32 PyTorch oracle on host; images/s = 1/(20*t_step + t_vae)",
+                                    "unet_cfg_step_s": ts[0], "vae_decode_s": t_vae}
+        print(json.dumps(line))
+    ctx.release()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--images-per-step", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,12 +71,13 @@ SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, 
  *   e  = (g == 1) ? eps_c : g*eps_c + (1-g)*eps_u          (separate roundings, as the host loops)
  *   y0 = (x + (-sigma_s)*e) / alpha_s
  *   x  = c_x*x  [+ c_prev*y_prev]  + c_y0*y0 ;  y_prev = y0
- * x, y_prev fp32 (updated in place); eps_* f32 or bf16; x_bf16_out optional bf16 copy of the new x
- * (next UNet input).  order 1 ignores y_prev on input.  Bit-exact vs the reference in fp32.
+ * x, y_prev fp32 (updated in place); eps_* f32 or bf16; x_copy optional second fp32 destination for
+ * the new x (the uncond batch slot of the next UNet input).  order 1 ignores y_prev on input.
+ * Bit-exact vs the reference in fp32.
  * ------------------------------------------------------------------------------------------- */
 SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, const void* eps_c, const void* eps_u,
                                int eps_dtype, size_t n, float guidance, float sigma_s, float alpha_s, float c_x,
-                               float c_prev, float c_y0, int order, void* x_bf16_out);
+                               float c_prev, float c_y0, int order, float* x_copy);
 
 /* Host-side schedule tables. Replaces DPMSolver::DPMSolver / ::prepare, dpm_solver.cpp:84-131.
  * Each out array has steps+1 floats (may be NULL). Returns 0 or a negative status. */

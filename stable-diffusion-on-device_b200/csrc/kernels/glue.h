@@ -8,6 +8,7 @@ int gather_f32(cudaStream_t s, const float* src, float* dst, int n, const int* m
 int silu_f32_to_bf16(cudaStream_t s, const float* x, void* y_bf16, size_t n, int apply_silu);
 int latent_prequant(cudaStream_t s, const float* z, void* y_bf16, size_t rows, const float* w, const float* b, float inv_scale);
 int vae_post(cudaStream_t s, const float* x, uint8_t* u8, float* img, size_t n);
+int broadcast_rows(cudaStream_t s, float* dst, const float* src, int rows, int width);
 int fill_f32(cudaStream_t s, float* x, size_t n, float v);
 int scale_f32(cudaStream_t s, float* x, size_t n, float v);
 }  // namespace sdod

@@ -62,6 +62,12 @@ __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float s) {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) x[i] *= s;
 }
 
+__global__ void broadcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int width) {
+    const size_t total = static_cast<size_t>(rows) * width;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = src[i % width];
+}
+
 static inline int g1(size_t n) {
     size_t g = (n + 255) / 256;
     if (g > 148 * 32) g = 148 * 32;
@@ -93,6 +99,11 @@ int vae_post(cudaStream_t s, const float* x, uint8_t* u8, float* img, size_t n) 
     vae_post_kernel<<<g1(n), 256, 0, s>>>(x, u8, img, n);
     count_launch();
     return check_launch("vae_post_kernel");
+}
+int broadcast_rows(cudaStream_t s, float* dst, const float* src, int rows, int width) {
+    broadcast_rows_kernel<<<g1(static_cast<size_t>(rows) * width), 256, 0, s>>>(dst, src, rows, width);
+    count_launch();
+    return check_launch("broadcast_rows_kernel");
 }
 int fill_f32(cudaStream_t s, float* x, size_t n, float v) {
     fill_f32_kernel<<<g1(n), 256, 0, s>>>(x, n, v);

@@ -42,7 +42,7 @@ SDOD_DEVICE float dpm_one(float x, float ec, float eu, float& yprev, const StepC
 
 template <typename E>
 __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(float* __restrict__ x, float* __restrict__ y_prev, const E* __restrict__ eps_c,
-                                                           const E* __restrict__ eps_u, size_t n, StepCoef k, bf16* __restrict__ x_bf16) {
+                                                           const E* __restrict__ eps_u, size_t n, StepCoef k, float* __restrict__ x_copy) {
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         float yp = (k.order == 2) ? y_prev[i] : 0.f;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(float* __restrict__ x
         const float xn = dpm_one(x[i], ec, eu, yp, k);
         x[i] = xn;
         y_prev[i] = yp;
-        if (x_bf16) x_bf16[i] = __float2bfloat16(xn);
+        if (x_copy) x_copy[i] = xn;
     }
 }
 
@@ -130,7 +130,7 @@ extern "C" {
 
 SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, const void* eps_c, const void* eps_u, int eps_dtype,
                                size_t n, float guidance, float sigma_s, float alpha_s, float c_x, float c_prev, float c_y0, int order,
-                               void* x_bf16_out) {
+                               float* x_copy) {
     if (!x || !y_prev || !eps_c) return fail(kInvalidArgument, "cfg_dpm_step: NULL tensor");
     if (order != 1 && order != 2) return fail(kInvalidArgument, "cfg_dpm_step: order must be 1 or 2");
     StepCoef k;
@@ -146,11 +146,9 @@ SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, co
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = grid_for(n, 256);
     if (eps_dtype == SDOD_F32)
-        cfg_dpm_step_kernel<float><<<grid, 256, 0, s>>>(x, y_prev, static_cast<const float*>(eps_c), static_cast<const float*>(eps_u), n, k,
-                                                        static_cast<bf16*>(x_bf16_out));
+        cfg_dpm_step_kernel<float><<<grid, 256, 0, s>>>(x, y_prev, static_cast<const float*>(eps_c), static_cast<const float*>(eps_u), n, k, x_copy);
     else if (eps_dtype == SDOD_BF16)
-        cfg_dpm_step_kernel<bf16><<<grid, 256, 0, s>>>(x, y_prev, static_cast<const bf16*>(eps_c), static_cast<const bf16*>(eps_u), n, k,
-                                                       static_cast<bf16*>(x_bf16_out));
+        cfg_dpm_step_kernel<bf16><<<grid, 256, 0, s>>>(x, y_prev, static_cast<const bf16*>(eps_c), static_cast<const bf16*>(eps_u), n, k, x_copy);
     else
         return fail(kInvalidArgument, "cfg_dpm_step: unknown eps dtype");
     count_launch();

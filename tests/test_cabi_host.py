@@ -81,3 +81,31 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     lib = _cabi.lib()
     st = lib.sdod_randn(None, ctypes.c_void_p(16), 16, 0, 0)
     assert st != 0 and lib.sdod_last_error()
+
+
+def test_libsdod_api_argument_and_context_errors_without_gpu():
+    """Status codes / strings / validation order of the reference API (libsdod.cpp:48-111, errors.cpp:8-15)."""
+    from sdod import libsdod as A
+    lib = A.api()
+    want = [b"No error", b"Invalid context", b"Invalid argument", b"Failed to allocate memory or initialise an object",
+            b"Runtime error occurred", b"Internal error occurred"]
+    assert [lib.libsdod_get_error_description(i) for i in range(6)] == want
+    assert lib.libsdod_get_error_description(6) is None and lib.libsdod_get_error_description(-1) is None
+    assert lib.libsdod_setup(None, b".", 4, 64, 8, 20, 2, 1) == A.INVALID_ARGUMENT
+    assert b"should not be nullptr" in lib.libsdod_get_last_error_extra_info(A.INVALID_ARGUMENT, None)
+    ctx = ctypes.c_void_p(1234)
+    assert lib.libsdod_setup(ctypes.byref(ctx), b".", 4, 64, 8, 20, 2, 1) == A.INVALID_ARGUMENT       # must be NULL on entry
+    ctx = ctypes.c_void_p()
+    assert lib.libsdod_setup(ctypes.byref(ctx), b".", 4, 64, 8, 20, 9, 1) == A.INVALID_ARGUMENT       # bad log level
+    assert lib.libsdod_setup(ctypes.byref(ctx), b".", 3, 64, 8, 20, 2, 1) == A.INVALID_ARGUMENT
+    assert lib.libsdod_setup(ctypes.byref(ctx), b".", 4, 48, 8, 20, 2, 1) == A.INVALID_ARGUMENT
+    assert not ctx
+    for fn, args in ((lib.libsdod_set_steps, (None, 20)), (lib.libsdod_release, (None,)), (lib.libsdod_ref_context, (None,))):
+        assert fn(*args) == A.INVALID_CONTEXT
+    assert b"context is nullptr" in lib.libsdod_get_last_error_extra_info(A.INVALID_CONTEXT, None)
+    bogus = (ctypes.c_uint * 8)(1, 2, 3, 4, 5, 6, 7, 8)
+    assert lib.libsdod_release(ctypes.cast(bogus, ctypes.c_void_p)) == A.INVALID_CONTEXT
+    assert b"magic header mismatch" in lib.libsdod_get_last_error_extra_info(A.INVALID_CONTEXT, None)
+    if not torch.cuda.is_available():
+        assert lib.libsdod_setup(ctypes.byref(ctx), b"random-init", 4, 64, 8, 20, 0, 1) == A.RUNTIME_ERROR    # no CPU fallback
+        assert b"no CUDA device" in lib.libsdod_get_last_error_extra_info(A.RUNTIME_ERROR, None)

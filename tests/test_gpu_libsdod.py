@@ -1,0 +1,92 @@
+"""GPU: the libsdod C API end to end (setup -> generate -> release) vs the oracle generate loop on identical
+random-init weights, latents and conditioning.  North-star bar: final-image PSNR >= 35 dB after 20 steps."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from sdod import libsdod as A
+    from sdod import model as M
+from oracle import ldm_oracle as L
+from oracle import pipeline as P
+
+
+def psnr_u8(a, b):
+    mse = ((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean()
+    return 10 * math.log10(255.0 ** 2 / max(mse, 1e-12))
+
+
+@pytest.fixture(scope="module")
+def models_dir(tmp_path_factory):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    d = tmp_path_factory.mktemp("models")
+    unet, vae = L.make_unet(0), L.make_vae(0)
+    M.save_weight_file(str(d / "unet.sdodw"), unet.state_dict())
+    M.save_weight_file(str(d / "vae_decoder.sdodw"), vae.state_dict())
+    return str(d), unet, vae
+
+
+@pytest.mark.parametrize("S,n,guidance", [(16, 2, 7.5), (32, 1, 7.5), (16, 1, 1.0)])
+def test_generate_20_steps_vs_oracle_loop(models_dir, S, n, guidance):
+    d, unet, vae = models_dir
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(n, 4, S, S, generator=g)
+    g2 = torch.Generator().manual_seed(2)
+    cond, uncond = torch.randn(n, 77, 768, generator=g2), torch.randn(n, 77, 768, generator=g2)
+    want_u8, want_img, want_lat = P.generate(unet, vae, cond, uncond, lat, guidance, 20, device="cuda")
+    with A.Context(d, latent_spatial=S, steps=20, max_images=n, device=0) as ctx:
+        imgs, lat_out = ctx.generate(cond.numpy(), uncond.numpy(), lat.numpy(), guidance, return_latents=True)
+        t = ctx.last_timings()
+    rel = np.linalg.norm(lat_out - want_lat) / np.linalg.norm(want_lat)
+    p = psnr_u8(imgs, want_u8)
+    print("S=%d n=%d g=%.1f: final-latent rel-L2 %.3e, image PSNR %.1f dB, iteration %.2f ms" % (S, n, guidance, rel, p, t["iteration_ms"]))
+    assert imgs.shape == (n, 8 * S, 8 * S, 3) and p >= 35.0 and rel < 5e-2
+
+
+def test_full_size_512_generate(models_dir):
+    d, unet, vae = models_dir
+    lat = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(5))
+    g2 = torch.Generator().manual_seed(6)
+    cond, uncond = torch.randn(1, 77, 768, generator=g2), torch.randn(1, 77, 768, generator=g2)
+    want_u8, _, want_lat = P.generate(unet, vae, cond, uncond, lat, 7.5, 20, device="cuda")
+    with A.Context(d, latent_spatial=64, steps=20, max_images=1, device=0) as ctx:
+        imgs, lat_out = ctx.generate(cond.numpy(), uncond.numpy(), lat.numpy(), 7.5, return_latents=True)
+        imgs2 = ctx.generate(cond.numpy(), uncond.numpy(), lat.numpy(), 7.5)
+        t = ctx.last_timings()
+    p = psnr_u8(imgs, want_u8)
+    print("512x512 20-step CFG: PSNR %.1f dB, rel-L2 %.3e, timings %s" % (p, np.linalg.norm(lat_out - want_lat) / np.linalg.norm(want_lat), t))
+    assert p >= 35.0
+    assert np.array_equal(imgs, imgs2)           # deterministic; y_prev persistence never leaks into step 0
+
+
+def test_reference_style_app_flow():
+    """csrc/libsdod/test/simple_app.cpp:7-37 through the same eight symbols."""
+    lib = A.api()
+    ctx = ctypes.c_void_p()
+    assert lib.libsdod_setup(ctypes.byref(ctx), b"random-init:3", 4, 16, 8, 20, A.LOG_ERROR, 1) == 0
+    img, n = ctypes.POINTER(ctypes.c_ubyte)(), ctypes.c_uint(0)
+    assert lib.libsdod_generate_image(ctx, b"A photograph of an astronaut riding a horse", 7.5, ctypes.byref(img), ctypes.byref(n)) == 0
+    assert n.value == 3 * 128 * 128 and bool(img)
+    first = np.ctypeslib.as_array(img, shape=(n.value,)).copy()
+    ctypes.CDLL(None).free(img)                                        # library malloc()s, caller free()s
+    buf = (ctypes.c_ubyte * (n.value + 100))()
+    pbuf, n2 = ctypes.cast(buf, ctypes.POINTER(ctypes.c_ubyte)), ctypes.c_uint(n.value + 100)
+    assert lib.libsdod_b200_set_seed(ctx, 11) == 0
+    assert lib.libsdod_generate_image(ctx, b"A photograph of an astronaut riding a horse", 7.5, ctypes.byref(pbuf), ctypes.byref(n2)) == 0
+    assert n2.value == n.value                                        # bytes written reported back (libsdod.h:108-111)
+    small, n3 = ctypes.cast(buf, ctypes.POINTER(ctypes.c_ubyte)), ctypes.c_uint(10)
+    assert lib.libsdod_generate_image(ctx, b"x", 7.5, ctypes.byref(small), ctypes.byref(n3)) == A.INVALID_ARGUMENT
+    assert b"too small" in lib.libsdod_get_last_error_extra_info(A.INVALID_ARGUMENT, ctx)
+    assert first.std() > 1
+    assert lib.libsdod_set_steps(ctx, 10) == 0 and lib.libsdod_set_steps(ctx, 0) == A.INVALID_ARGUMENT
+    assert lib.libsdod_ref_context(ctx) == 0
+    assert lib.libsdod_release(ctx) == 0 and lib.libsdod_release(ctx) == 0
+    assert lib.libsdod_release(ctx) == A.INVALID_CONTEXT                # released handle is detected
+    assert b"released" in lib.libsdod_get_last_error_extra_info(A.INVALID_CONTEXT, None)
