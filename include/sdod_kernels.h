@@ -132,6 +132,10 @@ typedef struct sdod_gemm_desc {
     sdod_epilogue epi;
 } sdod_gemm_desc;
 SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d);
+/* Optional split-K scratch for the calling thread's subsequent sdod_gemm_bf16 / sdod_conv3x3_bf16 calls (small-M
+ * layers spread their K loop over the chip; the last CTA of each tile folds the partials).  ws: fp32 scratch;
+ * counters: n_counters zero-initialised uint32 (the kernels reset them).  Pass NULLs to disable. */
+SDOD_API int sdod_set_splitk_workspace(float* ws, size_t ws_bytes, unsigned int* counters, int n_counters);
 
 /* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC:  Y[B,H,W,Cout] = epilogue( X (*) Wt )
  * X bf16 [B,H,W,Cin] (Cin % 64 == 0), Wt bf16 [Cout, 9*Cin] with k = (ky*3+kx)*Cin + c.

@@ -131,6 +131,23 @@ SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zof
     }
 }
 
+// acc[16] (columns j..j+15 of `row`) += the other splits' partials (own split z is still in TMEM)
+template <int BN>
+SDOD_DEVICE void add_partials(uint32_t (&acc)[16], const float* ws_tile, int split, int zs, int j, int row) {
+    for (int z = 0; z < split; ++z) {
+        if (z == zs) continue;
+        const float4* src = reinterpret_cast<const float4*>(ws_tile + static_cast<long long>(z) * (BN * kBlockM) + ((j >> 4) * kBlockM + row) * 16);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 v = __ldcg(src + q4);
+            acc[4 * q4 + 0] = __float_as_uint(__uint_as_float(acc[4 * q4 + 0]) + v.x);
+            acc[4 * q4 + 1] = __float_as_uint(__uint_as_float(acc[4 * q4 + 1]) + v.y);
+            acc[4 * q4 + 2] = __float_as_uint(__uint_as_float(acc[4 * q4 + 2]) + v.z);
+            acc[4 * q4 + 3] = __float_as_uint(__uint_as_float(acc[4 * q4 + 3]) + v.w);
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
@@ -145,10 +162,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    volatile uint32_t* split_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y, bz = blockIdx.z;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int bz = mp.split > 1 ? 0 : blockIdx.z;            // batch index (split-K only when batch == 1)
+    const int zs = mp.split > 1 ? blockIdx.z : 0;            // split index
+    const int kb0 = zs * mp.kb_per_split;
+    const int kb1 = mp.split > 1 ? min(mp.k_blocks, kb0 + mp.kb_per_split) : mp.k_blocks;
     const int m0 = m_tile * kBlockM, n0 = n_tile * BN;
 
     if (warp == 0 && lane == 0) {
@@ -184,9 +206,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     x0 = rem - y0 * mp.W;
                 }
             }
-            for (int kb = 0; kb < mp.k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int it = kb - kb0;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                 if (mp.conv) {
@@ -204,9 +227,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         if (lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
-            for (int kb = 0; kb < mp.k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int it = kb - kb0;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kABytes);
@@ -214,7 +238,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     tc_mma_bf16(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
-                                idesc, (kb | k) != 0);
+                                idesc, (it | k) != 0);
                 }
                 tc_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
             }
@@ -234,6 +258,36 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         const float* rb = nullptr;
         if (ep.row_bias && row_ok) rb = ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N);
 
+        // ---- split-K: publish this CTA's partial tile; the last CTA of the tile folds all partials and runs the epilogue
+        const float* ws_tile = nullptr;
+        if (mp.split > 1) {
+            const long long tile_id = static_cast<long long>(m_tile) * gridDim.x + n_tile;
+            float* wst = mp.ws + tile_id * mp.split * (BN * kBlockM);
+            float* mine = wst + static_cast<long long>(zs) * (BN * kBlockM);
+#pragma unroll 1
+            for (int j = 0; j < BN; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                float4* dst = reinterpret_cast<float4*>(mine + ((j >> 4) * kBlockM + row) * 16);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
+                                          __uint_as_float(acc[4 * q4 + 3]));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) *split_flag = (atomicAdd(&mp.counters[tile_id], 1u) == static_cast<unsigned>(mp.split - 1)) ? 1u : 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*split_flag == 0u) {
+                ws_tile = nullptr;
+                goto epilogue_done;
+            }
+            __threadfence();
+            if (threadIdx.x == 64) mp.counters[tile_id] = 0;      // self-resetting
+            ws_tile = wst;
+        }
+
         if (ep.act == SDOD_ACT_GEGLU) {
             constexpr int HALF = BN / 2;
             const int n_out_total = mp.N / 2;
@@ -243,6 +297,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 tmem_ld16(taddr + j, a);
                 tmem_ld16(taddr + HALF + j, g);
                 tmem_ld_wait();
+                if (ws_tile) {
+                    add_partials<BN>(a, ws_tile, mp.split, zs, j, row);
+                    add_partials<BN>(g, ws_tile, mp.split, zs, HALF + j, row);
+                }
                 if (row_ok) {
 #pragma unroll
                     for (int h8 = 0; h8 < 2; ++h8) {
@@ -267,6 +325,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
+                if (ws_tile) add_partials<BN>(acc, ws_tile, mp.split, zs, j, row);
                 if (row_ok) {
 #pragma unroll
                     for (int h8 = 0; h8 < 2; ++h8) {
@@ -288,6 +347,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 }
             }
         }
+    epilogue_done:
         tc_fence_before();
     }
     __syncthreads();
@@ -308,7 +368,7 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
-    dim3 grid(n_tiles, m_tiles, batch);
+    dim3 grid(n_tiles, m_tiles, mp.split > 1 ? mp.split : batch);
     gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, mp, ep);
     count_launch();
     return check_launch("gemm_tcgen05_kernel");
@@ -326,28 +386,46 @@ static int dispatch_gemm(int bn, cudaStream_t stream, const CUtensorMap& tmA, co
     return fail(kInvalidArgument, "unsupported block_n " + std::to_string(bn));
 }
 
-// Tile-width heuristic: fewest padded columns first, then enough CTAs to fill the chip.
+// Tile width: the candidate (160 / 128 / 64) that wastes the fewest padded columns, wider first.
+// (Measured on B200: 128- and 160-wide tiles with 2 CTAs/SM beat 256-wide by ~5 % on large GEMMs, and
+// divide the SD channel counts 320/640/960/1280/1920/3840 exactly.)  GEGLU tiles are fixed at 256.
 int pick_block_n(int M, int N, int batch, int act) {
+    (void)M; (void)batch;
     if (act == SDOD_ACT_GEGLU) return 256;
     if (N <= 32) return 32;
     if (N <= 64) return 64;
-    const int m_tiles = (M + kBlockM - 1) / kBlockM;
-    const int cands[4] = {256, 160, 128, 64};
+    const int cands[3] = {160, 128, 64};
     int best = 128;
-    double best_cost = 1e30;
-    const int sms = 148;
-    for (int c = 0; c < 4; ++c) {
+    long long best_pad = 1LL << 60;
+    for (int c = 0; c < 3; ++c) {
         const int bn = cands[c];
-        const int n_tiles = (N + bn - 1) / bn;
-        const long long tiles = static_cast<long long>(m_tiles) * n_tiles * batch;
-        const int per_sm = bn >= 256 ? 1 : 2;
-        const long long waves = (tiles + sms * per_sm - 1) / (sms * per_sm);
-        // per-tile time ~ max(MMA issue (bn), smem feed floor) + fixed overhead; 2 co-resident CTAs share the pipe
-        const double tile_t = (bn < 128 ? 128.0 : static_cast<double>(bn)) * per_sm + 24.0;
-        const double cost = static_cast<double>(waves) * tile_t;
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+        const long long pad = static_cast<long long>((N + bn - 1) / bn) * bn - N;
+        if (pad < best_pad) { best_pad = pad; best = bn; }
     }
     return best;
+}
+
+static thread_local SplitKWorkspace g_splitk;
+void set_splitk_workspace(const SplitKWorkspace& w) { g_splitk = w; }
+
+// Split-K factor: small-M layers (8x8 / 16x16 levels at batch 2) have too few output tiles to fill 148 SMs and
+// are bound by streaming the weights; splitting K spreads that stream over the whole chip.
+static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, int batch) {
+    mp->split = 1; mp->kb_per_split = mp->k_blocks; mp->ws = nullptr; mp->counters = nullptr;
+    if (batch != 1 || !g_splitk.ws) return;
+    const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+    if (tiles >= 120 || tiles > g_splitk.n_counters) return;
+    int split = static_cast<int>((2 * 148 + tiles - 1) / tiles);
+    const int max_by_k = mp->k_blocks / 4;                    // at least 4 K blocks (256 deep) per split
+    if (split > max_by_k) split = max_by_k;
+    if (split > 32) split = 32;
+    const size_t per_tile = static_cast<size_t>(bn) * kBlockM * sizeof(float);
+    while (split > 1 && static_cast<size_t>(tiles) * split * per_tile > g_splitk.ws_bytes) --split;
+    if (split < 2) return;
+    const int kbps = (mp->k_blocks + split - 1) / split;
+    split = (mp->k_blocks + kbps - 1) / kbps;                 // no empty splits
+    if (split < 2) return;
+    mp->split = split; mp->kb_per_split = kbps; mp->ws = g_splitk.ws; mp->counters = g_splitk.counters;
 }
 
 static int validate_epilogue(const sdod_epilogue& ep, int N) {
@@ -391,6 +469,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     }
     MainloopParams mp{};
     mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
+    choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.N + bn - 1) / bn;
@@ -441,6 +520,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
+    choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     out->m_tiles = (M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.Cout + bn - 1) / bn;
@@ -457,6 +537,12 @@ int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d) {
 }  // namespace sdod
 
 extern "C" {
+SDOD_API int sdod_set_splitk_workspace(float* ws, size_t ws_bytes, unsigned int* counters, int n_counters) {
+    sdod::SplitKWorkspace w;
+    if (ws && counters && n_counters > 0) { w.ws = ws; w.ws_bytes = ws_bytes; w.counters = counters; w.n_counters = n_counters; }
+    sdod::set_splitk_workspace(w);
+    return sdod::kOk;
+}
 SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d) {
     if (!d) return sdod::fail(sdod::kInvalidArgument, "sdod_gemm_bf16: desc is NULL");
     return sdod::gemm_bf16(static_cast<cudaStream_t>(stream), *d);

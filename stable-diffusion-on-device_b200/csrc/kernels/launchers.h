@@ -16,6 +16,10 @@ struct MainloopParams {
     int H, W;          // conv: output spatial size
     int bw, bh, bb;    // conv: TMA box (pixels); bw*bh*bb == 128
     int w_batched;     // W has a batch dimension
+    int split;         // split-K factor (grid.z when batch == 1); 1 = off
+    int kb_per_split;  // K blocks per split
+    float* ws;         // split-K partial tiles: [tile][split][BN/16][128][16] fp32
+    unsigned int* counters;   // one ticket per output tile, self-resetting
 };
 
 struct GemmLaunch {
@@ -33,6 +37,9 @@ struct AttnLaunch {
 };
 
 int pick_block_n(int M, int N, int batch, int act);
+// Split-K scratch shared by all GEMM/conv launches on one stream (launches are serialised by stream order).
+struct SplitKWorkspace { float* ws = nullptr; size_t ws_bytes = 0; unsigned int* counters = nullptr; int n_counters = 0; };
+void set_splitk_workspace(const SplitKWorkspace& w);     // thread-local "current" workspace used by *_prepare
 int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out);
 int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);

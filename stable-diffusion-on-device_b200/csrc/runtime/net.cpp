@@ -132,6 +132,10 @@ int Plan::run(cudaStream_t s, bool use_graph) {
 NetBase::NetBase(const WeightStore* ws, unsigned long long seed) : ws_(ws), random_(ws == nullptr), seed_(seed) {
     gn_ws_bytes_ = sdod_group_norm_workspace(256, 1, 1, 64, SDOD_NHWC);
     gn_ws_ = dev_alloc(gn_ws_bytes_, true);
+    skw_.ws_bytes = static_cast<size_t>(64) << 20;
+    skw_.ws = static_cast<float*>(dev_alloc(skw_.ws_bytes, false));
+    skw_.n_counters = 4096;
+    skw_.counters = static_cast<unsigned int*>(dev_alloc(skw_.n_counters * sizeof(unsigned int), true));
 }
 
 NetBase::~NetBase() {
@@ -294,6 +298,7 @@ Act NetBase::ln(const Act& x, const std::string& prefix) {
 
 int NetBase::gemm_into(const sdod_gemm_desc& d) {
     auto g = std::make_shared<GemmLaunch>();
+    set_splitk_workspace(skw_);
     check(gemm_prepare(d, g.get()));
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
     return kOk;
@@ -331,6 +336,7 @@ Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const floa
     if (residual) { d.epi.residual = residual->p; d.epi.ldr = residual->C; d.epi.residual_f32 = residual->f32 ? 1 : 0; }
     d.epi.alpha = 1.0f; d.epi.out_mode = (out_f32 || stream_out) ? SDOD_OUT_F32 : SDOD_OUT_BF16;
     auto g = std::make_shared<GemmLaunch>();
+    set_splitk_workspace(skw_);
     check(conv3x3_prepare(d, g.get()));
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
     return y;

@@ -126,6 +126,7 @@ protected:
     Plan* plan_ = nullptr;
     void* gn_ws_ = nullptr;
     size_t gn_ws_bytes_ = 0;
+    SplitKWorkspace skw_;                                 // split-K partial tiles + tickets (zeroed once, self-resetting)
 };
 
 }  // namespace sdod

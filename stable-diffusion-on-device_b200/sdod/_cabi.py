@@ -54,6 +54,7 @@ _SIGS = {
     "sdod_randn": (c_int, [c_vp, c_vp, c_sz, ctypes.c_ulonglong, ctypes.c_ulonglong]),
     "sdod_image_to_u8": (c_int, [c_vp, c_vp, c_int, c_vp, c_sz]),
     "sdod_gemm_bf16": (c_int, [c_vp, ctypes.POINTER(GemmDesc)]),
+    "sdod_set_splitk_workspace": (c_int, [c_vp, c_sz, c_vp, c_int]),
     "sdod_conv3x3_bf16": (c_int, [c_vp, ctypes.POINTER(ConvDesc)]),
     "sdod_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f]),
     "sdod_softmax_rows": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_ll, c_f]),

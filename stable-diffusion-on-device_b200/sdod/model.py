@@ -39,7 +39,7 @@ class Weights:
         return int(C.lib().sdod_weights_count(self._h))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and C is not None:
             C.lib().sdod_weights_destroy(self._h)
             self._h = None
 
@@ -94,7 +94,7 @@ class UNet:
         return int(C.lib().sdod_unet_launches_per_forward(self._h, B))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and C is not None:
             C.lib().sdod_unet_destroy(self._h)
             self._h = None
 
@@ -116,6 +116,6 @@ class VaeDecoder:
         return u8, img
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and C is not None:
             C.lib().sdod_vae_destroy(self._h)
             self._h = None

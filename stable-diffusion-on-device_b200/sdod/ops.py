@@ -326,6 +326,21 @@ def nhwc_to_nchw_f32(x):
     return out
 
 
+_splitk = {}
+
+
+def enable_splitk(enable=True, device="cuda", mbytes=64):
+    """Give this thread's GEMM / conv calls a split-K scratch (small-M layers); enable=False turns it off."""
+    if not enable:
+        C.check(C.lib().sdod_set_splitk_workspace(None, 0, None, 0), "sdod_set_splitk_workspace")
+        return
+    key = torch.device(device).index or 0
+    if key not in _splitk:
+        _splitk[key] = (torch.empty(mbytes << 18, dtype=torch.float32, device=device), torch.zeros(4096, dtype=torch.int32, device=device))
+    ws, cnt = _splitk[key]
+    C.check(C.lib().sdod_set_splitk_workspace(ws.data_ptr(), ws.numel() * 4, cnt.data_ptr(), cnt.numel()), "sdod_set_splitk_workspace")
+
+
 def launch_count():
     return int(C.lib().sdod_launch_count())
 

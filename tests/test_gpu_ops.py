@@ -357,3 +357,39 @@ def test_fp32_stream_variants():
     assert torch.equal(ops.upsample2x(xi), ops.upsample2x(bf(xi)))
     assert torch.equal(ops.im2col3x3(xi, 2), ops.im2col3x3(bf(xi), 2))
     assert torch.equal(ops.concat_channels(xi, xi * 2), torch.cat([xi, xi * 2], -1))
+
+
+# ------------------------------------------------------------------------------------------ split-K
+@pytest.mark.parametrize("M,N,K", [(128, 1280, 11520), (512, 1280, 2560), (100, 320, 1280), (128, 10240, 1280)])
+def test_gemm_split_k(M, N, K):
+    torch.manual_seed(M + K)
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+    want = a.float() @ w.float().t() + bias + res
+    ops.enable_splitk(True)
+    try:
+        got = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)
+        got2 = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)            # tickets reset themselves
+        if N == 10240:
+            wp, bp = ops.pack_geglu_weight(w, bias, 256)
+            gg = torch.ops.sdod.linear(a, wp, bp, None, C.ACT_GEGLU)
+            h = a.float() @ w.float().t() + bias
+            assert rel_err(gg, h[:, :N // 2] * F.gelu(h[:, N // 2:])) < TOL_BF16
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want) < TOL_F32 and torch.equal(got, got2)
+
+
+def test_conv_split_k_small_spatial():
+    torch.manual_seed(5)
+    x = bf(torch.randn(2, 8, 8, 2560)).to(DEV)
+    w = bf(torch.randn(1280, 2560, 3, 3) / (9 * 2560) ** 0.5).to(DEV)
+    bias = torch.randn(1280, device=DEV)
+    want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    wt = ops.pack_conv3x3_weight(w.float())
+    ops.enable_splitk(True)
+    try:
+        got = torch.ops.sdod.conv3x3(x, wt, bias)
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want) < TOL_BF16
