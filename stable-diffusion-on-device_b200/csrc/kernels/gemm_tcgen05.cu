@@ -131,20 +131,94 @@ SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zof
     }
 }
 
-// acc[16] (columns j..j+15 of `row`) += the other splits' partials (own split z is still in TMEM)
-template <int BN>
-SDOD_DEVICE void add_partials(uint32_t (&acc)[16], const float* ws_tile, int split, int zs, int j, int row) {
-    for (int z = 0; z < split; ++z) {
-        if (z == zs) continue;
-        const float4* src = reinterpret_cast<const float4*>(ws_tile + static_cast<long long>(z) * (BN * kBlockM) + ((j >> 4) * kBlockM + row) * 16);
+// Epilogue of 16 accumulator columns [n, n+16) of output row m: alpha, bias, timestep row-bias, activation, residual, store.
+SDOD_DEVICE void epilogue_plain16(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n, const uint32_t (&acc)[16]) {
+    if (m >= mp.M) return;
+    const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
+    const float* rb = ep.row_bias ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 v = __ldcg(src + q4);
-            acc[4 * q4 + 0] = __float_as_uint(__uint_as_float(acc[4 * q4 + 0]) + v.x);
-            acc[4 * q4 + 1] = __float_as_uint(__uint_as_float(acc[4 * q4 + 1]) + v.y);
-            acc[4 * q4 + 2] = __float_as_uint(__uint_as_float(acc[4 * q4 + 2]) + v.z);
-            acc[4 * q4 + 3] = __float_as_uint(__uint_as_float(acc[4 * q4 + 3]) + v.w);
+    for (int h8 = 0; h8 < 2; ++h8) {
+        const int nn = n + h8 * 8;
+        if (nn < mp.N) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float x = __uint_as_float(acc[h8 * 8 + i]) * ep.alpha;
+                if (nn + i < mp.N) {
+                    if (ep.bias) x += ep.bias[nn + i];
+                    if (rb) x += rb[nn + i];
+                }
+                v[i] = apply_act(x, ep.act);
+            }
+            store8(ep, zc, zr, m, nn, mp.N, v);
         }
+    }
+}
+
+// GEGLU: tile columns [0,BN/2) hold the value half, [BN/2,BN) the gate half; j indexes the value half.
+template <int BN>
+SDOD_DEVICE void epilogue_geglu16(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n_tile, int j, const uint32_t (&a)[16],
+                                  const uint32_t (&g)[16]) {
+    if (m >= mp.M) return;
+    constexpr int HALF = BN / 2;
+    const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
+    const int n_out_total = mp.N / 2;
+    const int n0 = n_tile * BN;
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+        float v[8];
+        const int no = n_tile * HALF + j + h8 * 8;   // output column
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int na = n0 + j + h8 * 8 + i;
+            const int ng = na + HALF;
+            float av = __uint_as_float(a[h8 * 8 + i]) * ep.alpha;
+            float gv = __uint_as_float(g[h8 * 8 + i]) * ep.alpha;
+            if (ep.bias && ng < mp.N) { av += ep.bias[na]; gv += ep.bias[ng]; }
+            v[i] = av * gelu_f(gv);
+        }
+        if (no < n_out_total) store8(ep, zc, zr, m, no, n_out_total, v);
+    }
+}
+
+// Split-K second phase: one thread per (tile, 16-column chunk, row) folds the `split` partials in fixed order and
+// runs the shared epilogue.  grid = (chunks per tile, tiles), block = 128 rows.
+template <int BN>
+__global__ void __launch_bounds__(128) splitk_reduce_kernel(const MainloopParams mp, const sdod_epilogue ep, int n_tiles) {
+    const int tile = blockIdx.y, row = threadIdx.x;
+    const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+    const int m = m_tile * kBlockM + row;
+    const float* base = mp.ws + static_cast<long long>(tile) * mp.split * (BN * kBlockM);
+    auto fold = [&](int j, uint32_t (&acc)[16]) {
+        float s[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[i] = 0.f;
+        const float4* src = reinterpret_cast<const float4*>(base + ((j >> 4) * kBlockM + row) * 16);
+#pragma unroll 4
+        for (int z = 0; z < mp.split; ++z) {
+            const float4* p = src + static_cast<long long>(z) * (BN * kBlockM / 4);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 v = __ldcg(p + q4);
+                s[4 * q4] += v.x; s[4 * q4 + 1] += v.y; s[4 * q4 + 2] += v.z; s[4 * q4 + 3] += v.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(s[i]);
+    };
+    if (ep.act == SDOD_ACT_GEGLU) {
+        constexpr int HALF = BN / 2;
+        const int j = blockIdx.x * 16;
+        if (j >= HALF) return;
+        uint32_t a[16], g[16];
+        fold(j, a);
+        fold(HALF + j, g);
+        epilogue_geglu16<BN>(ep, mp, 0, m, n_tile, j, a, g);
+    } else {
+        const int j = blockIdx.x * 16;
+        uint32_t acc[16];
+        fold(j, acc);
+        epilogue_plain16(ep, mp, 0, m, n_tile * BN + j, acc);
     }
 }
 
@@ -162,7 +236,6 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    volatile uint32_t* split_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,19 +324,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        const bool row_ok = m < mp.M;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const long long zc = static_cast<long long>(bz) * ep.strideC;
-        const long long zr = static_cast<long long>(bz) * ep.strideR;
-        const float* rb = nullptr;
-        if (ep.row_bias && row_ok) rb = ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N);
-
-        // ---- split-K: publish this CTA's partial tile; the last CTA of the tile folds all partials and runs the epilogue
-        const float* ws_tile = nullptr;
         if (mp.split > 1) {
+            // split-K: publish this CTA's fp32 partial tile ([chunk16][row][16], coalesced); splitk_reduce_kernel folds
+            // the partials in fixed order (deterministic) and applies the epilogue.
             const long long tile_id = static_cast<long long>(m_tile) * gridDim.x + n_tile;
-            float* wst = mp.ws + tile_id * mp.split * (BN * kBlockM);
-            float* mine = wst + static_cast<long long>(zs) * (BN * kBlockM);
+            float* mine = mp.ws + (tile_id * mp.split + zs) * (BN * kBlockM);
 #pragma unroll 1
             for (int j = 0; j < BN; j += 16) {
                 uint32_t acc[16];
@@ -275,49 +341,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
                                           __uint_as_float(acc[4 * q4 + 3]));
             }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) *split_flag = (atomicAdd(&mp.counters[tile_id], 1u) == static_cast<unsigned>(mp.split - 1)) ? 1u : 0u;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*split_flag == 0u) {
-                ws_tile = nullptr;
-                goto epilogue_done;
-            }
-            __threadfence();
-            if (threadIdx.x == 64) mp.counters[tile_id] = 0;      // self-resetting
-            ws_tile = wst;
-        }
-
-        if (ep.act == SDOD_ACT_GEGLU) {
+        } else if (ep.act == SDOD_ACT_GEGLU) {
             constexpr int HALF = BN / 2;
-            const int n_out_total = mp.N / 2;
 #pragma unroll 1
             for (int j = 0; j < HALF; j += 16) {
                 uint32_t a[16], g[16];
                 tmem_ld16(taddr + j, a);
                 tmem_ld16(taddr + HALF + j, g);
                 tmem_ld_wait();
-                if (ws_tile) {
-                    add_partials<BN>(a, ws_tile, mp.split, zs, j, row);
-                    add_partials<BN>(g, ws_tile, mp.split, zs, HALF + j, row);
-                }
-                if (row_ok) {
-#pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        float v[8];
-                        const int no = n_tile * HALF + j + h8 * 8;   // output column
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int na = n0 + j + h8 * 8 + i;
-                            const int ng = na + HALF;
-                            float av = __uint_as_float(a[h8 * 8 + i]) * ep.alpha;
-                            float gv = __uint_as_float(g[h8 * 8 + i]) * ep.alpha;
-                            if (ep.bias && ng < mp.N) { av += ep.bias[na]; gv += ep.bias[ng]; }
-                            v[i] = av * gelu_f(gv);
-                        }
-                        if (no < n_out_total) store8(ep, zc, zr, m, no, n_out_total, v);
-                    }
-                }
+                epilogue_geglu16<BN>(ep, mp, bz, m, n_tile, j, a, g);
             }
         } else {
 #pragma unroll 1
@@ -325,29 +357,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
-                if (ws_tile) add_partials<BN>(acc, ws_tile, mp.split, zs, j, row);
-                if (row_ok) {
-#pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        const int n = n0 + j + h8 * 8;
-                        if (n < mp.N) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float x = __uint_as_float(acc[h8 * 8 + i]) * ep.alpha;
-                                if (n + i < mp.N) {
-                                    if (ep.bias) x += ep.bias[n + i];
-                                    if (rb) x += rb[n + i];
-                                }
-                                v[i] = apply_act(x, ep.act);
-                            }
-                            store8(ep, zc, zr, m, n, mp.N, v);
-                        }
-                    }
-                }
+                epilogue_plain16(ep, mp, bz, m, n0 + j, acc);
             }
         }
-    epilogue_done:
         tc_fence_before();
     }
     __syncthreads();
@@ -371,7 +383,14 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
     dim3 grid(n_tiles, m_tiles, mp.split > 1 ? mp.split : batch);
     gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, mp, ep);
     count_launch();
-    return check_launch("gemm_tcgen05_kernel");
+    SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
+    if (mp.split > 1) {
+        dim3 rgrid(BN / 16, m_tiles * n_tiles);
+        splitk_reduce_kernel<BN><<<rgrid, 128, 0, stream>>>(mp, ep, n_tiles);
+        count_launch();
+        return check_launch("splitk_reduce_kernel");
+    }
+    return kOk;
 }
 
 static int dispatch_gemm(int bn, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
@@ -414,7 +433,7 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
     mp->split = 1; mp->kb_per_split = mp->k_blocks; mp->ws = nullptr; mp->counters = nullptr;
     if (batch != 1 || !g_splitk.ws) return;
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
-    if (tiles >= 120 || tiles > g_splitk.n_counters) return;
+    if (tiles >= 120) return;
     int split = static_cast<int>((2 * 148 + tiles - 1) / tiles);
     const int max_by_k = mp->k_blocks / 4;                    // at least 4 K blocks (256 deep) per split
     if (split > max_by_k) split = max_by_k;

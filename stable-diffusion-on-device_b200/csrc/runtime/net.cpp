@@ -300,7 +300,7 @@ int NetBase::gemm_into(const sdod_gemm_desc& d) {
     auto g = std::make_shared<GemmLaunch>();
     set_splitk_workspace(skw_);
     check(gemm_prepare(d, g.get()));
-    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1);
     return kOk;
 }
 
@@ -338,7 +338,7 @@ Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const floa
     auto g = std::make_shared<GemmLaunch>();
     set_splitk_workspace(skw_);
     check(conv3x3_prepare(d, g.get()));
-    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); });
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1);
     return y;
 }
 
