@@ -181,8 +181,9 @@ SDOD_DEVICE void epilogue_geglu16(const sdod_epilogue& ep, const MainloopParams&
     }
 }
 
-// Split-K second phase: one thread per (tile, 16-column chunk, row) folds the `split` partials in fixed order and
-// runs the shared epilogue.  grid = (chunks per tile, tiles), block = 128 rows.
+// Split-K second phase: a warp-wide slab of 32 rows x 16 columns per warp; each thread folds the `split` partials of
+// 16 columns in fixed order (deterministic), 8 independent 16-B loads in flight, then runs the shared epilogue.
+// grid = (BN/16 chunks, tiles), block = 128 rows.
 template <int BN>
 __global__ void __launch_bounds__(128) splitk_reduce_kernel(const MainloopParams mp, const sdod_epilogue ep, int n_tiles) {
     const int tile = blockIdx.y, row = threadIdx.x;
@@ -190,21 +191,30 @@ __global__ void __launch_bounds__(128) splitk_reduce_kernel(const MainloopParams
     const int m = m_tile * kBlockM + row;
     const float* base = mp.ws + static_cast<long long>(tile) * mp.split * (BN * kBlockM);
     auto fold = [&](int j, uint32_t (&acc)[16]) {
-        float s[16];
+        float4 s[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s[i] = 0.f;
+        for (int i = 0; i < 4; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* src = reinterpret_cast<const float4*>(base + ((j >> 4) * kBlockM + row) * 16);
-#pragma unroll 4
-        for (int z = 0; z < mp.split; ++z) {
-            const float4* p = src + static_cast<long long>(z) * (BN * kBlockM / 4);
+        int z = 0;
+        for (; z + 2 <= mp.split; z += 2) {
+            float4 v[8];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 v = __ldcg(p + q4);
-                s[4 * q4] += v.x; s[4 * q4 + 1] += v.y; s[4 * q4 + 2] += v.z; s[4 * q4 + 3] += v.w;
-            }
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) v[u * 4 + q4] = __ldcg(src + static_cast<long long>(z + u) * (BN * kBlockM / 4) + q4);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) { s[q4].x += v[u * 4 + q4].x; s[q4].y += v[u * 4 + q4].y; s[q4].z += v[u * 4 + q4].z; s[q4].w += v[u * 4 + q4].w; }
         }
+        for (; z < mp.split; ++z)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(s[i]);
+            for (int q4 = 0; q4 < 4; ++q4) { const float4 v = __ldcg(src + static_cast<long long>(z) * (BN * kBlockM / 4) + q4); s[q4].x += v.x; s[q4].y += v.y; s[q4].z += v.z; s[q4].w += v.w; }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            acc[4 * q4] = __float_as_uint(s[q4].x); acc[4 * q4 + 1] = __float_as_uint(s[q4].y);
+            acc[4 * q4 + 2] = __float_as_uint(s[q4].z); acc[4 * q4 + 3] = __float_as_uint(s[q4].w);
+        }
     };
     if (ep.act == SDOD_ACT_GEGLU) {
         constexpr int HALF = BN / 2;
@@ -437,7 +447,7 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
     int split = static_cast<int>((2 * 148 + tiles - 1) / tiles);
     const int max_by_k = mp->k_blocks / 4;                    // at least 4 K blocks (256 deep) per split
     if (split > max_by_k) split = max_by_k;
-    if (split > 32) split = 32;
+    if (split > 8) split = 8;                                 // bounds the partial-tile traffic (L2-resident)
     const size_t per_tile = static_cast<size_t>(bn) * kBlockM * sizeof(float);
     while (split > 1 && static_cast<size_t>(tiles) * split * per_tile > g_splitk.ws_bytes) --split;
     if (split < 2) return;

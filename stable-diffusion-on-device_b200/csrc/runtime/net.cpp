@@ -299,7 +299,9 @@ Act NetBase::ln(const Act& x, const std::string& prefix) {
 int NetBase::gemm_into(const sdod_gemm_desc& d) {
     auto g = std::make_shared<GemmLaunch>();
     set_splitk_workspace(skw_);
-    check(gemm_prepare(d, g.get()));
+    const int st_prep = gemm_prepare(d, g.get());
+    set_splitk_workspace(SplitKWorkspace{});              // never leave a pointer to this net's scratch behind
+    check(st_prep);
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1);
     return kOk;
 }
@@ -337,7 +339,9 @@ Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const floa
     d.epi.alpha = 1.0f; d.epi.out_mode = (out_f32 || stream_out) ? SDOD_OUT_F32 : SDOD_OUT_BF16;
     auto g = std::make_shared<GemmLaunch>();
     set_splitk_workspace(skw_);
-    check(conv3x3_prepare(d, g.get()));
+    const int st_prep = conv3x3_prepare(d, g.get());
+    set_splitk_workspace(SplitKWorkspace{});
+    check(st_prep);
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1);
     return y;
 }
