@@ -239,6 +239,51 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_cfg_split(args, rank, world, local_rank):
+    """CFG split over GPU pairs: rank 2k = cond half, rank 2k+1 = uncond half, one NCCL all-gather of eps per step."""
+    import torch
+    import torch.distributed as dist
+    from sdod import model as M
+    from sdod import ops
+    from sdod import parallel as P
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    groups = P.make_pair_groups(world)
+    pair, role = P.pair_layout(rank, world)
+    n = args.images_per_step
+    unet = M.UNet(None, seed=0, latent_hw=64, max_batch=n)
+    vae = M.VaeDecoder(None, seed=1, latent_hw=64, max_batch=max(1, (n + 1) // 2))
+    g = torch.Generator().manual_seed(2 + pair)
+    cond, uncond = torch.randn(n, 77, 768, generator=g), torch.randn(n, 77, 768, generator=g)
+    unet.set_context((cond if role == 0 else uncond).to(dev))
+    emb_all = unet.time_embed(torch.tensor(ops.dpm_schedule(20)["model_ts"][:20], device=dev))
+    lat = torch.randn(n, 64, 64, 4, generator=torch.Generator().manual_seed(1 + pair)).to(dev)
+    s = torch.cuda.Stream(device=dev)
+    times = []
+    with torch.cuda.stream(s):
+        for it in range(max(args.warmup, 3) + args.steps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            x, imgs, nbytes = P.gpu_cfg_split_generate(unet, vae, emb_all, lat, 7.5, groups[pair], role, 20)
+            b.record(s)
+            s.synchronize()
+            if it >= max(args.warmup, 3):
+                times.append(a.elapsed_time(b))
+    t = torch.tensor([sum(times) / 1000.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        images = args.steps * n * (world // 2)
+        print(json.dumps({"metric": METRIC, "value": images / t.item(), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": 1000.0 * t.item() / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                          "data": "synthetic", "config": {"workload": WORKLOAD, "images_per_step_per_pair": n, "parallelism": "cfg-split x%d pairs" % (world // 2),
+                                                          "exchange": "2-rank NCCL all-gather of eps per step, %d bytes per rank per image-step" % (64 * 64 * 4 * 4)},
+                          "eps_bytes_exchanged_per_generate": nbytes}))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -247,10 +292,13 @@ def main():
     ap.add_argument("--images-per-step", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="sample-parallel", choices=["sample-parallel", "cfg-split"])
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.mode == "cfg-split":
+        run_cfg_split(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 
