@@ -42,6 +42,8 @@ SDOD_API int sdod_unet_set_context(sdod_unet* u, sdod_stream_t stream, const voi
  * replays a CUDA graph captured on first use for this B. */
 SDOD_API int sdod_unet_forward(sdod_unet* u, sdod_stream_t stream, const float* x, const float* emb, float* eps, int B, int use_graph);
 SDOD_API unsigned long long sdod_unet_launches_per_forward(const sdod_unet* u, int B);
+/* Per-op device times of the forward plan (eager, CUDA events between ops), written as "ms<TAB>name" lines into buf. */
+SDOD_API int sdod_unet_profile(sdod_unet* u, sdod_stream_t stream, int B, int iters, char* buf, size_t buf_bytes);
 
 SDOD_API int sdod_vae_create(sdod_vae** out, const sdod_weights* weights, unsigned long long seed, int latent_hw, int max_batch);
 SDOD_API void sdod_vae_destroy(sdod_vae* v);

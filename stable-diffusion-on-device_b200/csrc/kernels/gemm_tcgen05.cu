@@ -26,12 +26,18 @@ constexpr int kBlockK = 64;                    // 64 bf16 = one 128-byte swizzle
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kGemmThreads = 192;
 
-template <int BN>
+// DEEP = false: shallow ring so that 2 CTAs co-reside per SM (one CTA's epilogue overlaps the other's mainloop) — used when
+//                the grid is larger than one wave.
+// DEEP = true : single-wave grids (<= 148 CTAs, the batch-2 UNet case): one CTA owns the SM, so the ring takes all of
+//                shared memory; by Little's law the per-SM load bandwidth is bytes-in-flight / L2 latency, and at 3 stages
+//                the K loop ran latency-bound at ~1.3 us per K block (profiles/r01_*).
+template <int BN, bool DEEP>
 struct GemmCfg {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // 2 CTAs/SM when they fit (epilogue of one overlaps the mainloop of the other)
-    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int kShallow = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int kDeepRaw = (220 * 1024 - 2048) / kStageBytes;
+    static constexpr int kStages = DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow;
     static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -232,11 +238,11 @@ __global__ void __launch_bounds__(128) splitk_reduce_kernel(const MainloopParams
     }
 }
 
-template <int BN>
+template <int BN, bool DEEP>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, DEEP>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -380,18 +386,27 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN>
-static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
-                       const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
-    using Cfg = GemmCfg<BN>;
+template <int BN, bool DEEP>
+static int launch_gemm_cfg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
+                           const sdod_epilogue& ep, dim3 grid) {
+    using Cfg = GemmCfg<BN, DEEP>;
     static bool configured = false;
     if (!configured) {
-        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
+    gemm_tcgen05_kernel<BN, DEEP><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, mp, ep);
+    return kOk;
+}
+
+template <int BN>
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
+                       const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
     dim3 grid(n_tiles, m_tiles, mp.split > 1 ? mp.split : batch);
-    gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, mp, ep);
+    const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
+    if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true>(stream, tmA, tmW, mp, ep, grid)));
+    else SDOD_TRY((launch_gemm_cfg<BN, false>(stream, tmA, tmW, mp, ep, grid)));
     count_launch();
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
     if (mp.split > 1) {

@@ -1,5 +1,8 @@
 // extern "C" surface of include/sdod_model.h
+#include <cstring>
 #include <new>
+#include <string>
+#include <vector>
 
 #include "sdod_model.h"
 #include "unet.h"
@@ -72,6 +75,17 @@ SDOD_API int sdod_unet_forward(sdod_unet* u, sdod_stream_t stream, const float* 
 }
 SDOD_API unsigned long long sdod_unet_launches_per_forward(const sdod_unet* u, int B) {
     return u ? u->net->launches_per_forward(B) : 0;
+}
+
+SDOD_API int sdod_unet_profile(sdod_unet* u, sdod_stream_t stream, int B, int iters, char* buf, size_t buf_bytes) {
+    if (!u || !buf || buf_bytes == 0) return fail(kInvalidArgument, "unet_profile: bad arguments");
+    std::vector<std::pair<std::string, float>> rows;
+    SDOD_TRY(u->net->profile_forward(static_cast<cudaStream_t>(stream), B, iters, &rows));
+    std::string out;
+    for (auto& r : rows) out += std::to_string(r.second) + "\t" + r.first + "\n";
+    if (out.size() + 1 > buf_bytes) out.resize(buf_bytes - 1);
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return kOk;
 }
 
 SDOD_API int sdod_vae_create(sdod_vae** out, const sdod_weights* weights, unsigned long long seed, int latent_hw, int max_batch) {

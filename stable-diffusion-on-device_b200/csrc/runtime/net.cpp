@@ -128,6 +128,31 @@ int Plan::run(cudaStream_t s, bool use_graph) {
     return kOk;
 }
 
+int Plan::profile(cudaStream_t s, int iters, std::vector<std::pair<std::string, float>>* out) {
+    const size_t n = ops_.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) SDOD_TRY(check_cuda(cudaEventCreate(&e), "cudaEventCreate"));
+    std::vector<double> acc(n, 0.0);
+    SDOD_TRY(run_eager(s));
+    for (int it = 0; it < iters; ++it) {
+        SDOD_TRY(check_cuda(cudaEventRecord(ev[0], s), "cudaEventRecord"));
+        for (size_t i = 0; i < n; ++i) {
+            SDOD_TRY(ops_[i](s));
+            SDOD_TRY(check_cuda(cudaEventRecord(ev[i + 1], s), "cudaEventRecord"));
+        }
+        SDOD_TRY(check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize"));
+        for (size_t i = 0; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            acc[i] += ms;
+        }
+    }
+    out->clear();
+    for (size_t i = 0; i < n; ++i) out->emplace_back(names_[i], static_cast<float>(acc[i] / iters));
+    for (auto& e : ev) cudaEventDestroy(e);
+    return kOk;
+}
+
 // ------------------------------------------------------------------------------------------ NetBase
 NetBase::NetBase(const WeightStore* ws, unsigned long long seed) : ws_(ws), random_(ws == nullptr), seed_(seed) {
     gn_ws_bytes_ = sdod_group_norm_workspace(256, 1, 1, 64, SDOD_NHWC);
@@ -281,7 +306,8 @@ Act NetBase::gn(const Act& x, const std::string& prefix, float eps, bool silu) {
     const void* xp = x.p;
     void* yp = y.p;
     const int B = x.B, C = x.C, HW = x.H * x.W, s = silu ? 1 : 0, idt = x.dtype();
-    plan_->push([=](cudaStream_t st) { return group_norm_nhwc(st, xp, idt, yp, SDOD_BF16, w, b, nullptr, B, C, HW, 32, eps, s, ws, wsb); }, 2);
+    plan_->push([=](cudaStream_t st) { return group_norm_nhwc(st, xp, idt, yp, SDOD_BF16, w, b, nullptr, B, C, HW, 32, eps, s, ws, wsb); }, 2,
+                "gn " + std::string(x.f32 ? "f32" : "bf16") + " HW" + std::to_string(HW) + " C" + std::to_string(C));
     return y;
 }
 
@@ -292,7 +318,7 @@ Act NetBase::ln(const Act& x, const std::string& prefix) {
     const void* xp = x.p;
     void* yp = y.p;
     const int rows = x.M(), C = x.C, idt = x.dtype();
-    plan_->push([=](cudaStream_t st) { return sdod_layer_norm(st, xp, idt, yp, w, b, rows, C, 1e-5f); });
+    plan_->push([=](cudaStream_t st) { return sdod_layer_norm(st, xp, idt, yp, w, b, rows, C, 1e-5f); }, 1, "ln rows" + std::to_string(rows) + " C" + std::to_string(C));
     return y;
 }
 
@@ -302,7 +328,9 @@ int NetBase::gemm_into(const sdod_gemm_desc& d) {
     const int st_prep = gemm_prepare(d, g.get());
     set_splitk_workspace(SplitKWorkspace{});              // never leave a pointer to this net's scratch behind
     check(st_prep);
-    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1,
+                "gemm M" + std::to_string(d.M) + " N" + std::to_string(d.N) + " K" + std::to_string(d.K) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split) +
+                    (d.batch > 1 ? " batch" + std::to_string(d.batch) : ""));
     return kOk;
 }
 
@@ -342,7 +370,8 @@ Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const floa
     const int st_prep = conv3x3_prepare(d, g.get());
     set_splitk_workspace(SplitKWorkspace{});
     check(st_prep);
-    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1,
+                "conv3 HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split));
     return y;
 }
 
@@ -352,7 +381,7 @@ Act NetBase::to_bf16(const Act& x) {
     const float* xp = static_cast<const float*>(x.p);
     void* yp = y.p;
     const size_t n = static_cast<size_t>(x.M()) * x.C;
-    plan_->push([=](cudaStream_t st) { return sdod_cast_f32_to_bf16(st, xp, yp, n); });
+    plan_->push([=](cudaStream_t st) { return sdod_cast_f32_to_bf16(st, xp, yp, n); }, 1, "cast_f32_bf16");
     return y;
 }
 
@@ -367,7 +396,7 @@ Act NetBase::conv3_im2col(const Act& x, const std::string& prefix, int cout, int
         const void* xp = x.p;
         void* cp = cols.p;
         const int B = x.B, H = x.H, W = x.W, C = x.C, idt = x.dtype();
-        plan_->push([=](cudaStream_t st) { return sdod_im2col3x3(st, xp, idt, cp, B, H, W, C, stride, Kpad); });
+        plan_->push([=](cudaStream_t st) { return sdod_im2col3x3(st, xp, idt, cp, B, H, W, C, stride, Kpad); }, 1, "im2col");
     }
     LinearOpts o;
     o.bias = bias;
@@ -391,7 +420,7 @@ Act NetBase::upsample(const Act& x) {
     const void* xp = x.p;
     void* yp = y.p;
     const int B = x.B, H = x.H, W = x.W, C = x.C, idt = x.dtype();
-    plan_->push([=](cudaStream_t st) { return sdod_upsample2x_nhwc(st, xp, idt, yp, B, H, W, C); });
+    plan_->push([=](cudaStream_t st) { return sdod_upsample2x_nhwc(st, xp, idt, yp, B, H, W, C); }, 1, "upsample2x");
     return y;
 }
 
@@ -402,7 +431,7 @@ Act NetBase::concat(const Act& a, const Act& b) {
     void* yp = y.p;
     const int Ca = a.C, Cb = b.C, dt = a.dtype();
     const long long rows = a.M();
-    plan_->push([=](cudaStream_t st) { return sdod_concat_channels(st, ap, Ca, bp, Cb, yp, rows, dt); });
+    plan_->push([=](cudaStream_t st) { return sdod_concat_channels(st, ap, Ca, bp, Cb, yp, rows, dt); }, 1, "concat");
     return y;
 }
 

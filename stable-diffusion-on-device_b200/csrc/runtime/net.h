@@ -62,7 +62,13 @@ struct Act {
 class Plan {
 public:
     ~Plan();
-    void push(std::function<int(cudaStream_t)> f, unsigned launches = 1) { ops_.push_back(std::move(f)); launches_ += launches; }
+    void push(std::function<int(cudaStream_t)> f, unsigned launches = 1, std::string name = "op") {
+        ops_.push_back(std::move(f));
+        names_.push_back(std::move(name));
+        launches_ += launches;
+    }
+    // Eager pass with a CUDA event between consecutive ops (hot caches, real launch gaps): per-op milliseconds, averaged.
+    int profile(cudaStream_t s, int iters, std::vector<std::pair<std::string, float>>* out);
     int run(cudaStream_t s, bool use_graph);
     unsigned long long launches() const { return launches_; }
     size_t size() const { return ops_.size(); }
@@ -70,6 +76,7 @@ public:
 private:
     int run_eager(cudaStream_t s);
     std::vector<std::function<int(cudaStream_t)>> ops_;
+    std::vector<std::string> names_;
     unsigned long long launches_ = 0;
     bool warmed_ = false;
     cudaGraphExec_t exec_ = nullptr;

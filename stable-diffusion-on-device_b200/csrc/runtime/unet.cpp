@@ -117,7 +117,8 @@ void UNet::attention_op(const void* qh, const void* kh, const void* vt, void* ou
     const HeadGeom g = head_geom(C);
     auto a = std::make_shared<AttnLaunch>();
     check(attention_prepare(a.get(), qh, kh, vt, out, B, kHeads, tokens, n_kv, g.dh, g.dpad, pad8(n_kv), 1.0f / std::sqrt(static_cast<float>(g.dh))));
-    plan_->push([a](cudaStream_t st) { return attention_launch(*a, st); });
+    plan_->push([a](cudaStream_t st) { return attention_launch(*a, st); }, 1,
+                "attn Nq" + std::to_string(tokens) + " Nkv" + std::to_string(n_kv) + " d" + std::to_string(g.dh));
 }
 
 Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level) {
@@ -400,6 +401,14 @@ int UNet::forward(cudaStream_t s, const float* x, const float* emb, float* eps, 
         return kOk;
     } catch (const std::exception& e) {
         return fail(kCudaError, std::string("unet forward: ") + e.what());
+    }
+}
+
+int UNet::profile_forward(cudaStream_t s, int B, int iters, std::vector<std::pair<std::string, float>>* out) {
+    try {
+        return forward_plan(B)->profile(s, iters, out);
+    } catch (const std::exception& e) {
+        return fail(kCudaError, std::string("unet profile: ") + e.what());
     }
 }
 

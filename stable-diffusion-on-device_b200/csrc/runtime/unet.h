@@ -12,6 +12,7 @@ public:
     int set_context(cudaStream_t s, const void* context, int dtype, int B);
     int forward(cudaStream_t s, const float* x, const float* emb, float* eps, int B, bool use_graph);
     unsigned long long launches_per_forward(int B);
+    int profile_forward(cudaStream_t s, int B, int iters, std::vector<std::pair<std::string, float>>* out);
 
     // persistent I/O buffers (fp32): callers may write/read these directly to skip the staging copies
     float* x_in() { return x_in_; }

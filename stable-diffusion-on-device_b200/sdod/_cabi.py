@@ -78,6 +78,7 @@ _SIGS = {
     "sdod_unet_set_context": (c_int, [c_vp, c_vp, c_vp, c_int, c_int]),
     "sdod_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
     "sdod_unet_launches_per_forward": (ctypes.c_ulonglong, [c_vp, c_int]),
+    "sdod_unet_profile": (c_int, [c_vp, c_vp, c_int, c_int, ctypes.c_char_p, c_sz]),
     "sdod_vae_create": (c_int, [ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_int, c_int]),
     "sdod_vae_destroy": (None, [c_vp]),
     "sdod_vae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int]),

@@ -90,6 +90,13 @@ class UNet:
         emb = emb.to("cuda", torch.float32).contiguous()
         return self.forward_nhwc(x_nhwc, emb, use_graph).permute(0, 3, 1, 2).contiguous()
 
+    def profile(self, B, iters=5):
+        """[(ms, op name)] of the forward plan, eager with CUDA events between ops (hot caches)."""
+        buf = ctypes.create_string_buffer(1 << 20)
+        C.check(C.lib().sdod_unet_profile(self._h, _stream(), B, iters, buf, len(buf)), "sdod_unet_profile")
+        rows = [l.split("\t") for l in buf.value.decode().strip().split("\n") if l]
+        return [(float(a), b) for a, b in rows]
+
     def launches_per_forward(self, B):
         return int(C.lib().sdod_unet_launches_per_forward(self._h, B))
 
