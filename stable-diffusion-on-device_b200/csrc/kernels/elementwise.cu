@@ -31,7 +31,7 @@ SDOD_DEVICE uint4 pack8(const float* f) {
 }
 
 // ---------------------------------------------------------------- LayerNorm: one warp per row
-constexpr int kLnMaxVecPerLane = 8;   // width <= 32*8*8 = 2048
+constexpr int kLnMaxVecPerLane = 8;   // width <= 32*8*8 = 2048 (instantiated per width class to keep registers low)
 template <typename T> SDOD_DEVICE void ld8(const T* p, float* f);
 template <> SDOD_DEVICE void ld8<bf16>(const bf16* p, float* f) { unpack8(*reinterpret_cast<const uint4*>(p), f); }
 template <> SDOD_DEVICE void ld8<float>(const float* p, float* f) {
@@ -39,7 +39,7 @@ template <> SDOD_DEVICE void ld8<float>(const float* p, float* f) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
                                                          const float* __restrict__ b, int rows, int width, float eps) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -47,10 +47,10 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x
     if (warp >= rows) return;
     const int nvec = width >> 3;
     const T* xr = x + static_cast<size_t>(warp) * width;
-    float v[kLnMaxVecPerLane][8];
+    float v[NV][8];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVecPerLane; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int i = lane + k * 32;
         if (i < nvec) {
             ld8<T>(xr + i * 8, v[k]);
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x
     const float mean = warp_sum(s) / static_cast<float>(width);
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVecPerLane; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int i = lane + k * 32;
         if (i < nvec) {
 #pragma unroll
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x
     const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(width) + eps);
     uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(warp) * width);
 #pragma unroll
-    for (int k = 0; k < kLnMaxVecPerLane; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int i = lane + k * 32;
         if (i < nvec) {
             float o[8];
@@ -248,10 +248,19 @@ SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, 
     if (width % 8 != 0 || width > 32 * 8 * kLnMaxVecPerLane) return fail(kUnsupported, "layer_norm: width must be a multiple of 8 and <= 2048");
     const int warps_per_block = 8;
     const int grid = (rows + warps_per_block - 1) / warps_per_block;
-    if (in_dtype == SDOD_F32)
-        layer_norm_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);
-    else
-        layer_norm_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);
+    const int nv = (width / 8 + 31) / 32;
+#define SDOD_LN(NV)                                                                                                                              \
+    do {                                                                                                                                         \
+        if (in_dtype == SDOD_F32)                                                                                                                \
+            layer_norm_kernel<float, NV><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps); \
+        else                                                                                                                                     \
+            layer_norm_kernel<bf16, NV><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);  \
+    } while (0)
+    if (nv <= 2) SDOD_LN(2);
+    else if (nv <= 3) SDOD_LN(3);
+    else if (nv <= 5) SDOD_LN(5);
+    else SDOD_LN(8);
+#undef SDOD_LN
     count_launch();
     return check_launch("layer_norm_kernel");
 }

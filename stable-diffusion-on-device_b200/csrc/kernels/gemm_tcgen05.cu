@@ -137,27 +137,30 @@ SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zof
     }
 }
 
-// Epilogue of 16 accumulator columns [n, n+16) of output row m: alpha, bias, timestep row-bias, activation, residual, store.
-SDOD_DEVICE void epilogue_plain16(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n, const uint32_t (&acc)[16]) {
-    if (m >= mp.M) return;
+// Epilogue of 8 accumulator columns [n, n+8) of output row m: alpha, bias, timestep row-bias, activation, residual, store.
+SDOD_DEVICE void epilogue_plain8(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n, const float (&acc)[8]) {
+    if (m >= mp.M || n >= mp.N) return;
     const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
     const float* rb = ep.row_bias ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float x = acc[i] * ep.alpha;
+        if (n + i < mp.N) {
+            if (ep.bias) x += ep.bias[n + i];
+            if (rb) x += rb[n + i];
+        }
+        v[i] = apply_act(x, ep.act);
+    }
+    store8(ep, zc, zr, m, n, mp.N, v);
+}
+SDOD_DEVICE void epilogue_plain16(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n, const uint32_t (&acc)[16]) {
 #pragma unroll
     for (int h8 = 0; h8 < 2; ++h8) {
-        const int nn = n + h8 * 8;
-        if (nn < mp.N) {
-            float v[8];
+        float a8[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float x = __uint_as_float(acc[h8 * 8 + i]) * ep.alpha;
-                if (nn + i < mp.N) {
-                    if (ep.bias) x += ep.bias[nn + i];
-                    if (rb) x += rb[nn + i];
-                }
-                v[i] = apply_act(x, ep.act);
-            }
-            store8(ep, zc, zr, m, nn, mp.N, v);
-        }
+        for (int i = 0; i < 8; ++i) a8[i] = __uint_as_float(acc[h8 * 8 + i]);
+        epilogue_plain8(ep, mp, bz, m, n + h8 * 8, a8);
     }
 }
 
@@ -187,55 +190,63 @@ SDOD_DEVICE void epilogue_geglu16(const sdod_epilogue& ep, const MainloopParams&
     }
 }
 
-// Split-K second phase: a warp-wide slab of 32 rows x 16 columns per warp; each thread folds the `split` partials of
-// 16 columns in fixed order (deterministic), 8 independent 16-B loads in flight, then runs the shared epilogue.
-// grid = (BN/16 chunks, tiles), block = 128 rows.
+// Split-K second phase: folds the `split` partial tiles in fixed order (deterministic) and runs the shared epilogue.
+// Plain epilogues: 256 threads = 128 rows x 2 column octets, so a warp reads 16 rows x 64 B contiguous partials and writes
+// 16 row segments of 32 B (fp32) — coalesced both ways.  grid = (BN/16 chunks, tiles).
 template <int BN>
-__global__ void __launch_bounds__(128) splitk_reduce_kernel(const MainloopParams mp, const sdod_epilogue ep, int n_tiles) {
-    const int tile = blockIdx.y, row = threadIdx.x;
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams mp, const sdod_epilogue ep, int n_tiles) {
+    const int tile = blockIdx.y;
     const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
-    const int m = m_tile * kBlockM + row;
     const float* base = mp.ws + static_cast<long long>(tile) * mp.split * (BN * kBlockM);
-    auto fold = [&](int j, uint32_t (&acc)[16]) {
-        float4 s[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* src = reinterpret_cast<const float4*>(base + ((j >> 4) * kBlockM + row) * 16);
+    const long long zstride4 = BN * kBlockM / 4;
+    if (ep.act != SDOD_ACT_GEGLU) {
+        const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+        const int j = blockIdx.x * 16;
+        const float4* src = reinterpret_cast<const float4*>(base + ((j >> 4) * kBlockM + row) * 16 + half * 8);
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         int z = 0;
-        for (; z + 2 <= mp.split; z += 2) {
+        for (; z + 4 <= mp.split; z += 4) {
             float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < 4; ++u) { v[2 * u] = __ldcg(src + (z + u) * zstride4); v[2 * u + 1] = __ldcg(src + (z + u) * zstride4 + 1); }
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) v[u * 4 + q4] = __ldcg(src + static_cast<long long>(z + u) * (BN * kBlockM / 4) + q4);
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) { s[q4].x += v[u * 4 + q4].x; s[q4].y += v[u * 4 + q4].y; s[q4].z += v[u * 4 + q4].z; s[q4].w += v[u * 4 + q4].w; }
+            for (int u = 0; u < 4; ++u) {
+                s0.x += v[2 * u].x; s0.y += v[2 * u].y; s0.z += v[2 * u].z; s0.w += v[2 * u].w;
+                s1.x += v[2 * u + 1].x; s1.y += v[2 * u + 1].y; s1.z += v[2 * u + 1].z; s1.w += v[2 * u + 1].w;
+            }
         }
-        for (; z < mp.split; ++z)
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) { const float4 v = __ldcg(src + static_cast<long long>(z) * (BN * kBlockM / 4) + q4); s[q4].x += v.x; s[q4].y += v.y; s[q4].z += v.z; s[q4].w += v.w; }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            acc[4 * q4] = __float_as_uint(s[q4].x); acc[4 * q4 + 1] = __float_as_uint(s[q4].y);
-            acc[4 * q4 + 2] = __float_as_uint(s[q4].z); acc[4 * q4 + 3] = __float_as_uint(s[q4].w);
+        for (; z < mp.split; ++z) {
+            const float4 a = __ldcg(src + z * zstride4), b = __ldcg(src + z * zstride4 + 1);
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
         }
-    };
-    if (ep.act == SDOD_ACT_GEGLU) {
-        constexpr int HALF = BN / 2;
-        const int j = blockIdx.x * 16;
-        if (j >= HALF) return;
-        uint32_t a[16], g[16];
-        fold(j, a);
-        fold(HALF + j, g);
-        epilogue_geglu16<BN>(ep, mp, 0, m, n_tile, j, a, g);
-    } else {
-        const int j = blockIdx.x * 16;
-        uint32_t acc[16];
-        fold(j, acc);
-        epilogue_plain16(ep, mp, 0, m, n_tile * BN + j, acc);
+        const float acc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        epilogue_plain8(ep, mp, 0, m_tile * kBlockM + row, n_tile * BN + j + half * 8, acc);
+        return;
     }
+    // GEGLU: value and gate halves are BN/2 apart; one thread per row
+    if (threadIdx.x >= 128) return;
+    const int row = threadIdx.x;
+    constexpr int HALF = BN / 2;
+    const int j = blockIdx.x * 16;
+    if (j >= HALF) return;
+    auto fold = [&](int jj, uint32_t (&acc)[16]) {
+        float sacc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc[i] = 0.f;
+        const float4* src = reinterpret_cast<const float4*>(base + ((jj >> 4) * kBlockM + row) * 16);
+        for (int z = 0; z < mp.split; ++z)
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 v = __ldcg(src + z * zstride4 + q4);
+                sacc[4 * q4] += v.x; sacc[4 * q4 + 1] += v.y; sacc[4 * q4 + 2] += v.z; sacc[4 * q4 + 3] += v.w;
+            }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(sacc[i]);
+    };
+    uint32_t a[16], g[16];
+    fold(j, a);
+    fold(HALF + j, g);
+    epilogue_geglu16<BN>(ep, mp, 0, m_tile * kBlockM + row, n_tile, j, a, g);
 }
 
 template <int BN, bool DEEP>
@@ -367,6 +378,77 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 tmem_ld_wait();
                 epilogue_geglu16<BN>(ep, mp, bz, m, n_tile, j, a, g);
             }
+        } else if (ep.out_mode == SDOD_OUT_BF16 || ep.out_mode == SDOD_OUT_F32) {
+            // Coalesced epilogue.  Phase 1: each thread owns one accumulator row (tcgen05.ld 32x32b): alpha, bias, timestep
+            // row-bias and activation in registers, then 16-B st.shared into a padded staging tile (the TMA ring is idle:
+            // tmem_full fired after every MMA retired).  Phase 2: the warp walks its 32 rows; lanes run along the columns,
+            // so residual loads and output stores are full 128-B lines instead of 32 scattered 16-B pieces.
+            constexpr int LDS = BN + 4;                       // (BN+4) % 32 == 4 words: conflict-free 16-B row-strided stores
+            float* stg = reinterpret_cast<float*>(smem) + q * (32 * LDS);
+            const float* rb = (ep.row_bias && m < mp.M) ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
+#pragma unroll 2
+            for (int j = 0; j < BN; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = n0 + j + i;
+                    float x = __uint_as_float(acc[i]) * ep.alpha;
+                    if (n < mp.N) {
+                        if (ep.bias) x += ep.bias[n];
+                        if (rb) x += rb[n];
+                    }
+                    v[i] = apply_act(x, ep.act);
+                }
+                float4* dst = reinterpret_cast<float4*>(stg + lane * LDS + j);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            }
+            __syncwarp();
+            const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
+            const bool vec_ok = (mp.N % 4 == 0) && (ep.ldc % 4 == 0) && (!ep.residual || ep.ldr % 4 == 0);
+            const int rows_here = min(32, mp.M - (m0 + q * 32));
+#pragma unroll 2
+            for (int r = 0; r < rows_here; ++r) {
+                const long long mr = m0 + q * 32 + r;
+                for (int c4 = lane; c4 < BN / 4; c4 += 32) {
+                    const int n = n0 + c4 * 4;
+                    if (n >= mp.N) break;
+                    float4 o = *reinterpret_cast<const float4*>(stg + r * LDS + c4 * 4);
+                    if (vec_ok) {
+                        if (ep.residual) {
+                            if (ep.residual_f32) {
+                                const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + zr + mr * ep.ldr + n);
+                                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                            } else {
+                                const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) + zr + mr * ep.ldr + n);
+                                const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y);
+                                o.x += a.x; o.y += a.y; o.z += b.x; o.w += b.y;
+                            }
+                        }
+                        if (ep.out_mode == SDOD_OUT_F32) {
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + zc + mr * ep.ldc + n) = o;
+                        } else {
+                            uint2 w;
+                            w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n) = w;
+                        }
+                    } else {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (n + i >= mp.N) break;
+                            float x = ov[i];
+                            if (ep.residual) x += ep.residual_f32 ? reinterpret_cast<const float*>(ep.residual)[zr + mr * ep.ldr + n + i]
+                                                                  : __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[zr + mr * ep.ldr + n + i]);
+                            if (ep.out_mode == SDOD_OUT_F32) reinterpret_cast<float*>(ep.C)[zc + mr * ep.ldc + n + i] = x;
+                            else reinterpret_cast<bf16*>(ep.C)[zc + mr * ep.ldc + n + i] = __float2bfloat16(x);
+                        }
+                    }
+                }
+            }
         } else {
 #pragma unroll 1
             for (int j = 0; j < BN; j += 16) {
@@ -411,7 +493,7 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
     if (mp.split > 1) {
         dim3 rgrid(BN / 16, m_tiles * n_tiles);
-        splitk_reduce_kernel<BN><<<rgrid, 128, 0, stream>>>(mp, ep, n_tiles);
+        splitk_reduce_kernel<BN><<<rgrid, 256, 0, stream>>>(mp, ep, n_tiles);
         count_launch();
         return check_launch("splitk_reduce_kernel");
     }

@@ -317,10 +317,20 @@ __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __res
     __syncthreads();
     if (is_last) {
         __threadfence();
+        // fold the S slab partials: `lanes` threads per group each take a strided subset, then a fixed-order smem fold
+        const int lanes = max(1, min(static_cast<int>(blockDim.x) / G, 16));
+        float* fold = gsm;                                    // [G][lanes][2], gsm is free now
+        if (static_cast<int>(threadIdx.x) < G * lanes) {
+            const int gg = threadIdx.x / lanes, l = threadIdx.x - gg * lanes;
+            float a = 0.f, b = 0.f;
+            const float2* src = reinterpret_cast<const float2*>(partials + (static_cast<long long>(n) * S * G + gg) * 2);
+            for (int q = l; q < S; q += lanes) { const float2 v = __ldcg(src + static_cast<long long>(q) * G); a += v.x; b += v.y; }
+            fold[(gg * lanes + l) * 2] = a; fold[(gg * lanes + l) * 2 + 1] = b;
+        }
+        __syncthreads();
         for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
             float a = 0.f, b = 0.f;
-            const float* src = partials + (static_cast<long long>(n) * S * G + gg) * 2;
-            for (int q = 0; q < S; ++q) { a += __ldcg(src + static_cast<long long>(q) * G * 2); b += __ldcg(src + static_cast<long long>(q) * G * 2 + 1); }
+            for (int l = 0; l < lanes; ++l) { a += fold[(gg * lanes + l) * 2]; b += fold[(gg * lanes + l) * 2 + 1]; }
             const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
             const float m = a / cnt;
             const float var = fmaxf(b / cnt - m * m, 0.f);
