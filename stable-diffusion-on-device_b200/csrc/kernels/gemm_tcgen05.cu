@@ -410,32 +410,62 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
             const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
             const bool vec_ok = (mp.N % 4 == 0) && (ep.ldc % 4 == 0) && (!ep.residual || ep.ldr % 4 == 0);
             const int rows_here = min(32, mp.M - (m0 + q * 32));
-#pragma unroll 2
-            for (int r = 0; r < rows_here; ++r) {
-                const long long mr = m0 + q * 32 + r;
-                for (int c4 = lane; c4 < BN / 4; c4 += 32) {
-                    const int n = n0 + c4 * 4;
-                    if (n >= mp.N) break;
-                    float4 o = *reinterpret_cast<const float4*>(stg + r * LDS + c4 * 4);
-                    if (vec_ok) {
-                        if (ep.residual) {
-                            if (ep.residual_f32) {
-                                const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + zr + mr * ep.ldr + n);
-                                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                            } else {
-                                const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) + zr + mr * ep.ldr + n);
-                                const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y);
-                                o.x += a.x; o.y += a.y; o.z += b.x; o.w += b.y;
+            if (vec_ok) {
+                // rows in groups of 4: all residual loads of the group are issued before any store (stores to C could alias
+                // the residual as far as the compiler knows, which otherwise serialises one L2 round trip per row)
+                constexpr int NC4 = (BN / 4 + 31) / 32;
+                constexpr int RG = 4;
+                for (int r0 = 0; r0 < rows_here; r0 += RG) {
+                    float4 res[RG][NC4];
+                    if (ep.residual) {
+#pragma unroll
+                        for (int rr = 0; rr < RG; ++rr) {
+                            const long long mr = m0 + q * 32 + r0 + rr;
+#pragma unroll
+                            for (int ci = 0; ci < NC4; ++ci) {
+                                const int c4 = lane + ci * 32;
+                                const int n = n0 + c4 * 4;
+                                res[rr][ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (r0 + rr < rows_here && c4 < BN / 4 && n < mp.N) {
+                                    if (ep.residual_f32) {
+                                        res[rr][ci] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + zr + mr * ep.ldr + n));
+                                    } else {
+                                        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) + zr + mr * ep.ldr + n));
+                                        const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+                                        res[rr][ci] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                    }
+                                }
                             }
                         }
-                        if (ep.out_mode == SDOD_OUT_F32) {
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + zc + mr * ep.ldc + n) = o;
-                        } else {
-                            uint2 w;
-                            w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n) = w;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < RG; ++rr) {
+                        const long long mr = m0 + q * 32 + r0 + rr;
+#pragma unroll
+                        for (int ci = 0; ci < NC4; ++ci) {
+                            const int c4 = lane + ci * 32;
+                            const int n = n0 + c4 * 4;
+                            if (r0 + rr < rows_here && c4 < BN / 4 && n < mp.N) {
+                                float4 o = *reinterpret_cast<const float4*>(stg + (r0 + rr) * LDS + c4 * 4);
+                                if (ep.residual) { o.x += res[rr][ci].x; o.y += res[rr][ci].y; o.z += res[rr][ci].z; o.w += res[rr][ci].w; }
+                                if (ep.out_mode == SDOD_OUT_F32) {
+                                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + zc + mr * ep.ldc + n) = o;
+                                } else {
+                                    uint2 w;
+                                    w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n) = w;
+                                }
+                            }
                         }
-                    } else {
+                    }
+                }
+            } else {
+                for (int r = 0; r < rows_here; ++r) {
+                    const long long mr = m0 + q * 32 + r;
+                    for (int c4 = lane; c4 < BN / 4; c4 += 32) {
+                        const int n = n0 + c4 * 4;
+                        if (n >= mp.N) break;
+                        const float4 o = *reinterpret_cast<const float4*>(stg + r * LDS + c4 * 4);
                         const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
