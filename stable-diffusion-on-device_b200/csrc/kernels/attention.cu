@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
     using Cfg = AttCfg<DH>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned shared-space pointer
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Cfg::kQBytes;
     uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;

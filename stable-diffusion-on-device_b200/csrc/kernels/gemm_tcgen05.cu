@@ -137,6 +137,54 @@ SDOD_DEVICE void store8(const sdod_epilogue& ep, long long zoff_c, long long zof
     }
 }
 
+// v[0..NV) = act(v * alpha + bias[n..] + rb[n..]) with every runtime branch hoisted out of the element loop and 16-B
+// parameter loads (the per-element branchy form cost ~70 SASS instructions per element and made the epilogue
+// instruction-bound: 15 us of a 23 us K=320 GEMM, profiles/r01_gemm_phase_timing.txt).
+template <int NV>
+SDOD_DEVICE void bias_act(float (&v)[NV], const sdod_epilogue& ep, const float* rb, int n, int N) {
+    static_assert(NV % 4 == 0, "NV must be a multiple of 4");
+    if (ep.alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] *= ep.alpha;
+    }
+    const bool full = (n + NV <= N);
+    if (ep.bias) {
+        const float* b = ep.bias + n;
+        if (full && ((reinterpret_cast<uintptr_t>(b) & 15) == 0)) {
+#pragma unroll
+            for (int q4 = 0; q4 < NV / 4; ++q4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(b) + q4);
+                v[4 * q4] += t.x; v[4 * q4 + 1] += t.y; v[4 * q4 + 2] += t.z; v[4 * q4 + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (n + i < N) v[i] += b[i];
+        }
+    }
+    if (rb) {
+        const float* b = rb + n;
+        if (full && ((reinterpret_cast<uintptr_t>(b) & 15) == 0)) {
+#pragma unroll
+            for (int q4 = 0; q4 < NV / 4; ++q4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(b) + q4);
+                v[4 * q4] += t.x; v[4 * q4 + 1] += t.y; v[4 * q4 + 2] += t.z; v[4 * q4 + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (n + i < N) v[i] += b[i];
+        }
+    }
+    if (ep.act == SDOD_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = silu_f(v[i]);
+    } else if (ep.act == SDOD_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = gelu_f(v[i]);
+    }
+}
+
 // Epilogue of 8 accumulator columns [n, n+8) of output row m: alpha, bias, timestep row-bias, activation, residual, store.
 SDOD_DEVICE void epilogue_plain8(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n, const float (&acc)[8]) {
     if (m >= mp.M || n >= mp.N) return;
@@ -144,14 +192,8 @@ SDOD_DEVICE void epilogue_plain8(const sdod_epilogue& ep, const MainloopParams& 
     const float* rb = ep.row_bias ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float x = acc[i] * ep.alpha;
-        if (n + i < mp.N) {
-            if (ep.bias) x += ep.bias[n + i];
-            if (rb) x += rb[n + i];
-        }
-        v[i] = apply_act(x, ep.act);
-    }
+    for (int i = 0; i < 8; ++i) v[i] = acc[i];
+    bias_act<8>(v, ep, rb, n, mp.N);
     store8(ep, zc, zr, m, n, mp.N, v);
 }
 SDOD_DEVICE void epilogue_plain16(const sdod_epilogue& ep, const MainloopParams& mp, int bz, int m, int n, const uint32_t (&acc)[16]) {
@@ -173,19 +215,30 @@ SDOD_DEVICE void epilogue_geglu16(const sdod_epilogue& ep, const MainloopParams&
     const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
     const int n_out_total = mp.N / 2;
     const int n0 = n_tile * BN;
+    float av[16], gv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { av[i] = __uint_as_float(a[i]) * ep.alpha; gv[i] = __uint_as_float(g[i]) * ep.alpha; }
+    if (ep.bias) {
+        const int na = n0 + j, ng = na + HALF;
+        if (ng + 16 <= mp.N && ((reinterpret_cast<uintptr_t>(ep.bias + na) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ep.bias + ng) & 15) == 0)) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 ta = __ldg(reinterpret_cast<const float4*>(ep.bias + na) + q4), tg = __ldg(reinterpret_cast<const float4*>(ep.bias + ng) + q4);
+                av[4 * q4] += ta.x; av[4 * q4 + 1] += ta.y; av[4 * q4 + 2] += ta.z; av[4 * q4 + 3] += ta.w;
+                gv[4 * q4] += tg.x; gv[4 * q4 + 1] += tg.y; gv[4 * q4 + 2] += tg.z; gv[4 * q4 + 3] += tg.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (ng + i < mp.N) { av[i] += ep.bias[na + i]; gv[i] += ep.bias[ng + i]; }
+        }
+    }
 #pragma unroll
     for (int h8 = 0; h8 < 2; ++h8) {
         float v[8];
         const int no = n_tile * HALF + j + h8 * 8;   // output column
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int na = n0 + j + h8 * 8 + i;
-            const int ng = na + HALF;
-            float av = __uint_as_float(a[h8 * 8 + i]) * ep.alpha;
-            float gv = __uint_as_float(g[h8 * 8 + i]) * ep.alpha;
-            if (ep.bias && ng < mp.N) { av += ep.bias[na]; gv += ep.bias[ng]; }
-            v[i] = av * gelu_f(gv);
-        }
+        for (int i = 0; i < 8; ++i) v[i] = av[h8 * 8 + i] * gelu_f(gv[h8 * 8 + i]);
         if (no < n_out_total) store8(ep, zc, zr, m, no, n_out_total, v);
     }
 }
@@ -256,7 +309,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
     using Cfg = GemmCfg<BN, DEEP>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a shared-space pointer
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * kABytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes);
@@ -379,82 +432,93 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 epilogue_geglu16<BN>(ep, mp, bz, m, n_tile, j, a, g);
             }
         } else if (ep.out_mode == SDOD_OUT_BF16 || ep.out_mode == SDOD_OUT_F32) {
-            // Coalesced epilogue.  Phase 1: each thread owns one accumulator row (tcgen05.ld 32x32b): alpha, bias, timestep
-            // row-bias and activation in registers, then 16-B st.shared into a padded staging tile (the TMA ring is idle:
-            // tmem_full fired after every MMA retired).  Phase 2: the warp walks its 32 rows; lanes run along the columns,
-            // so residual loads and output stores are full 128-B lines instead of 32 scattered 16-B pieces.
+            // Coalesced epilogue.  Phase 1: each thread owns one accumulator row (tcgen05.ld 32x32b) and copies it with 16-B
+            // st.shared into a padded staging tile (the TMA ring is idle: tmem_full fired after every MMA retired).
+            // Phase 2: the warp walks its 32 rows, lanes run along the columns: bias is lane-constant (loaded once), row-bias
+            // and residual loads and the output stores are full 128-B lines; 8 rows of loads are in flight before any store.
             constexpr int LDS = BN + 4;                       // (BN+4) % 32 == 4 words: conflict-free 16-B row-strided stores
             float* stg = reinterpret_cast<float*>(smem) + q * (32 * LDS);
-            const float* rb = (ep.row_bias && m < mp.M) ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
 #pragma unroll 2
             for (int j = 0; j < BN; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int n = n0 + j + i;
-                    float x = __uint_as_float(acc[i]) * ep.alpha;
-                    if (n < mp.N) {
-                        if (ep.bias) x += ep.bias[n];
-                        if (rb) x += rb[n];
-                    }
-                    v[i] = apply_act(x, ep.act);
-                }
                 float4* dst = reinterpret_cast<float4*>(stg + lane * LDS + j);
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                for (int q4 = 0; q4 < 4; ++q4)
+                    dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
+                                          __uint_as_float(acc[4 * q4 + 3]));
             }
             __syncwarp();
             const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
-            const bool vec_ok = (mp.N % 4 == 0) && (ep.ldc % 4 == 0) && (!ep.residual || ep.ldr % 4 == 0);
+            const bool vec_ok = (mp.N % 4 == 0) && (ep.ldc % 4 == 0) && (!ep.residual || ep.ldr % 4 == 0) &&
+                                (!ep.row_bias || (ep.ld_row_bias ? ep.ld_row_bias : mp.N) % 4 == 0);
             const int rows_here = min(32, mp.M - (m0 + q * 32));
+            const long long ldrb = ep.ld_row_bias ? ep.ld_row_bias : mp.N;
             if (vec_ok) {
-                // rows in groups of 4: all residual loads of the group are issued before any store (stores to C could alias
-                // the residual as far as the compiler knows, which otherwise serialises one L2 round trip per row)
                 constexpr int NC4 = (BN / 4 + 31) / 32;
-                constexpr int RG = 4;
+                constexpr int RG = 8;
+                float4 bias4[NC4];
+                bool col_ok[NC4];
+#pragma unroll
+                for (int ci = 0; ci < NC4; ++ci) {
+                    const int c4 = lane + ci * 32;
+                    const int n = n0 + c4 * 4;
+                    col_ok[ci] = (c4 < BN / 4) && (n < mp.N);
+                    bias4[ci] = (ep.bias && col_ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 for (int r0 = 0; r0 < rows_here; r0 += RG) {
-                    float4 res[RG][NC4];
-                    if (ep.residual) {
+                    float4 add[RG][NC4];
 #pragma unroll
-                        for (int rr = 0; rr < RG; ++rr) {
-                            const long long mr = m0 + q * 32 + r0 + rr;
+                    for (int rr = 0; rr < RG; ++rr) {
+                        const long long mr = m0 + q * 32 + r0 + rr;
+                        const bool row_in = (r0 + rr < rows_here);
 #pragma unroll
-                            for (int ci = 0; ci < NC4; ++ci) {
-                                const int c4 = lane + ci * 32;
-                                const int n = n0 + c4 * 4;
-                                res[rr][ci] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (r0 + rr < rows_here && c4 < BN / 4 && n < mp.N) {
-                                    if (ep.residual_f32) {
-                                        res[rr][ci] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + zr + mr * ep.ldr + n));
-                                    } else {
-                                        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) + zr + mr * ep.ldr + n));
-                                        const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-                                        res[rr][ci] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                                    }
+                        for (int ci = 0; ci < NC4; ++ci) {
+                            const int n = n0 + (lane + ci * 32) * 4;
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (row_in && col_ok[ci] && ep.residual) {
+                                if (ep.residual_f32) {
+                                    t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + zr + mr * ep.ldr + n));
+                                } else {
+                                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) + zr + mr * ep.ldr + n));
+                                    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+                                    t = make_float4(lo.x, lo.y, hi.x, hi.y);
                                 }
                             }
+                            add[rr][ci] = t;
                         }
                     }
 #pragma unroll
                     for (int rr = 0; rr < RG; ++rr) {
                         const long long mr = m0 + q * 32 + r0 + rr;
+                        if (r0 + rr >= rows_here) break;
 #pragma unroll
                         for (int ci = 0; ci < NC4; ++ci) {
+                            if (!col_ok[ci]) continue;
                             const int c4 = lane + ci * 32;
                             const int n = n0 + c4 * 4;
-                            if (r0 + rr < rows_here && c4 < BN / 4 && n < mp.N) {
-                                float4 o = *reinterpret_cast<const float4*>(stg + (r0 + rr) * LDS + c4 * 4);
-                                if (ep.residual) { o.x += res[rr][ci].x; o.y += res[rr][ci].y; o.z += res[rr][ci].z; o.w += res[rr][ci].w; }
-                                if (ep.out_mode == SDOD_OUT_F32) {
-                                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + zc + mr * ep.ldc + n) = o;
-                                } else {
-                                    uint2 w;
-                                    w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
-                                    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n) = w;
-                                }
+                            const float4 a4 = *reinterpret_cast<const float4*>(stg + (r0 + rr) * LDS + c4 * 4);
+                            float v[4] = {fmaf(a4.x, ep.alpha, bias4[ci].x), fmaf(a4.y, ep.alpha, bias4[ci].y), fmaf(a4.z, ep.alpha, bias4[ci].z),
+                                          fmaf(a4.w, ep.alpha, bias4[ci].w)};
+                            if (ep.row_bias) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(ep.row_bias + (mr / ep.rows_per_group) * ldrb + n));
+                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                            }
+                            if (ep.act == SDOD_ACT_SILU) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[i] = silu_f(v[i]);
+                            } else if (ep.act == SDOD_ACT_GELU) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+                            }
+                            const float4 o = make_float4(v[0] + add[rr][ci].x, v[1] + add[rr][ci].y, v[2] + add[rr][ci].z, v[3] + add[rr][ci].w);
+                            if (ep.out_mode == SDOD_OUT_F32) {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + zc + mr * ep.ldc + n) = o;
+                            } else {
+                                uint2 w;
+                                w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n) = w;
                             }
                         }
                     }
@@ -462,20 +526,18 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
             } else {
                 for (int r = 0; r < rows_here; ++r) {
                     const long long mr = m0 + q * 32 + r;
-                    for (int c4 = lane; c4 < BN / 4; c4 += 32) {
-                        const int n = n0 + c4 * 4;
+                    const float* rbp = ep.row_bias ? ep.row_bias + (mr / ep.rows_per_group) * ldrb : nullptr;
+                    for (int c = lane; c < BN; c += 32) {
+                        const int n = n0 + c;
                         if (n >= mp.N) break;
-                        const float4 o = *reinterpret_cast<const float4*>(stg + r * LDS + c4 * 4);
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (n + i >= mp.N) break;
-                            float x = ov[i];
-                            if (ep.residual) x += ep.residual_f32 ? reinterpret_cast<const float*>(ep.residual)[zr + mr * ep.ldr + n + i]
-                                                                  : __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[zr + mr * ep.ldr + n + i]);
-                            if (ep.out_mode == SDOD_OUT_F32) reinterpret_cast<float*>(ep.C)[zc + mr * ep.ldc + n + i] = x;
-                            else reinterpret_cast<bf16*>(ep.C)[zc + mr * ep.ldc + n + i] = __float2bfloat16(x);
-                        }
+                        float x = stg[r * LDS + c] * ep.alpha;
+                        if (ep.bias) x += ep.bias[n];
+                        if (rbp) x += rbp[n];
+                        x = apply_act(x, ep.act);
+                        if (ep.residual) x += ep.residual_f32 ? reinterpret_cast<const float*>(ep.residual)[zr + mr * ep.ldr + n]
+                                                              : __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[zr + mr * ep.ldr + n]);
+                        if (ep.out_mode == SDOD_OUT_F32) reinterpret_cast<float*>(ep.C)[zc + mr * ep.ldc + n] = x;
+                        else reinterpret_cast<bf16*>(ep.C)[zc + mr * ep.ldc + n] = __float2bfloat16(x);
                     }
                 }
             }
