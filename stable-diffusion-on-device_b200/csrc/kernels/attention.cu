@@ -21,22 +21,22 @@ namespace sdod {
 
 constexpr int kAttThreads = 192;
 constexpr int kBQ = 128;    // query rows per CTA
-constexpr int kBKV = 128;   // keys per tile
+constexpr int kBKV = 64;    // keys per tile: one thread holds a whole S row (64 fp32) in registers -> S is read from TMEM once
 
 template <int DH>
 struct AttCfg {
     static constexpr int kNK = (DH + 63) / 64;            // 64-wide d chunks of Q / K
     static constexpr int kKSteps = (DH + 15) / 16;        // UMMA K steps for S = Q K^T
-    static constexpr int kDV = ((DH + 15) / 16) * 16;     // N of the PV MMA (rows of V^T tile)
-    static constexpr int kStages = DH > 80 ? 1 : 2;
+    static constexpr int kDV = ((DH + 15) / 16) * 16;     // N of the PV MMA (rows of the V^T tile)
+    static constexpr int kStages = DH > 80 ? 3 : 4;
     static constexpr int kQBytes = kNK * kBQ * 128;
     static constexpr int kKBytes = kNK * kBKV * 128;
-    static constexpr int kVBytes = 2 * kDV * 128;         // two 64-key chunks, kDV rows of 128 B
-    static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;   // keep chunk bases 1024-B aligned
-    static constexpr int kStageBytes = kKBytes + 2 * kVChunk;
-    static constexpr int kPBytes = 2 * kBQ * 128;
+    static constexpr int kVBytes = kDV * 128;             // one 64-key chunk, kDV rows of 128 B
+    static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;
+    static constexpr int kStageBytes = kKBytes + kVChunk;
+    static constexpr int kPBytes = kBQ * 128;             // one P buffer: 128 rows x 64 keys bf16
     static constexpr int kTmemCols = (128 + kDV) <= 256 ? 256 : 512;
-    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBytes + 1024 + 256;
 };
 
 SDOD_DEVICE float ex2(float x) {
@@ -45,6 +45,10 @@ SDOD_DEVICE float ex2(float x) {
     return y;
 }
 
+// Pipeline (per CTA, 128 queries):  the MMA thread issues  S_0, S_1, PV_0, S_2, PV_1, ...  so QK^T of the next tile runs
+// on the tensor pipe while the softmax warps work on the current one (S double-buffered in TMEM columns [0,64) / [64,128),
+// P double-buffered in smem).  The O rescale is lazy: a row keeps its old reference max until the true max has grown by
+// more than 2^8, so most tiles skip the TMEM round trip and never wait for the previous PV.
 template <int DH>
 __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
@@ -57,14 +61,15 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Cfg::kQBytes;
     uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;                 // [STAGES]
     uint64_t* kv_empty = kv_full + STAGES;        // [STAGES]
-    uint64_t* s_full = kv_empty + STAGES;
-    uint64_t* s_free = s_full + 1;
-    uint64_t* p_full = s_free + 1;
-    uint64_t* o_ready = p_full + 1;
+    uint64_t* s_full = kv_empty + STAGES;         // [2]
+    uint64_t* s_free = s_full + 2;                // [2]
+    uint64_t* p_full = s_free + 2;                // [2]
+    uint64_t* p_free = p_full + 2;                // [2]
+    uint64_t* o_ready = p_free + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,9 +83,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 128);
-        mbar_init(p_full, 128);
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 128); mbar_init(&p_full[b], 128); mbar_init(&p_free[b], 1); }
         mbar_init(o_ready, 1);
         fence_mbar_init();
     }
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    const uint32_t tmem_O = tmem_base + 128;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
                 uint8_t* sK = sKV + st * Cfg::kStageBytes;
                 uint8_t* sV = sK + Cfg::kKBytes;
                 for (int c = 0; c < Cfg::kNK; ++c) tma_load_3d(sK + c * (kBKV * 128), &tmK, &kv_full[st], c * 64, j * kBKV, bh);
-                for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * Cfg::kVChunk, &tmV, &kv_full[st], j * kBKV + c * 64, 0, bh);
+                tma_load_3d(sV, &tmV, &kv_full[st], j * kBKV, 0, bh);
             }
         }
     } else if (warp == 1) {
@@ -114,113 +117,111 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
             constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, Cfg::kDV);
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
             mbar_wait(q_full, 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % STAGES;
-                const uint32_t ph = (j / STAGES) & 1;
-                const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
-                const uint32_t v_addr = k_addr + Cfg::kKBytes;
-                mbar_wait(&kv_full[st], ph);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);       // softmax has drained S of the previous tile
-                tc_fence_after();
+            for (int j = 0; j <= n_tiles; ++j) {
+                if (j < n_tiles) {                                   // S_j = Q K_j^T -> S buffer j&1
+                    const int st = j % STAGES;
+                    mbar_wait(&kv_full[st], (j / STAGES) & 1);
+                    if (j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
 #pragma unroll
-                for (int k = 0; k < Cfg::kKSteps; ++k) {
-                    const uint32_t off = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
-                    tc_mma_bf16(tmem_S, make_kmajor_sw128_desc(q_addr + off), make_kmajor_sw128_desc(k_addr + off), idesc_s, k != 0);
+                    for (int k = 0; k < Cfg::kKSteps; ++k) {
+                        const uint32_t qoff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                        const uint32_t koff = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
+                        tc_mma_bf16(tmem_base + (j & 1) * 64, make_kmajor_sw128_desc(q_addr + qoff), make_kmajor_sw128_desc(k_addr + koff), idesc_s, k != 0);
+                    }
+                    tc_commit(&s_full[j & 1]);
                 }
-                tc_commit(s_full);
-                mbar_wait(p_full, j & 1);                        // P_j in smem, O rescaled
-                tc_fence_after();
+                if (j >= 1) {                                        // O += P_i V_i for the previous tile
+                    const int i = j - 1, st = i % STAGES;
+                    mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
+                    const uint32_t pb = p_addr + (i & 1) * Cfg::kPBytes;
 #pragma unroll
-                for (int k = 0; k < kBKV / 16; ++k) {
-                    const uint32_t poff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
-                    const uint32_t voff = (k >> 2) * Cfg::kVChunk + (k & 3) * 32;
-                    tc_mma_bf16(tmem_O, make_kmajor_sw128_desc(p_addr + poff), make_kmajor_sw128_desc(v_addr + voff), idesc_o,
-                                (j | k) != 0);
+                    for (int k = 0; k < kBKV / 16; ++k)
+                        tc_mma_bf16(tmem_O, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | k) != 0);
+                    tc_commit(&kv_empty[st]);
+                    tc_commit(&p_free[i & 1]);
+                    tc_commit(o_ready);
                 }
-                tc_commit(&kv_empty[st]);
-                tc_commit(o_ready);
             }
         }
     } else {
-        // ---------------------------------------------------------------- softmax / correction / epilogue
+        // ---------------------------------------------------------------- softmax / lazy correction / epilogue
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         float m_run = -INFINITY, l_run = 0.f;
-        uint8_t* p_row0 = sP + row * 128;           // chunk 0; chunk 1 at + kBQ*128
         const int sw = row & 7;
         for (int j = 0; j < n_tiles; ++j) {
+            const int b = j & 1, u = j >> 1;
             const int kv_valid = min(kBKV, Nkv - j * kBKV);
-            mbar_wait(s_full, j & 1);
+            mbar_wait(&s_full[b], u & 1);
             tc_fence_after();
-            // pass A: row max (scaled into the exp2 domain)
-            float mx = m_run;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, v);
+            uint32_t sv[64];
+            {
+                uint32_t lo[32], hi[32];
+                tmem_ld32(tmem_base + lane_off + b * 64, lo);
+                tmem_ld32(tmem_base + lane_off + b * 64 + 32, hi);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]) * scale_log2);
+                for (int i = 0; i < 32; ++i) { sv[i] = lo[i]; sv[32 + i] = hi[i]; }
             }
-            const float alpha = ex2(m_run - mx);     // 0 on the first tile (m_run = -inf)
-            // O of the previous tile must be complete before it is rescaled and before P is overwritten
-            if (j > 0) {
-                mbar_wait(o_ready, (j - 1) & 1);
-                tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-                    for (int c = 0; c < Cfg::kDV / 16; ++c) {
-                        uint32_t o[16];
-                        tmem_ld16(tmem_O + lane_off + c * 16, o);
-                        tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_free[b]);                 // S buffer b may be overwritten by S_{j+2}
+            float mx = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st16(tmem_O + lane_off + c * 16, o);
-                    }
-                    tmem_st_wait();
-                }
+            for (int i = 0; i < 64; ++i) {
+                float t = __uint_as_float(sv[i]) * scale_log2;
+                t = (i < kv_valid) ? t : -INFINITY;
+                sv[i] = __float_as_uint(t);
+                mx = fmaxf(mx, t);
             }
-            // pass B: P = exp2(s*scale - max), row sum, bf16 -> swizzled smem
+            // lazy reference max: only move it when the true max grew by more than 2^8 (P stays <= 256, exact in the ratio O/l)
+            const bool need = (mx > m_run + 8.0f);
+            const float m_new = need ? mx : m_run;
+            const float alpha = ex2(m_run - m_new);   // 1 when unchanged, 0 on the first tile
             float lsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, v);
-                tmem_ld_wait();
-                uint8_t* prow = p_row0 + (c >> 1) * (kBQ * 128);
+            uint32_t pk[32];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float p[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int col = c * 32 + u * 8 + i;
-                        const float e = ex2(__uint_as_float(v[u * 8 + i]) * scale_log2 - mx);
-                        p[i] = col < kv_valid ? e : 0.f;
-                        lsum += p[i];
-                    }
-                    uint4 w;
-                    w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
-                    w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
-                    const int unit = (c & 1) * 4 + u;                // 16-B unit within the 128-B row
-                    *reinterpret_cast<uint4*>(prow + ((unit ^ sw) << 4)) = w;
-                }
+            for (int i = 0; i < 32; ++i) {
+                const float p0 = ex2(__uint_as_float(sv[2 * i]) - m_new), p1 = ex2(__uint_as_float(sv[2 * i + 1]) - m_new);
+                lsum += p0 + p1;
+                pk[i] = pack_bf16x2(p0, p1);
             }
             l_run = l_run * alpha + lsum;
-            m_run = mx;
+            m_run = m_new;
+            if (j >= 2) mbar_wait(&p_free[b], (u - 1) & 1);          // PV_{j-2} has consumed P buffer b
+            uint8_t* prow = sP + b * Cfg::kPBytes + row * 128;
+#pragma unroll
+            for (int un = 0; un < 8; ++un)
+                *reinterpret_cast<uint4*>(prow + ((un ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+                mbar_wait(o_ready, (j - 1) & 1);                     // PV_{j-1} complete: O may be rescaled
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < Cfg::kDV / 16; ++c) {
+                    uint32_t o[16];
+                    tmem_ld16(tmem_O + lane_off + c * 16, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(tmem_O + lane_off + c * 16, o);
+                }
+                tmem_st_wait();
+            }
             tc_fence_before();
-            mbar_arrive(s_free);                 // S may be overwritten by the next QK^T
             fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the UMMA async proxy
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[b]);
         }
         // epilogue: O / l
         mbar_wait(o_ready, (n_tiles - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
-        const int b = bh / heads, h = bh - b * heads;
+        const int bb = bh / heads, h = bh - bb * heads;
         const int qi = q0 + row;
-        bf16* orow = O + (static_cast<long long>(b) * Nq + qi) * (heads * DH) + h * DH;
+        bf16* orow = O + (static_cast<long long>(bb) * Nq + qi) * (heads * DH) + h * DH;
 #pragma unroll 1
         for (int c = 0; c < Cfg::kDV / 16; ++c) {
             uint32_t o[16];
