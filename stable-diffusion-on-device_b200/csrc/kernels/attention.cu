@@ -197,8 +197,11 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
 #pragma unroll
             for (int un = 0; un < 8; ++un)
                 *reinterpret_cast<uint4*>(prow + ((un ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
-            if (j > 0 && __any_sync(0xffffffffu, need)) {
-                mbar_wait(o_ready, (j - 1) & 1);                     // PV_{j-1} complete: O may be rescaled
+            // o_ready must be observed every tile, in lockstep: an mbarrier parity wait is only meaningful while the waiter is at
+            // most one phase behind (skipping phases let the final wait fall through before PV had run).  PV_{j-1} was issued
+            // a whole softmax iteration ago, so this wait is almost always already satisfied.
+            if (j > 0) mbar_wait(o_ready, (j - 1) & 1);
+            if (j > 0 && __any_sync(0xffffffffu, need)) {            // PV_{j-1} complete: O may be rescaled
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < Cfg::kDV / 16; ++c) {

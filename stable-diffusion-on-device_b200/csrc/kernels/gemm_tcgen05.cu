@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
                                           __uint_as_float(acc[4 * q4 + 3]));
             }
-        } else if (ep.act == SDOD_ACT_GEGLU) {
+        } else if (ep.act == SDOD_ACT_GEGLU && !(ep.out_mode == SDOD_OUT_BF16 && mp.N % 8 == 0 && ep.ldc % 4 == 0)) {
             constexpr int HALF = BN / 2;
 #pragma unroll 1
             for (int j = 0; j < HALF; j += 16) {
@@ -455,7 +455,37 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                                 (!ep.row_bias || (ep.ld_row_bias ? ep.ld_row_bias : mp.N) % 4 == 0);
             const int rows_here = min(32, mp.M - (m0 + q * 32));
             const long long ldrb = ep.ld_row_bias ? ep.ld_row_bias : mp.N;
-            if (vec_ok) {
+            if (ep.act == SDOD_ACT_GEGLU) {
+                // value half = tile columns [0,BN/2), gate half = [BN/2,BN); lanes run along the BN/2 output columns
+                constexpr int HALF = BN / 2;
+                constexpr int NG4 = (HALF / 4 + 31) / 32;
+                const int n_out_total = mp.N / 2;
+                float4 bv[NG4], bg[NG4];
+                bool ok[NG4];
+#pragma unroll
+                for (int ci = 0; ci < NG4; ++ci) {
+                    const int c = (lane + ci * 32) * 4;
+                    ok[ci] = (c < HALF) && (n_tile * HALF + c < n_out_total);
+                    bv[ci] = (ep.bias && ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bg[ci] = (ep.bias && ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + HALF + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                for (int r = 0; r < rows_here; ++r) {
+                    const long long mr = m0 + q * 32 + r;
+#pragma unroll
+                    for (int ci = 0; ci < NG4; ++ci) {
+                        if (!ok[ci]) continue;
+                        const int c = (lane + ci * 32) * 4;
+                        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS + c);
+                        const float4 g4 = *reinterpret_cast<const float4*>(stg + r * LDS + HALF + c);
+                        uint2 w;
+                        w.x = pack_bf16x2(fmaf(a4.x, ep.alpha, bv[ci].x) * gelu_f(fmaf(g4.x, ep.alpha, bg[ci].x)),
+                                          fmaf(a4.y, ep.alpha, bv[ci].y) * gelu_f(fmaf(g4.y, ep.alpha, bg[ci].y)));
+                        w.y = pack_bf16x2(fmaf(a4.z, ep.alpha, bv[ci].z) * gelu_f(fmaf(g4.z, ep.alpha, bg[ci].z)),
+                                          fmaf(a4.w, ep.alpha, bv[ci].w) * gelu_f(fmaf(g4.w, ep.alpha, bg[ci].w)));
+                        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n_tile * HALF + c) = w;
+                    }
+                }
+            } else if (vec_ok) {
                 constexpr int NC4 = (BN / 4 + 31) / 32;
                 constexpr int RG = 8;
                 float4 bias4[NC4];
