@@ -19,6 +19,8 @@ with torch.cuda.stream(s):
     for _ in range(3):
         net.forward_nhwc(x, emb)
     rows = net.profile(B, 5)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+open(os.path.join(ROOT, "gpurun_out", "plan_ops_b%d.txt" % B), "w").write("\n".join("%.4f\t%s" % r for r in rows))
 tot = sum(r[0] for r in rows)
 print("ops %d  total %.3f ms (eager, per-op events)" % (len(rows), tot))
 agg = collections.OrderedDict()
