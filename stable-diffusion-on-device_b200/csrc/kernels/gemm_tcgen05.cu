@@ -5,8 +5,10 @@
 // One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
 //   warp 1      : MMA issuer    (one thread issues tcgen05.mma 128xBNx16, commits to mbarriers)
-//   warps 2..5  : epilogue      (tcgen05.ld 32x32b -> bias / temb row-bias / SiLU / GELU / GEGLU /
-//                                residual -> bf16|fp32 stores, incl. attention head-split layouts)
+//   warps 2..9  : epilogue      (tcgen05.ld 32x32b -> bias / temb row-bias / SiLU / GELU / GEGLU /
+//                                residual -> bf16|fp32 stores, incl. attention head-split layouts).
+//                                Two warps share each TMEM lane quarter (column halves in phase 1, row halves in
+//                                phase 2): with one warp per SM sub-partition every dependent latency was exposed.
 // Conv mode feeds the same mainloop: the A tile for tap (ky,kx) and channel block c is one 4-D TMA
 // box {64 ch, bw, bh, bb} of the NHWC activation at (c, x0+kx-1, y0+ky-1, b0); TMA's out-of-bounds
 // zero fill supplies the padding, so no im2col buffer exists in HBM.
@@ -24,7 +26,7 @@ namespace sdod {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                    // 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 // DEEP = false: shallow ring so that 2 CTAs co-reside per SM (one CTA's epilogue overlaps the other's mainloop) — used when
 //                the grid is larger than one wave.
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
 }
 
 template <int BN, bool DEEP>
-__global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
     using Cfg = GemmCfg<BN, DEEP>;
@@ -402,16 +404,18 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which of the quarter's two warps
         const int row = q * 32 + lane;
         const int m = m0 + row;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        constexpr int CH = BN / 2;                    // columns per warp in the row-per-thread phases
         if (mp.split > 1) {
             // split-K: publish this CTA's fp32 partial tile ([chunk16][row][16], coalesced); splitk_reduce_kernel folds
             // the partials in fixed order (deterministic) and applies the epilogue.
             const long long tile_id = static_cast<long long>(m_tile) * gridDim.x + n_tile;
             float* mine = mp.ws + (tile_id * mp.split + zs) * (BN * kBlockM);
 #pragma unroll 1
-            for (int j = 0; j < BN; j += 16) {
+            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         } else if (ep.act == SDOD_ACT_GEGLU && !(ep.out_mode == SDOD_OUT_BF16 && mp.N % 8 == 0 && ep.ldc % 4 == 0)) {
             constexpr int HALF = BN / 2;
 #pragma unroll 1
-            for (int j = 0; j < HALF; j += 16) {
+            for (int j = half * (HALF / 2); j < (half + 1) * (HALF / 2); j += 16) {
                 uint32_t a[16], g[16];
                 tmem_ld16(taddr + j, a);
                 tmem_ld16(taddr + HALF + j, g);
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
             constexpr int LDS = BN + 4;                       // (BN+4) % 32 == 4 words: conflict-free 16-B row-strided stores
             float* stg = reinterpret_cast<float*>(smem) + q * (32 * LDS);
 #pragma unroll 2
-            for (int j = 0; j < BN; j += 16) {
+            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -449,11 +453,16 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
                                           __uint_as_float(acc[4 * q4 + 3]));
             }
-            __syncwarp();
+            // both warps of this lane quarter have staged their columns (named barrier per quarter, 64 threads)
+            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
             const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
             const bool vec_ok = (mp.N % 4 == 0) && (ep.ldc % 4 == 0) && (!ep.residual || ep.ldr % 4 == 0) &&
                                 (!ep.row_bias || (ep.ld_row_bias ? ep.ld_row_bias : mp.N) % 4 == 0);
-            const int rows_here = min(32, mp.M - (m0 + q * 32));
+            const int rows_here = min(32, mp.M - (m0 + q * 32));     // valid rows of this quarter; this warp takes [r_lo, r_hi)
+            const int r_lo = half * 16, r_hi = min(rows_here, r_lo + 16);
             const long long ldrb = ep.ld_row_bias ? ep.ld_row_bias : mp.N;
             if (ep.act == SDOD_ACT_GEGLU) {
                 // value half = tile columns [0,BN/2), gate half = [BN/2,BN); lanes run along the BN/2 output columns
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     bv[ci] = (ep.bias && ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     bg[ci] = (ep.bias && ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + HALF + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                for (int r = 0; r < rows_here; ++r) {
+                for (int r = r_lo; r < r_hi; ++r) {
                     const long long mr = m0 + q * 32 + r;
 #pragma unroll
                     for (int ci = 0; ci < NG4; ++ci) {
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                 }
             } else if (vec_ok) {
                 constexpr int NC4 = (BN / 4 + 31) / 32;
-                constexpr int RG = 8;
+                constexpr int RG = DEEP ? 8 : 4;
                 float4 bias4[NC4];
                 bool col_ok[NC4];
 #pragma unroll
@@ -497,12 +506,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     col_ok[ci] = (c4 < BN / 4) && (n < mp.N);
                     bias4[ci] = (ep.bias && col_ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                for (int r0 = 0; r0 < rows_here; r0 += RG) {
+                for (int r0 = r_lo; r0 < r_hi; r0 += RG) {
                     float4 add[RG][NC4];
 #pragma unroll
                     for (int rr = 0; rr < RG; ++rr) {
                         const long long mr = m0 + q * 32 + r0 + rr;
-                        const bool row_in = (r0 + rr < rows_here);
+                        const bool row_in = (r0 + rr < r_hi);
 #pragma unroll
                         for (int ci = 0; ci < NC4; ++ci) {
                             const int n = n0 + (lane + ci * 32) * 4;
@@ -522,7 +531,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
 #pragma unroll
                     for (int rr = 0; rr < RG; ++rr) {
                         const long long mr = m0 + q * 32 + r0 + rr;
-                        if (r0 + rr >= rows_here) break;
+                        if (r0 + rr >= r_hi) break;
 #pragma unroll
                         for (int ci = 0; ci < NC4; ++ci) {
                             if (!col_ok[ci]) continue;
@@ -554,7 +563,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
                     }
                 }
             } else {
-                for (int r = 0; r < rows_here; ++r) {
+                for (int r = r_lo; r < r_hi; ++r) {
                     const long long mr = m0 + q * 32 + r;
                     const float* rbp = ep.row_bias ? ep.row_bias + (mr / ep.rows_per_group) * ldrb : nullptr;
                     for (int c = lane; c < BN; c += 32) {
@@ -573,7 +582,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
             }
         } else {
 #pragma unroll 1
-            for (int j = 0; j < BN; j += 16) {
+            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
