@@ -170,26 +170,34 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
             }
             tc_fence_before();
             mbar_arrive(&s_free[b]);                 // S buffer b may be overwritten by S_{j+2}
-            float mx = -INFINITY;
+            // row max in raw units (4 independent chains), masking only on the ragged last tile
+            if (kv_valid < kBKV) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                float t = __uint_as_float(sv[i]) * scale_log2;
-                t = (i < kv_valid) ? t : -INFINITY;
-                sv[i] = __float_as_uint(t);
-                mx = fmaxf(mx, t);
+                for (int i = 0; i < 64; ++i)
+                    if (i >= kv_valid) sv[i] = 0xff800000u;          // -inf
             }
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[i + c]));
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2;   // scale_log2 > 0
             // lazy reference max: only move it when the true max grew by more than 2^8 (P stays <= 256, exact in the ratio O/l)
             const bool need = (mx > m_run + 8.0f);
             const float m_new = need ? mx : m_run;
             const float alpha = ex2(m_run - m_new);   // 1 when unchanged, 0 on the first tile
-            float lsum = 0.f;
+            const float neg_m = -m_new;
+            float ls4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float p0 = ex2(__uint_as_float(sv[2 * i]) - m_new), p1 = ex2(__uint_as_float(sv[2 * i + 1]) - m_new);
-                lsum += p0 + p1;
+                const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), scale_log2, neg_m));
+                const float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, neg_m));
+                ls4[i & 3] += p0 + p1;
                 pk[i] = pack_bf16x2(p0, p1);
             }
+            const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
             l_run = l_run * alpha + lsum;
             m_run = m_new;
             if (j >= 2) mbar_wait(&p_free[b], (u - 1) & 1);          // PV_{j-2} has consumed P buffer b
