@@ -5,10 +5,12 @@
 // Warp roles (192 threads):
 //   warp 0     : TMA producer — Q once, then K / V^T tiles through an mbarrier ring
 //   warp 1     : MMA issuer   — S = Q K^T and O += P V on tcgen05, accumulators in TMEM
-//   warps 2..5 : softmax      — one thread per query row: tcgen05.ld S, online max/sum in the exp2
-//                domain, O rescale in TMEM (tcgen05.ld/st) only when some row's max moved,
+//   warps 2..9 : softmax      — two threads per query row (each owns 32 of the tile's 64 keys; warps w and
+//                w+4 share a TMEM lane quarter): tcgen05.ld S once, online max/sum in the exp2 domain
+//                (row max exchanged through smem + a 64-thread named barrier), lazy O rescale in TMEM,
 //                P (bf16) written into 128B-swizzled smem as the A operand of the PV MMA;
-//                final O / l -> bf16 [B, Nq, heads*head_dim]
+//                final O / l -> bf16 [B, Nq, heads*head_dim].  8 softmax warps = 2-4 per SM sub-partition,
+//                enough to hide the MUFU / TMEM / barrier latencies that 4 warps left exposed.
 // TMEM columns: S at [0,128), O at [128, 128+dv).  Everything is K-major + SWIZZLE_128B: K^T comes
 // for free from the HEADS layout, V is stored transposed (HEADS_T) by the producing GEMM epilogue.
 #include "../common.cuh"
@@ -19,7 +21,7 @@
 
 namespace sdod {
 
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
 constexpr int kBQ = 128;    // query rows per CTA
 constexpr int kBKV = 64;    // keys per tile: one thread holds a whole S row (64 fp32) in registers -> S is read from TMEM once
 
@@ -36,7 +38,7 @@ struct AttCfg {
     static constexpr int kStageBytes = kKBytes + kVChunk;
     static constexpr int kPBytes = kBQ * 128;             // one P buffer: 128 rows x 64 keys bf16
     static constexpr int kTmemCols = (128 + kDV) <= 256 ? 256 : 512;
-    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBytes + 1024 + 256 + 3 * 256 * 4;   // + row-max / row-sum exchange
 };
 
 SDOD_DEVICE float ex2(float x) {
@@ -50,7 +52,7 @@ SDOD_DEVICE float ex2(float x) {
 // P double-buffered in smem).  The O rescale is lazy: a row keeps its old reference max until the true max has grown by
 // more than 2^8, so most tiles skip the TMEM round trip and never wait for the previous PV.
 template <int DH>
-__global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O,
                                                                  int heads, int Nq, int Nkv, float scale_log2) {
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
     uint64_t* p_free = p_full + 2;                // [2]
     uint64_t* o_ready = p_free + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+    float* xch = reinterpret_cast<float*>(bars + 32);          // [2 tile parities][2 halves][128 rows] partner exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, bh = blockIdx.y;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 128); mbar_init(&p_full[b], 128); mbar_init(&p_free[b], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 256); mbar_init(&p_full[b], 256); mbar_init(&p_free[b], 1); }
         mbar_init(o_ready, 1);
         fence_mbar_init();
     }
@@ -149,70 +152,71 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
         }
     } else {
         // ---------------------------------------------------------------- softmax / lazy correction / epilogue
-        const int q = warp & 3;
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int half = (warp - 2) >> 2;             // which 32 of the tile's 64 keys this thread owns
         const int row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;         // l_run: partial row sum over this thread's keys
         const int sw = row & 7;
+        auto pair_sync = [&]() {
+            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+        };
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1, u = j >> 1;
-            const int kv_valid = min(kBKV, Nkv - j * kBKV);
+            const int kv_valid = min(kBKV, Nkv - j * kBKV) - half * 32;      // valid keys among this thread's 32
             mbar_wait(&s_full[b], u & 1);
             tc_fence_after();
-            uint32_t sv[64];
-            {
-                uint32_t lo[32], hi[32];
-                tmem_ld32(tmem_base + lane_off + b * 64, lo);
-                tmem_ld32(tmem_base + lane_off + b * 64 + 32, hi);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { sv[i] = lo[i]; sv[32 + i] = hi[i]; }
-            }
+            uint32_t sv[32];
+            tmem_ld32(tmem_base + lane_off + b * 64 + half * 32, sv);
+            tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&s_free[b]);                 // S buffer b may be overwritten by S_{j+2}
-            // row max in raw units (4 independent chains), masking only on the ragged last tile
-            if (kv_valid < kBKV) {
+            if (kv_valid < 32) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i)
+                for (int i = 0; i < 32; ++i)
                     if (i >= kv_valid) sv[i] = 0xff800000u;          // -inf
             }
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
+            for (int i = 0; i < 32; i += 4) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[i + c]));
             }
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2;   // scale_log2 > 0
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            xch[(b * 2 + half) * 128 + row] = mx;    // exchange the half-row max with the partner thread
+            pair_sync();
+            mx = fmaxf(mx, xch[(b * 2 + (half ^ 1)) * 128 + row]) * scale_log2;   // scale_log2 > 0
             // lazy reference max: only move it when the true max grew by more than 2^8 (P stays <= 256, exact in the ratio O/l)
             const bool need = (mx > m_run + 8.0f);
             const float m_new = need ? mx : m_run;
             const float alpha = ex2(m_run - m_new);   // 1 when unchanged, 0 on the first tile
             const float neg_m = -m_new;
             float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t pk[32];
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), scale_log2, neg_m));
                 const float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, neg_m));
                 ls4[i & 3] += p0 + p1;
                 pk[i] = pack_bf16x2(p0, p1);
             }
-            const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-            l_run = l_run * alpha + lsum;
+            l_run = l_run * alpha + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
             m_run = m_new;
             if (j >= 2) mbar_wait(&p_free[b], (u - 1) & 1);          // PV_{j-2} has consumed P buffer b
             uint8_t* prow = sP + b * Cfg::kPBytes + row * 128;
 #pragma unroll
-            for (int un = 0; un < 8; ++un)
-                *reinterpret_cast<uint4*>(prow + ((un ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
+            for (int un = 0; un < 4; ++un)
+                *reinterpret_cast<uint4*>(prow + (((half * 4 + un) ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
             // o_ready must be observed every tile, in lockstep: an mbarrier parity wait is only meaningful while the waiter is at
-            // most one phase behind (skipping phases let the final wait fall through before PV had run).  PV_{j-1} was issued
-            // a whole softmax iteration ago, so this wait is almost always already satisfied.
+            // most one phase behind.  PV_{j-1} was issued a whole softmax iteration ago, so this wait is almost always satisfied.
             if (j > 0) mbar_wait(o_ready, (j - 1) & 1);
-            if (j > 0 && __any_sync(0xffffffffu, need)) {            // PV_{j-1} complete: O may be rescaled
+            if (j > 0 && __any_sync(0xffffffffu, need)) {            // PV_{j-1} complete: O may be rescaled (chunks split by parity)
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < Cfg::kDV / 16; ++c) {
+                for (int c = half; c < Cfg::kDV / 16; c += 2) {
                     uint32_t o[16];
                     tmem_ld16(tmem_O + lane_off + c * 16, o);
                     tmem_ld_wait();
@@ -226,15 +230,17 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
             fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the UMMA async proxy
             mbar_arrive(&p_full[b]);
         }
-        // epilogue: O / l
+        // epilogue: O / l  (l = sum of the pair's partial sums)
+        xch[(4 + half) * 128 + row] = l_run;          // third region: never aliases a row-max slot still being read
+        pair_sync();
+        const float inv_l = 1.0f / (l_run + xch[(4 + (half ^ 1)) * 128 + row]);
         mbar_wait(o_ready, (n_tiles - 1) & 1);
         tc_fence_after();
-        const float inv_l = 1.0f / l_run;
         const int bb = bh / heads, h = bh - bb * heads;
         const int qi = q0 + row;
         bf16* orow = O + (static_cast<long long>(bb) * Nq + qi) * (heads * DH) + h * DH;
 #pragma unroll 1
-        for (int c = 0; c < Cfg::kDV / 16; ++c) {
+        for (int c = half; c < Cfg::kDV / 16; c += 2) {
             uint32_t o[16];
             tmem_ld16(tmem_O + lane_off + c * 16, o);
             tmem_ld_wait();
