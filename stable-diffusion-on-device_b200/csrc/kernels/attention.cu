@@ -52,8 +52,7 @@ SDOD_DEVICE float ex2(float x) {
 // P double-buffered in smem).  The O rescale is lazy: a row keeps its old reference max until the true max has grown by
 // more than 2^8, so most tiles skip the TMEM round trip and never wait for the previous PV.
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel err 7.7e-5 — well inside bf16 P).
-// The d=40 layers are bound by the 16 exp/clk/SM MUFU unit, not by the tensor pipe; evaluating 3 of every 8 exponentials
-// here balances MUFU against the ALU pipe (FA4's trick).
+// Kept for the record: swapping 3 of every 8 MUFU exponentials for this did not pay off in round 1 (see the softmax loop).
 SDOD_DEVICE float ex2_poly(float x) {
     x = fmaxf(x, -120.0f);
     const float t = x + 12582912.0f;                 // 1.5 * 2^23: round to nearest integer in the low mantissa bits
@@ -212,9 +211,10 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float x0 = fmaf(__uint_as_float(sv[2 * i]), scale_log2, neg_m), x1 = fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, neg_m);
-                const bool poly = ((i & 7) == 1) || ((i & 7) == 4) || ((i & 7) == 6);      // 3 of 8 pairs off the MUFU
-                const float p0 = poly ? ex2_poly(x0) : ex2(x0);
-                const float p1 = poly ? ex2_poly(x1) : ex2(x1);
+                // (measured r1: moving 3/8 of these onto ex2_poly made the kernel 20 % slower — the loop is issue/smem-bound,
+                //  not MUFU-bound, at 16 softmax warps per SM; profiles/r01_attention_notes.txt)
+                const float p0 = ex2(x0);
+                const float p1 = ex2(x1);
                 ls4[i & 3] += p0 + p1;
                 pk[i] = pack_bf16x2(p0, p1);
             }
