@@ -117,7 +117,7 @@ typedef struct sdod_epilogue {
     long long ldr;
     long long strideR;
     float alpha;
-    int act;                 /* sdod_act; GEGLU: tile columns [0,BN/2) = value, [BN/2,BN) = gate    */
+    int act;                 /* sdod_act; GEGLU: tile columns [0,BN/2) = value, [BN/2,BN) = gate (default BN 128) */
     int out_mode;            /* sdod_out_mode                                                      */
     int heads, head_dim, tokens, dpad, tok_pad;   /* HEADS / HEADS_T / QKV modes                   */
     int vt_rows;             /* HEADS_T / QKV: rows allocated per head in the V^T buffer           */

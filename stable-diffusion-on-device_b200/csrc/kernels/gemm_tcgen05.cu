@@ -648,7 +648,7 @@ static int dispatch_gemm(int bn, cudaStream_t stream, const CUtensorMap& tmA, co
 // divide the SD channel counts 320/640/960/1280/1920/3840 exactly.)  GEGLU tiles are fixed at 256.
 int pick_block_n(int M, int N, int batch, int act) {
     (void)M; (void)batch;
-    if (act == SDOD_ACT_GEGLU) return 256;
+    if (act == SDOD_ACT_GEGLU) return 128;
     if (N <= 32) return 32;
     if (N <= 64) return 64;
     const int cands[3] = {160, 128, 64};
@@ -707,7 +707,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     if (d.lda % 8 != 0 || d.ldw % 8 != 0) return fail(kInvalidArgument, "gemm: lda/ldw must be multiples of 8 elements");
     SDOD_TRY(validate_epilogue(d.epi, d.N));
     int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, d.batch, d.epi.act);
-    if (d.epi.act == SDOD_ACT_GEGLU && bn != 256 && d.block_n == 0) bn = 256;
+
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;

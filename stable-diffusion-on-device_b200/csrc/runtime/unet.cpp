@@ -177,7 +177,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     Act n3 = ln(h3, tb + ".norm3");
     std::vector<int> rowmap(8 * C);
     {
-        const int half = 128, n = 4 * C;   // block_n 256: [128 value rows | 128 gate rows] per tile
+        const int half = 64, n = 4 * C;    // block_n 128: [64 value rows | 64 gate rows] per tile (2 CTAs/SM: epilogues overlap mainloops)
         int idx = 0;
         for (int t = 0; t < n / half; ++t) {
             for (int i = 0; i < half; ++i) rowmap[idx++] = t * half + i;
@@ -187,7 +187,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     LinearOpts og;
     og.bias = gather_bias(tb + ".ff.net.0.proj.bias", 8 * C, rowmap);
     og.act = SDOD_ACT_GEGLU;
-    og.block_n = 256;
+    og.block_n = 128;
     Act gg = linear(n3, pack_linear(tb + ".ff.net.0.proj.weight", 8 * C, C, 0, &rowmap), 8 * C, og);
     release(n3);
     LinearOpts o3;

@@ -254,7 +254,7 @@ def pack_conv3x3_weight(w_oihw, kpad=None):
     return out
 
 
-def pack_geglu_weight(w, bias, block_n=256):
+def pack_geglu_weight(w, bias, block_n=128):
     """Interleave GEGLU projection rows so each block_n-row tile holds [value half | gate half]."""
     n2 = w.shape[0]
     n = n2 // 2

@@ -212,7 +212,11 @@ def test_gemm_geglu_packed():
     bias = torch.randn(8 * Cc, device=DEV)
     h = a.float() @ w.float().t() + bias
     want = h[:, :4 * Cc] * F.gelu(h[:, 4 * Cc:])
-    wp, bp = ops.pack_geglu_weight(w, bias, 256)
+    for bn in (128, 256):
+        wp, bp = ops.pack_geglu_weight(w, bias, bn)
+        got = torch.ops.sdod.linear(a, wp, bp, None, C.ACT_GEGLU, 1.0, False, None, 0, bn)
+        assert got.shape == (M, 4 * Cc) and rel_err(got, want) < TOL_BF16
+    wp, bp = ops.pack_geglu_weight(w, bias)
     got = torch.ops.sdod.linear(a, wp, bp, None, C.ACT_GEGLU)
     assert got.shape == (M, 4 * Cc) and rel_err(got, want) < TOL_BF16
 
@@ -371,7 +375,7 @@ def test_gemm_split_k(M, N, K):
         got = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)
         got2 = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)            # tickets reset themselves
         if N == 10240:
-            wp, bp = ops.pack_geglu_weight(w, bias, 256)
+            wp, bp = ops.pack_geglu_weight(w, bias)
             gg = torch.ops.sdod.linear(a, wp, bp, None, C.ACT_GEGLU)
             h = a.float() @ w.float().t() + bias
             assert rel_err(gg, h[:, :N // 2] * F.gelu(h[:, N // 2:])) < TOL_BF16
