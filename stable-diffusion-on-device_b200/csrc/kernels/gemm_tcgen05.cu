@@ -21,6 +21,8 @@
 #include "launchers.h"
 #include "sdod_kernels.h"
 
+#include <type_traits>
+
 namespace sdod {
 
 constexpr int kBlockM = 128;
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             // and residual loads and the output stores are full 128-B lines; 8 rows of loads are in flight before any store.
             constexpr int LDS = BN + 4;                       // (BN+4) % 32 == 4 words: conflict-free 16-B row-strided stores
             float* stg = reinterpret_cast<float*>(smem) + q * (32 * LDS);
-#pragma unroll 2
+#pragma unroll 1
             for (int j = half * CH; j < (half + 1) * CH; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
@@ -495,8 +497,11 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                     }
                 }
             } else if (vec_ok) {
+                // Compact code matters here: the fully unrolled, activation-generic form of this loop was ~5k SASS instructions
+                // executed once per tile, i.e. pure instruction-cache misses (8 us per tile).  One non-unrolled row-group loop
+                // per activation, selected outside the loop.
                 constexpr int NC4 = (BN / 4 + 31) / 32;
-                constexpr int RG = DEEP ? 8 : 4;
+                constexpr int RG = 4;
                 float4 bias4[NC4];
                 bool col_ok[NC4];
 #pragma unroll
@@ -506,62 +511,73 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                     col_ok[ci] = (c4 < BN / 4) && (n < mp.N);
                     bias4[ci] = (ep.bias && col_ok[ci]) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                for (int r0 = r_lo; r0 < r_hi; r0 += RG) {
-                    float4 add[RG][NC4];
+                const bool has_res = ep.residual != nullptr, res32 = ep.residual_f32 != 0, out32 = (ep.out_mode == SDOD_OUT_F32);
+                const float* res_f = reinterpret_cast<const float*>(ep.residual) + zr;
+                const bf16* res_h = reinterpret_cast<const bf16*>(ep.residual) + zr;
+                float* out_f = reinterpret_cast<float*>(ep.C) + zc;
+                bf16* out_h = reinterpret_cast<bf16*>(ep.C) + zc;
+                auto run_rows = [&](auto act_tag) {
+                    constexpr int ACT = decltype(act_tag)::value;
+#pragma unroll 1
+                    for (int r0 = r_lo; r0 < r_hi; r0 += RG) {
+                        float4 add[RG][NC4];
 #pragma unroll
-                    for (int rr = 0; rr < RG; ++rr) {
-                        const long long mr = m0 + q * 32 + r0 + rr;
-                        const bool row_in = (r0 + rr < r_hi);
+                        for (int rr = 0; rr < RG; ++rr) {
+                            const long long mr = m0 + q * 32 + r0 + rr;
 #pragma unroll
-                        for (int ci = 0; ci < NC4; ++ci) {
-                            const int n = n0 + (lane + ci * 32) * 4;
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (row_in && col_ok[ci] && ep.residual) {
-                                if (ep.residual_f32) {
-                                    t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + zr + mr * ep.ldr + n));
-                                } else {
-                                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) + zr + mr * ep.ldr + n));
-                                    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-                                    t = make_float4(lo.x, lo.y, hi.x, hi.y);
+                            for (int ci = 0; ci < NC4; ++ci) {
+                                const int n = n0 + (lane + ci * 32) * 4;
+                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (has_res && (r0 + rr < r_hi) && col_ok[ci]) {
+                                    if (res32) {
+                                        t = __ldg(reinterpret_cast<const float4*>(res_f + mr * ep.ldr + n));
+                                    } else {
+                                        const uint2 u2 = __ldg(reinterpret_cast<const uint2*>(res_h + mr * ep.ldr + n));
+                                        const float2 lo = unpack_bf16x2(u2.x), hi = unpack_bf16x2(u2.y);
+                                        t = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                    }
+                                }
+                                add[rr][ci] = t;
+                            }
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < RG; ++rr) {
+                            const long long mr = m0 + q * 32 + r0 + rr;
+#pragma unroll
+                            for (int ci = 0; ci < NC4; ++ci) {
+                                if ((r0 + rr < r_hi) && col_ok[ci]) {
+                                    const int c4 = lane + ci * 32;
+                                    const int n = n0 + c4 * 4;
+                                    const float4 a4 = *reinterpret_cast<const float4*>(stg + (r0 + rr) * LDS + c4 * 4);
+                                    float v[4] = {fmaf(a4.x, ep.alpha, bias4[ci].x), fmaf(a4.y, ep.alpha, bias4[ci].y), fmaf(a4.z, ep.alpha, bias4[ci].z),
+                                                  fmaf(a4.w, ep.alpha, bias4[ci].w)};
+                                    if (ep.row_bias) {
+                                        const float4 t = __ldg(reinterpret_cast<const float4*>(ep.row_bias + (mr / ep.rows_per_group) * ldrb + n));
+                                        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                                    }
+                                    if (ACT == SDOD_ACT_SILU) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) v[i] = silu_f(v[i]);
+                                    } else if (ACT == SDOD_ACT_GELU) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+                                    }
+                                    const float4 o = make_float4(v[0] + add[rr][ci].x, v[1] + add[rr][ci].y, v[2] + add[rr][ci].z, v[3] + add[rr][ci].w);
+                                    if (out32) {
+                                        *reinterpret_cast<float4*>(out_f + mr * ep.ldc + n) = o;
+                                    } else {
+                                        uint2 w;
+                                        w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
+                                        *reinterpret_cast<uint2*>(out_h + mr * ep.ldc + n) = w;
+                                    }
                                 }
                             }
-                            add[rr][ci] = t;
                         }
                     }
-#pragma unroll
-                    for (int rr = 0; rr < RG; ++rr) {
-                        const long long mr = m0 + q * 32 + r0 + rr;
-                        if (r0 + rr >= r_hi) break;
-#pragma unroll
-                        for (int ci = 0; ci < NC4; ++ci) {
-                            if (!col_ok[ci]) continue;
-                            const int c4 = lane + ci * 32;
-                            const int n = n0 + c4 * 4;
-                            const float4 a4 = *reinterpret_cast<const float4*>(stg + (r0 + rr) * LDS + c4 * 4);
-                            float v[4] = {fmaf(a4.x, ep.alpha, bias4[ci].x), fmaf(a4.y, ep.alpha, bias4[ci].y), fmaf(a4.z, ep.alpha, bias4[ci].z),
-                                          fmaf(a4.w, ep.alpha, bias4[ci].w)};
-                            if (ep.row_bias) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(ep.row_bias + (mr / ep.rows_per_group) * ldrb + n));
-                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                            }
-                            if (ep.act == SDOD_ACT_SILU) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) v[i] = silu_f(v[i]);
-                            } else if (ep.act == SDOD_ACT_GELU) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
-                            }
-                            const float4 o = make_float4(v[0] + add[rr][ci].x, v[1] + add[rr][ci].y, v[2] + add[rr][ci].z, v[3] + add[rr][ci].w);
-                            if (ep.out_mode == SDOD_OUT_F32) {
-                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + zc + mr * ep.ldc + n) = o;
-                            } else {
-                                uint2 w;
-                                w.x = pack_bf16x2(o.x, o.y); w.y = pack_bf16x2(o.z, o.w);
-                                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.C) + zc + mr * ep.ldc + n) = w;
-                            }
-                        }
-                    }
-                }
+                };
+                if (ep.act == SDOD_ACT_SILU) run_rows(std::integral_constant<int, SDOD_ACT_SILU>{});
+                else if (ep.act == SDOD_ACT_GELU) run_rows(std::integral_constant<int, SDOD_ACT_GELU>{});
+                else run_rows(std::integral_constant<int, SDOD_ACT_NONE>{});
             } else {
                 for (int r = r_lo; r < r_hi; ++r) {
                     const long long mr = m0 + q * 32 + r;

@@ -22,7 +22,7 @@ lib.sdod_debug_gemm_times(buf.ctypes.data, 1024 * 8)
 bn = 256 if mode == "geglu" else 160
 t = buf.reshape(1024, 8)[: min(1024, ((M + 127) // 128) * ((N + bn - 1) // bn))].astype(np.int64)
 t0 = t[:, 0].min()
-rel = t[:, :6] - t0
+rel = t[:, :8] - t0
 print("M%d N%d K%d %s  CTAs %d   (ns since first CTA start; median over CTAs | max)" % (M, N, K, mode, len(t)))
-for i, name in enumerate(["start", "setup done", "mainloop done", "phase1 done", "epilogue done", "exit"]):
+for i, name in enumerate(["start", "setup done", "mainloop done", "phase1 done", "epilogue done", "exit", "p2 bias loaded", "p2 first group done"]):
     print("  %-14s median %7d   max %7d" % (name, np.median(rel[:, i]), rel[:, i].max()))
