@@ -74,6 +74,12 @@ SDOD_DEVICE void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// tensor store shared -> global (bulk async-group completion); out-of-bounds parts of the box are clipped
+SDOD_DEVICE void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // 1-D bulk copy global -> shared (bytes multiple of 16, both 16-B aligned)
 SDOD_DEVICE void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile(

@@ -42,6 +42,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+    return encode_tmap(out, base, 2, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0);
+}
+
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(kNoDevice, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
     cuuint64_t gdim[5];
@@ -57,10 +62,12 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(kInvalidArgument, "TMA base must be 16-byte aligned");
     for (int i = 0; i + 1 < rank; ++i)
         if (gstr[i] % 16 != 0) return fail(kInvalidArgument, "TMA strides must be multiples of 16 bytes");
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                    gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(kCudaError, "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string(static_cast<int>(r)));
     return kOk;
 }

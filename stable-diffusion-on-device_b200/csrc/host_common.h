@@ -27,6 +27,9 @@ int check_launch(const char* what);                  // cudaGetLastError()
 // entries (stride of dim i+1). swizzle128: CU_TENSOR_MAP_SWIZZLE_128B else NONE.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+// General form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 0 / 32 / 64 / 128.
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 int device_sm_count();
 

@@ -21,6 +21,7 @@
 #include "launchers.h"
 #include "sdod_kernels.h"
 
+#include <cstring>
 #include <type_traits>
 
 namespace sdod {
@@ -43,7 +44,7 @@ struct GemmCfg {
     static constexpr int kDeepRaw = (220 * 1024 - 2048) / kStageBytes;
     static constexpr int kStages = DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow;
     static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
 };
 
 SDOD_DEVICE float apply_act(float v, int act) {
@@ -309,6 +310,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
 template <int BN, bool DEEP>
 __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
+                                                                      const __grid_constant__ CUtensorMap tmC,
+                                                                      const __grid_constant__ CUtensorMap tmR,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
     using Cfg = GemmCfg<BN, DEEP>;
     constexpr int STAGES = Cfg::kStages;
@@ -319,7 +322,9 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* res_bar = tmem_full_bar + 1;                    // [4] residual tiles landed (TMA epilogue), one per lane quarter
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [BN] bias tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -340,6 +345,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -403,6 +409,10 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
         }
     } else {
         // -------------------------------------------------------------------- epilogue
+        if (mp.tma_epi) {                              // stage this tile's bias while the mainloop runs
+            for (int i = threadIdx.x - 64; i < BN; i += 256) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -436,6 +446,94 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 tmem_ld16(taddr + HALF + j, g);
                 tmem_ld_wait();
                 epilogue_geglu16<BN>(ep, mp, bz, m, n_tile, j, a, g);
+            }
+        } else if (mp.tma_epi) {
+            // TMA epilogue.  The idle TMA ring becomes a staging area of 32x32-element boxes (128-B or 64-B swizzled rows).
+            // If there is a residual of the output's dtype it is TMA-loaded straight into those boxes while the accumulator
+            // is read; each thread (one accumulator row) applies alpha/bias/timestep-bias/activation in registers, adds the
+            // staged residual in place, and one elected thread per lane quarter hands the boxes to TMA stores: no per-row
+            // global load/store instructions, tails clipped by the tensor map.
+            constexpr int NB = BN / 32;
+            const bool f32 = (mp.c_bytes == 4);
+            const uint32_t box_bytes = f32 ? 4096u : 2048u;
+            uint8_t* qbase = smem + q * (NB * 4096);
+            if (mp.tma_epi == 2 && half == 0 && lane == 0) {
+                mbar_arrive_expect_tx(&res_bar[q], NB * box_bytes);
+                for (int bx = 0; bx < NB; ++bx) tma_load_3d(qbase + bx * 4096, &tmR, &res_bar[q], n0 + bx * 32, m0 + q * 32, bz);
+            }
+            const float* rb = (ep.row_bias && m < mp.M) ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
+            bool res_waited = (mp.tma_epi != 2);
+#pragma unroll 1
+            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j + 4 * q4);
+                    v[4 * q4] = fmaf(__uint_as_float(acc[4 * q4]), ep.alpha, b4.x);
+                    v[4 * q4 + 1] = fmaf(__uint_as_float(acc[4 * q4 + 1]), ep.alpha, b4.y);
+                    v[4 * q4 + 2] = fmaf(__uint_as_float(acc[4 * q4 + 2]), ep.alpha, b4.z);
+                    v[4 * q4 + 3] = fmaf(__uint_as_float(acc[4 * q4 + 3]), ep.alpha, b4.w);
+                }
+                if (rb) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + j + i < mp.N) v[i] += __ldg(rb + n0 + j + i);
+                }
+                if (ep.act == SDOD_ACT_SILU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+                } else if (ep.act == SDOD_ACT_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+                }
+                if (!res_waited) { mbar_wait(&res_bar[q], 0); res_waited = true; }
+                uint8_t* box = qbase + (j >> 5) * 4096;
+                if (f32) {
+                    uint8_t* rowp = box + lane * 128;
+                    const int u0 = (j & 31) >> 2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float4* cell = reinterpret_cast<float4*>(rowp + (((u0 + k) ^ (lane & 7)) << 4));
+                        float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        if (mp.tma_epi == 2) { const float4 r4 = *cell; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                        *cell = o;
+                    }
+                } else {
+                    uint8_t* rowp = box + lane * 64;
+                    const int u0 = (j & 31) >> 3;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        uint4* cell = reinterpret_cast<uint4*>(rowp + (((u0 + k) ^ ((lane >> 1) & 3)) << 4));
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = v[8 * k + i];
+                        if (mp.tma_epi == 2) {
+                            const uint4 r4 = *cell;
+                            float2 t;
+                            t = unpack_bf16x2(r4.x); o[0] += t.x; o[1] += t.y;
+                            t = unpack_bf16x2(r4.y); o[2] += t.x; o[3] += t.y;
+                            t = unpack_bf16x2(r4.z); o[4] += t.x; o[5] += t.y;
+                            t = unpack_bf16x2(r4.w); o[6] += t.x; o[7] += t.y;
+                        }
+                        uint4 w;
+                        w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+                        *cell = w;
+                    }
+                }
+            }
+            fence_proxy_async_smem();                  // staged tile (generic-proxy writes) -> visible to the TMA engine
+            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
+                for (int bx = 0; bx < NB; ++bx)
+                    if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * 4096, n0 + bx * 32, m0 + q * 32, bz);
+                bulk_commit();
+                bulk_wait_read_all();                  // smem may be released once the stores have read it
             }
         } else if (ep.out_mode == SDOD_OUT_BF16 || ep.out_mode == SDOD_OUT_F32) {
             // Coalesced epilogue.  Phase 1: each thread owns one accumulator row (tcgen05.ld 32x32b) and copies it with 16-B
@@ -616,8 +714,8 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
 
 // ------------------------------------------------------------------------------------------ host
 template <int BN, bool DEEP>
-static int launch_gemm_cfg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
-                           const sdod_epilogue& ep, dim3 grid) {
+static int launch_gemm_cfg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                           const MainloopParams& mp, const sdod_epilogue& ep, dim3 grid) {
     using Cfg = GemmCfg<BN, DEEP>;
     static bool configured = false;
     if (!configured) {
@@ -625,17 +723,17 @@ static int launch_gemm_cfg(cudaStream_t stream, const CUtensorMap& tmA, const CU
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
-    gemm_tcgen05_kernel<BN, DEEP><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, mp, ep);
+    gemm_tcgen05_kernel<BN, DEEP><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, tmC, tmR, mp, ep);
     return kOk;
 }
 
 template <int BN>
-static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
-                       const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                       const MainloopParams& mp, const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
     dim3 grid(n_tiles, m_tiles, mp.split > 1 ? mp.split : batch);
     const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
-    if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true>(stream, tmA, tmW, mp, ep, grid)));
-    else SDOD_TRY((launch_gemm_cfg<BN, false>(stream, tmA, tmW, mp, ep, grid)));
+    if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true>(stream, tmA, tmW, tmC, tmR, mp, ep, grid)));
+    else SDOD_TRY((launch_gemm_cfg<BN, false>(stream, tmA, tmW, tmC, tmR, mp, ep, grid)));
     count_launch();
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
     if (mp.split > 1) {
@@ -647,14 +745,14 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
     return kOk;
 }
 
-static int dispatch_gemm(int bn, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const MainloopParams& mp,
-                         const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
+static int dispatch_gemm(const GemmLaunch& g, cudaStream_t stream) {
+    const int bn = g.bn;
     switch (bn) {
-        case 32: return launch_gemm<32>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
-        case 64: return launch_gemm<64>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
-        case 128: return launch_gemm<128>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
-        case 160: return launch_gemm<160>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
-        case 256: return launch_gemm<256>(stream, tmA, tmW, mp, ep, m_tiles, n_tiles, batch);
+        case 32: return launch_gemm<32>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+        case 64: return launch_gemm<64>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+        case 128: return launch_gemm<128>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+        case 160: return launch_gemm<160>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+        case 256: return launch_gemm<256>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
     }
     return fail(kInvalidArgument, "unsupported block_n " + std::to_string(bn));
 }
@@ -676,6 +774,39 @@ int pick_block_n(int M, int N, int batch, int act) {
         if (pad < best_pad) { best_pad = pad; best = bn; }
     }
     return best;
+}
+
+// TMA-store epilogue eligibility: row-major bf16/fp32 output, 16-B aligned rows, no GEGLU / split-K, and a residual
+// (if any) of the output's own dtype so it can be staged and added in place.
+static int setup_tma_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, int N, int batch) {
+    MainloopParams& mp = out->mp;
+    mp.tma_epi = 0;
+    mp.c_bytes = ep.out_mode == SDOD_OUT_F32 ? 4 : 2;
+    std::memset(&out->tmC, 0, sizeof(CUtensorMap));
+    std::memset(&out->tmR, 0, sizeof(CUtensorMap));
+    if (mp.split > 1 || ep.act == SDOD_ACT_GEGLU) return kOk;
+    if (ep.out_mode != SDOD_OUT_BF16 && ep.out_mode != SDOD_OUT_F32) return kOk;
+    const int es = mp.c_bytes;
+    if ((reinterpret_cast<uintptr_t>(ep.C) & 15) || (ep.ldc * es) % 16 || (batch > 1 && (ep.strideC * es) % 16)) return kOk;
+    if (ep.residual) {
+        const bool r32 = ep.residual_f32 != 0;
+        if (r32 != (es == 4)) return kOk;
+        if ((reinterpret_cast<uintptr_t>(ep.residual) & 15) || (ep.ldr * es) % 16 || (batch > 1 && (ep.strideR * es) % 16)) return kOk;
+    }
+    const uint32_t box[3] = {32, 32, 1};
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), static_cast<uint64_t>(batch)};
+        uint64_t strides[2] = {static_cast<uint64_t>(ep.ldc) * es, static_cast<uint64_t>(batch > 1 ? ep.strideC : static_cast<long long>(M) * ep.ldc) * es};
+        SDOD_TRY(encode_tmap(&out->tmC, ep.C, es, 3, dims, strides, box, es == 4 ? 128 : 64));
+    }
+    mp.tma_epi = 1;
+    if (ep.residual) {
+        uint64_t dims[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), static_cast<uint64_t>(batch)};
+        uint64_t strides[2] = {static_cast<uint64_t>(ep.ldr) * es, static_cast<uint64_t>(batch > 1 ? ep.strideR : static_cast<long long>(M) * ep.ldr) * es};
+        SDOD_TRY(encode_tmap(&out->tmR, ep.residual, es, 3, dims, strides, box, es == 4 ? 128 : 64));
+        mp.tma_epi = 2;
+    }
+    return kOk;
 }
 
 static thread_local SplitKWorkspace g_splitk;
@@ -744,6 +875,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
+    SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.N + bn - 1) / bn;
     out->batch = d.batch;
@@ -751,7 +883,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
 }
 
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
-    return dispatch_gemm(g.bn, stream, g.tmA, g.tmW, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+    return dispatch_gemm(g, stream);
 }
 
 int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
@@ -795,6 +927,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
+    SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));
     out->m_tiles = (M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.Cout + bn - 1) / bn;
     out->batch = 1;

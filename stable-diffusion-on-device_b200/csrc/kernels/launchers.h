@@ -20,10 +20,12 @@ struct MainloopParams {
     int kb_per_split;  // K blocks per split
     float* ws;         // split-K partial tiles: [tile][split][BN/16][128][16] fp32
     unsigned int* counters;   // one ticket per output tile, self-resetting
+    int tma_epi;       // 0: LSU epilogue; 1: TMA-store epilogue; 2: TMA-store + residual TMA-loaded and added in place
+    int c_bytes;       // output element size for the TMA epilogue (2 | 4)
 };
 
 struct GemmLaunch {
-    CUtensorMap tmA, tmW;
+    CUtensorMap tmA, tmW, tmC, tmR;
     MainloopParams mp;
     sdod_epilogue ep;
     int bn, m_tiles, n_tiles, batch;
