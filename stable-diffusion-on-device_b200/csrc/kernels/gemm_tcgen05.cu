@@ -437,6 +437,50 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                     dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
                                           __uint_as_float(acc[4 * q4 + 3]));
             }
+        } else if (mp.tma_epi && ep.act == SDOD_ACT_GEGLU) {
+            // GEGLU through the TMA epilogue: value half = tile columns [0,BN/2), gate half = [BN/2,BN); the output tile is
+            // BN/2 bf16 columns wide (64-B swizzled 32x32 boxes).
+            constexpr int HALF = BN / 2;
+            constexpr int NBG = HALF / 32 > 0 ? HALF / 32 : 1;
+            constexpr int CHG = HALF / 2;
+            uint8_t* qbase = smem + q * (NBG * 4096);
+#pragma unroll 1
+            for (int j = half * CHG; j < (half + 1) * CHG; j += 16) {
+                uint32_t a[16], g[16];
+                tmem_ld16(taddr + j, a);
+                tmem_ld16(taddr + HALF + j, g);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 ba = *reinterpret_cast<const float4*>(s_bias + j + 4 * q4);
+                    const float4 bg = *reinterpret_cast<const float4*>(s_bias + HALF + j + 4 * q4);
+                    v[4 * q4] = fmaf(__uint_as_float(a[4 * q4]), ep.alpha, ba.x) * gelu_f(fmaf(__uint_as_float(g[4 * q4]), ep.alpha, bg.x));
+                    v[4 * q4 + 1] = fmaf(__uint_as_float(a[4 * q4 + 1]), ep.alpha, ba.y) * gelu_f(fmaf(__uint_as_float(g[4 * q4 + 1]), ep.alpha, bg.y));
+                    v[4 * q4 + 2] = fmaf(__uint_as_float(a[4 * q4 + 2]), ep.alpha, ba.z) * gelu_f(fmaf(__uint_as_float(g[4 * q4 + 2]), ep.alpha, bg.z));
+                    v[4 * q4 + 3] = fmaf(__uint_as_float(a[4 * q4 + 3]), ep.alpha, ba.w) * gelu_f(fmaf(__uint_as_float(g[4 * q4 + 3]), ep.alpha, bg.w));
+                }
+                uint8_t* rowp = qbase + (j >> 5) * 4096 + lane * 64;
+                const int u0 = (j & 31) >> 3;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    uint4 w;
+                    w.x = pack_bf16x2(v[8 * k], v[8 * k + 1]); w.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+                    w.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]); w.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+                    *reinterpret_cast<uint4*>(rowp + (((u0 + k) ^ ((lane >> 1) & 3)) << 4)) = w;
+                }
+            }
+            fence_proxy_async_smem();
+            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
+                for (int bx = 0; bx < NBG; ++bx)
+                    if (n_tile * HALF + bx * 32 < mp.N / 2) tma_store_3d(&tmC, qbase + bx * 4096, n_tile * HALF + bx * 32, m0 + q * 32, bz);
+                bulk_commit();
+                bulk_wait_read_all();
+            }
         } else if (ep.act == SDOD_ACT_GEGLU && !(ep.out_mode == SDOD_OUT_BF16 && mp.N % 8 == 0 && ep.ldc % 4 == 0)) {
             constexpr int HALF = BN / 2;
 #pragma unroll 1
@@ -778,14 +822,18 @@ int pick_block_n(int M, int N, int batch, int act) {
 
 // TMA-store epilogue eligibility: row-major bf16/fp32 output, 16-B aligned rows, no GEGLU / split-K, and a residual
 // (if any) of the output's own dtype so it can be staged and added in place.
-static int setup_tma_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, int N, int batch) {
+static int setup_tma_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, int N, int batch) {   // N by value: halved for GEGLU
     MainloopParams& mp = out->mp;
     mp.tma_epi = 0;
     mp.c_bytes = ep.out_mode == SDOD_OUT_F32 ? 4 : 2;
     std::memset(&out->tmC, 0, sizeof(CUtensorMap));
     std::memset(&out->tmR, 0, sizeof(CUtensorMap));
-    if (mp.split > 1 || ep.act == SDOD_ACT_GEGLU) return kOk;
+    if (mp.split > 1) return kOk;
     if (ep.out_mode != SDOD_OUT_BF16 && ep.out_mode != SDOD_OUT_F32) return kOk;
+    if (ep.act == SDOD_ACT_GEGLU) {
+        if (ep.out_mode != SDOD_OUT_BF16 || ep.residual || (out->bn / 2) % 32 != 0) return kOk;
+        N = N / 2;                                   // the output tensor holds the value*gelu(gate) half
+    }
     const int es = mp.c_bytes;
     if ((reinterpret_cast<uintptr_t>(ep.C) & 15) || (ep.ldc * es) % 16 || (batch > 1 && (ep.strideC * es) % 16)) return kOk;
     if (ep.residual) {
