@@ -803,9 +803,12 @@ static int dispatch_gemm(const GemmLaunch& g, cudaStream_t stream) {
 
 // Tile width: the candidate (160 / 128 / 64) that wastes the fewest padded columns, wider first.
 // (Measured on B200: 128- and 160-wide tiles with 2 CTAs/SM beat 256-wide by ~5 % on large GEMMs, and
-// divide the SD channel counts 320/640/960/1280/1920/3840 exactly.)  GEGLU tiles are fixed at 256.
-int pick_block_n(int M, int N, int batch, int act) {
-    (void)M; (void)batch;
+// divide the SD channel counts 320/640/960/1280/1920/3840 exactly.)  GEGLU tiles are 128 wide (64 value | 64 gate).
+int pick_block_n(int M, int N, int batch, int act) { return pick_block_n_k(M, N, batch, act, 1 << 30); }
+
+// With a short K loop (<= 24 blocks) a split-K pair of kernels costs more than it saves: prefer a narrower tile that
+// yields >= 100 CTAs in a single kernel with the TMA epilogue (measured r1: M2048 N640 K640 15.6 us as bn160 split 2).
+int pick_block_n_k(int M, int N, int batch, int act, int k_blocks) {
     if (act == SDOD_ACT_GEGLU) return 128;
     if (N <= 32) return 32;
     if (N <= 64) return 64;
@@ -816,6 +819,12 @@ int pick_block_n(int M, int N, int batch, int act) {
         const int bn = cands[c];
         const long long pad = static_cast<long long>((N + bn - 1) / bn) * bn - N;
         if (pad < best_pad) { best_pad = pad; best = bn; }
+    }
+    const long long m_tiles = (M + kBlockM - 1) / kBlockM;
+    auto tiles = [&](int bn) { return m_tiles * ((N + bn - 1) / bn) * batch; };
+    if (k_blocks <= 24 && tiles(best) < 100) {
+        if (best > 128 && tiles(128) >= 100) return 128;
+        if (tiles(64) >= 60) return 64;
     }
     return best;
 }
@@ -867,6 +876,7 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
     if (batch != 1 || !g_splitk.ws) return;
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
     if (tiles >= 120) return;
+    if (tiles >= 60 && mp->k_blocks <= 24) return;             // short K: one kernel with the TMA epilogue beats split + reduce
     int split = static_cast<int>((2 * 148 + tiles - 1) / tiles);
     const int max_by_k = mp->k_blocks / 4;                    // at least 4 K blocks (256 deep) per split
     if (split > max_by_k) split = max_by_k;
@@ -901,7 +911,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     if (d.K % kBlockK != 0) return fail(kInvalidArgument, "gemm: K must be a multiple of 64 (pad the operand)");
     if (d.lda % 8 != 0 || d.ldw % 8 != 0) return fail(kInvalidArgument, "gemm: lda/ldw must be multiples of 8 elements");
     SDOD_TRY(validate_epilogue(d.epi, d.N));
-    int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, d.batch, d.epi.act);
+    int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, d.K / kBlockK);
 
 
     CUtensorMap& tmA = out->tmA;
@@ -952,7 +962,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     const int bb = 128 / (bw * bh);
     const int M = d.B * d.H * d.W;
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
-    const int bn = d.block_n ? d.block_n : pick_block_n(M, d.Cout, 1, d.epi.act);
+    const int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, 9 * d.Cin / kBlockK);
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;

@@ -39,6 +39,7 @@ struct AttnLaunch {
 };
 
 int pick_block_n(int M, int N, int batch, int act);
+int pick_block_n_k(int M, int N, int batch, int act, int k_blocks);
 // Split-K scratch shared by all GEMM/conv launches on one stream (launches are serialised by stream order).
 struct SplitKWorkspace { float* ws = nullptr; size_t ws_bytes = 0; unsigned int* counters = nullptr; int n_counters = 0; };
 void set_splitk_workspace(const SplitKWorkspace& w);     // thread-local "current" workspace used by *_prepare
