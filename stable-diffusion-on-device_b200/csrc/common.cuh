@@ -206,12 +206,15 @@ SDOD_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // instead of erff's long polynomial — the GEGLU epilogue evaluates it on 21 M elements per 64x64 transformer block.
 SDOD_DEVICE float erf_fast(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));   // 1 ulp; the IEEE form is a 6-instruction sequence
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float y = 1.0f - p * t * __expf(-ax * ax);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+    const float y = fmaf(-p * t, e, 1.0f);
     return copysignf(y, x);
 }
 SDOD_DEVICE float gelu_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }

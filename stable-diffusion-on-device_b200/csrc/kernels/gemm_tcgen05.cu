@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                                                                       const __grid_constant__ CUtensorMap tmW,
                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                       const __grid_constant__ CUtensorMap tmR,
+                                                                      const __grid_constant__ CUtensorMap tmC2,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
     using Cfg = GemmCfg<BN, DEEP>;
     constexpr int STAGES = Cfg::kStages;
@@ -490,6 +491,67 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 tmem_ld16(taddr + HALF + j, g);
                 tmem_ld_wait();
                 epilogue_geglu16<BN>(ep, mp, bz, m, n_tile, j, a, g);
+            }
+        } else if (BN == 160 && mp.tma_epi == 3) {
+            // Attention operand layouts through TMA stores.  SD head dims (40 / 80 / 160) are multiples of 40, so a 160-wide
+            // tile is four 40-column boxes, each inside one head, and the whole tile is Q, K or V (heads*head_dim % 160 == 0).
+            // Q/K box: [32 tokens][40 d] (80-B rows: conflict-free 16-B stores) -> HEADS [B*heads, tokens, dpad] at (d0, tok, bh).
+            // V box  : [40 d][32 tokens] (thread = token writes a column)       -> HEADS_T [B*heads, vt_rows, tok_pad] at (tok, d0, bh).
+            constexpr int BOXB = 40 * 32 * 2;
+            uint8_t* qbase = smem + q * (4 * BOXB);
+            const int Cw = ep.heads * ep.head_dim;
+            const int which = ep.out_mode == SDOD_OUT_QKV ? n0 / Cw : (ep.out_mode == SDOD_OUT_HEADS_T ? 2 : 0);
+#pragma unroll 1
+            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j + 4 * q4);
+                    v[4 * q4] = fmaf(__uint_as_float(acc[4 * q4]), ep.alpha, b4.x);
+                    v[4 * q4 + 1] = fmaf(__uint_as_float(acc[4 * q4 + 1]), ep.alpha, b4.y);
+                    v[4 * q4 + 2] = fmaf(__uint_as_float(acc[4 * q4 + 2]), ep.alpha, b4.z);
+                    v[4 * q4 + 3] = fmaf(__uint_as_float(acc[4 * q4 + 3]), ep.alpha, b4.w);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int g8 = (j >> 3) + k;                 // 8-column group of the tile; 5 groups per box
+                    const int bx = g8 / 5, unit = g8 - bx * 5;
+                    uint8_t* box = qbase + bx * BOXB;
+                    if (which < 2) {
+                        uint4 w;
+                        w.x = pack_bf16x2(v[8 * k], v[8 * k + 1]); w.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+                        w.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]); w.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+                        *reinterpret_cast<uint4*>(box + lane * 80 + unit * 16) = w;
+                    } else {
+                        bf16* col = reinterpret_cast<bf16*>(box + unit * 8 * 64) + lane;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) col[i * 32] = __float2bfloat16(v[8 * k + i]);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            const int mq = m0 + q * 32;
+            if (half == 0 && lane == 0 && mq < mp.M) {
+                const int b = mq / ep.tokens, tok = mq - b * ep.tokens;
+                for (int bx = 0; bx < 4; ++bx) {
+                    const int n = n0 + bx * 40;
+                    if (n >= mp.N) break;
+                    const int nn = ep.out_mode == SDOD_OUT_QKV ? n - which * Cw : n;
+                    const int h = nn / ep.head_dim, d0 = nn - h * ep.head_dim;
+                    const int bh = b * ep.heads + h;
+                    if (which == 0) tma_store_3d(&tmC, qbase + bx * BOXB, d0, tok, bh);
+                    else if (which == 1) tma_store_3d(&tmR, qbase + bx * BOXB, d0, tok, bh);
+                    else tma_store_3d(&tmC2, qbase + bx * BOXB, tok, d0, bh);
+                }
+                bulk_commit();
+                bulk_wait_read_all();
             }
         } else if (mp.tma_epi) {
             // TMA epilogue.  The idle TMA ring becomes a staging area of 32x32-element boxes (128-B or 64-B swizzled rows).
@@ -758,8 +820,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
 
 // ------------------------------------------------------------------------------------------ host
 template <int BN, bool DEEP>
-static int launch_gemm_cfg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
-                           const MainloopParams& mp, const sdod_epilogue& ep, dim3 grid) {
+static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) {
     using Cfg = GemmCfg<BN, DEEP>;
     static bool configured = false;
     if (!configured) {
@@ -767,22 +828,22 @@ static int launch_gemm_cfg(cudaStream_t stream, const CUtensorMap& tmA, const CU
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
-    gemm_tcgen05_kernel<BN, DEEP><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, tmC, tmR, mp, ep);
+    gemm_tcgen05_kernel<BN, DEEP><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
     return kOk;
 }
 
 template <int BN>
-static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
-                       const MainloopParams& mp, const sdod_epilogue& ep, int m_tiles, int n_tiles, int batch) {
-    dim3 grid(n_tiles, m_tiles, mp.split > 1 ? mp.split : batch);
+static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
+    const MainloopParams& mp = g.mp;
+    dim3 grid(g.n_tiles, g.m_tiles, mp.split > 1 ? mp.split : g.batch);
     const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
-    if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true>(stream, tmA, tmW, tmC, tmR, mp, ep, grid)));
-    else SDOD_TRY((launch_gemm_cfg<BN, false>(stream, tmA, tmW, tmC, tmR, mp, ep, grid)));
+    if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true>(stream, g, grid)));
+    else SDOD_TRY((launch_gemm_cfg<BN, false>(stream, g, grid)));
     count_launch();
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
     if (mp.split > 1) {
-        dim3 rgrid(BN / 16, m_tiles * n_tiles);
-        splitk_reduce_kernel<BN><<<rgrid, 256, 0, stream>>>(mp, ep, n_tiles);
+        dim3 rgrid(BN / 16, g.m_tiles * g.n_tiles);
+        splitk_reduce_kernel<BN><<<rgrid, 256, 0, stream>>>(mp, g.ep, g.n_tiles);
         count_launch();
         return check_launch("splitk_reduce_kernel");
     }
@@ -792,11 +853,11 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 static int dispatch_gemm(const GemmLaunch& g, cudaStream_t stream) {
     const int bn = g.bn;
     switch (bn) {
-        case 32: return launch_gemm<32>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
-        case 64: return launch_gemm<64>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
-        case 128: return launch_gemm<128>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
-        case 160: return launch_gemm<160>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
-        case 256: return launch_gemm<256>(stream, g.tmA, g.tmW, g.tmC, g.tmR, g.mp, g.ep, g.m_tiles, g.n_tiles, g.batch);
+        case 32: return launch_gemm<32>(stream, g);
+        case 64: return launch_gemm<64>(stream, g);
+        case 128: return launch_gemm<128>(stream, g);
+        case 160: return launch_gemm<160>(stream, g);
+        case 256: return launch_gemm<256>(stream, g);
     }
     return fail(kInvalidArgument, "unsupported block_n " + std::to_string(bn));
 }
@@ -866,6 +927,51 @@ static int setup_tma_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, i
     return kOk;
 }
 
+// Head-layout outputs (attention operands) through TMA stores: see the `tma_epi == 3` branch of the kernel.
+static bool heads_tma_eligible(const sdod_epilogue& ep, int M, int N, int batch) {
+    if (ep.out_mode != SDOD_OUT_HEADS && ep.out_mode != SDOD_OUT_HEADS_T && ep.out_mode != SDOD_OUT_QKV) return false;
+    if (batch != 1 || ep.residual || ep.row_bias || ep.act != SDOD_ACT_NONE) return false;
+    if (ep.head_dim % 40 != 0 || ep.tokens % 32 != 0 || M % ep.tokens != 0 || N % 40 != 0) return false;
+    const int Cw = ep.heads * ep.head_dim;
+    if (ep.out_mode == SDOD_OUT_QKV ? (Cw % 160 != 0) : (N != Cw)) return false;
+    const bool need_q = ep.out_mode != SDOD_OUT_HEADS_T, need_v = ep.out_mode != SDOD_OUT_HEADS;
+    if (need_q && (ep.dpad % 8 != 0 || ep.dpad < ep.head_dim)) return false;
+    if (need_v && (ep.tok_pad % 8 != 0 || ep.tok_pad < ep.tokens)) return false;
+    if (reinterpret_cast<uintptr_t>(ep.C) & 15) return false;
+    if (ep.out_mode == SDOD_OUT_QKV && ((reinterpret_cast<uintptr_t>(ep.C2) & 15) || (reinterpret_cast<uintptr_t>(ep.C3) & 15))) return false;
+    return true;
+}
+
+static int setup_heads_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, int N, int batch) {
+    std::memset(&out->tmC2, 0, sizeof(CUtensorMap));
+    MainloopParams& mp = out->mp;
+    if (mp.split > 1 || out->bn != 160 || !heads_tma_eligible(ep, M, N, batch)) return kOk;
+    const uint64_t BH = static_cast<uint64_t>(M / ep.tokens) * ep.heads;
+    auto q_map = [&](CUtensorMap* tm, void* base) {
+        uint64_t dims[3] = {static_cast<uint64_t>(ep.dpad), static_cast<uint64_t>(ep.tokens), BH};
+        uint64_t strides[2] = {static_cast<uint64_t>(ep.dpad) * 2, static_cast<uint64_t>(ep.tokens) * ep.dpad * 2};
+        const uint32_t box[3] = {40, 32, 1};
+        return encode_tmap(tm, base, 2, 3, dims, strides, box, 0);
+    };
+    auto v_map = [&](CUtensorMap* tm, void* base) {
+        uint64_t dims[3] = {static_cast<uint64_t>(ep.tok_pad), static_cast<uint64_t>(ep.vt_rows), BH};
+        uint64_t strides[2] = {static_cast<uint64_t>(ep.tok_pad) * 2, static_cast<uint64_t>(ep.vt_rows) * ep.tok_pad * 2};
+        const uint32_t box[3] = {32, 40, 1};
+        return encode_tmap(tm, base, 2, 3, dims, strides, box, 0);
+    };
+    if (ep.out_mode == SDOD_OUT_HEADS) {
+        SDOD_TRY(q_map(&out->tmC, ep.C));
+    } else if (ep.out_mode == SDOD_OUT_HEADS_T) {
+        SDOD_TRY(v_map(&out->tmC2, ep.C));
+    } else {
+        SDOD_TRY(q_map(&out->tmC, ep.C));
+        SDOD_TRY(q_map(&out->tmR, ep.C2));
+        SDOD_TRY(v_map(&out->tmC2, ep.C3));
+    }
+    mp.tma_epi = 3;
+    return kOk;
+}
+
 static thread_local SplitKWorkspace g_splitk;
 void set_splitk_workspace(const SplitKWorkspace& w) { g_splitk = w; }
 
@@ -912,7 +1018,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     if (d.lda % 8 != 0 || d.ldw % 8 != 0) return fail(kInvalidArgument, "gemm: lda/ldw must be multiples of 8 elements");
     SDOD_TRY(validate_epilogue(d.epi, d.N));
     int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, d.K / kBlockK);
-
+    if (!d.block_n && d.N % 160 == 0 && heads_tma_eligible(d.epi, d.M, d.N, d.batch)) bn = 160;   // four 40-column head boxes per tile
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;
@@ -934,6 +1040,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
+    SDOD_TRY(setup_heads_epilogue(out, d.epi, d.M, d.N, d.batch));
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.N + bn - 1) / bn;
     out->batch = d.batch;
@@ -986,6 +1093,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));
+    std::memset(&out->tmC2, 0, sizeof(CUtensorMap));
     out->m_tiles = (M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.Cout + bn - 1) / bn;
     out->batch = 1;

@@ -25,7 +25,7 @@ struct MainloopParams {
 };
 
 struct GemmLaunch {
-    CUtensorMap tmA, tmW, tmC, tmR;
+    CUtensorMap tmA, tmW, tmC, tmR, tmC2;   // tmC2: V^T boxes of the head-layout TMA epilogue
     MainloopParams mp;
     sdod_epilogue ep;
     int bn, m_tiles, n_tiles, batch;

@@ -329,7 +329,7 @@ def test_attention_peaked_softmax_rescale_path():
     assert rel_err(got, _attn_ref(q, k, v, heads)) < TOL_BF16
 
 
-@pytest.mark.parametrize("heads,dh,tokens", [(8, 40, 256), (8, 80, 64), (8, 160, 64), (8, 40, 77)])
+@pytest.mark.parametrize("heads,dh,tokens", [(8, 40, 256), (8, 80, 64), (8, 160, 64), (8, 40, 77), (4, 64, 128), (8, 40, 1024), (8, 40, 96)])
 def test_qkv_projection_writes_attention_layouts(heads, dh, tokens):
     torch.manual_seed(dh + tokens)
     B, Cc = 2, heads * dh
