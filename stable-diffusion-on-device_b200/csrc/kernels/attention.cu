@@ -5,13 +5,12 @@
 // Warp roles (192 threads):
 //   warp 0     : TMA producer — Q once, then K / V^T tiles through an mbarrier ring
 //   warp 1     : MMA issuer   — S = Q K^T and O += P V on tcgen05, accumulators in TMEM
-//   warps 2..9 : softmax      — two threads per query row (each owns 32 of the tile's 64 keys; warps w and
-//                w+4 share a TMEM lane quarter): tcgen05.ld S once, online max/sum in the exp2 domain
-//                (row max exchanged through smem + a 64-thread named barrier), lazy O rescale in TMEM,
-//                P (bf16) written into 128B-swizzled smem as the A operand of the PV MMA;
-//                final O / l -> bf16 [B, Nq, heads*head_dim].  8 softmax warps = 2-4 per SM sub-partition,
-//                enough to hide the MUFU / TMEM / barrier latencies that 4 warps left exposed.
-// TMEM columns: S at [0,128), O at [128, 128+dv).  Everything is K-major + SWIZZLE_128B: K^T comes
+//   warps 2..9 : softmax      — two threads per query row; thread `half` owns 32 of each tile's 64 keys and its own
+//                O accumulator (PV runs as two K=32 MMAs), so the halves are independent online softmaxes in the exp2
+//                domain (packed-fp32 FFMA2 + MUFU.EX2), each with a lazy O rescale in TMEM; P (bf16) goes into
+//                128B-swizzled smem as the A operand of the PV MMAs; the halves are merged once at the end:
+//                O = (O_0 w_0 + O_1 w_1) -> bf16 [B, Nq, heads*head_dim].
+// TMEM columns: S at [0,128) (two 64-key buffers), O_0 at [128, 128+dv), O_1 at [128+dv, 128+2dv).  Everything is K-major + SWIZZLE_128B: K^T comes
 // for free from the HEADS layout, V is stored transposed (HEADS_T) by the producing GEMM epilogue.
 #include "../common.cuh"
 #include "../host_common.h"
@@ -37,7 +36,7 @@ struct AttCfg {
     static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;
     static constexpr int kStageBytes = kKBytes + kVChunk;
     static constexpr int kPBytes = kBQ * 128;             // one P buffer: 128 rows x 64 keys bf16
-    static constexpr int kTmemCols = (128 + kDV) <= 256 ? 256 : 512;
+    static constexpr int kTmemCols = (128 + 2 * kDV) <= 256 ? 256 : 512;   // S double buffer + two O accumulators
     static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBytes + 1024 + 256 + 3 * 256 * 4;   // + row-max / row-sum exchange
 };
 
@@ -154,8 +153,9 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                     const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
                     const uint32_t pb = p_addr + (i & 1) * Cfg::kPBytes;
 #pragma unroll
-                    for (int k = 0; k < kBKV / 16; ++k)
-                        tc_mma_bf16(tmem_O, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | k) != 0);
+                    for (int k = 0; k < kBKV / 16; ++k)    // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
+                        tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
+                                    (i | (k & 1)) != 0);
                     tc_commit(&kv_empty[st]);
                     tc_commit(&p_free[i & 1]);
                     tc_commit(o_ready);
@@ -164,18 +164,18 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
         }
     } else {
         // ---------------------------------------------------------------- softmax / lazy correction / epilogue
+        // Two threads per query row, and they never talk during the KV loop: thread `half` owns keys [32*half, 32*half+32) of
+        // every tile AND its own accumulator O_half (PV is issued as two K=32 MMAs), so each keeps a private reference max /
+        // row sum — no per-tile max exchange, no pair barrier.  The two partial results are merged once, in the epilogue:
+        //   O = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m)),  m = max(m_0, m_1).
         const int q = warp & 3;                       // TMEM lane quarter
-        const int half = (warp - 2) >> 2;             // which 32 of the tile's 64 keys this thread owns
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;         // l_run: partial row sum over this thread's keys
+        const uint32_t tmem_mine = tmem_O + lane_off + half * Cfg::kDV;
+        float m_run = -1.0e30f, l_run = 0.f;          // finite "minus infinity": a half with no valid key yet keeps p = 0, alpha = 1
         const int sw = row & 7;
-        auto pair_sync = [&]() {
-            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-            else asm volatile("bar.sync 4, 64;" ::: "memory");
-        };
+        const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1, u = j >> 1;
             const int kv_valid = min(kBKV, Nkv - j * kBKV) - half * 32;      // valid keys among this thread's 32
@@ -197,28 +197,31 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
 #pragma unroll
                 for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[i + c]));
             }
-            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            xch[(b * 2 + half) * 128 + row] = mx;    // exchange the half-row max with the partner thread
-            pair_sync();
-            mx = fmaxf(mx, xch[(b * 2 + (half ^ 1)) * 128 + row]) * scale_log2;   // scale_log2 > 0
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2;   // scale_log2 > 0
             // lazy reference max: only move it when the true max grew by more than 2^8 (P stays <= 256, exact in the ratio O/l)
             const bool need = (mx > m_run + 8.0f);
             const float m_new = need ? mx : m_run;
-            const float alpha = ex2(m_run - m_new);   // 1 when unchanged, 0 on the first tile
-            const float neg_m = -m_new;
-            float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float alpha = ex2(m_run - m_new);   // 1 when unchanged, 0 on the first real tile
+            const uint64_t negm2 = pack_f32x2(-m_new, -m_new);
+            uint64_t ls2[2] = {0ull, 0ull};
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float x0 = fmaf(__uint_as_float(sv[2 * i]), scale_log2, neg_m), x1 = fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, neg_m);
-                // (measured r1: moving 3/8 of these onto ex2_poly made the kernel 20 % slower — the loop is issue/smem-bound,
-                //  not MUFU-bound, at 16 softmax warps per SM; profiles/r01_attention_notes.txt)
+                // x = s * scale - m for two keys in one FFMA2 (sm_100 packed fp32), then MUFU.EX2 each
+                float x0, x1;
+                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), scale2, negm2), x0, x1);
+                // (measured r1: moving 3/8 of these onto ex2_poly made the kernel 20 % slower — profiles/r01_attention_notes.txt)
                 const float p0 = ex2(x0);
                 const float p1 = ex2(x1);
-                ls4[i & 3] += p0 + p1;
+                ls2[i & 1] = add_f32x2(ls2[i & 1], pack_f32x2(p0, p1));
                 pk[i] = pack_bf16x2(p0, p1);
             }
-            l_run = l_run * alpha + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
+            {
+                float a0, a1, a2, a3;
+                unpack_f32x2(ls2[0], a0, a1);
+                unpack_f32x2(ls2[1], a2, a3);
+                l_run = fmaf(l_run, alpha, (a0 + a1) + (a2 + a3));
+            }
             m_run = m_new;
             if (j >= 2) mbar_wait(&p_free[b], (u - 1) & 1);          // PV_{j-2} has consumed P buffer b
             uint8_t* prow = sP + b * Cfg::kPBytes + row * 128;
@@ -228,16 +231,16 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             // o_ready must be observed every tile, in lockstep: an mbarrier parity wait is only meaningful while the waiter is at
             // most one phase behind.  PV_{j-1} was issued a whole softmax iteration ago, so this wait is almost always satisfied.
             if (j > 0) mbar_wait(o_ready, (j - 1) & 1);
-            if (j > 0 && __any_sync(0xffffffffu, need)) {            // PV_{j-1} complete: O may be rescaled (chunks split by parity)
+            if (j > 0 && __any_sync(0xffffffffu, need)) {            // PV_{j-1} complete: this warp's accumulator may be rescaled
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = half; c < Cfg::kDV / 16; c += 2) {
+                for (int c = 0; c < Cfg::kDV / 16; ++c) {
                     uint32_t o[16];
-                    tmem_ld16(tmem_O + lane_off + c * 16, o);
+                    tmem_ld16(tmem_mine + c * 16, o);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st16(tmem_O + lane_off + c * 16, o);
+                    tmem_st16(tmem_mine + c * 16, o);
                 }
                 tmem_st_wait();
             }
@@ -245,30 +248,38 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the UMMA async proxy
             mbar_arrive(&p_full[b]);
         }
-        // epilogue: O / l  (l = sum of the pair's partial sums)
-        xch[(4 + half) * 128 + row] = l_run;          // third region: never aliases a row-max slot still being read
-        pair_sync();
-        const float inv_l = 1.0f / (l_run + xch[(4 + (half ^ 1)) * 128 + row]);
+        // epilogue: merge the two halves of each row
+        xch[half * 128 + row] = m_run;
+        xch[(2 + half) * 128 + row] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        const float m_o = xch[(half ^ 1) * 128 + row], l_o = xch[(2 + (half ^ 1)) * 128 + row];
+        const float m_all = fmaxf(m_run, m_o);
+        const float f_me = ex2(m_run - m_all), f_ot = ex2(m_o - m_all);
+        const float inv_l = 1.0f / fmaf(l_run, f_me, l_o * f_ot);
+        const float w_me = f_me * inv_l, w_ot = f_ot * inv_l;
         mbar_wait(o_ready, (n_tiles - 1) & 1);
         tc_fence_after();
         const int bb = bh / heads, h = bh - bb * heads;
         const int qi = q0 + row;
         bf16* orow = O + (static_cast<long long>(bb) * Nq + qi) * (heads * DH) + h * DH;
+        const uint32_t tmem_other = tmem_O + lane_off + (half ^ 1) * Cfg::kDV;
 #pragma unroll 1
         for (int c = half; c < Cfg::kDV / 16; c += 2) {
-            uint32_t o[16];
-            tmem_ld16(tmem_O + lane_off + c * 16, o);
+            uint32_t o[16], o2[16];
+            tmem_ld16(tmem_mine + c * 16, o);
+            tmem_ld16(tmem_other + c * 16, o2);
             tmem_ld_wait();
             if (qi < Nq) {
 #pragma unroll
                 for (int h8 = 0; h8 < 2; ++h8) {
                     const int d0 = c * 16 + h8 * 8;
                     if (d0 < DH) {     // DH % 8 == 0
+                        float r[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) r[i] = fmaf(__uint_as_float(o[h8 * 8 + i]), w_me, __uint_as_float(o2[h8 * 8 + i]) * w_ot);
                         uint4 w;
-                        w.x = pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l);
-                        w.y = pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l);
-                        w.z = pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l);
-                        w.w = pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l);
+                        w.x = pack_bf16x2(r[0], r[1]); w.y = pack_bf16x2(r[2], r[3]);
+                        w.z = pack_bf16x2(r[4], r[5]); w.w = pack_bf16x2(r[6], r[7]);
                         *reinterpret_cast<uint4*>(orow + d0) = w;
                     }
                 }
