@@ -15,6 +15,7 @@
 //
 // Layer list served (reference evidence: analyze_results.py:25-87; executed by the opaque
 // unet/decoder graphs at csrc/libsdod/src/context.cpp:352,366,387).
+#include <cstdlib>
 #include "../common.cuh"
 #include "../host_common.h"
 #include "../launch_count.h"
@@ -36,15 +37,19 @@ constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 // DEEP = true : single-wave grids (<= 148 CTAs, the batch-2 UNet case): one CTA owns the SM, so the ring takes all of
 //                shared memory; by Little's law the per-SM load bandwidth is bytes-in-flight / L2 latency, and at 3 stages
 //                the K loop ran latency-bound at ~1.3 us per K block (profiles/r01_*).
-template <int BN, bool DEEP>
+// PAIR = true : two CTAs on the SMs of one TPC run each K block as ONE tcgen05.mma.cta_group::2 (M = 256): every CTA loads
+//                its own 128 A rows but only half of the B tile, so the weight traffic L2 -> SM halves.  Long-K layers are
+//                bound by exactly that traffic (~6300 B/clk chip-wide from L2; profiles/r01_gemm_l2_bound.txt).
+template <int BN, bool DEEP, bool PAIR = false>
 struct GemmCfg {
-    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBlockK * 2;   // B rows held by this CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kShallow = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int kShallow = PAIR ? (BN >= 256 ? 5 : 4) : ((BN >= 256) ? 4 : (BN >= 128 ? 3 : 4));
     static constexpr int kDeepRaw = (220 * 1024 - 2048) / kStageBytes;
     static constexpr int kStages = DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow;
     static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
+    static_assert(kStages * kStageBytes >= 512 * (BN + 4), "the idle ring doubles as the epilogue staging area");
 };
 
 SDOD_DEVICE float apply_act(float v, int act) {
@@ -307,17 +312,18 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
     epilogue_geglu16<BN>(ep, mp, 0, m_tile * kBlockM + row, n_tile, j, a, g);
 }
 
-template <int BN, bool DEEP>
+template <int BN, bool DEEP, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                       const __grid_constant__ CUtensorMap tmR,
                                                                       const __grid_constant__ CUtensorMap tmC2,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
-    using Cfg = GemmCfg<BN, DEEP>;
+    using Cfg = GemmCfg<BN, DEEP, PAIR>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a shared-space pointer
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the CTA pair (issues the MMAs)
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * kABytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes);
@@ -329,7 +335,8 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    // pair grids put M on x: the two CTAs of a cluster (dims 2x1x1, as cta_group::2 kernels must be launched) are consecutive M tiles
+    const int n_tile = PAIR ? blockIdx.y : blockIdx.x, m_tile = PAIR ? blockIdx.x : blockIdx.y;
     const int bz = mp.split > 1 ? 0 : blockIdx.z;            // batch index (split-K only when batch == 1)
     const int zs = mp.split > 1 ? blockIdx.z : 0;            // split index
     const int kb0 = zs * mp.kb_per_split;
@@ -349,15 +356,20 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers exist before any TMA / commit of ours can signal them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------------------------------------------------------- TMA producer
+            const uint32_t leader_full = PAIR ? mapa_shared(&full_bar[0], 0) : 0u;   // pair: all bytes are credited to the leader
             int b0 = 0, y0 = 0, x0 = 0;
             if (mp.conv) {
                 const int hw = mp.H * mp.W;
@@ -370,11 +382,29 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                     x0 = rem - y0 * mp.W;
                 }
             }
-            for (int kb = kb0; kb < kb1; ++kb) {
-                const int it = kb - kb0;
+            // K rotation: M tile i starts its K loop i*rot blocks in, so the CTAs of a wave do not all pull the same weight
+            // tile out of the same few L2 slices at the same moment (the sum over K is order-independent up to fp32 rounding,
+            // and the order is fixed per tile, so results stay deterministic).
+            const int nkb = kb1 - kb0;
+            int kb = kb0 + (mp.k_rot ? static_cast<int>((static_cast<long long>(PAIR ? m_tile >> 1 : m_tile) * mp.k_rot) % nkb) : 0);
+            for (int it = 0; it < nkb; ++it, kb = (kb + 1 == kb1 ? kb0 : kb + 1)) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
+                if (PAIR) {
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);     // both CTAs' A + B halves
+                    const uint32_t fb = leader_full + s * 8;
+                    if (mp.conv) {
+                        const int tap = kb / mp.cin_blocks;
+                        const int cb = kb - tap * mp.cin_blocks;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        tma_load_4d_pair(sA + s * kABytes, &tmA, fb, cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+                    } else {
+                        tma_load_3d_pair(sA + s * kABytes, &tmA, fb, kb * kBlockK, m0, bz);
+                    }
+                    tma_load_3d_pair(sB + s * Cfg::kBBytes, &tmW, fb, kb * kBlockK, n0 + static_cast<int>(rank) * (BN / 2), mp.w_batched ? bz : 0);
+                    continue;
+                }
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                 if (mp.conv) {
                     const int tap = kb / mp.cin_blocks;
@@ -388,9 +418,9 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+        if (lane == 0 && rank == 0) {
+            // ---------------------------------------------------------------- MMA issuer (pair: the leader drives both SMs)
+            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BN);
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int it = kb - kb0;
                 const int s = it % STAGES;
@@ -401,12 +431,16 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                    tc_mma_bf16(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
-                                idesc, (it | k) != 0);
+                    if (PAIR) tc_mma_bf16_pair(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                                               idesc, (it | k) != 0);
+                    else tc_mma_bf16(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                                     idesc, (it | k) != 0);
                 }
-                tc_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
+                if (PAIR) tc_commit_pair(&empty_bar[s]);   // frees the slot in both CTAs when these MMAs retire
+                else tc_commit(&empty_bar[s]);
             }
-            tc_commit(tmem_full_bar);       // accumulator complete
+            if (PAIR) tc_commit_pair(tmem_full_bar);       // accumulator complete (each CTA holds its own 128 rows)
+            else tc_commit(tmem_full_bar);
         }
     } else {
         // -------------------------------------------------------------------- epilogue
@@ -425,10 +459,10 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
         if (mp.split > 1) {
             // split-K: publish this CTA's fp32 partial tile ([chunk16][row][16], coalesced); splitk_reduce_kernel folds
             // the partials in fixed order (deterministic) and applies the epilogue.
-            const long long tile_id = static_cast<long long>(m_tile) * gridDim.x + n_tile;
+            const long long tile_id = static_cast<long long>(m_tile) * (PAIR ? gridDim.y : gridDim.x) + n_tile;
             float* mine = mp.ws + (tile_id * mp.split + zs) * (BN * kBlockM);
 #pragma unroll 1
-            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+            for (int j = half * CH; j < (half + 1) * CH && m0 < mp.M; j += 16) {    // (m0 >= M: padding CTA of an odd pair grid)
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -812,23 +846,43 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
         tc_fence_before();
     }
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the pair may still touch it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN, bool DEEP>
+template <int BN, bool DEEP, bool PAIR>
 static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) {
-    using Cfg = GemmCfg<BN, DEEP>;
+    using Cfg = GemmCfg<BN, DEEP, PAIR>;
     static bool configured = false;
     if (!configured) {
-        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, DEEP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
-    gemm_tcgen05_kernel<BN, DEEP><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
+    if (!PAIR) {
+        gemm_tcgen05_kernel<BN, DEEP, PAIR><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
+        return kOk;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // two consecutive M tiles
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
+    if (e != cudaSuccess) {
+        int nc = -1;
+        cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nc, gemm_tcgen05_kernel<BN, DEEP, PAIR>, &cfg);
+        return fail(kCudaError, std::string("cudaLaunchKernelEx(gemm pair bn=") + std::to_string(BN) + " deep=" + std::to_string(DEEP) + " grid=" +
+                                    std::to_string(grid.x) + "x" + std::to_string(grid.y) + "x" + std::to_string(grid.z) + " smem=" +
+                                    std::to_string(Cfg::kSmemBytes) + "): " + cudaGetErrorName(e) + "; max active clusters " + std::to_string(nc) +
+                                    " (" + cudaGetErrorName(e2) + ")");
+    }
     return kOk;
 }
 
@@ -836,9 +890,18 @@ template <int BN>
 static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     const MainloopParams& mp = g.mp;
     dim3 grid(g.n_tiles, g.m_tiles, mp.split > 1 ? mp.split : g.batch);
+    if (g.pair) grid = dim3((g.m_tiles + 1) & ~1, g.n_tiles, grid.z);
     const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
-    if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true>(stream, g, grid)));
-    else SDOD_TRY((launch_gemm_cfg<BN, false>(stream, g, grid)));
+    if constexpr (BN >= 128) {
+        if (g.pair) {
+            if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true, true>(stream, g, grid)));
+            else SDOD_TRY((launch_gemm_cfg<BN, false, true>(stream, g, grid)));
+        }
+    }
+    if (!g.pair) {
+        if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true, false>(stream, g, grid)));
+        else SDOD_TRY((launch_gemm_cfg<BN, false, false>(stream, g, grid)));
+    }
     count_launch();
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
     if (mp.split > 1) {
@@ -860,6 +923,17 @@ static int dispatch_gemm(const GemmLaunch& g, cudaStream_t stream) {
         case 256: return launch_gemm<256>(stream, g);
     }
     return fail(kInvalidArgument, "unsupported block_n " + std::to_string(bn));
+}
+
+// CTA pairs (cta_group::2) for multi-wave implicit-GEMM convolutions (K = 9*Cin >= 45 blocks): measured on B200 (r1,
+// tools/conv_sweep.py) they gain 5-14 % there (B8 32x32 1280->640: 99 -> 87 us) because each SM pulls half the weight bytes
+// per K block; single-wave grids and short-K linear layers lose 3-15 % to the cluster launch / sync cost, so they stay
+// unpaired.  SDOD_GEMM_PAIR=0 disables pairs, =2 forces them wherever legal (A/B measurements).
+static bool use_pair(int bn, int m_tiles, int n_tiles, bool conv) {
+    static const int env = [] { const char* e = std::getenv("SDOD_GEMM_PAIR"); return e ? std::atoi(e) : 1; }();
+    if (!env || bn < 128 || m_tiles < 2) return false;
+    if (env == 2) return (m_tiles % 2 == 0) || m_tiles >= 9;
+    return conv && (m_tiles % 2 == 0) && static_cast<long long>(m_tiles) * n_tiles > 148;
 }
 
 // Tile width: the candidate (160 / 128 / 64) that wastes the fewest padded columns, wider first.
@@ -972,6 +1046,11 @@ static int setup_heads_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M,
     return kOk;
 }
 
+static int k_rotation(int k_blocks) {
+    static const int env = [] { const char* e = std::getenv("SDOD_GEMM_KROT"); return e ? std::atoi(e) : 0; }();
+    return k_blocks >= 8 ? env : 0;
+}
+
 static thread_local SplitKWorkspace g_splitk;
 void set_splitk_workspace(const SplitKWorkspace& w) { g_splitk = w; }
 
@@ -1019,6 +1098,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     SDOD_TRY(validate_epilogue(d.epi, d.N));
     int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, d.K / kBlockK);
     if (!d.block_n && d.N % 160 == 0 && heads_tma_eligible(d.epi, d.M, d.N, d.batch)) bn = 160;   // four 40-column head boxes per tile
+    const bool pair = use_pair(bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, false);
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;
@@ -1032,11 +1112,13 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     {
         uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N), static_cast<uint64_t>(wb ? d.batch : 1)};
         uint64_t strides[2] = {static_cast<uint64_t>(d.ldw) * 2, static_cast<uint64_t>(wb ? d.strideW : static_cast<long long>(d.N) * d.ldw) * 2};
-        uint32_t box[3] = {kBlockK, static_cast<uint32_t>(bn), 1};
+        uint32_t box[3] = {kBlockK, static_cast<uint32_t>(pair ? bn / 2 : bn), 1};
         SDOD_TRY(encode_tmap_bf16(&tmW, d.W, 3, dims, strides, box, true));
     }
+    out->pair = pair ? 1 : 0;
     MainloopParams mp{};
     mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
+    mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
@@ -1070,6 +1152,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     const int M = d.B * d.H * d.W;
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
     const int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, 9 * d.Cin / kBlockK);
+    const bool pair = use_pair(bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, true);
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;
@@ -1084,12 +1167,14 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     {
         uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(d.Cout), 1};
         uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * d.Cout * 2};
-        uint32_t box[3] = {kBlockK, static_cast<uint32_t>(bn), 1};
+        uint32_t box[3] = {kBlockK, static_cast<uint32_t>(pair ? bn / 2 : bn), 1};
         SDOD_TRY(encode_tmap_bf16(&tmW, d.Wt, 3, dims, strides, box, true));
     }
+    out->pair = pair ? 1 : 0;
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
+    mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));

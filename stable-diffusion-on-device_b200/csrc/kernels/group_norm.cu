@@ -60,11 +60,7 @@ template <typename T> SDOD_DEVICE T from_f(float v);
 template <> SDOD_DEVICE float from_f<float>(float v) { return v; }
 template <> SDOD_DEVICE bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
 
-SDOD_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 SDOD_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-SDOD_DEVICE void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 SDOD_DEVICE float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
     uint32_t a = smem_u32(local_ptr), ra;
     float v;

@@ -22,6 +22,7 @@ struct MainloopParams {
     unsigned int* counters;   // one ticket per output tile, self-resetting
     int tma_epi;       // 0: LSU epilogue; 1: TMA-store epilogue; 2: TMA-store + residual TMA-loaded and added in place
     int c_bytes;       // output element size for the TMA epilogue (2 | 4)
+    int k_rot;         // K-loop start rotation per M tile (in K blocks); 0 = every tile starts at block 0
 };
 
 struct GemmLaunch {
@@ -29,6 +30,7 @@ struct GemmLaunch {
     MainloopParams mp;
     sdod_epilogue ep;
     int bn, m_tiles, n_tiles, batch;
+    int pair;   // 1: launched as 2-CTA clusters running tcgen05 cta_group::2
 };
 
 struct AttnLaunch {

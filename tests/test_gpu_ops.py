@@ -233,7 +233,8 @@ def test_gemm_batched():
 
 # ------------------------------------------------------------------------------------------ conv3x3
 CONV_CASES = [(2, 16, 16, 64, 64), (1, 8, 8, 128, 320), (3, 8, 8, 64, 128), (2, 64, 64, 320, 320), (2, 32, 32, 640, 640),
-              (1, 16, 16, 1280, 1280), (1, 128, 128, 128, 128), (1, 256, 256, 64, 64), (2, 4, 4, 64, 96), (1, 64, 64, 320, 4)]
+              (1, 16, 16, 1280, 1280), (1, 128, 128, 128, 128), (1, 256, 256, 64, 64), (2, 4, 4, 64, 96), (1, 64, 64, 320, 4),
+              (2, 64, 64, 64, 640), (3, 64, 64, 64, 384)]   # the last two launch as CTA pairs (> 148 tiles, even M tiles)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_CASES)
@@ -247,6 +248,21 @@ def test_conv3x3_implicit_gemm(B, H, W, Cin, Cout):
     assert torch.equal(wt.view(Cout, 3, 3, Cin), w.permute(0, 2, 3, 1).contiguous())
     got = torch.ops.sdod.conv3x3(x.permute(0, 2, 3, 1).contiguous(), wt, bias)
     assert got.shape == (B, H, W, Cout) and rel_err(got, want) < TOL_BF16
+
+
+def test_conv3x3_cta_pair_epilogues():
+    """Multi-wave conv grids run as 2-CTA clusters (tcgen05 cta_group::2): check the epilogue variants on that path."""
+    torch.manual_seed(22)
+    B, H, W, Cin, Cout = 4, 64, 64, 64, 320          # 128 M tiles x 2 N tiles
+    x = bf(torch.randn(B, H, W, Cin)).to(DEV)
+    w = bf(torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    bias, temb = torch.randn(Cout, device=DEV), torch.randn(B, Cout, device=DEV)
+    res = bf(torch.randn(B, H, W, Cout)).to(DEV)
+    base = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    wt = ops.pack_conv3x3_weight(w.float())
+    assert rel_err(torch.ops.sdod.conv3x3(x, wt, bias, None, temb), base + temb[:, None, None, :]) < TOL_BF16
+    assert rel_err(torch.ops.sdod.conv3x3(x, wt, bias, res), base + res.float()) < TOL_BF16
+    assert rel_err(torch.ops.sdod.conv3x3(x, wt, bias, None, None, C.ACT_SILU), F.silu(base)) < TOL_BF16
 
 
 def test_conv3x3_fused_temb_and_residual():
