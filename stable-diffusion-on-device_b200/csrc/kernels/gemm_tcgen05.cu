@@ -31,6 +31,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                    // 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kGemmThreadsPersist = 576;   // persistent variant: 16 epilogue warps (four per lane quarter) on the one CTA of an SM
 
 // DEEP = false: shallow ring so that 2 CTAs co-reside per SM (one CTA's epilogue overlaps the other's mainloop) — used when
 //                the grid is larger than one wave.
@@ -40,16 +41,24 @@ constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 // PAIR = true : two CTAs on the SMs of one TPC run each K block as ONE tcgen05.mma.cta_group::2 (M = 256): every CTA loads
 //                its own 128 A rows but only half of the B tile, so the weight traffic L2 -> SM halves.  Long-K layers are
 //                bound by exactly that traffic (~6300 B/clk chip-wide from L2; profiles/r01_gemm_l2_bound.txt).
-template <int BN, bool DEEP, bool PAIR = false>
+// PERSIST = true: one CTA per SM walks a strided list of output tiles.  The TMA ring keeps running across tile boundaries,
+//                the accumulator is double-buffered in TMEM (2 x BN columns) and the epilogue stages its output in its
+//                own shared-memory region, so tile i's epilogue overlaps tile i+1's loads and MMAs.  Short-K layers
+//                (K = 320 / 640: 5-10 K blocks) were bound by the per-CTA fill + drain chain (~6 us per 128x128 tile whose
+//                MMAs take 0.7 us, profiles/r01_hot_kernels_ncu.txt); persistence hides that chain behind the next tile.
+template <int BN, bool DEEP, bool PAIR = false, bool PERSIST = false>
 struct GemmCfg {
     static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBlockK * 2;   // B rows held by this CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kShallow = PAIR ? (BN >= 256 ? 5 : 4) : ((BN >= 256) ? 4 : (BN >= 128 ? 3 : 4));
     static constexpr int kDeepRaw = (220 * 1024 - 2048) / kStageBytes;
-    static constexpr int kStages = DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow;
-    static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
-    static_assert(kStages * kStageBytes >= 512 * (BN + 4), "the idle ring doubles as the epilogue staging area");
+    static constexpr int kEpiBytes = PERSIST ? BN * 512 : 0;          // dedicated epilogue staging (4 quarters x BN/32 boxes x 4 KiB)
+    static constexpr int kPersistRaw = (232448 - 1024 - 256 - 2048 - kEpiBytes) / kStageBytes;
+    static constexpr int kStages = PERSIST ? (kPersistRaw > 8 ? 8 : kPersistRaw) : (DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow);
+    static constexpr int kTmemCols = PERSIST ? (2 * BN <= 256 ? 256 : 512) : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias tiles*/;
+    static_assert(PERSIST || kStages * kStageBytes >= 512 * (BN + 4), "the idle ring doubles as the epilogue staging area");
+    static_assert(kSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
 };
 
 SDOD_DEVICE float apply_act(float v, int act) {
@@ -312,36 +321,47 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
     epilogue_geglu16<BN>(ep, mp, 0, m_tile * kBlockM + row, n_tile, j, a, g);
 }
 
-template <int BN, bool DEEP, bool PAIR>
-__global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+#define SDOD_TILE_LOOP for (int t = PERSIST ? static_cast<int>(blockIdx.x) : 0, iter = 0; t < (PERSIST ? mp.tiles_total : 1); t += (PERSIST ? static_cast<int>(gridDim.x) : 1), ++iter)
+#define SDOD_TILE_COORDS                                                                                               \
+    const int n_tile = PERSIST ? t % mp.n_tiles : static_cast<int>(PAIR ? blockIdx.y : blockIdx.x);                    \
+    const int m_tile = PERSIST ? (t / mp.n_tiles) % mp.m_tiles : static_cast<int>(PAIR ? blockIdx.x : blockIdx.y);     \
+    const int bz = PERSIST ? t / (mp.n_tiles * mp.m_tiles) : (mp.split > 1 ? 0 : static_cast<int>(blockIdx.z));        \
+    const int m0 = m_tile * kBlockM, n0 = n_tile * BN;                                                                 \
+    (void)bz; (void)m0; (void)n0;
+
+template <int BN, bool DEEP, bool PAIR, bool PERSIST>
+__global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, (DEEP || PERSIST) ? 1 : 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                       const __grid_constant__ CUtensorMap tmR,
                                                                       const __grid_constant__ CUtensorMap tmC2,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
-    using Cfg = GemmCfg<BN, DEEP, PAIR>;
+    using Cfg = GemmCfg<BN, DEEP, PAIR, PERSIST>;
+    static_assert(!(PAIR && PERSIST), "persistent CTA pairs are not implemented");
     constexpr int STAGES = Cfg::kStages;
+    constexpr int EW = PERSIST ? 16 : 8;          // epilogue warps: NPART per TMEM lane quarter, each owning a column range
+    constexpr int NPART = EW / 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a shared-space pointer
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the CTA pair (issues the MMAs)
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes);
+    uint8_t* stage = PERSIST ? sB + STAGES * Cfg::kBBytes : smem;     // epilogue staging: own region, or the idle ring
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint64_t* res_bar = tmem_full_bar + 1;                    // [4] residual tiles landed (TMA epilogue), one per lane quarter
+    uint64_t* tmem_full_bar = empty_bar + STAGES;             // [2] accumulator ready (one per TMEM buffer)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2] accumulator drained by the epilogue (persistent only)
+    uint64_t* res_bar = tmem_empty_bar + 2;                   // [4] residual tiles landed (TMA epilogue), one per lane quarter
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [BN] bias tile
+    float* s_bias_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2][BN] bias tiles
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // pair grids put M on x: the two CTAs of a cluster (dims 2x1x1, as cta_group::2 kernels must be launched) are consecutive M tiles
-    const int n_tile = PAIR ? blockIdx.y : blockIdx.x, m_tile = PAIR ? blockIdx.x : blockIdx.y;
-    const int bz = mp.split > 1 ? 0 : blockIdx.z;            // batch index (split-K only when batch == 1)
-    const int zs = mp.split > 1 ? blockIdx.z : 0;            // split index
+    // Tile coordinates come from SDOD_TILE_COORDS inside each role's tile loop (one trip unless PERSIST).  Pair grids put M on
+    // x: the two CTAs of a cluster (dims 2x1x1, as cta_group::2 kernels must be launched) are consecutive M tiles.
+    const int zs = (!PERSIST && mp.split > 1) ? blockIdx.z : 0;            // split index (split-K only when batch == 1)
     const int kb0 = zs * mp.kb_per_split;
-    const int kb1 = mp.split > 1 ? min(mp.k_blocks, kb0 + mp.kb_per_split) : mp.k_blocks;
-    const int m0 = m_tile * kBlockM, n0 = n_tile * BN;
+    const int kb1 = (!PERSIST && mp.split > 1) ? min(mp.k_blocks, kb0 + mp.kb_per_split) : mp.k_blocks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -352,7 +372,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 32 * EW); }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
@@ -370,6 +390,9 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
         if (lane == 0) {
             // ---------------------------------------------------------------- TMA producer
             const uint32_t leader_full = PAIR ? mapa_shared(&full_bar[0], 0) : 0u;   // pair: all bytes are credited to the leader
+            int g = 0;                                         // ring position, keeps counting across tiles
+            SDOD_TILE_LOOP {
+            SDOD_TILE_COORDS
             int b0 = 0, y0 = 0, x0 = 0;
             if (mp.conv) {
                 const int hw = mp.H * mp.W;
@@ -387,9 +410,9 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             // and the order is fixed per tile, so results stay deterministic).
             const int nkb = kb1 - kb0;
             int kb = kb0 + (mp.k_rot ? static_cast<int>((static_cast<long long>(PAIR ? m_tile >> 1 : m_tile) * mp.k_rot) % nkb) : 0);
-            for (int it = 0; it < nkb; ++it, kb = (kb + 1 == kb1 ? kb0 : kb + 1)) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+            for (int it = 0; it < nkb; ++it, ++g, kb = (kb + 1 == kb1 ? kb0 : kb + 1)) {
+                const int s = g % STAGES;
+                const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (PAIR) {
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);     // both CTAs' A + B halves
@@ -416,53 +439,71 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 }
                 tma_load_3d(sB + s * Cfg::kBBytes, &tmW, &full_bar[s], kb * kBlockK, n0, mp.w_batched ? bz : 0);
             }
+            }   // tile loop
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ---------------------------------------------------------------- MMA issuer (pair: the leader drives both SMs)
             constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BN);
-            for (int kb = kb0; kb < kb1; ++kb) {
+            int g = 0;
+            SDOD_TILE_LOOP {
+            const int ab = PERSIST ? (iter & 1) : 0;                 // TMEM accumulator buffer of this tile
+            const uint32_t tmem_acc = tmem_base + ab * BN;
+            if (PERSIST && iter >= 2) {                               // the epilogue of tile iter-2 has drained this buffer
+                mbar_wait(&tmem_empty_bar[ab], ((iter >> 1) - 1) & 1);
+                tc_fence_after();
+            }
+            for (int kb = kb0; kb < kb1; ++kb, ++g) {
                 const int it = kb - kb0;
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+                const int s = g % STAGES;
+                const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kABytes);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                    if (PAIR) tc_mma_bf16_pair(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                    if (PAIR) tc_mma_bf16_pair(tmem_acc, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
                                                idesc, (it | k) != 0);
-                    else tc_mma_bf16(tmem_base, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                    else tc_mma_bf16(tmem_acc, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
                                      idesc, (it | k) != 0);
                 }
                 if (PAIR) tc_commit_pair(&empty_bar[s]);   // frees the slot in both CTAs when these MMAs retire
                 else tc_commit(&empty_bar[s]);
             }
-            if (PAIR) tc_commit_pair(tmem_full_bar);       // accumulator complete (each CTA holds its own 128 rows)
-            else tc_commit(tmem_full_bar);
+            if (PAIR) tc_commit_pair(&tmem_full_bar[ab]);       // accumulator complete (each CTA holds its own 128 rows)
+            else tc_commit(&tmem_full_bar[ab]);
+            }   // tile loop
         }
     } else {
         // -------------------------------------------------------------------- epilogue
+        SDOD_TILE_LOOP {
+        SDOD_TILE_COORDS
+        const int ab = PERSIST ? (iter & 1) : 0;
+        float* s_bias = s_bias_base + ab * BN;         // double-buffered: a fast warp may already stage the next tile's bias
         if (mp.tma_epi) {                              // stage this tile's bias while the mainloop runs
-            for (int i = threadIdx.x - 64; i < BN; i += 256) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
-            asm volatile("bar.sync 5, 256;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
+            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");   // (persistent: also orders the previous tile's staging reads/stores)
         }
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(&tmem_full_bar[ab], PERSIST ? ((iter >> 1) & 1) : 0);
         tc_fence_after();
+        const uint32_t res_parity = PERSIST ? (iter & 1) : 0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which of the quarter's two warps
+        const int half = (warp - 2) >> 2;             // which of the quarter's NPART warps
+        // this warp's columns, in 16-column units: [j_lo, j_hi) of the BN-wide tile, [g_lo, g_hi) of a GEGLU half tile
+        const int j_lo = 16 * (((BN / 16) * half) / NPART), j_hi = 16 * (((BN / 16) * (half + 1)) / NPART);
+        const int g_lo = 16 * (((BN / 32) * half) / NPART), g_hi = 16 * (((BN / 32) * (half + 1)) / NPART);
+        auto quarter_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(32 * NPART) : "memory"); };
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        constexpr int CH = BN / 2;                    // columns per warp in the row-per-thread phases
+        const uint32_t taddr = tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16);
         if (mp.split > 1) {
             // split-K: publish this CTA's fp32 partial tile ([chunk16][row][16], coalesced); splitk_reduce_kernel folds
             // the partials in fixed order (deterministic) and applies the epilogue.
             const long long tile_id = static_cast<long long>(m_tile) * (PAIR ? gridDim.y : gridDim.x) + n_tile;
             float* mine = mp.ws + (tile_id * mp.split + zs) * (BN * kBlockM);
 #pragma unroll 1
-            for (int j = half * CH; j < (half + 1) * CH && m0 < mp.M; j += 16) {    // (m0 >= M: padding CTA of an odd pair grid)
+            for (int j = j_lo; j < j_hi && m0 < mp.M; j += 16) {    // (m0 >= M: padding CTA of an odd pair grid)
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -477,10 +518,9 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             // BN/2 bf16 columns wide (64-B swizzled 32x32 boxes).
             constexpr int HALF = BN / 2;
             constexpr int NBG = HALF / 32 > 0 ? HALF / 32 : 1;
-            constexpr int CHG = HALF / 2;
-            uint8_t* qbase = smem + q * (NBG * 4096);
+            uint8_t* qbase = stage + q * (NBG * 4096);
 #pragma unroll 1
-            for (int j = half * CHG; j < (half + 1) * CHG; j += 16) {
+            for (int j = g_lo; j < g_hi; j += 16) {
                 uint32_t a[16], g[16];
                 tmem_ld16(taddr + j, a);
                 tmem_ld16(taddr + HALF + j, g);
@@ -506,10 +546,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 }
             }
             fence_proxy_async_smem();
-            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            quarter_sync();
             if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
                 for (int bx = 0; bx < NBG; ++bx)
                     if (n_tile * HALF + bx * 32 < mp.N / 2) tma_store_3d(&tmC, qbase + bx * 4096, n_tile * HALF + bx * 32, m0 + q * 32, bz);
@@ -519,7 +556,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
         } else if (ep.act == SDOD_ACT_GEGLU && !(ep.out_mode == SDOD_OUT_BF16 && mp.N % 8 == 0 && ep.ldc % 4 == 0)) {
             constexpr int HALF = BN / 2;
 #pragma unroll 1
-            for (int j = half * (HALF / 2); j < (half + 1) * (HALF / 2); j += 16) {
+            for (int j = g_lo; j < g_hi; j += 16) {
                 uint32_t a[16], g[16];
                 tmem_ld16(taddr + j, a);
                 tmem_ld16(taddr + HALF + j, g);
@@ -532,11 +569,11 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             // Q/K box: [32 tokens][40 d] (80-B rows: conflict-free 16-B stores) -> HEADS [B*heads, tokens, dpad] at (d0, tok, bh).
             // V box  : [40 d][32 tokens] (thread = token writes a column)       -> HEADS_T [B*heads, vt_rows, tok_pad] at (tok, d0, bh).
             constexpr int BOXB = 40 * 32 * 2;
-            uint8_t* qbase = smem + q * (4 * BOXB);
+            uint8_t* qbase = stage + q * (4 * BOXB);
             const int Cw = ep.heads * ep.head_dim;
             const int which = ep.out_mode == SDOD_OUT_QKV ? n0 / Cw : (ep.out_mode == SDOD_OUT_HEADS_T ? 2 : 0);
 #pragma unroll 1
-            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+            for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -567,10 +604,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 }
             }
             fence_proxy_async_smem();
-            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            quarter_sync();
             const int mq = m0 + q * 32;
             if (half == 0 && lane == 0 && mq < mp.M) {
                 const int b = mq / ep.tokens, tok = mq - b * ep.tokens;
@@ -596,7 +630,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             constexpr int NB = BN / 32;
             const bool f32 = (mp.c_bytes == 4);
             const uint32_t box_bytes = f32 ? 4096u : 2048u;
-            uint8_t* qbase = smem + q * (NB * 4096);
+            uint8_t* qbase = stage + q * (NB * 4096);
             if (mp.tma_epi == 2 && half == 0 && lane == 0) {
                 mbar_arrive_expect_tx(&res_bar[q], NB * box_bytes);
                 for (int bx = 0; bx < NB; ++bx) tma_load_3d(qbase + bx * 4096, &tmR, &res_bar[q], n0 + bx * 32, m0 + q * 32, bz);
@@ -604,7 +638,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             const float* rb = (ep.row_bias && m < mp.M) ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
             bool res_waited = (mp.tma_epi != 2);
 #pragma unroll 1
-            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+            for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -629,7 +663,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
                 }
-                if (!res_waited) { mbar_wait(&res_bar[q], 0); res_waited = true; }
+                if (!res_waited) { mbar_wait(&res_bar[q], res_parity); res_waited = true; }
                 uint8_t* box = qbase + (j >> 5) * 4096;
                 if (f32) {
                     uint8_t* rowp = box + lane * 128;
@@ -665,10 +699,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                 }
             }
             fence_proxy_async_smem();                  // staged tile (generic-proxy writes) -> visible to the TMA engine
-            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            quarter_sync();
             if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
                 for (int bx = 0; bx < NB; ++bx)
                     if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * 4096, n0 + bx * 32, m0 + q * 32, bz);
@@ -681,9 +712,9 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             // Phase 2: the warp walks its 32 rows, lanes run along the columns: bias is lane-constant (loaded once), row-bias
             // and residual loads and the output stores are full 128-B lines; 8 rows of loads are in flight before any store.
             constexpr int LDS = BN + 4;                       // (BN+4) % 32 == 4 words: conflict-free 16-B row-strided stores
-            float* stg = reinterpret_cast<float*>(smem) + q * (32 * LDS);
+            float* stg = reinterpret_cast<float*>(stage) + q * (32 * LDS);
 #pragma unroll 1
-            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+            for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -694,15 +725,12 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
                                           __uint_as_float(acc[4 * q4 + 3]));
             }
             // both warps of this lane quarter have staged their columns (named barrier per quarter, 64 threads)
-            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            quarter_sync();
             const long long zc = static_cast<long long>(bz) * ep.strideC, zr = static_cast<long long>(bz) * ep.strideR;
             const bool vec_ok = (mp.N % 4 == 0) && (ep.ldc % 4 == 0) && (!ep.residual || ep.ldr % 4 == 0) &&
                                 (!ep.row_bias || (ep.ld_row_bias ? ep.ld_row_bias : mp.N) % 4 == 0);
             const int rows_here = min(32, mp.M - (m0 + q * 32));     // valid rows of this quarter; this warp takes [r_lo, r_hi)
-            const int r_lo = half * 16, r_hi = min(rows_here, r_lo + 16);
+            const int r_lo = half * (32 / NPART), r_hi = min(rows_here, r_lo + 32 / NPART);
             const long long ldrb = ep.ld_row_bias ? ep.ld_row_bias : mp.N;
             if (ep.act == SDOD_ACT_GEGLU) {
                 // value half = tile columns [0,BN/2), gate half = [BN/2,BN); lanes run along the BN/2 output columns
@@ -836,7 +864,7 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             }
         } else {
 #pragma unroll 1
-            for (int j = half * CH; j < (half + 1) * CH; j += 16) {
+            for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + j, acc);
                 tmem_ld_wait();
@@ -844,6 +872,8 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
             }
         }
         tc_fence_before();
+        if (PERSIST) mbar_arrive(&tmem_empty_bar[ab]);     // every TMEM read of this buffer has completed (tcgen05.wait::ld above)
+        }   // tile loop
     }
     __syncthreads();
     if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the pair may still touch it
@@ -855,17 +885,17 @@ __global__ void __launch_bounds__(kGemmThreads, DEEP ? 1 : 2) gemm_tcgen05_kerne
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN, bool DEEP, bool PAIR>
+template <int BN, bool DEEP, bool PAIR, bool PERSIST = false>
 static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) {
-    using Cfg = GemmCfg<BN, DEEP, PAIR>;
+    using Cfg = GemmCfg<BN, DEEP, PAIR, PERSIST>;
     static bool configured = false;
     if (!configured) {
-        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, DEEP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
     if (!PAIR) {
-        gemm_tcgen05_kernel<BN, DEEP, PAIR><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
+        gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST><<<grid, PERSIST ? kGemmThreadsPersist : kGemmThreads, Cfg::kSmemBytes, stream>>>(g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
         return kOk;
     }
     cudaLaunchConfig_t cfg{};
@@ -874,10 +904,10 @@ static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // two consecutive M tiles
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
     if (e != cudaSuccess) {
         int nc = -1;
-        cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nc, gemm_tcgen05_kernel<BN, DEEP, PAIR>, &cfg);
+        cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nc, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, &cfg);
         return fail(kCudaError, std::string("cudaLaunchKernelEx(gemm pair bn=") + std::to_string(BN) + " deep=" + std::to_string(DEEP) + " grid=" +
                                     std::to_string(grid.x) + "x" + std::to_string(grid.y) + "x" + std::to_string(grid.z) + " smem=" +
                                     std::to_string(Cfg::kSmemBytes) + "): " + cudaGetErrorName(e) + "; max active clusters " + std::to_string(nc) +
@@ -892,6 +922,14 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     dim3 grid(g.n_tiles, g.m_tiles, mp.split > 1 ? mp.split : g.batch);
     if (g.pair) grid = dim3((g.m_tiles + 1) & ~1, g.n_tiles, grid.z);
     const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
+    if constexpr (BN == 128 || BN == 160) {
+        if (g.persist) {
+            const int sms = device_sm_count();
+            SDOD_TRY((launch_gemm_cfg<BN, true, false, true>(stream, g, dim3(mp.tiles_total < sms ? mp.tiles_total : sms))));
+            count_launch();
+            return check_launch("gemm_tcgen05_kernel (persistent)");
+        }
+    }
     if constexpr (BN >= 128) {
         if (g.pair) {
             if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true, true>(stream, g, grid)));
@@ -1046,6 +1084,22 @@ static int setup_heads_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M,
     return kOk;
 }
 
+// Persistent scheduling for short-K, multi-wave GEMMs with a TMA epilogue: the per-tile fill/drain chain dominates there.
+// SDOD_GEMM_PERSIST=0 disables it, =2 uses it wherever legal (A/B measurements).
+static void choose_persist(GemmLaunch* out) {
+    static const int env = [] { const char* e = std::getenv("SDOD_GEMM_PERSIST"); return e ? std::atoi(e) : 1; }();
+    MainloopParams& mp = out->mp;
+    mp.n_tiles = out->n_tiles; mp.m_tiles = out->m_tiles;
+    mp.tiles_total = out->n_tiles * out->m_tiles * out->batch;
+    out->persist = 0;
+    if (!env || out->pair || mp.split > 1 || !mp.tma_epi || (out->bn != 128 && out->bn != 160)) return;
+    const int sms = device_sm_count();
+    if (env == 2) { out->persist = mp.tiles_total > sms; return; }
+    // measured (tools/hot_kernels.py, B200 r1): K=320 GEGLU 111.6 -> 92.2 us, QKV 87.0 -> 82.9 us; K=1280 (20 blocks) 46.1 -> 58.3 us,
+    // where two co-resident CTAs with their own rings hide the loads better than one 4-stage ring
+    out->persist = (mp.tiles_total >= 3 * sms && mp.k_blocks <= 10) ? 1 : 0;
+}
+
 static int k_rotation(int k_blocks) {
     static const int env = [] { const char* e = std::getenv("SDOD_GEMM_KROT"); return e ? std::atoi(e) : 0; }();
     return k_blocks >= 8 ? env : 0;
@@ -1126,6 +1180,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.N + bn - 1) / bn;
     out->batch = d.batch;
+    choose_persist(out);
     return kOk;
 }
 
@@ -1182,6 +1237,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     out->m_tiles = (M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.Cout + bn - 1) / bn;
     out->batch = 1;
+    choose_persist(out);
     return kOk;
 }
 

@@ -23,6 +23,7 @@ struct MainloopParams {
     int tma_epi;       // 0: LSU epilogue; 1: TMA-store epilogue; 2: TMA-store + residual TMA-loaded and added in place
     int c_bytes;       // output element size for the TMA epilogue (2 | 4)
     int k_rot;         // K-loop start rotation per M tile (in K blocks); 0 = every tile starts at block 0
+    int n_tiles, m_tiles, tiles_total;   // persistent scheduling: tile t -> (t % n_tiles, (t / n_tiles) % m_tiles, t / (n_tiles*m_tiles))
 };
 
 struct GemmLaunch {
@@ -31,6 +32,7 @@ struct GemmLaunch {
     sdod_epilogue ep;
     int bn, m_tiles, n_tiles, batch;
     int pair;   // 1: launched as 2-CTA clusters running tcgen05 cta_group::2
+    int persist;   // 1: one CTA per SM walks the tile list (TMEM double-buffered accumulator)
 };
 
 struct AttnLaunch {

@@ -221,6 +221,40 @@ def test_gemm_geglu_packed():
     assert got.shape == (M, 4 * Cc) and rel_err(got, want) < TOL_BF16
 
 
+def test_gemm_persistent_scheduler_epilogues():
+    """Short-K GEMMs with >= 3 waves of tiles run as one persistent CTA per SM (TMEM double-buffered accumulators, the TMA
+    ring running across tile boundaries): every epilogue that can take that path, including a ragged last M tile."""
+    torch.manual_seed(13)
+    M, N, K = 16384 - 40, 640, 128                     # 128 x 4 tiles of 128x160; last M tile has 88 valid rows
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias, res = torch.randn(N, device=DEV), bf(torch.randn(M, N)).to(DEV)
+    res32 = torch.randn(M, N, device=DEV)
+    rowb = torch.randn(4, N, device=DEV)
+    base = a.float() @ w.float().t()
+    assert rel_err(torch.ops.sdod.linear(a, w, bias), base + bias) < TOL_BF16
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, res), base + bias + res.float()) < TOL_BF16
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, res32, 0, 1.0, True), base + bias + res32) < TOL_F32
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, None, C.ACT_GELU), F.gelu(base + bias)) < TOL_BF16
+    want = base + bias + rowb.repeat_interleave(M // 4, dim=0)
+    assert rel_err(torch.ops.sdod.linear(a, w, bias, None, 0, 1.0, False, rowb, M // 4), want) < TOL_BF16
+    # GEGLU (128-wide tiles) and the attention-layout epilogue
+    Cc = 320
+    a2 = bf(torch.randn(8192, Cc)).to(DEV)
+    w2 = bf(torch.randn(8 * Cc, Cc) / Cc ** 0.5).to(DEV)
+    b2 = torch.randn(8 * Cc, device=DEV)
+    h = a2.float() @ w2.float().t() + b2
+    wp, bp = ops.pack_geglu_weight(w2, b2)
+    assert rel_err(torch.ops.sdod.linear(a2, wp, bp, None, C.ACT_GEGLU), h[:, :4 * Cc] * F.gelu(h[:, 4 * Cc:])) < TOL_BF16
+    heads, dh, tokens, B = 8, 40, 4096, 3
+    x = bf(torch.randn(B * tokens, Cc)).to(DEV)
+    wq = bf(torch.randn(3 * Cc, Cc) / Cc ** 0.5).to(DEV)
+    qkv = bf(x.float() @ wq.float().t()).view(B, tokens, 3, Cc)
+    qh, kh, vt = ops.qkv_project(x, wq, heads, dh, tokens)
+    for got, want in ((qh, ops.pack_heads(qkv[:, :, 0], heads, dh)), (kh, ops.pack_heads(qkv[:, :, 1], heads, dh)),
+                      (vt, ops.pack_heads(qkv[:, :, 2], heads, dh, True))):
+        assert got.shape == want.shape and rel_err(got, want) < TOL_BF16
+
+
 def test_gemm_batched():
     torch.manual_seed(13)
     a, w = bf(torch.randn(6, 200, 128)).to(DEV), bf(torch.randn(6, 328, 128) / 11).to(DEV)
