@@ -285,6 +285,8 @@ def run_cfg_split(args, rank, world, local_rank):
 
 
 def main():
+    if os.environ.get("SDOD_GEMM_DBG"):
+        raise SystemExit("SDOD_GEMM_DBG (timing experiments that skip loads or MMAs) must not be set for a benchmark run")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

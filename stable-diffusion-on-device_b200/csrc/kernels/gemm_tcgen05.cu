@@ -414,6 +414,10 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 const int s = g % STAGES;
                 const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
+                if (mp.dbg == 1) {                              // measurement aid: MMA + epilogue only, operands are whatever is in smem
+                    if (!PAIR || rank == 0) mbar_arrive(&full_bar[s]);
+                    continue;
+                }
                 if (PAIR) {
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);     // both CTAs' A + B halves
                     const uint32_t fb = leader_full + s * 8;
@@ -461,6 +465,11 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kABytes);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
+                if (mp.dbg == 2) {                              // measurement aid: loads only, slots are released at once
+                    if (PAIR) tc_commit_pair(&empty_bar[s]);
+                    else tc_commit(&empty_bar[s]);
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     if (PAIR) tc_mma_bf16_pair(tmem_acc, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
@@ -1100,6 +1109,11 @@ static void choose_persist(GemmLaunch* out) {
     out->persist = (mp.tiles_total >= 3 * sms && mp.k_blocks <= 10) ? 1 : 0;
 }
 
+static int debug_mode() {   // SDOD_GEMM_DBG=1: no operand loads, =2: no MMAs (results are garbage; timing experiments only)
+    static const int env = [] { const char* e = std::getenv("SDOD_GEMM_DBG"); return e ? std::atoi(e) : 0; }();
+    return env;
+}
+
 static int k_rotation(int k_blocks) {
     static const int env = [] { const char* e = std::getenv("SDOD_GEMM_KROT"); return e ? std::atoi(e) : 0; }();
     return k_blocks >= 8 ? env : 0;
@@ -1172,7 +1186,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     out->pair = pair ? 1 : 0;
     MainloopParams mp{};
     mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
-    mp.k_rot = k_rotation(mp.k_blocks);
+    mp.k_rot = k_rotation(mp.k_blocks); mp.dbg = debug_mode();
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
@@ -1229,7 +1243,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
-    mp.k_rot = k_rotation(mp.k_blocks);
+    mp.k_rot = k_rotation(mp.k_blocks); mp.dbg = debug_mode();
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));

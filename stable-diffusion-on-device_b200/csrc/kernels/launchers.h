@@ -22,6 +22,7 @@ struct MainloopParams {
     unsigned int* counters;   // one ticket per output tile, self-resetting
     int tma_epi;       // 0: LSU epilogue; 1: TMA-store epilogue; 2: TMA-store + residual TMA-loaded and added in place
     int c_bytes;       // output element size for the TMA epilogue (2 | 4)
+    int dbg;           // 0 normal; 1 skip operand loads; 2 skip MMAs (timing experiments, SDOD_GEMM_DBG)
     int k_rot;         // K-loop start rotation per M tile (in K blocks); 0 = every tile starts at block 0
     int n_tiles, m_tiles, tiles_total;   // persistent scheduling: tile t -> (t % n_tiles, (t / n_tiles) % m_tiles, t / (n_tiles*m_tiles))
 };
