@@ -201,6 +201,28 @@ def run_ours(args, rank, world, local_rank):
             step_ms.append(a.elapsed_time(b))
     unet_p50 = statistics.median(step_ms)
     unet_launches = unet.launches_per_forward(2)
+    del unet
+
+    # ---- dominant kernel (gemm_tcgen05_kernel: every linear layer and 3x3 conv of the step): device time of each of its
+    #      launches in one UNet pass at this run's batch (2 x images per step), CUDA events between the ops of the plan on
+    #      the launching stream; algorithmic FLOPs from the layer shapes.
+    Bk = 2 * n
+    unet_b = M.UNet(None, seed=0, latent_hw=64, max_batch=Bk)
+    unet_b.set_context(torch.randn(Bk, 77, 768, device=dev))
+    xb, embb = torch.randn(Bk, 64, 64, 4, device=dev), torch.randn(Bk, 1280, device=dev)
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            unet_b.forward_nhwc(xb, embb)
+        rows = unet_b.profile(Bk, 5)
+    gemm_ms, gemm_flop, gemm_n, all_ms = 0.0, 0.0, 0, 0.0
+    for ms, name in rows:
+        all_ms += ms
+        f = op_flops(name, Bk)
+        if f:
+            gemm_ms += ms
+            gemm_flop += f
+            gemm_n += 1
+    del unet_b
 
     tot_dev_s = sum(dev_ms) / 1000.0
     t_dev = torch.tensor([tot_dev_s, wall_e2e, wall_dev], dtype=torch.float64, device=dev)
@@ -221,10 +243,16 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": images / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * (2 * 77 * 768 * 4 + 4 * 64 * 64 * 4)),
                     "d2h_bytes_per_step": int(n * 512 * 512 * 3), "timing": "wall clock around libsdod_b200_generate with host buffers; max over ranks"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "UNet denoising step, batch 2 (one CUDA-graph replay of %d kernels)" % unet_launches,
-                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-                         "frac_of_burst_peak": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + " (sustained: timed inside a long step)",
-                         "algorithmic_tflop_per_launch": UNET_STEP_TFLOP, "traffic": None},
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel: the %d linear / conv3x3 launches of one batch-%d UNet pass" % (gemm_n, Bk),
+                         "achieved": gemm_flop / (gemm_ms * 1e-3) * 1e-12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": gemm_flop / (gemm_ms * 1e-3) * 1e-12 / pk["bf16_tflops_sustained"],
+                         "peak_source": pk["source"] + " (sustained: the launches are timed inside a long step)",
+                         "algorithmic_gflop_per_launch": gemm_flop / gemm_n * 1e-9, "avg_launch_us": 1e3 * gemm_ms / gemm_n,
+                         "share_of_unet_pass": gemm_ms / all_ms, "traffic": traffic_from_profiles(),
+                         "traffic_note": "mean dram__bytes_read+write per gemm_tcgen05 launch, ncu capture of the same pass (profiles/r01_gemm_traffic.json)"},
+            "step_roofline": {"bound": "tensor", "kernel": "whole UNet denoising step, batch 2 (one CUDA-graph replay of %d kernels)" % unet_launches,
+                              "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                              "frac_of_burst_peak": achieved / pk["bf16_tflops"], "algorithmic_tflop_per_launch": UNET_STEP_TFLOP},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
@@ -282,6 +310,27 @@ def run_cfg_split(args, rank, world, local_rank):
                                                           "exchange": "2-rank NCCL all-gather of eps per step, %d bytes per rank per image-step" % (64 * 64 * 4 * 4)},
                           "eps_bytes_exchanged_per_generate": nbytes}))
     dist.destroy_process_group()
+
+
+def op_flops(name, batch):
+    """Algorithmic FLOPs of one op of the UNet plan from its profile name (None for non-GEMM ops)."""
+    import re
+    m = re.match(r"gemm M(\d+) N(\d+) K(\d+)", name)
+    if m:
+        return 2.0 * int(m.group(1)) * int(m.group(2)) * int(m.group(3))
+    m = re.match(r"conv3 HW(\d+) Cin(\d+) Cout(\d+)", name)
+    if m:
+        return 2.0 * batch * int(m.group(1)) * int(m.group(3)) * 9 * int(m.group(2))
+    return None
+
+
+def traffic_from_profiles():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if absent)."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        return json.load(open(path))["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def main():
