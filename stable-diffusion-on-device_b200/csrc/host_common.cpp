@@ -1,6 +1,7 @@
 #include "host_common.h"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace sdod {
@@ -70,6 +71,17 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(kCudaError, "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string(static_cast<int>(r)));
     return kOk;
+}
+
+static thread_local bool g_pdl_thread = true;
+bool set_pdl_for_thread(bool on) {
+    const bool prev = g_pdl_thread;
+    g_pdl_thread = on;
+    return prev;
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("SDOD_PDL"); return !e || std::atoi(e) != 0; }();
+    return on && g_pdl_thread;
 }
 
 int device_sm_count() {

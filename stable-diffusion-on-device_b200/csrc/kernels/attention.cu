@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint32_t tmem_O = tmem_base + 128;
+    griddep_wait();                    // PDL: the setup above overlapped the projection GEMM's tail
+    griddep_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -337,8 +339,8 @@ static int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid((a.Nq + kBQ - 1) / kBQ, a.BH);
-    attention_kernel<DH><<<grid, kAttThreads, Cfg::kSmemBytes, stream>>>(a.tmQ, a.tmK, a.tmV, static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv,
-                                                                         a.scale_log2);
+    SDOD_TRY(check_cuda(launch_pdl(attention_kernel<DH>, grid, dim3(kAttThreads), Cfg::kSmemBytes, stream, a.tmQ, a.tmK, a.tmV,
+                                   static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv, a.scale_log2), "launch attention_kernel"));
     count_launch();
     return check_launch("attention_kernel");
 }

@@ -44,6 +44,8 @@ template <> SDOD_DEVICE void ld8<float>(const float* p, float* f) {
 template <typename T, int NV, int R>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
                                                          const float* __restrict__ b, int rows, int width, float eps) {
+    griddep_wait();
+    griddep_launch();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int row0 = warp * R;
@@ -184,6 +186,8 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y
 
 // ---------------------------------------------------------------- channel concat [rows,Ca] ++ [rows,Cb]
 __global__ void concat_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb, uint4* __restrict__ y, long long rows) {
+    griddep_wait();
+    griddep_launch();
     const int vt = va + vb;
     const size_t total = static_cast<size_t>(rows) * vt;
     for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -240,8 +244,17 @@ __global__ void im2col3x3_vec_kernel(const T* __restrict__ x, uint4* __restrict_
 }
 
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n) {
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        y[i] = __float2bfloat16(x[i]);
+    griddep_wait();
+    griddep_launch();
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nth = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const size_t n8 = vec ? n / 8 : 0;                      // 8 elements per thread: two 16-B loads, one 16-B store
+    for (size_t i = tid; i < n8; i += nth) {
+        const float4 lo = reinterpret_cast<const float4*>(x)[2 * i], hi = reinterpret_cast<const float4*>(x)[2 * i + 1];
+        float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        reinterpret_cast<uint4*>(y)[i] = pack8(f);
+    }
+    for (size_t i = n8 * 8 + tid; i < n; i += nth) y[i] = __float2bfloat16(x[i]);
 }
 __global__ void silu_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t n) {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -280,9 +293,9 @@ SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, 
     do {                                                                                                                                         \
         const unsigned grid = static_cast<unsigned>((rows + 8 * R - 1) / (8 * R));                                                               \
         if (in_dtype == SDOD_F32)                                                                                                                \
-            layer_norm_kernel<float, NV, R><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps); \
+            launch_pdl(layer_norm_kernel<float, NV, R>, dim3(grid), dim3(256), 0, ST(stream), static_cast<const float*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps); \
         else                                                                                                                                     \
-            layer_norm_kernel<bf16, NV, R><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);  \
+            launch_pdl(layer_norm_kernel<bf16, NV, R>, dim3(grid), dim3(256), 0, ST(stream), static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);  \
     } while (0)
     if (nv <= 2) SDOD_LN(2, 4);
     else if (nv <= 3) SDOD_LN(3, 2);
@@ -333,8 +346,9 @@ SDOD_API int sdod_concat_channels(sdod_stream_t stream, const void* a, int Ca, c
     if (!a || !b || !y || Ca % 8 != 0 || Cb % 8 != 0) return fail(kInvalidArgument, "concat_channels: NULL tensor or C % 8 != 0");
     const int per = dtype == SDOD_F32 ? 4 : 8;     // elements per 16-byte unit
     const size_t n = static_cast<size_t>(rows) * ((Ca + Cb) / per);
-    concat_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(a), Ca / per, static_cast<const uint4*>(b), Cb / per,
-                                                           static_cast<uint4*>(y), rows);
+    if (launch_pdl(concat_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, ST(stream), static_cast<const uint4*>(a), Ca / per, static_cast<const uint4*>(b),
+                   Cb / per, static_cast<uint4*>(y), rows) != cudaSuccess)
+        return check_launch("concat_kernel");
     count_launch();
     return check_launch("concat_kernel");
 }
@@ -362,7 +376,8 @@ SDOD_API int sdod_im2col3x3(sdod_stream_t stream, const void* x, int in_dtype, v
 SDOD_API int sdod_cast_f32_to_bf16(sdod_stream_t stream, const float* x, void* y, size_t n) {
     if (!x || !y) return fail(kInvalidArgument, "cast_f32_to_bf16: NULL tensor");
     if (n == 0) return kOk;
-    cast_f32_to_bf16_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(x, static_cast<bf16*>(y), n);
+    if (launch_pdl(cast_f32_to_bf16_kernel, dim3(ew_grid((n + 7) / 8, 256)), dim3(256), 0, ST(stream), x, static_cast<bf16*>(y), n) != cudaSuccess)
+        return check_launch("cast_f32_to_bf16_kernel");
     count_launch();
     return check_launch("cast_f32_to_bf16_kernel");
 }

@@ -267,6 +267,8 @@ SDOD_DEVICE void epilogue_geglu16(const sdod_epilogue& ep, const MainloopParams&
 // 16 row segments of 32 B (fp32) — coalesced both ways.  grid = (BN/16 chunks, tiles).
 template <int BN>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams mp, const sdod_epilogue ep, int n_tiles) {
+    griddep_wait();
+    griddep_launch();
     const int tile = blockIdx.y;
     const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
     const float* base = mp.ws + static_cast<long long>(tile) * mp.split * (BN * kBlockM);
@@ -385,6 +387,13 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     if (PAIR) cluster_sync_all();      // the peer's barriers exist before any TMA / commit of ours can signal them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    // PDL: everything above overlapped the previous kernel's tail; its outputs are visible from here.  CTA-pair kernels stay out of
+    // it (ordinary launch, no early trigger): a cta_group::2 TMEM allocation racing the neighbour kernel's allocation on the same
+    // SM pair deadlocked the step (B200, r1).
+    if (!PAIR) {
+        griddep_wait();
+        griddep_launch();
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -904,15 +913,16 @@ static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) 
         configured = true;
     }
     if (!PAIR) {
-        gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST><<<grid, PERSIST ? kGemmThreadsPersist : kGemmThreads, Cfg::kSmemBytes, stream>>>(g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
-        return kOk;
+        return check_cuda(launch_pdl(gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, grid, dim3(PERSIST ? kGemmThreadsPersist : kGemmThreads),
+                                     Cfg::kSmemBytes, stream, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep),
+                          "launch gemm_tcgen05_kernel");
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // two consecutive M tiles
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;      // no programmatic serialization for pairs (see the kernel)
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
     if (e != cudaSuccess) {
         int nc = -1;
@@ -953,7 +963,7 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
     if (mp.split > 1) {
         dim3 rgrid(BN / 16, g.m_tiles * g.n_tiles);
-        splitk_reduce_kernel<BN><<<rgrid, 256, 0, stream>>>(mp, g.ep, g.n_tiles);
+        SDOD_TRY(check_cuda(launch_pdl(splitk_reduce_kernel<BN>, rgrid, dim3(256), 0, stream, mp, g.ep, g.n_tiles), "launch splitk_reduce_kernel"));
         count_launch();
         return check_launch("splitk_reduce_kernel");
     }

@@ -255,6 +255,8 @@ __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __res
                                      unsigned int* __restrict__ counters, float* __restrict__ stats, int C, int HW, int G,
                                      int rows_per_slab, float eps) {
     constexpr int VEC = kNhwcVec;
+    griddep_wait();
+    griddep_launch();
     extern __shared__ float gsm[];          // [r][C][2] then reused
     __shared__ float pivots[64];
     __shared__ int is_last;
@@ -355,6 +357,8 @@ __global__ void gn_nhwc_apply_kernel(const TI* __restrict__ x, TO* __restrict__ 
                                      const float* __restrict__ bias, const float* __restrict__ add_nc,
                                      const float* __restrict__ stats, int C, int HW, int G, int rows_per_slab, int fuse_silu) {
     constexpr int VEC = kNhwcVec;
+    griddep_wait();
+    griddep_launch();
     const int n = blockIdx.y, slab = blockIdx.x;
     const int cvec = C / VEC;
     const int r = blockDim.x / cvec;
@@ -439,9 +443,11 @@ static int group_norm_nhwc_typed(cudaStream_t stream, const TI* x, TO* y, const 
         SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_stats_kernel<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                             "cudaFuncSetAttribute(gn stats)"));
     }
-    gn_nhwc_stats_kernel<TI><<<dim3(S, N), threads, smem, stream>>>(x, add_nc, partials, counters, stats, C, HW, G, rps, eps);
+    SDOD_TRY(check_cuda(launch_pdl(gn_nhwc_stats_kernel<TI>, dim3(S, N), dim3(threads), smem, stream, x, add_nc, partials, counters, stats, C, HW, G,
+                                   rps, eps), "launch gn_nhwc_stats_kernel"));
     SDOD_TRY(check_launch("gn_nhwc_stats_kernel"));
-    gn_nhwc_apply_kernel<TI, TO><<<dim3(S, N), threads, 0, stream>>>(x, y, weight, bias, add_nc, stats, C, HW, G, rps, fuse_silu);
+    SDOD_TRY(check_cuda(launch_pdl(gn_nhwc_apply_kernel<TI, TO>, dim3(S, N), dim3(threads), 0, stream, x, y, weight, bias, add_nc,
+                                   static_cast<const float*>(stats), C, HW, G, rps, fuse_silu), "launch gn_nhwc_apply_kernel"));
     count_launch(2);
     return check_launch("gn_nhwc_apply_kernel");
 }

@@ -396,7 +396,10 @@ int UNet::forward(cudaStream_t s, const float* x, const float* emb, float* eps, 
         const size_t nx = static_cast<size_t>(B) * hw_ * hw_ * 4 * sizeof(float);
         if (x != x_in_) SDOD_TRY(check_cuda(cudaMemcpyAsync(x_in_, x, nx, cudaMemcpyDeviceToDevice, s), "copy x"));
         if (emb != emb_in_) SDOD_TRY(check_cuda(cudaMemcpyAsync(emb_in_, emb, static_cast<size_t>(B) * kTed * sizeof(float), cudaMemcpyDeviceToDevice, s), "copy emb"));
-        SDOD_TRY(p->run(s, use_graph));
+        const bool prev = set_pdl_for_thread(B <= 4);     // baked into the graph at capture time; see host_common.h
+        const int st = p->run(s, use_graph);
+        set_pdl_for_thread(prev);
+        SDOD_TRY(st);
         if (eps != eps_out_) SDOD_TRY(check_cuda(cudaMemcpyAsync(eps, eps_out_, nx, cudaMemcpyDeviceToDevice, s), "copy eps"));
         return kOk;
     } catch (const std::exception& e) {
