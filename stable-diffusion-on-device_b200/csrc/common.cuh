@@ -96,6 +96,8 @@ SDOD_DEVICE void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
 SDOD_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 SDOD_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 SDOD_DEVICE void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk group of this thread have finished reading their shared-memory source
+SDOD_DEVICE void bulk_wait_read_but_last() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // ------------------------------------------------------------------ tcgen05 / TMEM
 template <int kCols>
@@ -300,6 +302,39 @@ SDOD_DEVICE uint64_t add_f32x2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
+}
+
+SDOD_DEVICE uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// Two exact-erf GELUs at once on the packed-fp32 pipe (same A&S 7.1.26 form as gelu_f; the polynomial carries negated
+// coefficients so that no operand negation is needed): ~11 issue slots per element instead of ~19.
+SDOD_DEVICE uint64_t gelu_f32x2(uint64_t x) {
+    const uint64_t z = mul_f32x2(x, pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f));
+    const uint64_t az = z & 0x7fffffff7fffffffull;
+    float d0, d1;
+    unpack_f32x2(fma_f32x2(pack_f32x2(0.3275911f, 0.3275911f), az, pack_f32x2(1.0f, 1.0f)), d0, d1);
+    float t0, t1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    const uint64_t t = pack_f32x2(t0, t1);
+    uint64_t q = fma_f32x2(pack_f32x2(-1.061405429f, -1.061405429f), t, pack_f32x2(1.453152027f, 1.453152027f));
+    q = fma_f32x2(q, t, pack_f32x2(-1.421413741f, -1.421413741f));
+    q = fma_f32x2(q, t, pack_f32x2(0.284496736f, 0.284496736f));
+    q = fma_f32x2(q, t, pack_f32x2(-0.254829592f, -0.254829592f));
+    q = mul_f32x2(q, t);                                                   // -(a1 t + ... + a5 t^5)
+    float a0, a1;
+    unpack_f32x2(mul_f32x2(mul_f32x2(az, pack_f32x2(1.2011224087864498f, 1.2011224087864498f)),
+                           mul_f32x2(az, pack_f32x2(-1.2011224087864498f, -1.2011224087864498f))), a0, a1);   // -z^2 log2(e)
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    const uint64_t y = fma_f32x2(q, pack_f32x2(e0, e1), pack_f32x2(1.0f, 1.0f));                             // erf(|z|)
+    const uint64_t erf2 = y | (z & 0x8000000080000000ull);                                                   // y >= 0: copy z's sign in
+    const uint64_t hx = mul_f32x2(x, pack_f32x2(0.5f, 0.5f));
+    return fma_f32x2(hx, erf2, hx);
 }
 
 SDOD_DEVICE float warp_sum(float v) {

@@ -53,10 +53,11 @@ struct GemmCfg {
     static constexpr int kShallow = PAIR ? (BN >= 256 ? 5 : 4) : ((BN >= 256) ? 4 : (BN >= 128 ? 3 : 4));
     static constexpr int kDeepRaw = (220 * 1024 - 2048) / kStageBytes;
     static constexpr int kEpiBytes = PERSIST ? BN * 512 : 0;          // dedicated epilogue staging (4 quarters x BN/32 boxes x 4 KiB)
-    static constexpr int kPersistRaw = (232448 - 1024 - 256 - 2048 - kEpiBytes) / kStageBytes;
+    static constexpr int kBiasBytes = 2 * BN * 4 < 1024 ? 1024 : 2 * BN * 4;      // two bias tiles (double-buffered when persistent)
+    static constexpr int kPersistRaw = (232448 - 1024 - 256 - kBiasBytes - kEpiBytes) / kStageBytes;
     static constexpr int kStages = PERSIST ? (kPersistRaw > 8 ? 8 : kPersistRaw) : (DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow);
     static constexpr int kTmemCols = PERSIST ? (2 * BN <= 256 ? 256 : 512) : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias tiles*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
     static_assert(PERSIST || kStages * kStageBytes >= 512 * (BN + 4), "the idle ring doubles as the epilogue staging area");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
 };
@@ -323,7 +324,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
     epilogue_geglu16<BN>(ep, mp, 0, m_tile * kBlockM + row, n_tile, j, a, g);
 }
 
-#define SDOD_TILE_LOOP for (int t = PERSIST ? static_cast<int>(blockIdx.x) : 0, iter = 0; t < (PERSIST ? mp.tiles_total : 1); t += (PERSIST ? static_cast<int>(gridDim.x) : 1), ++iter)
+// persistent CTAs take every gridDim.x-th tile (N fastest).  (Contiguous chunks per CTA, which would let the producer keep the A rows
+// resident across the N tiles of one M tile, measured 10 % slower on the 64x64 GEGLU projection: the CTAs of a wave then touch
+// 148 different A tiles at once instead of ~8, and the layer is epilogue-bound, not L2-bound — profiles/r01_gemm_load_vs_mma.txt.)
+#define SDOD_TILE_LOOP                                                                                                               \
+    for (int t = PERSIST ? static_cast<int>(blockIdx.x) : 0, iter = 0, t_end = PERSIST ? mp.tiles_total : 1; t < t_end;                \
+         t += (PERSIST ? static_cast<int>(gridDim.x) : 1), ++iter)
 #define SDOD_TILE_COORDS                                                                                               \
     const int n_tile = PERSIST ? t % mp.n_tiles : static_cast<int>(PAIR ? blockIdx.y : blockIdx.x);                    \
     const int m_tile = PERSIST ? (t / mp.n_tiles) % mp.m_tiles : static_cast<int>(PAIR ? blockIdx.x : blockIdx.y);     \
@@ -499,9 +505,20 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         SDOD_TILE_COORDS
         const int ab = PERSIST ? (iter & 1) : 0;
         float* s_bias = s_bias_base + ab * BN;         // double-buffered: a fast warp may already stage the next tile's bias
-        if (mp.tma_epi) {                              // stage this tile's bias while the mainloop runs
-            for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
+        // Bias tile: staged while the mainloop runs.  A persistent CTA stages tile i+1's bias during tile i's epilogue (the global
+        // load is issued here and parked in a register; it lands in the other buffer at the end of the iteration), so no tile starts
+        // with an exposed L2 round trip.
+        const int te = static_cast<int>(threadIdx.x) - 64;
+        float bias_next = 0.f;
+        const bool stage_next = PERSIST && mp.tma_epi && t + static_cast<int>(gridDim.x) < t_end && te < BN;
+        if (mp.tma_epi) {
+            if (!PERSIST || iter == 0)
+                for (int i = te; i < BN; i += 32 * EW) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
             asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");   // (persistent: also orders the previous tile's staging reads/stores)
+            if (stage_next) {
+                const int n_next = ((t + static_cast<int>(gridDim.x)) % mp.n_tiles) * BN + te;
+                bias_next = (ep.bias && n_next < mp.N) ? __ldg(ep.bias + n_next) : 0.f;
+            }
         }
         mbar_wait(&tmem_full_bar[ab], PERSIST ? ((iter >> 1) & 1) : 0);
         tc_fence_after();
@@ -536,7 +553,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             // BN/2 bf16 columns wide (64-B swizzled 32x32 boxes).
             constexpr int HALF = BN / 2;
             constexpr int NBG = HALF / 32 > 0 ? HALF / 32 : 1;
-            uint8_t* qbase = stage + q * (NBG * 4096);
+            // (persistent: two staging buffers, so this tile's stores may still be reading while the next tile is staged)
+            const bool dbuf = PERSIST && 8 * NBG * 4096 <= Cfg::kEpiBytes;
+            uint8_t* qbase = stage + (dbuf ? (iter & 1) * (Cfg::kEpiBytes / 2) : 0) + q * (NBG * 4096);
 #pragma unroll 1
             for (int j = g_lo; j < g_hi; j += 16) {
                 uint32_t a[16], g[16];
@@ -544,14 +563,18 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 tmem_ld16(taddr + HALF + j, g);
                 tmem_ld_wait();
                 float v[16];
+                const uint64_t alpha2 = pack_f32x2(ep.alpha, ep.alpha);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const float4 ba = *reinterpret_cast<const float4*>(s_bias + j + 4 * q4);
                     const float4 bg = *reinterpret_cast<const float4*>(s_bias + HALF + j + 4 * q4);
-                    v[4 * q4] = fmaf(__uint_as_float(a[4 * q4]), ep.alpha, ba.x) * gelu_f(fmaf(__uint_as_float(g[4 * q4]), ep.alpha, bg.x));
-                    v[4 * q4 + 1] = fmaf(__uint_as_float(a[4 * q4 + 1]), ep.alpha, ba.y) * gelu_f(fmaf(__uint_as_float(g[4 * q4 + 1]), ep.alpha, bg.y));
-                    v[4 * q4 + 2] = fmaf(__uint_as_float(a[4 * q4 + 2]), ep.alpha, ba.z) * gelu_f(fmaf(__uint_as_float(g[4 * q4 + 2]), ep.alpha, bg.z));
-                    v[4 * q4 + 3] = fmaf(__uint_as_float(a[4 * q4 + 3]), ep.alpha, ba.w) * gelu_f(fmaf(__uint_as_float(g[4 * q4 + 3]), ep.alpha, bg.w));
+                    // value * gelu(gate), two columns per packed-fp32 instruction
+                    const uint64_t a01 = fma_f32x2(pack_f32x2(__uint_as_float(a[4 * q4]), __uint_as_float(a[4 * q4 + 1])), alpha2, pack_f32x2(ba.x, ba.y));
+                    const uint64_t a23 = fma_f32x2(pack_f32x2(__uint_as_float(a[4 * q4 + 2]), __uint_as_float(a[4 * q4 + 3])), alpha2, pack_f32x2(ba.z, ba.w));
+                    const uint64_t g01 = fma_f32x2(pack_f32x2(__uint_as_float(g[4 * q4]), __uint_as_float(g[4 * q4 + 1])), alpha2, pack_f32x2(bg.x, bg.y));
+                    const uint64_t g23 = fma_f32x2(pack_f32x2(__uint_as_float(g[4 * q4 + 2]), __uint_as_float(g[4 * q4 + 3])), alpha2, pack_f32x2(bg.z, bg.w));
+                    unpack_f32x2(mul_f32x2(a01, gelu_f32x2(g01)), v[4 * q4], v[4 * q4 + 1]);
+                    unpack_f32x2(mul_f32x2(a23, gelu_f32x2(g23)), v[4 * q4 + 2], v[4 * q4 + 3]);
                 }
                 uint8_t* rowp = qbase + (j >> 5) * 4096 + lane * 64;
                 const int u0 = (j & 31) >> 3;
@@ -569,7 +592,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 for (int bx = 0; bx < NBG; ++bx)
                     if (n_tile * HALF + bx * 32 < mp.N / 2) tma_store_3d(&tmC, qbase + bx * 4096, n_tile * HALF + bx * 32, m0 + q * 32, bz);
                 bulk_commit();
-                bulk_wait_read_all();
+                if (dbuf) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
+                else bulk_wait_read_all();
             }
         } else if (ep.act == SDOD_ACT_GEGLU && !(ep.out_mode == SDOD_OUT_BF16 && mp.N % 8 == 0 && ep.ldc % 4 == 0)) {
             constexpr int HALF = BN / 2;
@@ -587,7 +611,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             // Q/K box: [32 tokens][40 d] (80-B rows: conflict-free 16-B stores) -> HEADS [B*heads, tokens, dpad] at (d0, tok, bh).
             // V box  : [40 d][32 tokens] (thread = token writes a column)       -> HEADS_T [B*heads, vt_rows, tok_pad] at (tok, d0, bh).
             constexpr int BOXB = 40 * 32 * 2;
-            uint8_t* qbase = stage + q * (4 * BOXB);
+            const bool dbuf = PERSIST && 8 * 4 * BOXB <= Cfg::kEpiBytes;
+            uint8_t* qbase = stage + (dbuf ? (iter & 1) * (Cfg::kEpiBytes / 2) : 0) + q * (4 * BOXB);
             const int Cw = ep.heads * ep.head_dim;
             const int which = ep.out_mode == SDOD_OUT_QKV ? n0 / Cw : (ep.out_mode == SDOD_OUT_HEADS_T ? 2 : 0);
 #pragma unroll 1
@@ -637,7 +662,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     else tma_store_3d(&tmC2, qbase + bx * BOXB, tok, d0, bh);
                 }
                 bulk_commit();
-                bulk_wait_read_all();
+                if (dbuf) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
+                else bulk_wait_read_all();
             }
         } else if (mp.tma_epi) {
             // TMA epilogue.  The idle TMA ring becomes a staging area of 32x32-element boxes (128-B or 64-B swizzled rows).
@@ -648,10 +674,12 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             constexpr int NB = BN / 32;
             const bool f32 = (mp.c_bytes == 4);
             const uint32_t box_bytes = f32 ? 4096u : 2048u;
-            uint8_t* qbase = stage + q * (NB * 4096);
+            const bool dbuf = PERSIST && !f32;           // bf16 boxes are 2 KiB: two staging buffers fit the region sized for fp32
+            const uint32_t bstr = dbuf ? 2048u : 4096u;  // box stride
+            uint8_t* qbase = stage + (dbuf ? (iter & 1) * (Cfg::kEpiBytes / 2) : 0) + q * (NB * bstr);
             if (mp.tma_epi == 2 && half == 0 && lane == 0) {
                 mbar_arrive_expect_tx(&res_bar[q], NB * box_bytes);
-                for (int bx = 0; bx < NB; ++bx) tma_load_3d(qbase + bx * 4096, &tmR, &res_bar[q], n0 + bx * 32, m0 + q * 32, bz);
+                for (int bx = 0; bx < NB; ++bx) tma_load_3d(qbase + bx * bstr, &tmR, &res_bar[q], n0 + bx * 32, m0 + q * 32, bz);
             }
             const float* rb = (ep.row_bias && m < mp.M) ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
             bool res_waited = (mp.tma_epi != 2);
@@ -682,7 +710,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
                 }
                 if (!res_waited) { mbar_wait(&res_bar[q], res_parity); res_waited = true; }
-                uint8_t* box = qbase + (j >> 5) * 4096;
+                uint8_t* box = qbase + (j >> 5) * bstr;
                 if (f32) {
                     uint8_t* rowp = box + lane * 128;
                     const int u0 = (j & 31) >> 2;
@@ -720,9 +748,10 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             quarter_sync();
             if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
                 for (int bx = 0; bx < NB; ++bx)
-                    if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * 4096, n0 + bx * 32, m0 + q * 32, bz);
+                    if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
                 bulk_commit();
-                bulk_wait_read_all();                  // smem may be released once the stores have read it
+                if (dbuf) bulk_wait_read_but_last();
+                else bulk_wait_read_all();             // smem may be released once the stores have read it
             }
         } else if (ep.out_mode == SDOD_OUT_BF16 || ep.out_mode == SDOD_OUT_F32) {
             // Coalesced epilogue.  Phase 1: each thread owns one accumulator row (tcgen05.ld 32x32b) and copies it with 16-B
@@ -890,8 +919,10 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             }
         }
         tc_fence_before();
+        if (stage_next) s_bias_base[(ab ^ 1) * BN + te] = bias_next;
         if (PERSIST) mbar_arrive(&tmem_empty_bar[ab]);     // every TMEM read of this buffer has completed (tcgen05.wait::ld above)
         }   // tile loop
+        if (PERSIST) bulk_wait_read_all();                 // (storing threads) shared memory stays valid until the last store has read it
     }
     __syncthreads();
     if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the pair may still touch it
