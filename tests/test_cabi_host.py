@@ -109,3 +109,32 @@ def test_libsdod_api_argument_and_context_errors_without_gpu():
     if not torch.cuda.is_available():
         assert lib.libsdod_setup(ctypes.byref(ctx), b"random-init", 4, 64, 8, 20, 0, 1) == A.RUNTIME_ERROR    # no CPU fallback
         assert b"no CUDA device" in lib.libsdod_get_last_error_extra_info(A.RUNTIME_ERROR, None)
+
+
+def test_checkpoint_conversion_roundtrip(tmp_path):
+    """SD checkpoint key layout -> models_dir files (row f2): prefixes stripped, tensors bit-identical, foreign keys dropped."""
+    import torch
+    from sdod import checkpoint as CK
+    g = torch.Generator().manual_seed(5)
+    full = {
+        "model.diffusion_model.time_embed.0.weight": torch.randn(8, 4, generator=g),
+        "model.diffusion_model.input_blocks.0.0.bias": torch.randn(6, generator=g),
+        "first_stage_model.decoder.conv_in.weight": torch.randn(3, 2, 3, 3, generator=g),
+        "first_stage_model.post_quant_conv.bias": torch.randn(4, generator=g),
+        "first_stage_model.encoder.conv_in.weight": torch.randn(2, 2, generator=g),      # not on the path
+        "cond_stage_model.transformer.text_model.embeddings.position_ids": torch.arange(5),
+    }
+    ck = tmp_path / "sd.ckpt"
+    torch.save({"state_dict": full}, ck)
+    nu, nv = CK.convert(str(ck), str(tmp_path / "models"))
+    assert (nu, nv) == (2, 2)
+    u = CK.read_weight_file(str(tmp_path / "models" / "unet.sdodw"))
+    v = CK.read_weight_file(str(tmp_path / "models" / "vae_decoder.sdodw"))
+    assert set(u) == {"time_embed.0.weight", "input_blocks.0.0.bias"} and set(v) == {"decoder.conv_in.weight", "post_quant_conv.bias"}
+    assert torch.equal(u["time_embed.0.weight"], full["model.diffusion_model.time_embed.0.weight"])
+    assert torch.equal(v["decoder.conv_in.weight"], full["first_stage_model.decoder.conv_in.weight"])
+    # bare module state_dicts (what the oracle produces) pass through unchanged
+    bu, bv = CK.split_sd_state_dict({"out.2.bias": torch.zeros(4), "decoder.norm_out.bias": torch.zeros(2)})
+    assert list(bu) == ["out.2.bias"] and list(bv) == ["decoder.norm_out.bias"]
+    with pytest.raises(ValueError):
+        CK.convert({"foo": torch.zeros(1)}, str(tmp_path / "none"))
