@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--images-per-step", type=int, default=4)
+    ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="sample-parallel", choices=["sample-parallel", "cfg-split"])
