@@ -225,15 +225,17 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                 l_run = fmaf(l_run, alpha, (a0 + a1) + (a2 + a3));
             }
             m_run = m_new;
-            if (j >= 2) mbar_wait(&p_free[b], (u - 1) & 1);          // PV_{j-2} has consumed P buffer b
+            // P buffer b is free: the MMA thread issues S_j after PV_{j-2}, and a tcgen05.commit covers every MMA issued before it, so
+            // having seen s_full for tile j already implies PV_{j-2} has consumed this buffer.  (A satisfied mbarrier wait still costs
+            // ~200 clk here — clock64 phase timing, profiles/r01_attention_notes.txt — so the loop keeps exactly one per tile.)
             uint8_t* prow = sP + b * Cfg::kPBytes + row * 128;
 #pragma unroll
             for (int un = 0; un < 4; ++un)
                 *reinterpret_cast<uint4*>(prow + (((half * 4 + un) ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
-            // o_ready must be observed every tile, in lockstep: an mbarrier parity wait is only meaningful while the waiter is at
-            // most one phase behind.  PV_{j-1} was issued a whole softmax iteration ago, so this wait is almost always satisfied.
-            if (j > 0) mbar_wait(o_ready, (j - 1) & 1);
-            if (j > 0 && __any_sync(0xffffffffu, need)) {            // PV_{j-1} complete: this warp's accumulator may be rescaled
+            if (j > 0 && __any_sync(0xffffffffu, need)) {            // rare: this warp's accumulator must be rescaled
+                // PV_{j-1} must have completed.  s_full(j) above proves PV_{j-2} has, so o_ready is either in phase j-1 (pending) or
+                // already past it: the parity test is unambiguous even though this wait is not taken every tile.
+                mbar_wait(o_ready, (j - 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < Cfg::kDV / 16; ++c) {
