@@ -48,7 +48,7 @@ SDOD_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 SDOD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) __trap();
+        if (++spins > (1u << 24)) __trap();   // a failed try_wait already suspends for a while: this is seconds, not a hot loop
     }
 }
 

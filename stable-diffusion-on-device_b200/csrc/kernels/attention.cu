@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     uint64_t* p_full = s_free + 2;                // [2]
     uint64_t* p_free = p_full + 2;                // [2]
     uint64_t* o_ready = p_free + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+    uint64_t* o_final = o_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
     float* xch = reinterpret_cast<float*>(bars + 32);          // [2 tile parities][2 halves][128 rows] partner exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 256); mbar_init(&p_full[b], 256); mbar_init(&p_free[b], 1); }
         mbar_init(o_ready, 1);
+        mbar_init(o_final, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                     tc_commit(o_ready);
                 }
             }
+            tc_commit(o_final);                                      // every PV has retired
         }
     } else {
         // ---------------------------------------------------------------- softmax / lazy correction / epilogue
@@ -261,7 +264,9 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
         const float f_me = ex2(m_run - m_all), f_ot = ex2(m_o - m_all);
         const float inv_l = 1.0f / fmaf(l_run, f_me, l_o * f_ot);
         const float w_me = f_me * inv_l, w_ot = f_ot * inv_l;
-        mbar_wait(o_ready, (n_tiles - 1) & 1);
+        // All PVs retired: a barrier of its own, committed once after the last PV.  (o_ready flips every tile and is no longer waited in
+        // lockstep, so its parity cannot tell "all done" from "two behind" here.)
+        mbar_wait(o_final, 0);
         tc_fence_after();
         const int bb = bh / heads, h = bh - bb * heads;
         const int qi = q0 + row;
