@@ -83,6 +83,13 @@ LIBSDOD_API const char* libsdod_get_last_error_extra_info(int errorcode, void* c
 /* Seed of the initial-noise generator (the reference's Context::set_seed, context.cpp:285-289, not exported there). */
 LIBSDOD_API int libsdod_b200_set_seed(void* context, unsigned long long seed);
 
+/* Sampler of the denoising loop.  DPM-Solver++(2M) is the reference's only sampler (dpm_solver.cpp) and the default; DDIM (eta 0) runs on the
+ * same fused CFG + update kernel with its own timestep / coefficient tables (sdod_ddim_schedule; SURVEY §8 row f4, parity unpinned: the
+ * reference tree has no DDIM).  Re-prepares the schedule for the current step count. */
+#define LIBSDOD_B200_SAMPLER_DPM 0
+#define LIBSDOD_B200_SAMPLER_DDIM 1
+LIBSDOD_API int libsdod_b200_set_sampler(void* context, int sampler);
+
 /* Batched generation with explicit inputs (all HOST pointers; copies are part of the call):
  *   cond, uncond : [n_images, 77, 768] fp32 text-encoder outputs (uncond may be NULL when guidance == 1)
  *   latents      : [n_images, 4, S, S] fp32 NCHW initial noise, or NULL to draw from the context's generator

@@ -87,6 +87,10 @@ SDOD_API int sdod_dpm_schedule(unsigned timesteps, float lin_start, float lin_en
 /* Per-step update coefficients derived from the tables exactly as dpm_solver.cpp:137,153-154,168-170. */
 SDOD_API int sdod_dpm_coeffs(unsigned timesteps, float lin_start, float lin_end, unsigned steps, unsigned step,
                              float* sigma_s, float* alpha_s, float* c_x, float* c_prev, float* c_y0, int* order);
+/* DDIM (eta 0) tables for the same fused step kernel (order 1): model_ts[steps] (descending integer timesteps, as floats) and
+ * coeffs[steps][5] = {sigma_s, alpha_s, c_x, c_prev(=0), c_y0}.  Not in the reference tree: restated from the public
+ * CompVis ddim.py ("uniform" timesteps i*(T/steps)+1, float64 alphas_cumprod of the scaled-linear betas); parity unpinned. */
+SDOD_API int sdod_ddim_schedule(unsigned timesteps, float lin_start, float lin_end, unsigned steps, float* model_ts, float* coeffs);
 
 /* Sinusoidal timestep features, cos first (context.cpp:257-275). out: fp32 [n_t, dim] on device. */
 SDOD_API int sdod_timestep_sinusoid(sdod_stream_t stream, const float* t_dev, int n_t, int dim, float max_period, float* out);

@@ -9,10 +9,13 @@ from . import sampler as S
 
 
 @torch.no_grad()
-def generate(unet, vae, cond, uncond, latents, guidance=7.5, steps=20, device="cpu", return_trace=False):
+def generate(unet, vae, cond, uncond, latents, guidance=7.5, steps=20, device="cpu", return_trace=False, sampler="dpm"):
     solver = S.OracleSolver()
     solver.prepare(steps)
     model_ts = solver.table("model_ts")[:steps]
+    if sampler == "ddim":                                                 # row f4; public CompVis ddim.py, parity unpinned
+        ddim_t, ddim_a, ddim_ap = S.ddim_tables(steps)
+        model_ts = ddim_t.astype(np.float32)
     n = latents.shape[0]
     x = latents.clone().float().cpu().numpy()
     unet, vae = unet.to(device), vae.to(device)
@@ -32,6 +35,9 @@ def generate(unet, vae, cond, uncond, latents, guidance=7.5, steps=20, device="c
             e_u = unet(xt, emb, uncond).cpu().numpy()
             e = np.stack([S.cfg_combine(e_c[i].ravel(), e_u[i].ravel(), guidance).reshape(e_c[i].shape) for i in range(n)])
         for i in range(n):
+            if sampler == "ddim":
+                x[i] = S.ddim_update(x[i], e[i].astype(np.float32), ddim_a[step], ddim_ap[step])
+                continue
             xi, ei = np.ascontiguousarray(x[i]).ravel(), np.ascontiguousarray(e[i]).ravel().copy()
             solvers[i].update(step, xi, ei)
             x[i] = xi.reshape(x[i].shape)

@@ -132,3 +132,26 @@ def seeded_trajectory(solver, steps=20, n=8):
         solver.update(s, x, e)
         out.append(x.copy())
     return np.stack(out)
+
+
+# ---------------------------------------------------------------------------------------------- DDIM (row f4)
+def ddim_tables(steps=20, timesteps=1000, lin_start=0.00085, lin_end=0.0120):
+    """ORACLE — DDIM (eta = 0) schedule, restated from the public CompVis stable-diffusion `ldm/models/diffusion/ddim.py` /
+    `ldm/modules/diffusionmodules/util.py` (make_beta_schedule 'linear', make_ddim_timesteps 'uniform', make_ddim_sampling_parameters).
+    The reference tree has no DDIM (README.md:61-62 only names the flag of its external ldm fork): PARITY UNPINNED.
+    Returns (t [steps] descending ints, a_t, a_prev) in float64."""
+    betas = np.linspace(lin_start ** 0.5, lin_end ** 0.5, timesteps, dtype=np.float64) ** 2
+    alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+    c = timesteps // steps
+    ddim_t = (np.arange(steps) * c) + 1                       # first `steps` entries of range(0, T, c) + 1
+    a = alphas_cumprod[np.minimum(ddim_t, timesteps - 1)]
+    a_prev = np.asarray([alphas_cumprod[0]] + alphas_cumprod[ddim_t[:-1]].tolist())
+    return ddim_t[::-1].copy(), a[::-1].copy(), a_prev[::-1].copy()
+
+
+def ddim_update(x, e, a_t, a_prev):
+    """x_{t-1} = sqrt(a_prev) * pred_x0 + sqrt(1 - a_prev) * e,  pred_x0 = (x - sqrt(1 - a_t) e) / sqrt(a_t)   (ddim.py p_sample_ddim, sigma = 0);
+    float32 tensors, float64 scalars rounded to float32 as torch does when a python/numpy scalar meets a float32 tensor."""
+    f = np.float32
+    pred_x0 = (x - f(np.sqrt(1.0 - a_t)) * e) / f(np.sqrt(a_t))
+    return f(np.sqrt(a_prev)) * pred_x0 + f(np.sqrt(1.0 - a_prev)) * e

@@ -98,7 +98,63 @@ DpmStep DpmSchedule::step(unsigned s) const {
 
 }  // namespace sdod
 
+namespace sdod {
+
+DdimSchedule::DdimSchedule(unsigned timesteps, float lin_start, float lin_end) {
+    if (timesteps < 2) throw std::invalid_argument("DdimSchedule: timesteps must be >= 2");
+    // betas = linspace(sqrt(lin_start), sqrt(lin_end), T, float64) ** 2 ; alphas_cumprod = cumprod(1 - betas)
+    alphas_cumprod_.resize(timesteps);
+    const double b0 = std::sqrt(static_cast<double>(lin_start)), b1 = std::sqrt(static_cast<double>(lin_end));
+    double cum = 1.0;
+    for (unsigned i = 0; i < timesteps; ++i) {
+        const double sb = b0 + (b1 - b0) * static_cast<double>(i) / static_cast<double>(timesteps - 1);
+        cum *= 1.0 - sb * sb;
+        alphas_cumprod_[i] = cum;
+    }
+}
+
+void DdimSchedule::prepare(unsigned steps) {
+    const unsigned T = static_cast<unsigned>(alphas_cumprod_.size());
+    if (steps < 1 || steps > T) throw std::invalid_argument("DdimSchedule: steps must be in [1, timesteps]");
+    const unsigned c = T / steps;                       // "uniform" spacing; t_i = i*c + 1, i in [0, steps)
+    model_ts.assign(steps, 0.f);
+    coeffs.assign(steps, DpmStep{});
+    for (unsigned k = 0; k < steps; ++k) {              // loop step k walks the timesteps downwards
+        const unsigned i = steps - 1 - k;
+        const unsigned t = i * c + 1;
+        const double a_t = alphas_cumprod_[t < T ? t : T - 1];
+        const double a_prev = i > 0 ? alphas_cumprod_[(i - 1) * c + 1] : alphas_cumprod_[0];
+        const double cx = std::sqrt(1.0 - a_prev) / std::sqrt(1.0 - a_t);
+        DpmStep s{};
+        s.sigma_s = static_cast<float>(std::sqrt(1.0 - a_t));
+        s.alpha_s = static_cast<float>(std::sqrt(a_t));
+        s.c_x = static_cast<float>(cx);
+        s.c_prev = 0.f;
+        s.c_y0 = static_cast<float>(std::sqrt(a_prev) - cx * std::sqrt(a_t));
+        s.order = 1;
+        coeffs[k] = s;
+        model_ts[k] = static_cast<float>(t);
+    }
+}
+
+}  // namespace sdod
+
 extern "C" {
+SDOD_API int sdod_ddim_schedule(unsigned timesteps, float lin_start, float lin_end, unsigned steps, float* model_ts, float* coeffs) {
+    try {
+        sdod::DdimSchedule sch(timesteps, lin_start, lin_end);
+        sch.prepare(steps);
+        for (unsigned k = 0; k < steps; ++k) {
+            const sdod::DpmStep s = sch.step(k);
+            if (model_ts) model_ts[k] = sch.model_ts[k];
+            if (coeffs) { coeffs[5 * k] = s.sigma_s; coeffs[5 * k + 1] = s.alpha_s; coeffs[5 * k + 2] = s.c_x; coeffs[5 * k + 3] = s.c_prev; coeffs[5 * k + 4] = s.c_y0; }
+        }
+    } catch (const std::exception& e) {
+        return sdod::fail(sdod::kInvalidArgument, std::string("ddim_schedule: ") + e.what());
+    }
+    return sdod::kOk;
+}
+
 
 SDOD_API int sdod_dpm_schedule(unsigned timesteps, float lin_start, float lin_end, unsigned steps, float* ts, float* log_alphas,
                                float* lambdas, float* sigmas, float* alphas, float* phis, float* i2rs, float* model_ts) {

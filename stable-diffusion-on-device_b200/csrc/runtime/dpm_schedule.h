@@ -28,4 +28,20 @@ private:
     unsigned steps_ = 0;
 };
 
+// DDIM (eta = 0) on the same fused kernel: x0 = (x - sqrt(1-a_t) e) / sqrt(a_t), x <- sqrt(a_prev) x0 + sqrt(1-a_prev) e, which in the kernel's
+// form is an order-1 step with c_x = sqrt(1-a_prev)/sqrt(1-a_t), c_y0 = sqrt(a_prev) - c_x sqrt(a_t).  Not in the reference tree (SURVEY §8 row
+// f4; the reference's README only names the flag of the external ldm fork): restated from the public CompVis `ddim.py` — "uniform"
+// timesteps i*(T/steps)+1, alphas_cumprod of the scaled-linear beta schedule in float64 — so its parity is unpinned.
+class DdimSchedule {
+public:
+    DdimSchedule(unsigned timesteps, float lin_start, float lin_end);
+    void prepare(unsigned steps);
+    unsigned steps() const { return static_cast<unsigned>(model_ts.size()); }
+    DpmStep step(unsigned s) const { return coeffs.at(s); }
+    std::vector<float> model_ts;        // [steps], descending integer timesteps fed to the UNet
+    std::vector<DpmStep> coeffs;        // [steps]
+private:
+    std::vector<double> alphas_cumprod_;
+};
+
 }  // namespace sdod

@@ -97,7 +97,7 @@ unsigned long long fnv1a(const char* s) {
 class Engine {
 public:
     Engine(const std::string& models_dir, unsigned latent_spatial, unsigned log_level, unsigned max_images, int device)
-        : log_(log_level), S_(static_cast<int>(latent_spatial)), max_images_(static_cast<int>(max_images)), device_(device), sched_(1000, 0.00085f, 0.0120f) {   // context.cpp:196
+        : log_(log_level), S_(static_cast<int>(latent_spatial)), max_images_(static_cast<int>(max_images)), device_(device), sched_(1000, 0.00085f, 0.0120f), ddim_(1000, 0.00085f, 0.0120f) {   // context.cpp:196
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
             cudaGetLastError();
@@ -158,6 +158,13 @@ public:
     size_t image_bytes() const { return static_cast<size_t>(3) * S_ * 8 * S_ * 8; }     // context.cpp:406-409
     Logger& logger() { return log_; }
     ErrorTable& errors() { return errors_; }
+    void set_sampler(int sampler) {
+        if (sampler != LIBSDOD_B200_SAMPLER_DPM && sampler != LIBSDOD_B200_SAMPLER_DDIM)
+            API_THROW(LIBSDOD_INVALID_ARGUMENT, "unknown sampler id: " + std::to_string(sampler));
+        sampler_ = sampler;
+        if (steps_) prepare_schedule(steps_);
+        log_.log(LIBSDOD_LOG_INFO, "Sampler: %s", sampler == LIBSDOD_B200_SAMPLER_DDIM ? "DDIM (eta 0)" : "DPM-Solver++(2M)");
+    }
     void set_seed(unsigned long long s) { seed_ = s; rng_offset_ = 0; log_.log(LIBSDOD_LOG_INFO, "Using seed: %llu", s); }
     const float* timings() const { return timings_; }
     int max_images() const { return max_images_; }
@@ -166,12 +173,14 @@ public:
         if (steps < 1 || steps > 1000) API_THROW(LIBSDOD_INVALID_ARGUMENT, "steps must be in [1, 1000], got: " + std::to_string(steps));
         if (device_ >= 0) CU(cudaSetDevice(device_));
         sched_.prepare(steps);
+        if (sampler_ == LIBSDOD_B200_SAMPLER_DDIM) ddim_.prepare(steps);
+        const float* model_ts = sampler_ == LIBSDOD_B200_SAMPLER_DDIM ? ddim_.model_ts.data() : sched_.model_ts.data();
         cudaFree(temb_);
         temb_ = nullptr;
         float* t_dev = nullptr;
         CU(cudaMalloc(reinterpret_cast<void**>(&temb_), static_cast<size_t>(steps) * 1280 * sizeof(float)));
         CU(cudaMalloc(reinterpret_cast<void**>(&t_dev), steps * sizeof(float)));
-        CU(cudaMemcpyAsync(t_dev, sched_.model_ts.data(), steps * sizeof(float), cudaMemcpyHostToDevice, stream_));   // first `steps` of steps+1 (context.cpp:267)
+        CU(cudaMemcpyAsync(t_dev, model_ts, steps * sizeof(float), cudaMemcpyHostToDevice, stream_));   // first `steps` of steps+1 (context.cpp:267)
         int st = unet_->time_embed(stream_, t_dev, static_cast<int>(steps), temb_);
         CU(cudaStreamSynchronize(stream_));
         cudaFree(t_dev);
@@ -243,7 +252,7 @@ public:
         for (unsigned step = 0; step < steps_; ++step) {
             SD(sdod::broadcast_rows(stream_, unet_->emb_in(), temb_ + static_cast<size_t>(step) * 1280, B, 1280));
             SD(unet_->forward(stream_, x, unet_->emb_in(), eps, B, true));
-            const sdod::DpmStep k = sched_.step(step);
+            const sdod::DpmStep k = sampler_ == LIBSDOD_B200_SAMPLER_DDIM ? ddim_.step(step) : sched_.step(step);
             SD(sdod_cfg_dpm_step(stream_, x, y_prev_, eps, cfg ? eps + lat : nullptr, SDOD_F32, lat, guidance, k.sigma_s, k.alpha_s, k.c_x,
                                  k.c_prev, k.c_y0, k.order, cfg ? x + lat : nullptr));
         }
@@ -274,6 +283,8 @@ private:
     ErrorTable errors_;
     int S_, max_images_, device_;
     sdod::DpmSchedule sched_;
+    sdod::DdimSchedule ddim_;
+    int sampler_ = LIBSDOD_B200_SAMPLER_DPM;
     unsigned steps_ = 0;
     std::unique_ptr<sdod::WeightStore> unet_w_, vae_w_;
     std::unique_ptr<sdod::UNet> unet_;
@@ -454,6 +465,13 @@ LIBSDOD_API int libsdod_b200_set_seed(void* context, unsigned long long seed) {
     if (int st = retrieve(context, &hnd, __func__)) return st;
     hnd->cptr->set_seed(seed);
     return LIBSDOD_NO_ERROR;
+}
+
+LIBSDOD_API int libsdod_b200_set_sampler(void* context, int sampler) {
+    Handle* hnd = nullptr;
+    if (int st = retrieve(context, &hnd, __func__)) return st;
+    Engine* e = hnd->cptr;
+    return guarded(&e->errors(), __func__, [&] { e->set_sampler(sampler); });
 }
 
 LIBSDOD_API int libsdod_b200_generate(void* context, unsigned int n_images, const float* cond, const float* uncond, const float* latents,

@@ -21,6 +21,7 @@ _SIGS = {
     "libsdod_get_error_description": (ctypes.c_char_p, [_i]),
     "libsdod_get_last_error_extra_info": (ctypes.c_char_p, [_i, _vp]),
     "libsdod_b200_set_seed": (_i, [_vp, ctypes.c_ulonglong]),
+    "libsdod_b200_set_sampler": (_i, [_vp, ctypes.c_int]),
     "libsdod_b200_generate": (_i, [_vp, _u, _vp, _vp, _vp, _f, _vp, _vp]),
     "libsdod_b200_generate_device": (_i, [_vp, _u, _vp, _vp, _vp, _f, _vp]),
     "libsdod_b200_setup": (_i, [ctypes.POINTER(_vp), ctypes.c_char_p, _u, _u, _u, _u, _i]),
@@ -78,6 +79,12 @@ class Context:
 
     def set_seed(self, seed):
         self._ok(api().libsdod_b200_set_seed(self._h, seed))
+
+    SAMPLERS = {"dpm": 0, "ddim": 1}
+
+    def set_sampler(self, name):
+        """'dpm' = DPM-Solver++(2M), the reference's sampler (default); 'ddim' = DDIM with eta 0 (row f4, parity unpinned)."""
+        self._ok(api().libsdod_b200_set_sampler(self._h, self.SAMPLERS[name] if isinstance(name, str) else int(name)))
 
     def generate_image(self, prompt, guidance_scale=7.5, out=None):
         side = self.latent_spatial * 8

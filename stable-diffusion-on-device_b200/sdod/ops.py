@@ -131,6 +131,18 @@ def dpm_coeffs(step, steps=20, timesteps=1000, lin_start=0.00085, lin_end=0.0120
     return dict(sigma_s=f[0].value, alpha_s=f[1].value, c_x=f[2].value, c_prev=f[3].value, c_y0=f[4].value, order=order.value)
 
 
+def ddim_schedule(steps=20, timesteps=1000, lin_start=0.00085, lin_end=0.0120):
+    """DDIM (eta 0) tables for sdod::cfg_dpm_step: model_ts [steps] and per-step dicts (order 1).  Public CompVis ddim.py, parity unpinned."""
+    import ctypes
+    import numpy as np
+    ts = np.zeros(steps, dtype=np.float32)
+    co = np.zeros((steps, 5), dtype=np.float32)
+    C.check(C.lib().sdod_ddim_schedule(timesteps, lin_start, lin_end, steps, ts.ctypes.data_as(ctypes.c_void_p), co.ctypes.data_as(ctypes.c_void_p)),
+            "sdod_ddim_schedule")
+    keys = ("sigma_s", "alpha_s", "c_x", "c_prev", "c_y0")
+    return ts, [dict(zip(keys, (float(v) for v in row)), order=1) for row in co]
+
+
 @torch.library.custom_op("sdod::cfg_dpm_step", mutates_args=("x", "y_prev"), device_types="cuda")
 def cfg_dpm_step(x: torch.Tensor, y_prev: torch.Tensor, eps_c: torch.Tensor, eps_u: Optional[torch.Tensor], guidance: float,
                  sigma_s: float, alpha_s: float, c_x: float, c_prev: float, c_y0: float, order: int) -> None:

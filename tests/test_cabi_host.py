@@ -138,3 +138,29 @@ def test_checkpoint_conversion_roundtrip(tmp_path):
     assert list(bu) == ["out.2.bias"] and list(bv) == ["decoder.norm_out.bias"]
     with pytest.raises(ValueError):
         CK.convert({"foo": torch.zeros(1)}, str(tmp_path / "none"))
+
+
+def test_ddim_tables_match_the_public_formulas():
+    """Row f4: the product's DDIM tables (sdod_ddim_schedule) against the numpy restatement of CompVis ddim.py, and the identity that makes
+    DDIM an order-1 step of the fused kernel: c_x*x + c_y0*(x - sigma*e)/alpha == sqrt(a_prev)*x0 + sqrt(1-a_prev)*e."""
+    from sdod import ops
+    from oracle import sampler as S
+    for steps in (20, 50, 8):
+        ts, co = ops.ddim_schedule(steps)
+        t, a, ap = S.ddim_tables(steps)
+        assert np.array_equal(ts, t.astype(np.float32)) and ts[0] > ts[-1] and ts[-1] == 1.0
+        for k in range(steps):
+            cx = np.sqrt(1 - ap[k]) / np.sqrt(1 - a[k])
+            want = (np.sqrt(1 - a[k]), np.sqrt(a[k]), cx, 0.0, np.sqrt(ap[k]) - cx * np.sqrt(a[k]))
+            got = (co[k]["sigma_s"], co[k]["alpha_s"], co[k]["c_x"], co[k]["c_prev"], co[k]["c_y0"])
+            assert np.allclose(got, np.asarray(want, dtype=np.float32), rtol=2e-7, atol=0) and co[k]["order"] == 1
+    rng = np.random.default_rng(3)
+    x, e = rng.standard_normal(64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    ts, co = ops.ddim_schedule(20)
+    t, a, ap = S.ddim_tables(20)
+    for k in (0, 7, 19):
+        y0 = (x - np.float32(co[k]["sigma_s"]) * e) / np.float32(co[k]["alpha_s"])
+        ours = np.float32(co[k]["c_x"]) * x + np.float32(co[k]["c_y0"]) * y0
+        assert np.allclose(ours, S.ddim_update(x, e, a[k], ap[k]), rtol=1e-4, atol=2e-5)
+    with pytest.raises(Exception):
+        ops.ddim_schedule(0)
