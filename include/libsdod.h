@@ -88,6 +88,7 @@ LIBSDOD_API int libsdod_b200_set_seed(void* context, unsigned long long seed);
  * reference tree has no DDIM).  Re-prepares the schedule for the current step count. */
 #define LIBSDOD_B200_SAMPLER_DPM 0
 #define LIBSDOD_B200_SAMPLER_DDIM 1
+#define LIBSDOD_B200_SAMPLER_PLMS 2   /* CompVis plms.py on the DDIM timesteps; first step = two UNet evaluations */
 LIBSDOD_API int libsdod_b200_set_sampler(void* context, int sampler);
 
 /* Batched generation with explicit inputs (all HOST pointers; copies are part of the call):

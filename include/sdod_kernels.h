@@ -91,6 +91,12 @@ SDOD_API int sdod_dpm_coeffs(unsigned timesteps, float lin_start, float lin_end,
  * coeffs[steps][5] = {sigma_s, alpha_s, c_x, c_prev(=0), c_y0}.  Not in the reference tree: restated from the public
  * CompVis ddim.py ("uniform" timesteps i*(T/steps)+1, float64 alphas_cumprod of the scaled-linear betas); parity unpinned. */
 SDOD_API int sdod_ddim_schedule(unsigned timesteps, float lin_start, float lin_end, unsigned steps, float* model_ts, float* coeffs);
+/* PLMS / linear-multistep variant of the fused step (public CompVis plms.py; parity unpinned, the reference tree has no PLMS):
+ *   e = CFG(eps_c, eps_u); if (e_out) e_out = e; e' = w[0] e + w[1] h1 + w[2] h2 + w[3] h3 (NULL history terms are skipped);
+ *   x0 = ((x_from ? x_from : x) - s_t e') / a_t;  x = a_prev x0 + s_prev e'   (a = sqrt(alphas_cumprod), s = sqrt(1 - alphas_cumprod)); x_copy as above. */
+SDOD_API int sdod_cfg_lms_step(sdod_stream_t stream, float* x, const float* x_from, const void* eps_c, const void* eps_u, int eps_dtype, size_t n,
+                               float guidance, const float* w, const float* h1, const float* h2, const float* h3, float* e_out, float a_t,
+                               float s_t, float a_prev, float s_prev, float* x_copy);
 
 /* Sinusoidal timestep features, cos first (context.cpp:257-275). out: fp32 [n_t, dim] on device. */
 SDOD_API int sdod_timestep_sinusoid(sdod_stream_t stream, const float* t_dev, int n_t, int dim, float max_period, float* out);

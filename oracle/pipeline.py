@@ -13,7 +13,7 @@ def generate(unet, vae, cond, uncond, latents, guidance=7.5, steps=20, device="c
     solver = S.OracleSolver()
     solver.prepare(steps)
     model_ts = solver.table("model_ts")[:steps]
-    if sampler == "ddim":                                                 # row f4; public CompVis ddim.py, parity unpinned
+    if sampler in ("ddim", "plms"):                                       # row f4; public CompVis ddim.py / plms.py, parity unpinned
         ddim_t, ddim_a, ddim_ap = S.ddim_tables(steps)
         model_ts = ddim_t.astype(np.float32)
     n = latents.shape[0]
@@ -25,6 +25,36 @@ def generate(unet, vae, cond, uncond, latents, guidance=7.5, steps=20, device="c
     for s in solvers:
         s.prepare(steps)
     trace = []
+
+    def model_eps(xn, step):
+        xt = torch.from_numpy(xn).to(device)
+        emb = emb_all[step:step + 1].expand(n, -1)
+        e_c = unet(xt, emb, cond).cpu().numpy()
+        if guidance == 1.0:
+            return e_c
+        e_u = unet(xt, emb, uncond).cpu().numpy()
+        return np.stack([S.cfg_combine(e_c[i].ravel(), e_u[i].ravel(), guidance).reshape(e_c[i].shape) for i in range(n)]).astype(np.float32)
+
+    if sampler == "plms":                                                  # plms.py p_sample_plms
+        old_eps = []
+        for step in range(steps):
+            e_t = model_eps(x, step)
+            if not old_eps and steps > 1:
+                x_prev = S.ddim_update(x, e_t, ddim_a[step], ddim_ap[step])
+                e_next = model_eps(x_prev, step + 1)
+                e_prime = np.float32(0.5) * e_t + np.float32(0.5) * e_next
+            elif not old_eps:
+                e_prime = e_t
+            else:
+                w = S.plms_step_weights(len(old_eps))
+                e_prime = np.float32(w[0]) * e_t
+                for wk, h in zip(w[1:], reversed(old_eps)):
+                    e_prime = e_prime + np.float32(wk) * h
+            x = S.ddim_update(x, e_prime.astype(np.float32), ddim_a[step], ddim_ap[step])
+            old_eps = (old_eps + [e_t])[-3:]
+            if return_trace:
+                trace.append(x.copy())
+        steps = 0                                                          # skip the DPM / DDIM loop below
     for step in range(steps):
         xt = torch.from_numpy(x).to(device)
         emb = emb_all[step:step + 1].expand(n, -1)

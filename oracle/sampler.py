@@ -155,3 +155,8 @@ def ddim_update(x, e, a_t, a_prev):
     f = np.float32
     pred_x0 = (x - f(np.sqrt(1.0 - a_t)) * e) / f(np.sqrt(a_t))
     return f(np.sqrt(a_prev)) * pred_x0 + f(np.sqrt(1.0 - a_prev)) * e
+
+
+def plms_step_weights(n_hist):
+    """Adams-Bashforth weights over (e_t, e_{t-1}, e_{t-2}, e_{t-3}) used by plms.py p_sample_plms once n_hist old eps exist (n_hist >= 1)."""
+    return {1: (3 / 2, -1 / 2, 0, 0), 2: (23 / 12, -16 / 12, 5 / 12, 0)}.get(n_hist, (55 / 24, -59 / 24, 37 / 24, -9 / 24))

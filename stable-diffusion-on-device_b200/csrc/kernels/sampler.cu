@@ -55,6 +55,38 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(float* __restrict__ x
     }
 }
 
+// PLMS / linear-multistep form of the same fusion (public CompVis plms.py, parity unpinned): CFG combine, optional store of the
+// combined eps into the history ring, e' = w0 e + w1 h1 + w2 h2 + w3 h3, x0 = (x_from - s_t e') / a_t, x = a_prev x0 + s_prev e'.
+// DDIM is w = (1,0,0,0); the first PLMS step calls it twice (second call: x_from = the saved x_t, h1 = the first eps, w = (1/2, 1/2)).
+struct LmsCoef {
+    float g, one_minus_g;
+    float w0, w1, w2, w3;
+    float a_t, s_t, a_prev, s_prev;
+    int cfg;
+};
+
+template <typename E>
+__global__ void __launch_bounds__(256) cfg_lms_step_kernel(float* __restrict__ x, const float* __restrict__ x_from, const E* __restrict__ eps_c,
+                                                           const E* __restrict__ eps_u, const float* h1, const float* h2, const float* h3,
+                                                           float* e_out, size_t n, LmsCoef k, float* __restrict__ x_copy) {
+    // (h1..h3 / e_out are slots of one history ring and e_out may BE the oldest slot: history is read before e_out is written)
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float e = eps_load<E>(eps_c, i);
+        if (k.cfg) e = __fadd_rn(__fmul_rn(e, k.g), __fmul_rn(eps_load<E>(eps_u, i), k.one_minus_g));
+        float ep = __fmul_rn(k.w0, e);
+        if (h1) ep = __fadd_rn(ep, __fmul_rn(k.w1, h1[i]));
+        if (h2) ep = __fadd_rn(ep, __fmul_rn(k.w2, h2[i]));
+        if (h3) ep = __fadd_rn(ep, __fmul_rn(k.w3, h3[i]));
+        if (e_out) e_out[i] = e;
+        const float xs = x_from ? x_from[i] : x[i];
+        const float x0 = __fdiv_rn(__fadd_rn(xs, -__fmul_rn(k.s_t, ep)), k.a_t);
+        const float xn = __fadd_rn(__fmul_rn(k.a_prev, x0), __fmul_rn(k.s_prev, ep));
+        x[i] = xn;
+        if (x_copy) x_copy[i] = xn;
+    }
+}
+
 __global__ void timestep_sinusoid_kernel(const float* __restrict__ t, int n_t, int dim, float log_period, float* __restrict__ out) {
     const int half = dim / 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,6 +185,30 @@ SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, co
         return fail(kInvalidArgument, "cfg_dpm_step: unknown eps dtype");
     count_launch();
     return check_launch("cfg_dpm_step_kernel");
+}
+
+SDOD_API int sdod_cfg_lms_step(sdod_stream_t stream, float* x, const float* x_from, const void* eps_c, const void* eps_u, int eps_dtype, size_t n,
+                               float guidance, const float* w, const float* h1, const float* h2, const float* h3, float* e_out, float a_t,
+                               float s_t, float a_prev, float s_prev, float* x_copy) {
+    if (!x || !eps_c || !w) return fail(kInvalidArgument, "cfg_lms_step: NULL tensor");
+    LmsCoef k;
+    k.g = guidance;
+    k.one_minus_g = 1 - guidance;
+    k.w0 = w[0]; k.w1 = w[1]; k.w2 = w[2]; k.w3 = w[3];
+    k.a_t = a_t; k.s_t = s_t; k.a_prev = a_prev; k.s_prev = s_prev;
+    k.cfg = (guidance == 1.0f) ? 0 : 1;
+    if (k.cfg && !eps_u) return fail(kInvalidArgument, "cfg_lms_step: eps_u required when guidance != 1");
+    if (n == 0) return kOk;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(n, 256);
+    if (eps_dtype == SDOD_F32)
+        cfg_lms_step_kernel<float><<<grid, 256, 0, s>>>(x, x_from, static_cast<const float*>(eps_c), static_cast<const float*>(eps_u), h1, h2, h3, e_out, n, k, x_copy);
+    else if (eps_dtype == SDOD_BF16)
+        cfg_lms_step_kernel<bf16><<<grid, 256, 0, s>>>(x, x_from, static_cast<const bf16*>(eps_c), static_cast<const bf16*>(eps_u), h1, h2, h3, e_out, n, k, x_copy);
+    else
+        return fail(kInvalidArgument, "cfg_lms_step: unknown eps dtype");
+    count_launch();
+    return check_launch("cfg_lms_step_kernel");
 }
 
 SDOD_API int sdod_timestep_sinusoid(sdod_stream_t stream, const float* t_dev, int n_t, int dim, float max_period, float* out) {

@@ -119,6 +119,8 @@ void DdimSchedule::prepare(unsigned steps) {
     const unsigned c = T / steps;                       // "uniform" spacing; t_i = i*c + 1, i in [0, steps)
     model_ts.assign(steps, 0.f);
     coeffs.assign(steps, DpmStep{});
+    sqrt_a_prev.assign(steps, 0.f);
+    sqrt_1m_a_prev.assign(steps, 0.f);
     for (unsigned k = 0; k < steps; ++k) {              // loop step k walks the timesteps downwards
         const unsigned i = steps - 1 - k;
         const unsigned t = i * c + 1;
@@ -133,6 +135,8 @@ void DdimSchedule::prepare(unsigned steps) {
         s.c_y0 = static_cast<float>(std::sqrt(a_prev) - cx * std::sqrt(a_t));
         s.order = 1;
         coeffs[k] = s;
+        sqrt_a_prev[k] = static_cast<float>(std::sqrt(a_prev));
+        sqrt_1m_a_prev[k] = static_cast<float>(std::sqrt(1.0 - a_prev));
         model_ts[k] = static_cast<float>(t);
     }
 }

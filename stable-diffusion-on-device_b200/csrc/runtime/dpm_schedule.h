@@ -40,6 +40,7 @@ public:
     DpmStep step(unsigned s) const { return coeffs.at(s); }
     std::vector<float> model_ts;        // [steps], descending integer timesteps fed to the UNet
     std::vector<DpmStep> coeffs;        // [steps]
+    std::vector<float> sqrt_a_prev, sqrt_1m_a_prev;   // [steps]  sqrt(a_prev), sqrt(1 - a_prev) (the PLMS step wants them unfolded)
 private:
     std::vector<double> alphas_cumprod_;
 };

@@ -149,7 +149,7 @@ public:
         cudaStreamSynchronize(stream_);
         unet_.reset();
         vae_.reset();
-        cudaFree(y_prev_); cudaFree(ctx_dev_); cudaFree(temb_);
+        cudaFree(y_prev_); cudaFree(ctx_dev_); cudaFree(temb_); cudaFree(plms_buf_);
         cudaFreeHost(pin_ctx_); cudaFreeHost(pin_lat_); cudaFreeHost(pin_img_);
         for (auto& e : ev_) cudaEventDestroy(e);
         cudaStreamDestroy(stream_);
@@ -159,11 +159,11 @@ public:
     Logger& logger() { return log_; }
     ErrorTable& errors() { return errors_; }
     void set_sampler(int sampler) {
-        if (sampler != LIBSDOD_B200_SAMPLER_DPM && sampler != LIBSDOD_B200_SAMPLER_DDIM)
+        if (sampler != LIBSDOD_B200_SAMPLER_DPM && sampler != LIBSDOD_B200_SAMPLER_DDIM && sampler != LIBSDOD_B200_SAMPLER_PLMS)
             API_THROW(LIBSDOD_INVALID_ARGUMENT, "unknown sampler id: " + std::to_string(sampler));
         sampler_ = sampler;
         if (steps_) prepare_schedule(steps_);
-        log_.log(LIBSDOD_LOG_INFO, "Sampler: %s", sampler == LIBSDOD_B200_SAMPLER_DDIM ? "DDIM (eta 0)" : "DPM-Solver++(2M)");
+        log_.log(LIBSDOD_LOG_INFO, "Sampler: %s", sampler == LIBSDOD_B200_SAMPLER_DDIM ? "DDIM (eta 0)" : sampler == LIBSDOD_B200_SAMPLER_PLMS ? "PLMS" : "DPM-Solver++(2M)");
     }
     void set_seed(unsigned long long s) { seed_ = s; rng_offset_ = 0; log_.log(LIBSDOD_LOG_INFO, "Using seed: %llu", s); }
     const float* timings() const { return timings_; }
@@ -173,8 +173,8 @@ public:
         if (steps < 1 || steps > 1000) API_THROW(LIBSDOD_INVALID_ARGUMENT, "steps must be in [1, 1000], got: " + std::to_string(steps));
         if (device_ >= 0) CU(cudaSetDevice(device_));
         sched_.prepare(steps);
-        if (sampler_ == LIBSDOD_B200_SAMPLER_DDIM) ddim_.prepare(steps);
-        const float* model_ts = sampler_ == LIBSDOD_B200_SAMPLER_DDIM ? ddim_.model_ts.data() : sched_.model_ts.data();
+        if (sampler_ != LIBSDOD_B200_SAMPLER_DPM) ddim_.prepare(steps);     // PLMS runs on the DDIM timesteps / alphas (plms.py)
+        const float* model_ts = sampler_ != LIBSDOD_B200_SAMPLER_DPM ? ddim_.model_ts.data() : sched_.model_ts.data();
         cudaFree(temb_);
         temb_ = nullptr;
         float* t_dev = nullptr;
@@ -206,6 +206,52 @@ public:
         std::vector<float> cond(77 * 768);
         prompt_embedding(prompt, cond.data());
         generate(1, cond.data(), uncond_default_.data(), nullptr, guidance, out, nullptr);
+    }
+
+    // PLMS (pseudo linear multistep, public CompVis plms.py p_sample_plms; row f4, parity unpinned): 4-term Adams-Bashforth over the CFG-combined
+    // eps, kept in a 3-slot device ring written by the fused step kernel itself; the first step is a pseudo improved-Euler step with a second
+    // UNet evaluation at the next timestep.
+    void plms_loop(float* x, float* eps, int B, size_t lat, bool cfg, float guidance) {
+        if (plms_cap_ < lat) {
+            cudaFree(plms_buf_);
+            plms_buf_ = nullptr;
+            CU(cudaMalloc(reinterpret_cast<void**>(&plms_buf_), 4 * lat * sizeof(float)));     // 3 history slots + the saved x_t
+            plms_cap_ = lat;
+        }
+        float* hist[3] = {plms_buf_, plms_buf_ + lat, plms_buf_ + 2 * lat};
+        float* x_saved = plms_buf_ + 3 * lat;
+        const float* eu = cfg ? eps + lat : nullptr;
+        float* xc = cfg ? x + lat : nullptr;
+        auto run_unet = [&](unsigned step) {
+            SD(sdod::broadcast_rows(stream_, unet_->emb_in(), temb_ + static_cast<size_t>(step) * 1280, B, 1280));
+            SD(unet_->forward(stream_, x, unet_->emb_in(), eps, B, true));
+        };
+        for (unsigned step = 0; step < steps_; ++step) {
+            const sdod::DpmStep k = ddim_.step(step);            // sigma_s = sqrt(1 - a_t), alpha_s = sqrt(a_t)
+            const float a_prev = ddim_.sqrt_a_prev[step], s_prev = ddim_.sqrt_1m_a_prev[step];
+            float* slot = hist[step % 3];
+            const float* h1 = step >= 1 ? hist[(step - 1) % 3] : nullptr;
+            const float* h2 = step >= 2 ? hist[(step - 2) % 3] : nullptr;
+            const float* h3 = step >= 3 ? hist[(step - 3) % 3] : nullptr;
+            run_unet(step);
+            if (step == 0 && steps_ > 1) {
+                const float w_euler[4] = {1.f, 0.f, 0.f, 0.f}, w_avg[4] = {0.5f, 0.5f, 0.f, 0.f};
+                CU(cudaMemcpyAsync(x_saved, x, lat * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+                SD(sdod_cfg_lms_step(stream_, x, nullptr, eps, eu, SDOD_F32, lat, guidance, w_euler, nullptr, nullptr, nullptr, slot, k.alpha_s, k.sigma_s,
+                                     a_prev, s_prev, xc));                                     // x_prev from e_t alone; e_t -> history
+                run_unet(1);                                                                    // e_t_next = model(x_prev, t_next)
+                SD(sdod_cfg_lms_step(stream_, x, x_saved, eps, eu, SDOD_F32, lat, guidance, w_avg, slot, nullptr, nullptr, nullptr, k.alpha_s, k.sigma_s,
+                                     a_prev, s_prev, xc));                                     // e' = (e_t + e_t_next) / 2 applied to the saved x_t
+                continue;
+            }
+            const float w1[4] = {1.f, 0.f, 0.f, 0.f};
+            const float w2[4] = {1.5f, -0.5f, 0.f, 0.f};
+            const float w3[4] = {23.f / 12.f, -16.f / 12.f, 5.f / 12.f, 0.f};
+            const float w4[4] = {55.f / 24.f, -59.f / 24.f, 37.f / 24.f, -9.f / 24.f};
+            const float* w = step == 0 ? w1 : step == 1 ? w2 : step == 2 ? w3 : w4;
+            // the ring slot being written (step % 3) is the one holding e_{t-3}: read it (h3) and write it in the same pass, element by element
+            SD(sdod_cfg_lms_step(stream_, x, nullptr, eps, eu, SDOD_F32, lat, guidance, w, h1, h2, h3, slot, k.alpha_s, k.sigma_s, a_prev, s_prev, xc));
+        }
     }
 
     // context.cpp:292-403, batched over n images
@@ -249,6 +295,9 @@ public:
         }
         if (cfg) CU(cudaMemcpyAsync(x + lat, x, lat * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
         // ---- denoising loop (context.cpp:342-382)
+        if (sampler_ == LIBSDOD_B200_SAMPLER_PLMS) {
+            plms_loop(x, eps, B, lat, cfg, guidance);
+        } else
         for (unsigned step = 0; step < steps_; ++step) {
             SD(sdod::broadcast_rows(stream_, unet_->emb_in(), temb_ + static_cast<size_t>(step) * 1280, B, 1280));
             SD(unet_->forward(stream_, x, unet_->emb_in(), eps, B, true));
@@ -284,6 +333,8 @@ private:
     int S_, max_images_, device_;
     sdod::DpmSchedule sched_;
     sdod::DdimSchedule ddim_;
+    float* plms_buf_ = nullptr;
+    size_t plms_cap_ = 0;
     int sampler_ = LIBSDOD_B200_SAMPLER_DPM;
     unsigned steps_ = 0;
     std::unique_ptr<sdod::WeightStore> unet_w_, vae_w_;

@@ -51,6 +51,7 @@ _SIGS = {
     "sdod_dpm_schedule": (c_int, [c_u, c_f, c_f, c_u] + [c_vp] * 8),
     "sdod_dpm_coeffs": (c_int, [c_u, c_f, c_f, c_u, c_u] + [c_vp] * 6),
     "sdod_ddim_schedule": (c_int, [c_u, c_f, c_f, c_u, c_vp, c_vp]),
+    "sdod_cfg_lms_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_sz, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_f, c_f, c_vp]),
     "sdod_timestep_sinusoid": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_vp]),
     "sdod_randn": (c_int, [c_vp, c_vp, c_sz, ctypes.c_ulonglong, ctypes.c_ulonglong]),
     "sdod_image_to_u8": (c_int, [c_vp, c_vp, c_int, c_vp, c_sz]),

@@ -80,7 +80,7 @@ class Context:
     def set_seed(self, seed):
         self._ok(api().libsdod_b200_set_seed(self._h, seed))
 
-    SAMPLERS = {"dpm": 0, "ddim": 1}
+    SAMPLERS = {"dpm": 0, "ddim": 1, "plms": 2}
 
     def set_sampler(self, name):
         """'dpm' = DPM-Solver++(2M), the reference's sampler (default); 'ddim' = DDIM with eta 0 (row f4, parity unpinned)."""

@@ -92,6 +92,25 @@ def test_reference_style_app_flow():
     assert b"released" in lib.libsdod_get_last_error_extra_info(A.INVALID_CONTEXT, None)
 
 
+def test_plms_sampler_vs_oracle_loop(models_dir):
+    """Row f4: PLMS (4-term eps history kept in a device ring by the fused step kernel; first step = two UNet evaluations) vs the oracle loop
+    restated from the public CompVis plms.py."""
+    d, unet, vae = models_dir
+    S, n = 16, 2
+    lat = torch.randn(n, 4, S, S, generator=torch.Generator().manual_seed(21))
+    g2 = torch.Generator().manual_seed(22)
+    cond, uncond = torch.randn(n, 77, 768, generator=g2), torch.randn(n, 77, 768, generator=g2)
+    want_u8, _, want_lat = P.generate(unet, vae, cond, uncond, lat, 7.5, 20, device="cuda", sampler="plms")
+    with A.Context(d, latent_spatial=S, steps=20, max_images=n, device=0) as ctx:
+        ctx.set_sampler("plms")
+        imgs, lat_out = ctx.generate(cond.numpy(), uncond.numpy(), lat.numpy(), 7.5, return_latents=True)
+        imgs2 = ctx.generate(cond.numpy(), uncond.numpy(), lat.numpy(), 7.5)
+    rel = np.linalg.norm(lat_out - want_lat) / np.linalg.norm(want_lat)
+    print("PLMS: final-latent rel-L2 %.3e, PSNR %.1f dB" % (rel, psnr_u8(imgs, want_u8)))
+    assert psnr_u8(imgs, want_u8) >= 35.0 and rel < 5e-2
+    assert np.array_equal(imgs, imgs2)               # the history ring carries nothing over between calls
+
+
 def test_ddim_sampler_vs_oracle_loop(models_dir):
     """Row f4: DDIM (eta 0) through the same fused CFG + update kernel (different timestep / coefficient tables) vs the oracle loop with the
     numpy DDIM update; then back to the reference's DPM-Solver++ to check the switch re-prepares the schedule."""
