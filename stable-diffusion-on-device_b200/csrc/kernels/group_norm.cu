@@ -17,6 +17,7 @@
 //    the partials in fixed order (deterministic) and publishes mean / rstd.
 //  * gn_nchw_generic_kernel  — any shape/alignment (two reads), used when the TMA path's
 //    alignment or capacity preconditions do not hold.
+#include <cstdlib>
 #include "../common.cuh"
 #include "../host_common.h"
 #include "../launch_count.h"
@@ -480,6 +481,10 @@ static int group_norm_typed(cudaStream_t stream, const T* x, T* y, const float* 
         int cs = 1;
         while (Lb / cs > 49152 && cs < 8) cs *= 2;
         while (static_cast<long long>(N) * G * cs < 2 * 148 && cs < 8 && Lb / (cs * 2) >= 8192) cs *= 2;
+        {
+            static const int env_cs = [] { const char* e = std::getenv("SDOD_GN_CS"); return e ? std::atoi(e) : 0; }();   // experiment knob
+            if (env_cs >= 1 && env_cs <= 8 && (env_cs & (env_cs - 1)) == 0 && Lb / env_cs <= 200 * 1024) cs = env_cs;
+        }
         while (cs > 1 && ((L % cs) != 0 || ((Lb / cs) % 16) != 0)) cs /= 2;
         const long long slab_bytes = Lb / cs;
         if (aligned && slab_bytes <= 200 * 1024 && slab_bytes >= 16 && (L / cs) % VEC == 0) {
