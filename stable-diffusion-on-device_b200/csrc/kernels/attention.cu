@@ -1,8 +1,8 @@
 // Fused flash-style attention for sm_100a (SpatialTransformer attn1 / attn2).
 //
-//   O = softmax(scale * Q K^T) V      per (batch*head), 128 query rows per CTA, KV tiles of 128.
+//   O = softmax(scale * Q K^T) V      per (batch*head), 128 query rows per CTA, KV tiles of 64 keys.
 //
-// Warp roles (192 threads):
+// Warp roles (320 threads):
 //   warp 0     : TMA producer — Q once, then K / V^T tiles through an mbarrier ring
 //   warp 1     : MMA issuer   — S = Q K^T and O += P V on tcgen05, accumulators in TMEM
 //   warps 2..9 : softmax      — two threads per query row; thread `half` owns 32 of each tile's 64 keys and its own

@@ -2,13 +2,14 @@
 //
 //   C[M,N] = epilogue( alpha * A[M,K] * W[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
+// One CTA computes 128 x BN output tiles.  Warp roles (320 threads; 576 in the persistent variant):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
-//   warp 1      : MMA issuer    (one thread issues tcgen05.mma 128xBNx16, commits to mbarriers)
-//   warps 2..9  : epilogue      (tcgen05.ld 32x32b -> bias / temb row-bias / SiLU / GELU / GEGLU /
-//                                residual -> bf16|fp32 stores, incl. attention head-split layouts).
-//                                Two warps share each TMEM lane quarter (column halves in phase 1, row halves in
-//                                phase 2): with one warp per SM sub-partition every dependent latency was exposed.
+//   warp 1      : MMA issuer    (one thread issues tcgen05.mma 128xBNx16 — or 256xBNx16 cta_group::2 for CTA pairs — and commits to mbarriers)
+//   warps 2..   : epilogue      (tcgen05.ld 32x32b -> alpha / bias / temb row-bias / SiLU / GELU / GEGLU / residual -> staged in shared
+//                                memory -> TMA stores; attention head layouts as TMA boxes; split-K partial dump; a coalesced LSU fallback).
+//                                8 warps (16 when persistent): NPART warps share each TMEM lane quarter and split its columns.
+// Variants (template flags, chosen per layer shape by the host code at the bottom of this file): shallow ring with 2 CTAs/SM, DEEP ring for
+// single-wave grids, PAIR = 2-CTA clusters on cta_group::2, PERSIST = one CTA per SM walking the tile list with a double-buffered TMEM accumulator.
 // Conv mode feeds the same mainloop: the A tile for tap (ky,kx) and channel block c is one 4-D TMA
 // box {64 ch, bw, bh, bb} of the NHWC activation at (c, x0+kx-1, y0+ky-1, b0); TMA's out-of-bounds
 // zero fill supplies the padding, so no im2col buffer exists in HBM.
