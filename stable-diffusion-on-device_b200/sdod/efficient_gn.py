@@ -44,6 +44,22 @@ def onnx_symbolic(g, input, num_groups, weight, bias, eps):
     return ret
 
 
+def register_onnx_symbolics(opset_version=13):
+    """Map ``torch.ops.sdod.group_norm`` to the reference's ONNX nodes for ``torch.onnx.export(..., custom_opsets={"sdod": 1}, dynamo=False)``
+    (reference tests/custom_export.py:21-30).  The fused extras (SiLU, temb add) have no node in the reference's op package
+    (csrc/sdod_ops/config/group_norm.json) and refuse to export."""
+    from torch.onnx import register_custom_op_symbolic, symbolic_helper
+
+    @symbolic_helper.parse_args("v", "i", "v", "v", "f", "b", "v")
+    def _group_norm(g, x, num_groups, weight, bias, eps, silu, add_nc):
+        if silu or not symbolic_helper._is_none(add_nc):
+            raise RuntimeError("sdod::group_norm: the fused SiLU / add_nc variants have no ONNX node in the reference op package")
+        w_none, b_none = symbolic_helper._is_none(weight), symbolic_helper._is_none(bias)
+        return onnx_symbolic(g, x, num_groups, None if w_none else weight, None if b_none else bias, eps)
+
+    register_custom_op_symbolic("sdod::group_norm", _group_norm, opset_version)
+
+
 class EfficientGN(nn.Module):
     def __init__(self, num_groups: int, num_channels: int, eps: float = 1e-5, affine: bool = True, device=None, dtype=None, impl=None) -> None:
         factory_kwargs = {"device": device, "dtype": dtype}

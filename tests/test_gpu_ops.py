@@ -447,3 +447,31 @@ def test_conv_split_k_small_spatial():
     finally:
         ops.enable_splitk(False)
     assert rel_err(got, want) < TOL_BF16
+
+
+def test_onnx_export_emits_the_reference_nodes(tmp_path):
+    """Row f3: exporting a module that holds an EfficientGN yields the reference's custom nodes (efficient_gn.py:14-26,
+    tests/custom_export.py:21-30): sdod::GroupNorm(input, weight, bias; num_groups, eps) and sdod::ParameterlessGroupNorm."""
+    from sdod import EfficientGN
+    from sdod.efficient_gn import register_onnx_symbolics
+    register_onnx_symbolics()
+    net = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 1), EfficientGN(2, 8), EfficientGN(4, 8, affine=False)).to(DEV)
+    x = torch.randn(1, 4, 8, 8, device=DEV)
+    path = str(tmp_path / "gn.onnx")
+    try:
+        torch.onnx.export(net, (x,), path, custom_opsets={"sdod": 1}, opset_version=13, dynamo=False)
+        blob = open(path, "rb").read()
+        assert b"GroupNorm" in blob and b"ParameterlessGroupNorm" in blob and b"sdod" in blob and b"num_groups" in blob and b"eps" in blob
+        return
+    except Exception as e:       # the serializer wants the `onnx` package, which this image lacks: check the converted graph instead
+        if "onnx" not in str(e).lower():
+            raise
+    try:
+        from torch.onnx._internal.torchscript_exporter import utils as tsu
+        tsu.GLOBALS.export_onnx_opset_version = 13
+        with tsu.exporter_context(net, torch.onnx.TrainingMode.EVAL, False):
+            graph, _, _ = tsu._model_to_graph(net, (x,), do_constant_folding=False)
+        text = str(graph)
+    except Exception as e:
+        pytest.skip("neither torch.onnx.export nor the graph conversion is usable without the onnx package: %r" % (e,))
+    assert "sdod::GroupNorm" in text and "sdod::ParameterlessGroupNorm" in text and "num_groups" in text and "eps" in text
