@@ -60,6 +60,16 @@ SDOD_API int sdod_group_norm_nhwc(sdod_stream_t stream, const void* x, int in_dt
                                   const float* bias, const float* add_nc, int N, int C, int HW, int num_groups, float eps,
                                   int fuse_silu, void* workspace, size_t workspace_bytes);
 
+/* Single-launch NHWC form for L2-resident tensors (the batch-2 UNet step): GroupNorm over the channel concatenation
+ * x = [xa | xb] (xa [N,HW,Ca], xb [N,HW,Cb] or NULL; Ca % 8 == 0) -> y [N,HW,Ca+Cb]; raw_bf16 (optional) receives the bf16
+ * copy of the un-normalised concatenation (the operand of the ResBlock's 1x1 skip_connection).  One cooperative grid
+ * (<= one CTA per SM) computes the statistics and applies them.  sdod_group_norm_nhwc2_supported() tells whether a
+ * shape qualifies (<= 48 MB input, N <= 128, C % 8 == 0); sdod_group_norm_nhwc() uses this form automatically when it does. */
+SDOD_API int sdod_group_norm_nhwc2(sdod_stream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y,
+                                   int out_dtype, void* raw_bf16, const float* weight, const float* bias, int N, int HW,
+                                   int num_groups, float eps, int fuse_silu, void* workspace, size_t workspace_bytes);
+SDOD_API int sdod_group_norm_nhwc2_supported(int N, int Ca, int Cb, int HW, int num_groups, int in_dtype);
+
 /* LayerNorm over the last dim (SpatialTransformer norm1/2/3). x [rows, width] f32|bf16 -> y bf16. */
 SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, void* y, const float* weight, const float* bias,
                              int rows, int width, float eps);
@@ -140,21 +150,28 @@ typedef struct sdod_gemm_desc {
     int M, N, K, batch;
     int block_n;             /* 0 = auto                                                           */
     sdod_epilogue epi;
+    /* optional second operand, K-concatenated:  C = epilogue(alpha * [A | A2] * W^T), W bf16 [N, K + K2]          */
+    const void* A2; long long lda2; int K2;            /* bf16 [M, K2] (batch == 1 only), K2 % 64 == 0; NULL = none */
 } sdod_gemm_desc;
 SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d);
 /* Optional split-K scratch for the calling thread's subsequent sdod_gemm_bf16 / sdod_conv3x3_bf16 calls (small-M
- * layers spread their K loop over the chip; the last CTA of each tile folds the partials).  ws: fp32 scratch;
- * counters: n_counters zero-initialised uint32 (the kernels reset them).  Pass NULLs to disable. */
+ * layers spread their K loop over the chip: the `split` CTAs of an output tile form a thread-block cluster, publish
+ * fp32 partial tiles to this L2-resident scratch and, after a cluster barrier, each folds 1/split of the tile in fixed
+ * order (deterministic) and runs the epilogue on it — one launch).  ws: fp32 scratch; counters: reserved (n_counters
+ * zero-initialised uint32).  Pass NULLs to disable. */
 SDOD_API int sdod_set_splitk_workspace(float* ws, size_t ws_bytes, unsigned int* counters, int n_counters);
 
 /* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC:  Y[B,H,W,Cout] = epilogue( X (*) Wt )
  * X bf16 [B,H,W,Cin] (Cin % 64 == 0), Wt bf16 [Cout, 9*Cin] with k = (ky*3+kx)*Cin + c.
- * upsample2x != 0: X is [B,H/2,W/2,Cin] and is read through a nearest-2x gather. */
+ * X2 != NULL fuses a 1x1 convolution of a second tensor into the same accumulator (the ResBlock skip_connection):
+ * Y = epilogue( X (*) Wt[:, :9*Cin] + X2 * Wt[:, 9*Cin:]^T ), X2 bf16 [B*H*W, Cin2] rows of ldx2 elements, Cin2 % 64 == 0,
+ * Wt then has 9*Cin + Cin2 columns. */
 typedef struct sdod_conv_desc {
     const void* X; const void* Wt;
     int B, H, W, Cin, Cout;
     int block_n;
     sdod_epilogue epi;       /* M = B*H*W rows, N = Cout                                            */
+    const void* X2; long long ldx2; int Cin2;
 } sdod_conv_desc;
 SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d);
 

@@ -264,7 +264,29 @@ SDOD_DEVICE void epilogue_geglu16(const sdod_epilogue& ep, const MainloopParams&
     }
 }
 
-// Split-K second phase: folds the `split` partial tiles in fixed order (deterministic) and runs the shared epilogue.
+// Fold the `split` fp32 partials of 8 accumulator columns (two float4 per split, `zstride4` float4 apart) in fixed z order.
+SDOD_DEVICE void fold_partials8(const float4* src, int split, long long zstride4, float (&acc)[8]) {
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    int z = 0;
+    for (; z + 4 <= split; z += 4) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[2 * u] = __ldcg(src + (z + u) * zstride4); v[2 * u + 1] = __ldcg(src + (z + u) * zstride4 + 1); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s0.x += v[2 * u].x; s0.y += v[2 * u].y; s0.z += v[2 * u].z; s0.w += v[2 * u].w;
+            s1.x += v[2 * u + 1].x; s1.y += v[2 * u + 1].y; s1.z += v[2 * u + 1].z; s1.w += v[2 * u + 1].w;
+        }
+    }
+    for (; z < split; ++z) {
+        const float4 a = __ldcg(src + z * zstride4), b = __ldcg(src + z * zstride4 + 1);
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+    }
+    acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w; acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
+}
+
+// Split-K second phase (fallback when the split CTAs cannot form a cluster, and for GEGLU): folds the `split` partial tiles in
+// fixed order (deterministic) and runs the shared epilogue.
 // Plain epilogues: 256 threads = 128 rows x 2 column octets, so a warp reads 16 rows x 64 B contiguous partials and writes
 // 16 row segments of 32 B (fp32) — coalesced both ways.  grid = (BN/16 chunks, tiles).
 template <int BN>
@@ -279,23 +301,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
         const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
         const int j = blockIdx.x * 16;
         const float4* src = reinterpret_cast<const float4*>(base + ((j >> 4) * kBlockM + row) * 16 + half * 8);
-        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-        int z = 0;
-        for (; z + 4 <= mp.split; z += 4) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { v[2 * u] = __ldcg(src + (z + u) * zstride4); v[2 * u + 1] = __ldcg(src + (z + u) * zstride4 + 1); }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                s0.x += v[2 * u].x; s0.y += v[2 * u].y; s0.z += v[2 * u].z; s0.w += v[2 * u].w;
-                s1.x += v[2 * u + 1].x; s1.y += v[2 * u + 1].y; s1.z += v[2 * u + 1].z; s1.w += v[2 * u + 1].w;
-            }
-        }
-        for (; z < mp.split; ++z) {
-            const float4 a = __ldcg(src + z * zstride4), b = __ldcg(src + z * zstride4 + 1);
-            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
-        }
-        const float acc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float acc[8];
+        fold_partials8(src, mp.split, zstride4, acc);
         epilogue_plain8(ep, mp, 0, m_tile * kBlockM + row, n_tile * BN + j + half * 8, acc);
         return;
     }
@@ -344,6 +351,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                       const __grid_constant__ CUtensorMap tmR,
                                                                       const __grid_constant__ CUtensorMap tmC2,
+                                                                      const __grid_constant__ CUtensorMap tmA2,
                                                                       const MainloopParams mp, const sdod_epilogue ep) {
     using Cfg = GemmCfg<BN, DEEP, PAIR, PERSIST>;
     static_assert(!(PAIR && PERSIST), "persistent CTA pairs are not implemented");
@@ -375,6 +383,20 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
+        if (mp.kb_a2 < mp.k_blocks) tma_prefetch_desc(&tmA2);
+    }
+    if (warp == 0 && lane >= 1 && mp.pf_bytes > 0) {
+        // Pull the NEXT layer's weights towards L2 while this kernel runs (weights are constants: no dependency on the predecessor, so
+        // this is issued before griddepcontrol.wait).  At batch 2 the step streams 1.7 GB of weights through ~200 short kernels; without
+        // the prefetch every kernel starts with an exposed HBM round trip and the deep levels run at ~1/3 of HBM bandwidth.
+        const long long ncta = static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z;
+        const long long cta = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const long long chunk = (((mp.pf_bytes + ncta - 1) / ncta) + 4095) & ~4095LL;
+        const long long end = min(mp.pf_bytes, (cta + 1) * chunk);
+        for (long long off = cta * chunk + (lane - 1) * 4096LL; off < end; off += 31 * 4096LL) {
+            const uint32_t nb = static_cast<uint32_t>(min(4096LL, end - off)) & ~15u;
+            if (nb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mp.pf_ptr + off), "r"(nb) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -430,14 +452,12 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 const int s = g % STAGES;
                 const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                if (mp.dbg == 1) {                              // measurement aid: MMA + epilogue only, operands are whatever is in smem
-                    if (!PAIR || rank == 0) mbar_arrive(&full_bar[s]);
-                    continue;
-                }
                 if (PAIR) {
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);     // both CTAs' A + B halves
                     const uint32_t fb = leader_full + s * 8;
-                    if (mp.conv) {
+                    if (kb >= mp.kb_a2) {                       // K-concatenated second operand: plain rows [m0, m0+128) of A2
+                        tma_load_3d_pair(sA + s * kABytes, &tmA2, fb, (kb - mp.kb_a2) * kBlockK, m0, bz);
+                    } else if (mp.conv) {
                         const int tap = kb / mp.cin_blocks;
                         const int cb = kb - tap * mp.cin_blocks;
                         const int ky = tap / 3, kx = tap - ky * 3;
@@ -449,7 +469,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     continue;
                 }
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                if (mp.conv) {
+                if (kb >= mp.kb_a2) {
+                    tma_load_3d(sA + s * kABytes, &tmA2, &full_bar[s], (kb - mp.kb_a2) * kBlockK, m0, bz);
+                } else if (mp.conv) {
                     const int tap = kb / mp.cin_blocks;
                     const int cb = kb - tap * mp.cin_blocks;
                     const int ky = tap / 3, kx = tap - ky * 3;
@@ -481,11 +503,6 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kABytes);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
-                if (mp.dbg == 2) {                              // measurement aid: loads only, slots are released at once
-                    if (PAIR) tc_commit_pair(&empty_bar[s]);
-                    else tc_commit(&empty_bar[s]);
-                    continue;
-                }
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     if (PAIR) tc_mma_bf16_pair(tmem_acc, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
@@ -925,6 +942,28 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }   // tile loop
         if (PERSIST) bulk_wait_read_all();                 // (storing threads) shared memory stays valid until the last store has read it
     }
+    if (!PAIR && !PERSIST && mp.split_cluster) {
+        // Split-K inside one launch: the `split` CTAs of this output tile are one thread-block cluster (1,1,split).  Each has published its
+        // fp32 partial tile to the L2-resident scratch above; after the cluster barrier (release/acquire at cluster scope) every CTA folds
+        // 1/split of the tile — warp tasks of 16 rows x 16 columns, dealt round-robin over the CTAs and their 8 epilogue warps — in fixed
+        // z order (deterministic, independent of arrival order) and runs the shared epilogue on it.
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+        if (warp >= 2) {
+            const int n_tile = static_cast<int>(blockIdx.x), m_tile = static_cast<int>(blockIdx.y);
+            const long long tile_id = static_cast<long long>(m_tile) * gridDim.x + n_tile;
+            const float* base = mp.ws + tile_id * mp.split * (BN * kBlockM);
+            const long long zstride4 = BN * kBlockM / 4;
+            constexpr int kTasks = (BN / 16) * 8;
+            const int row_in = lane >> 1, half = lane & 1;
+            for (int u = zs + mp.split * (warp - 2); u < kTasks; u += mp.split * 8) {
+                const int chunk = u >> 3, row = (u & 7) * 16 + row_in;
+                float acc[8];
+                fold_partials8(reinterpret_cast<const float4*>(base + (chunk * kBlockM + row) * 16 + half * 8), mp.split, zstride4, acc);
+                epilogue_plain8(ep, mp, 0, m_tile * kBlockM + row, n_tile * BN + chunk * 16 + half * 8, acc);
+            }
+        }
+    }
     __syncthreads();
     if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the pair may still touch it
     if (warp == 2) {
@@ -944,10 +983,23 @@ static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) 
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
-    if (!PAIR) {
+    if (!PAIR && !(g.mp.split > 1 && g.mp.split_cluster)) {
         return check_cuda(launch_pdl(gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, grid, dim3(PERSIST ? kGemmThreadsPersist : kGemmThreads),
-                                     Cfg::kSmemBytes, stream, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep),
+                                     Cfg::kSmemBytes, stream, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.tmA2, g.mp, g.ep),
                           "launch gemm_tcgen05_kernel");
+    }
+    if (!PAIR) {
+        // split-K cluster: the `split` CTAs of a tile (grid.z) are co-scheduled as one cluster and reduce in-kernel
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = static_cast<unsigned>(g.mp.split);
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.tmA2, g.mp, g.ep),
+                          "launch gemm_tcgen05_kernel (split-K cluster)");
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
@@ -955,7 +1007,7 @@ static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // two consecutive M tiles
     cfg.attrs = attr; cfg.numAttrs = 1;      // no programmatic serialization for pairs (see the kernel)
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.mp, g.ep);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.tmA2, g.mp, g.ep);
     if (e != cudaSuccess) {
         int nc = -1;
         cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nc, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, &cfg);
@@ -993,7 +1045,7 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     }
     count_launch();
     SDOD_TRY(check_launch("gemm_tcgen05_kernel"));
-    if (mp.split > 1) {
+    if (mp.split > 1 && !mp.split_cluster) {
         dim3 rgrid(BN / 16, g.m_tiles * g.n_tiles);
         SDOD_TRY(check_cuda(launch_pdl(splitk_reduce_kernel<BN>, rgrid, dim3(256), 0, stream, mp, g.ep, g.n_tiles), "launch splitk_reduce_kernel"));
         count_launch();
@@ -1151,11 +1203,6 @@ static void choose_persist(GemmLaunch* out) {
     out->persist = (mp.tiles_total >= 3 * sms && mp.k_blocks <= 10) ? 1 : 0;
 }
 
-static int debug_mode() {   // SDOD_GEMM_DBG=1: no operand loads, =2: no MMAs (results are garbage; timing experiments only)
-    static const int env = [] { const char* e = std::getenv("SDOD_GEMM_DBG"); return e ? std::atoi(e) : 0; }();
-    return env;
-}
-
 static int k_rotation(int k_blocks) {
     static const int env = [] { const char* e = std::getenv("SDOD_GEMM_KROT"); return e ? std::atoi(e) : 0; }();
     return k_blocks >= 8 ? env : 0;
@@ -1185,6 +1232,26 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
     mp->split = split; mp->kb_per_split = kbps; mp->ws = g_splitk.ws; mp->counters = g_splitk.counters;
 }
 
+// In-kernel reduction over a (1,1,split) cluster (one launch) unless SDOD_SPLITK_CLUSTER=0 (A/B measurements: separate reduce kernel).
+static int split_cluster_mode(const MainloopParams& mp, bool pair, int act) {
+    static const int env = [] { const char* e = std::getenv("SDOD_SPLITK_CLUSTER"); return e ? std::atoi(e) : 1; }();
+    return (env && mp.split > 1 && mp.split <= 8 && !pair && act != SDOD_ACT_GEGLU) ? 1 : 0;
+}
+
+// Second A operand (K-concatenated): bf16 [M, K2] rows of ld2 elements, loaded as plain {64, 128} boxes after tmA's K blocks.
+static int setup_second_operand(GemmLaunch* out, const void* A2, long long ld2, int K2, int M, int kb_main) {
+    std::memset(&out->tmA2, 0, sizeof(CUtensorMap));
+    out->mp.kb_a2 = 1 << 30;
+    if (!A2 || K2 <= 0) return kOk;
+    if (K2 % kBlockK != 0 || ld2 % 8 != 0) return fail(kInvalidArgument, "second operand: K2 must be a multiple of 64 and its row stride of 8 elements");
+    uint64_t dims[3] = {static_cast<uint64_t>(K2), static_cast<uint64_t>(M), 1};
+    uint64_t strides[2] = {static_cast<uint64_t>(ld2) * 2, static_cast<uint64_t>(M) * ld2 * 2};
+    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    SDOD_TRY(encode_tmap_bf16(&out->tmA2, A2, 3, dims, strides, box, true));
+    out->mp.kb_a2 = kb_main;
+    return kOk;
+}
+
 static int validate_epilogue(const sdod_epilogue& ep, int N) {
     if (!ep.C) return fail(kInvalidArgument, "epilogue: C is NULL");
     if (ep.row_bias && ep.rows_per_group <= 0) return fail(kInvalidArgument, "epilogue: rows_per_group must be > 0 with row_bias");
@@ -1205,8 +1272,11 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.batch <= 0) return fail(kInvalidArgument, "gemm: non-positive extent");
     if (d.K % kBlockK != 0) return fail(kInvalidArgument, "gemm: K must be a multiple of 64 (pad the operand)");
     if (d.lda % 8 != 0 || d.ldw % 8 != 0) return fail(kInvalidArgument, "gemm: lda/ldw must be multiples of 8 elements");
+    const int K2 = d.A2 ? d.K2 : 0;
+    if (K2 && d.batch != 1) return fail(kInvalidArgument, "gemm: a second operand needs batch == 1");
+    const int Ktot = d.K + K2;
     SDOD_TRY(validate_epilogue(d.epi, d.N));
-    int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, d.K / kBlockK);
+    int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, Ktot / kBlockK);
     if (!d.block_n && d.N % 160 == 0 && heads_tma_eligible(d.epi, d.M, d.N, d.batch)) bn = 160;   // four 40-column head boxes per tile
     const bool pair = use_pair(bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, false);
 
@@ -1220,17 +1290,20 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     }
     const bool wb = d.batch > 1 && d.strideW != 0;
     {
-        uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N), static_cast<uint64_t>(wb ? d.batch : 1)};
+        uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(d.N), static_cast<uint64_t>(wb ? d.batch : 1)};
         uint64_t strides[2] = {static_cast<uint64_t>(d.ldw) * 2, static_cast<uint64_t>(wb ? d.strideW : static_cast<long long>(d.N) * d.ldw) * 2};
         uint32_t box[3] = {kBlockK, static_cast<uint32_t>(pair ? bn / 2 : bn), 1};
         SDOD_TRY(encode_tmap_bf16(&tmW, d.W, 3, dims, strides, box, true));
     }
     out->pair = pair ? 1 : 0;
     MainloopParams mp{};
-    mp.M = d.M; mp.N = d.N; mp.k_blocks = d.K / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
-    mp.k_rot = k_rotation(mp.k_blocks); mp.dbg = debug_mode();
+    mp.M = d.M; mp.N = d.N; mp.k_blocks = Ktot / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
+    mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
+    mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
+    SDOD_TRY(setup_second_operand(out, d.A2, d.lda2, K2, d.M, d.K / kBlockK));
+    out->w_ptr = d.W; out->w_bytes = static_cast<long long>(d.N) * d.ldw * 2 * (wb ? d.batch : 1);
     SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
     SDOD_TRY(setup_heads_epilogue(out, d.epi, d.M, d.N, d.batch));
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
@@ -1262,7 +1335,8 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     const int bb = 128 / (bw * bh);
     const int M = d.B * d.H * d.W;
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
-    const int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, 9 * d.Cin / kBlockK);
+    const int Cin2 = d.X2 ? d.Cin2 : 0;
+    const int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, (9 * d.Cin + Cin2) / kBlockK);
     const bool pair = use_pair(bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, true);
 
     CUtensorMap& tmA = out->tmA;
@@ -1274,7 +1348,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
         uint32_t box[4] = {kBlockK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
         SDOD_TRY(encode_tmap_bf16(&tmA, d.X, 4, dims, strides, box, true));
     }
-    const int K = 9 * d.Cin;
+    const int K = 9 * d.Cin + Cin2;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(d.Cout), 1};
         uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * d.Cout * 2};
@@ -1285,9 +1359,12 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
-    mp.k_rot = k_rotation(mp.k_blocks); mp.dbg = debug_mode();
+    mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
+    mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
+    SDOD_TRY(setup_second_operand(out, d.X2, d.ldx2, Cin2, M, 9 * d.Cin / kBlockK));
+    out->w_ptr = d.Wt; out->w_bytes = static_cast<long long>(d.Cout) * K * 2;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));
     std::memset(&out->tmC2, 0, sizeof(CUtensorMap));
     out->m_tiles = (M + kBlockM - 1) / kBlockM;

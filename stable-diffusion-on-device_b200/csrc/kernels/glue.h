@@ -4,6 +4,8 @@
 #include <stdint.h>
 namespace sdod {
 int pack_rows(cudaStream_t s, const float* src, void* dst_bf16, int N, int K, int Kpad, const int* rowmap);
+int pack_rows_window(cudaStream_t s, const float* src, void* dst_bf16, int N, int K, long long ld, int col0);
+int add_f32(cudaStream_t s, const float* a, const float* b, float* dst, int n);
 int gather_f32(cudaStream_t s, const float* src, float* dst, int n, const int* map);
 int silu_f32_to_bf16(cudaStream_t s, const float* x, void* y_bf16, size_t n, int apply_silu);
 int latent_prequant(cudaStream_t s, const float* z, void* y_bf16, size_t rows, const float* w, const float* b, float inv_scale);

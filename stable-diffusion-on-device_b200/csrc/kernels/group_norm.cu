@@ -408,6 +408,167 @@ __global__ void gn_nhwc_apply_kernel(const TI* __restrict__ x, TO* __restrict__ 
     }
 }
 
+// Single-launch NHWC GroupNorm for tensors that live in L2 (the batch-2 UNet step: every tensor is <= 31 MB).
+// One grid of <= 148 CTAs, all co-resident: each CTA (sample n, row slab) accumulates pivot-shifted sums of its slab, publishes its per-group
+// partials, arrives on the sample's counter and waits until the sample's S slabs have arrived; then EVERY CTA folds the S partials in
+// the same fixed order (deterministic, bit-identical statistics in all CTAs) and normalises its own slab, which it re-reads from L1/L2.
+// x is the channel concatenation [xa | xb] (xb may be NULL): the UNet's skip concat never exists in memory, and `raw` (optional) receives
+// the bf16 copy of the un-normalised concatenation that the ResBlock's 1x1 skip convolution consumes — the former concat and cast
+// kernels.  Replaces 2 (+2) launches per GroupNorm by one.
+// Co-residency: the grid is sized <= #SMs with one CTA per SM's worth of resources, the predecessor kernel has completed when
+// griddepcontrol.wait returns and a PDL successor can only be launched once every CTA of this grid runs, so every CTA a spinning CTA
+// waits for is resident or about to be; the spin is bounded and traps instead of hanging the GPU.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict__ xa, int Ca, const TI* __restrict__ xb, int Cb,
+                                                            TO* __restrict__ y, bf16* __restrict__ raw, const float* __restrict__ weight,
+                                                            const float* __restrict__ bias, float* __restrict__ partials,
+                                                            unsigned int* __restrict__ counters, int HW, int G, int rows_per_slab, float eps,
+                                                            int fuse_silu) {
+    constexpr int VEC = kNhwcVec;
+    griddep_wait();
+    griddep_launch();
+    extern __shared__ float gsm[];          // [r][C][2], then [G][lanes][2]
+    __shared__ float pivots[64], s_mean[64], s_rstd[64];
+    const int C = Ca + Cb;
+    const int n = blockIdx.y, slab = blockIdx.x, S = gridDim.x;
+    const int cvec = C / VEC;
+    const int r = blockDim.x / cvec;
+    const int col = threadIdx.x % cvec, rr = threadIdx.x / cvec;
+    const bool active = rr < r;
+    const int cpg = C / G;
+    // this thread's 8 channels live in one of the two sources (Ca % 8 == 0)
+    const int c0 = col * VEC;
+    const bool from_b = c0 >= Ca;
+    const int ldx = from_b ? Cb : Ca;
+    const TI* xcol = (from_b ? xb + static_cast<long long>(n) * HW * Cb + (c0 - Ca) : xa + static_cast<long long>(n) * HW * Ca + c0);
+    for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+        const int c = gg * cpg;
+        pivots[gg] = c < Ca ? to_f<TI>(xa[static_cast<long long>(n) * HW * Ca + c]) : to_f<TI>(xb[static_cast<long long>(n) * HW * Cb + (c - Ca)]);
+    }
+    __syncthreads();
+    float K[VEC], s[VEC], ss[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { K[i] = pivots[(c0 + i) / cpg]; s[i] = 0.f; ss[i] = 0.f; }
+    const int p0 = slab * rows_per_slab;
+    const int p1 = min(HW, p0 + rows_per_slab);
+    if (active) {
+        int p = p0 + rr;
+        for (; p + 3 * r < p1; p += 4 * r) {
+            float e[4][VEC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8<TI>(xcol + static_cast<long long>(p + u * r) * ldx, e[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { float d = e[u][i] - K[i]; s[i] += d; ss[i] += d * d; }
+            }
+        }
+        for (; p < p1; p += r) {
+            float e[VEC];
+            load8<TI>(xcol + static_cast<long long>(p) * ldx, e);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { float d = e[i] - K[i]; s[i] += d; ss[i] += d * d; }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            gsm[(rr * C + c0 + i) * 2 + 0] = s[i];
+            gsm[(rr * C + c0 + i) * 2 + 1] = ss[i];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int q = 0; q < r; ++q) { a += gsm[(q * C + c) * 2]; b += gsm[(q * C + c) * 2 + 1]; }
+        gsm[c * 2] = a; gsm[c * 2 + 1] = b;
+    }
+    __syncthreads();
+    for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = gg * cpg; c < (gg + 1) * cpg; ++c) { a += gsm[c * 2]; b += gsm[c * 2 + 1]; }
+        float* dst = partials + ((static_cast<long long>(n) * S + slab) * G + gg) * 2;
+        dst[0] = a; dst[1] = b;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&counters[n], 1u);
+        unsigned int seen = 0, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + n) : "memory");
+            if (seen < static_cast<unsigned>(S) && ++spins > (1u << 22)) __trap();   // seconds, not a hot loop: a scheduling bug traps instead of hanging
+        } while (seen < static_cast<unsigned>(S));
+    }
+    __syncthreads();
+    {
+        const int lanes = max(1, min(static_cast<int>(blockDim.x) / G, 16));
+        float* fold = gsm;                                    // [G][lanes][2]
+        if (static_cast<int>(threadIdx.x) < G * lanes) {
+            const int gg = threadIdx.x / lanes, l = threadIdx.x - gg * lanes;
+            float a = 0.f, b = 0.f;
+            const float2* src = reinterpret_cast<const float2*>(partials + (static_cast<long long>(n) * S * G + gg) * 2);
+            for (int q = l; q < S; q += lanes) { const float2 v = __ldcg(src + static_cast<long long>(q) * G); a += v.x; b += v.y; }
+            fold[(gg * lanes + l) * 2] = a; fold[(gg * lanes + l) * 2 + 1] = b;
+        }
+        __syncthreads();
+        for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < lanes; ++l) { a += fold[(gg * lanes + l) * 2]; b += fold[(gg * lanes + l) * 2 + 1]; }
+            const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+            const float m = a / cnt;
+            const float var = fmaxf(b / cnt - m * m, 0.f);
+            s_mean[gg] = pivots[gg] + m;
+            s_rstd[gg] = rsqrtf(var + eps);
+        }
+    }
+    __syncthreads();
+    // every thread of this CTA is done with the partials: depart; the last CTA of the sample to depart re-arms both counters
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&counters[kGnCounterInts / 2 + n], 1u) == static_cast<unsigned>(S - 1)) {
+            counters[n] = 0;
+            counters[kGnCounterInts / 2 + n] = 0;
+        }
+    }
+    if (!active) return;
+    float A[VEC], B[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = c0 + i;
+        const int g = c / cpg;
+        const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
+        A[i] = s_rstd[g] * w;
+        B[i] = -s_mean[g] * s_rstd[g] * w + b;
+    }
+    TO* ycol = y + static_cast<long long>(n) * HW * C + c0;
+    bf16* rcol = raw ? raw + static_cast<long long>(n) * HW * C + c0 : nullptr;
+    int p = p0 + rr;
+    for (; p + 3 * r < p1; p += 4 * r) {
+        float e[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8<TI>(xcol + static_cast<long long>(p + u * r) * ldx, e[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (rcol) store8v<bf16>(rcol + static_cast<long long>(p + u * r) * C, e[u]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float o = fmaf(e[u][i], A[i], B[i]);
+                e[u][i] = fuse_silu ? silu_f(o) : o;
+            }
+            store8v<TO>(ycol + static_cast<long long>(p + u * r) * C, e[u]);
+        }
+    }
+    for (; p < p1; p += r) {
+        float e[VEC];
+        load8<TI>(xcol + static_cast<long long>(p) * ldx, e);
+        if (rcol) store8v<bf16>(rcol + static_cast<long long>(p) * C, e);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float o = fmaf(e[i], A[i], B[i]);
+            e[i] = fuse_silu ? silu_f(o) : o;
+        }
+        store8v<TO>(ycol + static_cast<long long>(p) * C, e);
+    }
+}
+
 static void nhwc_geometry(int N, int C, int HW, int vec, int* threads, int* slabs, int* rows_per_slab) {
     const int cvec = C / vec;
     int r = cvec >= 256 ? 1 : 256 / cvec;
@@ -453,12 +614,71 @@ static int group_norm_nhwc_typed(cudaStream_t stream, const TI* x, TO* y, const 
     return check_launch("gn_nhwc_apply_kernel");
 }
 
+// Single-launch path (gn_nhwc_fused_kernel): the whole tensor must sit in L2 (it is read twice) and the grid must be co-resident.
+static bool fused_env() {
+    static const int env = [] { const char* e = std::getenv("SDOD_GN_FUSED"); return e ? std::atoi(e) : 1; }();
+    return env != 0;
+}
+bool group_norm_fused_eligible(int N, int Ca, int Cb, int HW, int G, int in_dtype) {
+    const int C = Ca + Cb;
+    if (!fused_env() || N < 1 || N > kGnCounterInts / 2 || N > device_sm_count()) return false;
+    if (C % kNhwcVec != 0 || Ca % kNhwcVec != 0 || C / kNhwcVec > 512 || G > 64 || C % G != 0) return false;
+    const size_t bytes = static_cast<size_t>(N) * HW * C * (in_dtype == SDOD_F32 ? 4 : 2);
+    return bytes <= (static_cast<size_t>(48) << 20);
+}
+
+template <typename TI, typename TO>
+static int group_norm_fused_typed(cudaStream_t stream, const TI* xa, int Ca, const TI* xb, int Cb, TO* y, bf16* raw, const float* weight,
+                                  const float* bias, int N, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
+    const int C = Ca + Cb, cvec = C / kNhwcVec;
+    int r = std::max(1, 512 / cvec);
+    if (r > HW) r = HW;
+    const int threads = cvec * r;
+    int S = std::max(1, std::min(device_sm_count() / N, std::max(1, HW / (2 * r))));
+    const int rps = (HW + S - 1) / S;
+    S = (HW + rps - 1) / rps;
+    const size_t need = kGnCounterInts * sizeof(unsigned int) + static_cast<size_t>(N) * G * 2 * sizeof(float) * (1 + S);
+    if (!ws || ws_bytes < need) return fail(kInvalidArgument, "group_norm (fused): workspace too small (need " + std::to_string(need) + " bytes)");
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    float* partials = reinterpret_cast<float*>(counters + kGnCounterInts) + static_cast<size_t>(N) * G * 2;
+    const size_t smem = std::max(static_cast<size_t>(r) * C * 2 * sizeof(float), static_cast<size_t>(G) * 16 * 2 * sizeof(float));
+    if (smem > 48 * 1024)
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_fused_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                            "cudaFuncSetAttribute(gn fused)"));
+    SDOD_TRY(check_cuda(launch_pdl(gn_nhwc_fused_kernel<TI, TO>, dim3(S, N), dim3(threads), smem, stream, xa, Ca, xb, Cb, y, raw, weight, bias, partials,
+                                   counters, HW, G, rps, eps, fuse_silu), "launch gn_nhwc_fused_kernel"));
+    count_launch();
+    return check_launch("gn_nhwc_fused_kernel");
+}
+
+int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y, int out_dtype, void* raw_bf16,
+                     const float* weight, const float* bias, int N, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
+    if (!xa || !y || (Cb > 0 && !xb)) return fail(kInvalidArgument, "group_norm: NULL tensor");
+    if (!xb) Cb = 0;
+    if (N <= 0 || Ca <= 0 || Cb < 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");
+    if ((Ca + Cb) % G != 0) return fail(kInvalidArgument, "num_channels must be divisible by num_groups");
+    if ((weight == nullptr) != (bias == nullptr)) return fail(kInvalidArgument, "group_norm: weight and bias must both be given or both be NULL");
+    if (!group_norm_fused_eligible(N, Ca, Cb, HW, G, in_dtype))
+        return fail(kUnsupported, "group_norm (two-source / single-launch form): tensor too large for the L2-resident kernel or unsupported shape");
+#define SDOD_GN2_CASE(TI, TO) \
+    return group_norm_fused_typed<TI, TO>(stream, static_cast<const TI*>(xa), Ca, static_cast<const TI*>(xb), Cb, static_cast<TO*>(y), \
+                                          static_cast<bf16*>(raw_bf16), weight, bias, N, HW, G, eps, fuse_silu, ws, ws_bytes)
+    if (in_dtype == SDOD_F32 && out_dtype == SDOD_F32) SDOD_GN2_CASE(float, float);
+    if (in_dtype == SDOD_F32 && out_dtype == SDOD_BF16) SDOD_GN2_CASE(float, bf16);
+    if (in_dtype == SDOD_BF16 && out_dtype == SDOD_BF16) SDOD_GN2_CASE(bf16, bf16);
+    if (in_dtype == SDOD_BF16 && out_dtype == SDOD_F32) SDOD_GN2_CASE(bf16, float);
+#undef SDOD_GN2_CASE
+    return fail(kInvalidArgument, "group_norm: unknown dtype");
+}
+
 int group_norm_nhwc(cudaStream_t stream, const void* x, int in_dtype, void* y, int out_dtype, const float* weight, const float* bias,
                     const float* add_nc, int N, int C, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
     if (!x || !y) return fail(kInvalidArgument, "group_norm: NULL tensor");
     if (N <= 0 || C <= 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");
     if (C % G != 0) return fail(kInvalidArgument, "num_channels must be divisible by num_groups");
     if ((weight == nullptr) != (bias == nullptr)) return fail(kInvalidArgument, "group_norm: weight and bias must both be given or both be NULL");
+    if (!add_nc && group_norm_fused_eligible(N, C, 0, HW, G, in_dtype))
+        return group_norm_nhwc2(stream, x, C, nullptr, 0, in_dtype, y, out_dtype, nullptr, weight, bias, N, HW, G, eps, fuse_silu, ws, ws_bytes);
 #define SDOD_GN_CASE(TI, TO) \
     return group_norm_nhwc_typed<TI, TO>(stream, static_cast<const TI*>(x), static_cast<TO*>(y), weight, bias, add_nc, N, C, HW, G, eps, fuse_silu, ws, ws_bytes)
     if (in_dtype == SDOD_F32 && out_dtype == SDOD_F32) SDOD_GN_CASE(float, float);
@@ -543,6 +763,15 @@ SDOD_API int sdod_group_norm_nhwc(sdod_stream_t stream, const void* x, int in_dt
                                   void* workspace, size_t workspace_bytes) {
     return sdod::group_norm_nhwc(static_cast<cudaStream_t>(stream), x, in_dtype, y, out_dtype, weight, bias, add_nc, N, C, HW, num_groups, eps,
                                  fuse_silu, workspace, workspace_bytes);
+}
+SDOD_API int sdod_group_norm_nhwc2(sdod_stream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y, int out_dtype,
+                                   void* raw_bf16, const float* weight, const float* bias, int N, int HW, int num_groups, float eps,
+                                   int fuse_silu, void* workspace, size_t workspace_bytes) {
+    return sdod::group_norm_nhwc2(static_cast<cudaStream_t>(stream), xa, Ca, xb, Cb, in_dtype, y, out_dtype, raw_bf16, weight, bias, N, HW,
+                                  num_groups, eps, fuse_silu, workspace, workspace_bytes);
+}
+SDOD_API int sdod_group_norm_nhwc2_supported(int N, int Ca, int Cb, int HW, int num_groups, int in_dtype) {
+    return sdod::group_norm_fused_eligible(N, Ca, Cb, HW, num_groups, in_dtype) ? 1 : 0;
 }
 SDOD_API int sdod_group_norm(sdod_stream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc,
                              int N, int C, int HW, int num_groups, float eps, int dtype, int layout, int fuse_silu, void* workspace,

@@ -22,13 +22,21 @@ struct MainloopParams {
     unsigned int* counters;   // one ticket per output tile, self-resetting
     int tma_epi;       // 0: LSU epilogue; 1: TMA-store epilogue; 2: TMA-store + residual TMA-loaded and added in place
     int c_bytes;       // output element size for the TMA epilogue (2 | 4)
-    int dbg;           // 0 normal; 1 skip operand loads; 2 skip MMAs (timing experiments, SDOD_GEMM_DBG)
+    int split_cluster; // 1: the `split` CTAs of a tile form a thread-block cluster (1,1,split) and fold the partials in-kernel after a
+                       //    cluster barrier; 0: partials are folded by splitk_reduce_kernel (a second launch)
+    int kb_a2;         // first K block served by the second A operand (tmA2: plain [K2, M] rows, the K-concatenated skip / concat
+                       //    source); >= k_blocks when there is none
+    const char* pf_ptr;       // L2 prefetch of the NEXT layer's weights (constant data, issued before griddepcontrol.wait); NULL = none
+    long long pf_bytes;
     int k_rot;         // K-loop start rotation per M tile (in K blocks); 0 = every tile starts at block 0
     int n_tiles, m_tiles, tiles_total;   // persistent scheduling: tile t -> (t % n_tiles, (t / n_tiles) % m_tiles, t / (n_tiles*m_tiles))
 };
 
 struct GemmLaunch {
     CUtensorMap tmA, tmW, tmC, tmR, tmC2;   // tmC2: V^T boxes of the head-layout TMA epilogue
+    CUtensorMap tmA2;                       // second A operand (K-concatenated after tmA's blocks); zeroed when unused
+    const void* w_ptr;                      // this launch's weight matrix and its size: the previous launch prefetches it into L2
+    long long w_bytes;
     MainloopParams mp;
     sdod_epilogue ep;
     int bn, m_tiles, n_tiles, batch;
@@ -63,5 +71,11 @@ int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight,
 
 int group_norm_nhwc(cudaStream_t stream, const void* x, int in_dtype, void* y, int out_dtype, const float* weight, const float* bias,
                     const float* add_nc, int N, int C, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes);
+
+// Single-launch NHWC GroupNorm over the channel concatenation [xa | xb] (xb may be NULL) with an optional bf16 copy of the raw
+// concatenation; only for L2-resident tensors (group_norm_fused_eligible).
+bool group_norm_fused_eligible(int N, int Ca, int Cb, int HW, int G, int in_dtype);
+int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y, int out_dtype, void* raw_bf16,
+                     const float* weight, const float* bias, int N, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes);
 
 }  // namespace sdod

@@ -17,6 +17,19 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, bf16* __restrict
         dst[o] = __float2bfloat16(k < K ? src[static_cast<size_t>(r) * K + k] : 0.f);
     }
 }
+// dst[n*ld + col0 + k] = bf16(src[n*K + k]): a [N,K] fp32 matrix into a column window of a wider bf16 matrix (K-concatenated weights)
+__global__ void pack_rows_window_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int K, long long ld, int col0) {
+    const size_t total = static_cast<size_t>(N) * K;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = o % K;
+        const size_t n = o / K;
+        dst[n * ld + col0 + k] = __float2bfloat16(src[o]);
+    }
+}
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = a[i] + b[i];
+}
 __global__ void gather_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, const int* __restrict__ map) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[map ? map[i] : i];
@@ -79,6 +92,16 @@ int pack_rows(cudaStream_t s, const float* src, void* dst, int N, int K, int Kpa
     pack_rows_kernel<<<g1(static_cast<size_t>(N) * Kpad), 256, 0, s>>>(src, static_cast<bf16*>(dst), N, K, Kpad, rowmap);
     count_launch();
     return check_launch("pack_rows_kernel");
+}
+int pack_rows_window(cudaStream_t s, const float* src, void* dst, int N, int K, long long ld, int col0) {
+    pack_rows_window_kernel<<<g1(static_cast<size_t>(N) * K), 256, 0, s>>>(src, static_cast<bf16*>(dst), N, K, ld, col0);
+    count_launch();
+    return check_launch("pack_rows_window_kernel");
+}
+int add_f32(cudaStream_t s, const float* a, const float* b, float* dst, int n) {
+    add_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, dst, n);
+    count_launch();
+    return check_launch("add_f32_kernel");
 }
 int gather_f32(cudaStream_t s, const float* src, float* dst, int n, const int* map) {
     gather_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, dst, n, map);

@@ -1,7 +1,9 @@
 #include "net.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -238,6 +240,57 @@ void* NetBase::pack_conv3(const std::string& wname, int Cout, int Cin, int Kpad)
     return dst;
 }
 
+void* NetBase::pack_conv3_skip(const std::string& wname, const std::string& skip_wname, int Cout, int Cin, int Cskip) {
+    const std::string key = "cs|" + wname + "|" + skip_wname;
+    auto hit = cache_.find(key);
+    if (hit != cache_.end()) return hit->second;
+    const int K = 9 * Cin + Cskip;
+    const float* src = w32(wname, {Cout, Cin, 3, 3}, kInitWeight);
+    const float* ssrc = w32(skip_wname, {Cout, Cskip}, kInitWeight);      // ldm stores the 1x1 conv as [Cout, Cskip, 1, 1]
+    void* dst = dev_alloc(static_cast<size_t>(Cout) * K * 2, false);
+    cache_[key] = dst;
+    check(sdod_pack_conv3x3_weight(nullptr, src, dst, Cout, Cin, K));
+    check(pack_rows_window(nullptr, ssrc, dst, Cout, Cskip, K, 9 * Cin));
+    return dst;
+}
+
+const float* NetBase::sum_bias(const std::string& a, const std::string& b, int N) {
+    const std::string key = "sb|" + a + "|" + b;
+    auto hit = cache_.find(key);
+    if (hit != cache_.end()) return static_cast<const float*>(hit->second);
+    const float* pa = w32(a, {N}, kInitBias);
+    const float* pb = w32(b, {N}, kInitBias);
+    float* dst = static_cast<float*>(dev_alloc(N * sizeof(float), false));
+    cache_[key] = dst;
+    check(add_f32(nullptr, pa, pb, dst, N));
+    return dst;
+}
+
+void NetBase::begin_plan(Plan* p, bool prefetch_weights) {
+    static const int env = [] { const char* e = std::getenv("SDOD_W_PREFETCH"); return e ? std::atoi(e) : 1; }();
+    plan_ = p;
+    plan_gemms_.clear();
+    plan_prefetch_ = prefetch_weights && env != 0;
+}
+
+void NetBase::end_plan() {
+    // Launch i pulls launch i+1's weight matrix towards L2 (cp.async.bulk.prefetch.L2, see gemm_tcgen05_kernel); capped so that the
+    // prefetched bytes plus the step's activations stay well inside the 126 MB L2.
+    if (plan_prefetch_) {
+        for (size_t i = 0; i + 1 < plan_gemms_.size(); ++i) {
+            const GemmLaunch& nx = *plan_gemms_[i + 1];
+            if (!nx.w_ptr || nx.w_bytes < (64 << 10)) continue;
+            plan_gemms_[i]->mp.pf_ptr = static_cast<const char*>(nx.w_ptr);
+            plan_gemms_[i]->mp.pf_bytes = std::min<long long>(nx.w_bytes, 64LL << 20);
+        }
+    }
+    plan_gemms_.clear();
+    plan_ = nullptr;
+    // weight init / packing ran on the legacy default stream while plans run on the caller's (possibly non-blocking) stream:
+    // make every packed tensor visible before the plan's first launch
+    cudaDeviceSynchronize();
+}
+
 void* NetBase::pack_concat(const std::string& key, const std::vector<std::string>& wnames, const std::vector<int>& Ns, int K) {
     auto hit = cache_.find("k|" + key);
     if (hit != cache_.end()) return hit->second;
@@ -306,8 +359,41 @@ Act NetBase::gn(const Act& x, const std::string& prefix, float eps, bool silu) {
     const void* xp = x.p;
     void* yp = y.p;
     const int B = x.B, C = x.C, HW = x.H * x.W, s = silu ? 1 : 0, idt = x.dtype();
-    plan_->push([=](cudaStream_t st) { return group_norm_nhwc(st, xp, idt, yp, SDOD_BF16, w, b, nullptr, B, C, HW, 32, eps, s, ws, wsb); }, 2,
-                "gn " + std::string(x.f32 ? "f32" : "bf16") + " HW" + std::to_string(HW) + " C" + std::to_string(C));
+    const bool one = group_norm_fused_eligible(B, C, 0, HW, 32, idt);      // group_norm_nhwc picks the single-launch kernel itself
+    plan_->push([=](cudaStream_t st) { return group_norm_nhwc(st, xp, idt, yp, SDOD_BF16, w, b, nullptr, B, C, HW, 32, eps, s, ws, wsb); }, one ? 1 : 2,
+                std::string(one ? "gn1 " : "gn ") + std::string(x.f32 ? "f32" : "bf16") + " HW" + std::to_string(HW) + " C" + std::to_string(C));
+    return y;
+}
+
+Act NetBase::gn2(const Act& x, const Act* x2, const std::string& prefix, float eps, bool silu, Act* raw_out) {
+    const int Ca = x.C, Cb = x2 ? x2->C : 0, C = Ca + Cb;
+    if (x2 && (x2->f32 != x.f32 || x2->M() != x.M())) throw std::runtime_error("gn2: sources must share dtype and rows");
+    if (!group_norm_fused_eligible(x.B, Ca, Cb, x.H * x.W, 32, x.dtype())) {
+        // large tensors (big batches): materialise the concatenation, two-kernel GroupNorm, separate cast
+        Act cat = x;
+        bool own = false;
+        if (x2) { cat = concat(x, *x2); own = true; }
+        Act y = gn(cat, prefix, eps, silu);
+        if (raw_out) {
+            if (cat.f32) *raw_out = to_bf16(cat);
+            else if (own) { *raw_out = cat; own = false; }
+            else throw std::runtime_error("gn2: the raw copy of a single bf16 source is the source itself");
+        }
+        if (own) release(cat);
+        return y;
+    }
+    const float* w = w32(prefix + ".weight", {C}, kInitOnes);
+    const float* b = w32(prefix + ".bias", {C}, kInitZeros);
+    Act y = new_act(x.B, x.H, x.W, C);
+    void* rawp = nullptr;
+    if (raw_out) { *raw_out = new_act(x.B, x.H, x.W, C); rawp = raw_out->p; }
+    void* ws = gn_ws_;
+    const size_t wsb = gn_ws_bytes_;
+    const void *xp = x.p, *x2p = x2 ? x2->p : nullptr;
+    void* yp = y.p;
+    const int B = x.B, HW = x.H * x.W, s = silu ? 1 : 0, idt = x.dtype();
+    plan_->push([=](cudaStream_t st) { return group_norm_nhwc2(st, xp, Ca, x2p, Cb, idt, yp, SDOD_BF16, rawp, w, b, B, HW, 32, eps, s, ws, wsb); }, 1,
+                "gn1 " + std::string(x.f32 ? "f32" : "bf16") + " HW" + std::to_string(HW) + " C" + std::to_string(C) + (x2 ? "cat" : "") + (raw_out ? "+raw" : ""));
     return y;
 }
 
@@ -328,7 +414,8 @@ int NetBase::gemm_into(const sdod_gemm_desc& d) {
     const int st_prep = gemm_prepare(d, g.get());
     set_splitk_workspace(SplitKWorkspace{});              // never leave a pointer to this net's scratch behind
     check(st_prep);
-    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1,
+    note_gemm(g);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
                 "gemm M" + std::to_string(d.M) + " N" + std::to_string(d.N) + " K" + std::to_string(d.K) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split) +
                     (d.batch > 1 ? " batch" + std::to_string(d.batch) : ""));
     return kOk;
@@ -370,8 +457,31 @@ Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const floa
     const int st_prep = conv3x3_prepare(d, g.get());
     set_splitk_workspace(SplitKWorkspace{});
     check(st_prep);
-    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, g->mp.split > 1 ? 2 : 1,
+    note_gemm(g);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
                 "conv3 HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split));
+    return y;
+}
+
+Act NetBase::conv3_skip(const Act& x, const std::string& prefix, const std::string& skip_prefix, const Act& x_skip, int cout) {
+    if (x.f32 || x_skip.f32) throw std::runtime_error("conv3_skip: operands must be bf16");
+    if (x_skip.M() != x.M()) throw std::runtime_error("conv3_skip: row mismatch");
+    void* wt = pack_conv3_skip(prefix + ".weight", skip_prefix + ".weight", cout, x.C, x_skip.C);
+    const float* bias = sum_bias(prefix + ".bias", skip_prefix + ".bias", cout);
+    Act y = new_act(x.B, x.H, x.W, cout, true);
+    sdod_conv_desc d{};
+    d.X = x.p; d.Wt = wt; d.B = x.B; d.H = x.H; d.W = x.W; d.Cin = x.C; d.Cout = cout;
+    d.X2 = x_skip.p; d.ldx2 = x_skip.C; d.Cin2 = x_skip.C;
+    d.epi.C = y.p; d.epi.ldc = cout; d.epi.bias = bias; d.epi.alpha = 1.0f; d.epi.out_mode = SDOD_OUT_F32;
+    auto g = std::make_shared<GemmLaunch>();
+    set_splitk_workspace(skw_);
+    const int st_prep = conv3x3_prepare(d, g.get());
+    set_splitk_workspace(SplitKWorkspace{});
+    check(st_prep);
+    note_gemm(g);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
+                "conv3+skip HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + "+" + std::to_string(x_skip.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) +
+                    " split" + std::to_string(g->mp.split));
     return y;
 }
 

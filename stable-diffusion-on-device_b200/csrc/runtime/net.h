@@ -94,6 +94,9 @@ protected:
     const float* w32(const std::string& name, const std::vector<long long>& shape, InitKind kind);
     void* pack_linear(const std::string& wname, int N, int K, int Kpad = 0, const std::vector<int>* rowmap = nullptr);
     void* pack_conv3(const std::string& wname, int Cout, int Cin, int Kpad = 0);
+    // [Cout, 9*Cin + Cskip]: the conv3x3 weight followed by a 1x1 weight (K-concatenated: ResBlock out conv + skip_connection)
+    void* pack_conv3_skip(const std::string& wname, const std::string& skip_wname, int Cout, int Cin, int Cskip);
+    const float* sum_bias(const std::string& a, const std::string& b, int N);
     // rows of several [N_i, K] matrices stacked into one bf16 [sum N_i, K] matrix (fused QKV, all emb_layers)
     void* pack_concat(const std::string& key, const std::vector<std::string>& wnames, const std::vector<int>& Ns, int K);
     const float* concat_bias(const std::string& key, const std::vector<std::string>& bnames, const std::vector<int>& Ns);
@@ -104,6 +107,8 @@ protected:
     void release(Act& a);
     // ---- layer builders (append prepared launches to *plan_)
     Act gn(const Act& x, const std::string& prefix, float eps, bool silu);
+    // GroupNorm over the channel concatenation [x | x2] (x2 may be NULL); raw_out (optional) receives the bf16 un-normalised concatenation
+    Act gn2(const Act& x, const Act* x2, const std::string& prefix, float eps, bool silu, Act* raw_out);
     Act ln(const Act& x, const std::string& prefix);
     struct LinearOpts {
         const float* bias = nullptr;
@@ -117,12 +122,20 @@ protected:
     int gemm_into(const sdod_gemm_desc& d);                                           // fully custom epilogue
     Act conv3(const Act& x, const std::string& prefix, int cout, const float* row_bias, long long ld_row_bias, const Act* residual,
               bool stream_out = false, float* out_f32 = nullptr);
+    // out = conv3x3(x) + conv1x1(x_skip) + biases, one launch (skip weights K-concatenated); fp32 stream output
+    Act conv3_skip(const Act& x, const std::string& prefix, const std::string& skip_prefix, const Act& x_skip, int cout);
     Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride, bool stream_out = false);
     Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out = false);
     Act to_bf16(const Act& x);
     Act upsample(const Act& x);
     Act concat(const Act& a, const Act& b);
     void check(int status);                              // throws std::runtime_error with sdod last error
+    // plan-build bookkeeping: every GEMM/conv launch of the plan in order, so that each one can prefetch its successor's weights into L2
+    void begin_plan(Plan* p, bool prefetch_weights);
+    void end_plan();
+    void note_gemm(const std::shared_ptr<GemmLaunch>& g) { if (plan_) plan_gemms_.push_back(g); }
+    std::vector<std::shared_ptr<GemmLaunch>> plan_gemms_;
+    bool plan_prefetch_ = false;
 
     const WeightStore* ws_;
     bool random_;

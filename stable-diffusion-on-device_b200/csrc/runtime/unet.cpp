@@ -93,19 +93,23 @@ UNet::CtxBufs& UNet::ctx_bufs(const std::string& prefix, int C) {
 }
 
 // ---------------------------------------------------------------------------------------------- layers
-Act UNet::res_block(const Act& x, const std::string& prefix, int cout, int emb_index) {
-    Act h1 = gn(x, prefix + ".in_layers.0", 1e-5f, true);
+// ResBlock over the channel concatenation [x | x_cat] (x_cat = the popped skip tensor of an output block, else NULL).  The concatenation
+// never exists in fp32: the first GroupNorm reads both sources and, when the block changes the channel count, also emits the bf16 copy
+// that the 1x1 skip_connection consumes; that 1x1 convolution runs inside out_layers.3's K loop (K-concatenated weights, one accumulator).
+Act UNet::res_block(const Act& x, const Act* x_cat, const std::string& prefix, int cout, int emb_index) {
+    const int cin = x.C + (x_cat ? x_cat->C : 0);
+    const bool project = cin != cout;
+    if (x_cat && !project) throw std::runtime_error("res_block: a concatenated input needs a skip_connection");
+    Act raw;
+    Act h1 = gn2(x, x_cat, prefix + ".in_layers.0", 1e-5f, true, project ? &raw : nullptr);
     Act h2 = conv3(h1, prefix + ".in_layers.2", cout, emb_proj_ + emb_offsets_[emb_index], emb_total_, nullptr);
     release(h1);
     Act h3 = gn(h2, prefix + ".out_layers.0", 1e-5f, true);
     release(h2);
     Act out;
-    if (x.C != cout) {
-        Act xb = to_bf16(x);
-        Act s = conv1x1(xb, prefix + ".skip_connection", cout, nullptr, true);
-        release(xb);
-        out = conv3(h3, prefix + ".out_layers.3", cout, nullptr, 0, &s, true);
-        release(s);
+    if (project) {
+        out = conv3_skip(h3, prefix + ".out_layers.3", prefix + ".skip_connection", raw, cout);
+        release(raw);
     } else {
         out = conv3(h3, prefix + ".out_layers.3", cout, nullptr, 0, &x, true);
     }
@@ -205,7 +209,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
 // ---------------------------------------------------------------------------------------------- plans
 std::unique_ptr<Plan> UNet::build_forward(int B) {
     auto plan = std::make_unique<Plan>();
-    plan_ = plan.get();
+    begin_plan(plan.get(), B <= 4);      // small batches stream the weights from HBM every step: chain L2 prefetches through the GEMMs
     int emb_index = 0;
     // emb path: SiLU(emb) -> all 22 emb_layers Linear in one GEMM -> fp32 [B, emb_total]
     {
@@ -240,7 +244,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
     for (int level = 0; level < 4; ++level) {
         for (int i = 0; i < 2; ++i) {
             const std::string p = "input_blocks." + std::to_string(k++);
-            Act r = res_block(h, p + ".0", kMult[level] * kMc, emb_index++);
+            Act r = res_block(h, nullptr, p + ".0", kMult[level] * kMc, emb_index++);
             // h stays alive: it is in hs (skip connection)
             if (level < 3) {
                 Act t = spatial_transformer(r, p + ".1", level);
@@ -257,10 +261,10 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
         }
     }
     {
-        Act r = res_block(h, "middle_block.0", h.C, emb_index++);
+        Act r = res_block(h, nullptr, "middle_block.0", h.C, emb_index++);
         Act t = spatial_transformer(r, "middle_block.1", 3);
         release(r);
-        Act r2 = res_block(t, "middle_block.2", t.C, emb_index++);
+        Act r2 = res_block(t, nullptr, "middle_block.2", t.C, emb_index++);
         release(t);
         h = r2;     // previous h is hs.back(): released when popped
     }
@@ -271,11 +275,9 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
             const std::string p = "output_blocks." + std::to_string(k++);
             Act skip = hs.back();
             hs.pop_back();
-            Act cat = concat(h, skip);
+            Act r = res_block(h, &skip, p + ".0", kMult[level] * kMc, emb_index++);
             if (h_owned) release(h);
             release(skip);
-            Act r = res_block(cat, p + ".0", kMult[level] * kMc, emb_index++);
-            release(cat);
             int sub = 1;
             if (level < 3) {
                 Act t = spatial_transformer(r, p + ".1", level);
@@ -298,7 +300,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
     release(h);
     conv3(hn, "out.2", 4, nullptr, 0, nullptr, false, eps_out_);
     release(hn);
-    plan_ = nullptr;
+    end_plan();
     return plan;
 }
 
@@ -306,7 +308,7 @@ std::unique_ptr<Plan> UNet::build_context(int B) {
     // make sure every cross-attention block has registered its buffers
     if (ctx_order_.empty()) forward_plan(1);
     auto plan = std::make_unique<Plan>();
-    plan_ = plan.get();
+    begin_plan(plan.get(), false);
     Act ctx;
     ctx.p = ctx_bf16_; ctx.B = B; ctx.H = kCtxTokens; ctx.W = 1; ctx.C = kCtxDim;
     for (const std::string& name : ctx_order_) {
@@ -323,13 +325,13 @@ std::unique_ptr<Plan> UNet::build_context(int B) {
             gemm_into(d);
         }
     }
-    plan_ = nullptr;
+    end_plan();
     return plan;
 }
 
 std::unique_ptr<Plan> UNet::build_time_embed(int n) {
     auto plan = std::make_unique<Plan>();
-    plan_ = plan.get();
+    begin_plan(plan.get(), false);
     Act s0 = new_act(n, 1, 1, kMc);
     {
         const float* sin_in = temb_sin_;
@@ -347,7 +349,7 @@ std::unique_ptr<Plan> UNet::build_time_embed(int n) {
     d.epi.C = temb_out_; d.epi.ldc = kTed; d.epi.bias = w32("time_embed.2.bias", {kTed}, kInitBias); d.epi.alpha = 1.0f; d.epi.out_mode = SDOD_OUT_F32;
     gemm_into(d);
     release(h);
-    plan_ = nullptr;
+    end_plan();
     return plan;
 }
 

@@ -25,7 +25,7 @@ private:
     struct LevelBufs { void *qh, *kh, *vt; };
     struct CtxBufs { void *kh, *vt; int C; };
 
-    Act res_block(const Act& x, const std::string& prefix, int cout, int emb_index);
+    Act res_block(const Act& x, const Act* x_cat, const std::string& prefix, int cout, int emb_index);
     Act spatial_transformer(const Act& x, const std::string& prefix, int level);
     void attention_op(const void* qh, const void* kh, const void* vt, void* out, int B, int tokens, int n_kv, int C);
     CtxBufs& ctx_bufs(const std::string& prefix, int C);

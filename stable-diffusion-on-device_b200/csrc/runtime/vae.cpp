@@ -106,7 +106,7 @@ Act VaeDecoder::attn_block(const Act& x, const std::string& prefix) {
 
 std::unique_ptr<Plan> VaeDecoder::build(int B) {
     auto plan = std::make_unique<Plan>();
-    plan_ = plan.get();
+    begin_plan(plan.get(), false);
     Act z0 = new_act(B, hw_, hw_, 4);
     {
         const float* zin = z_in_;
@@ -149,7 +149,7 @@ std::unique_ptr<Plan> VaeDecoder::build(int B) {
         const size_t n = static_cast<size_t>(B) * 8 * hw_ * 8 * hw_ * 3;
         plan_->push([=](cudaStream_t st) { return vae_post(st, co, u8, img, n); });
     }
-    plan_ = nullptr;
+    end_plan();
     return plan;
 }
 

@@ -31,12 +31,13 @@ class Epilogue(ctypes.Structure):
 
 class GemmDesc(ctypes.Structure):
     _fields_ = [("A", c_vp), ("lda", c_ll), ("strideA", c_ll), ("W", c_vp), ("ldw", c_ll), ("strideW", c_ll),
-                ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int), ("block_n", c_int), ("epi", Epilogue)]
+                ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int), ("block_n", c_int), ("epi", Epilogue),
+                ("A2", c_vp), ("lda2", c_ll), ("K2", c_int)]
 
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [("X", c_vp), ("Wt", c_vp), ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("block_n", c_int), ("epi", Epilogue)]
+                ("block_n", c_int), ("epi", Epilogue), ("X2", c_vp), ("ldx2", c_ll), ("Cin2", c_int)]
 
 
 _SIGS = {
@@ -46,6 +47,8 @@ _SIGS = {
     "sdod_group_norm_workspace": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
     "sdod_group_norm": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_vp, c_sz]),
     "sdod_group_norm_nhwc": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_sz]),
+    "sdod_group_norm_nhwc2": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f, c_int, c_vp, c_sz]),
+    "sdod_group_norm_nhwc2_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "sdod_layer_norm": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f]),
     "sdod_cfg_dpm_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_sz, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_vp]),
     "sdod_dpm_schedule": (c_int, [c_u, c_f, c_f, c_u] + [c_vp] * 8),

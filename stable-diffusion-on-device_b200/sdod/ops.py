@@ -95,6 +95,21 @@ def group_norm_nhwc(x, num_groups, weight, bias, eps, silu=False, add_nc=None, o
     return y
 
 
+def group_norm_nhwc2(xa, xb, num_groups, weight, bias, eps, silu=False, want_raw=False, out_dtype=None):
+    """Single-launch GroupNorm over the channel concatenation [xa | xb] (xb may be None); xa/xb: [N, HW, C*] contiguous.
+    Returns y, or (y, raw) with raw = bf16 copy of the un-normalised concatenation.  L2-resident tensors only."""
+    _need_cuda(xa)
+    n, hw, ca = xa.shape
+    cb = 0 if xb is None else xb.shape[2]
+    y = torch.empty(n, hw, ca + cb, dtype=out_dtype or xa.dtype, device=xa.device)
+    raw = torch.empty(n, hw, ca + cb, dtype=torch.bfloat16, device=xa.device) if want_raw else None
+    w, b = _f32(weight), _f32(bias)
+    ws = _gn_workspace(xa.device, C.lib().sdod_group_norm_workspace(n, ca + cb, hw, num_groups, C.NHWC))
+    C.check(C.lib().sdod_group_norm_nhwc2(_stream(), _p(xa), ca, _p(xb), cb, _dt(xa), _p(y), _dt(y), _p(raw), _p(w), _p(b), n, hw, num_groups, eps,
+                                          int(silu), _p(ws), ws.numel()), "sdod_group_norm_nhwc2")
+    return (y, raw) if want_raw else y
+
+
 @torch.library.custom_op("sdod::layer_norm", mutates_args=(), device_types="cuda")
 def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
     _need_cuda(x)
@@ -198,10 +213,11 @@ def _epilogue(out, bias=None, row_bias=None, rows_per_group=0, residual=None, al
 @torch.library.custom_op("sdod::linear", mutates_args=(), device_types="cuda")
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
            act: int = 0, alpha: float = 1.0, out_f32: bool = False, row_bias: Optional[torch.Tensor] = None, rows_per_group: int = 0,
-           block_n: int = 0) -> torch.Tensor:
-    """y = act(alpha * a @ w^T + bias + row_bias[row // rows_per_group]) + residual on the tcgen05 GEMM.
-    a [M,K] or [B,M,K] bf16; w [N,K] or [B,N,K] bf16 (K % 64 == 0).  act=GEGLU expects w rows packed per 256-row tile."""
-    _need_cuda(a, w, bias, residual, row_bias)
+           block_n: int = 0, a2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(alpha * [a | a2] @ w^T + bias + row_bias[row // rows_per_group]) + residual on the tcgen05 GEMM.
+    a [M,K] or [B,M,K] bf16; w [N,K (+K2)] or [B,N,K] bf16 (K % 64 == 0); a2 [M,K2] optional second operand (K-concatenated).
+    act=GEGLU expects w rows packed per 256-row tile."""
+    _need_cuda(a, w, bias, residual, row_bias, a2)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     a, w = a.contiguous(), w.contiguous()
     batch = a.shape[0] if a.dim() == 3 else 1
@@ -214,25 +230,30 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     residual = None if residual is None else residual.contiguous()
     d = C.GemmDesc()
     d.A, d.lda, d.strideA = _p(a), K, M * K
-    d.W, d.ldw, d.strideW = _p(w), K, (N * K if w.dim() == 3 else 0)
+    d.W, d.ldw, d.strideW = _p(w), w.shape[-1], (N * K if w.dim() == 3 else 0)
     d.M, d.N, d.K, d.batch, d.block_n = M, N, K, batch, block_n
+    if a2 is not None:
+        a2 = a2.contiguous()
+        assert a2.dtype == torch.bfloat16 and a2.shape[0] == M and w.shape[-1] == K + a2.shape[1]
+        d.A2, d.lda2, d.K2 = _p(a2), a2.shape[1], a2.shape[1]
     d.epi = _epilogue(out, bias, row_bias, rows_per_group, residual, alpha, act)
     C.check(C.lib().sdod_gemm_bf16(_stream(), d), "sdod_gemm_bf16")
     return out
 
 
 @linear.register_fake
-def _(a, w, bias=None, residual=None, act=0, alpha=1.0, out_f32=False, row_bias=None, rows_per_group=0, block_n=0):
+def _(a, w, bias=None, residual=None, act=0, alpha=1.0, out_f32=False, row_bias=None, rows_per_group=0, block_n=0, a2=None):
     n = w.shape[-2] // 2 if act == C.ACT_GEGLU else w.shape[-2]
     return a.new_empty(a.shape[:-1] + (n,), dtype=torch.float32 if out_f32 else torch.bfloat16)
 
 
 @torch.library.custom_op("sdod::conv3x3", mutates_args=(), device_types="cuda")
 def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-            row_bias: Optional[torch.Tensor] = None, act: int = 0, block_n: int = 0) -> torch.Tensor:
+            row_bias: Optional[torch.Tensor] = None, act: int = 0, block_n: int = 0, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Implicit-GEMM conv3x3 (stride 1, pad 1).  x [B,H,W,Cin] bf16 NHWC, wt [Cout, 9*Cin] bf16 (k=(ky*3+kx)*Cin+c),
-    row_bias [B,Cout] (timestep-embedding add), residual [B,H,W,Cout].  Returns [B,H,W,Cout] bf16."""
-    _need_cuda(x, wt, bias, residual, row_bias)
+    row_bias [B,Cout] (timestep-embedding add), residual [B,H,W,Cout].  x2 [B,H,W,Cin2]: a fused 1x1 convolution whose
+    weights are wt[:, 9*Cin:].  Returns [B,H,W,Cout] bf16."""
+    _need_cuda(x, wt, bias, residual, row_bias, x2)
     assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and x.dim() == 4
     x, wt = x.contiguous(), wt.contiguous()
     B, H, W, Cin = x.shape
@@ -242,6 +263,10 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = No
     residual = None if residual is None else residual.contiguous()
     d = C.ConvDesc()
     d.X, d.Wt, d.B, d.H, d.W, d.Cin, d.Cout, d.block_n = _p(x), _p(wt), B, H, W, Cin, Cout, block_n
+    if x2 is not None:
+        x2 = x2.contiguous()
+        assert x2.dtype == torch.bfloat16 and x2.shape[:3] == x.shape[:3] and wt.shape[1] == 9 * Cin + x2.shape[3]
+        d.X2, d.ldx2, d.Cin2 = _p(x2), x2.shape[3], x2.shape[3]
     e = _epilogue(out.view(B * H * W, Cout), bias, row_bias, H * W, None, 1.0, act)
     if residual is not None:
         e.residual, e.ldr, e.strideR, e.residual_f32 = _p(residual), Cout, 0, int(residual.dtype == torch.float32)
@@ -251,7 +276,7 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = No
 
 
 @conv3x3.register_fake
-def _(x, wt, bias=None, residual=None, row_bias=None, act=0, block_n=0):
+def _(x, wt, bias=None, residual=None, row_bias=None, act=0, block_n=0, x2=None):
     return x.new_empty(x.shape[:3] + (wt.shape[0],))
 
 

@@ -80,6 +80,44 @@ def test_gn_nhwc_and_nchw_all_dtypes(shape, G, dtype):
     assert torch.equal(torch.ops.sdod.group_norm(x_cl, G, w.to(DEV), b.to(DEV), 1e-6, True, None), got_nhwc)
 
 
+@pytest.mark.parametrize("N,HW,Ca,Cb", [(2, 1024, 640, 320), (2, 64, 1280, 1280), (2, 4096, 320, 0), (1, 256, 1280, 640), (3, 4096, 640, 320),
+                                        (2, 64, 2560, 0), (7, 16, 64, 64)])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_gn_single_launch_two_sources(N, HW, Ca, Cb, dtype):
+    """gn_nhwc_fused_kernel: statistics + apply in one cooperative launch over the concatenation [xa | xb] (960 / 1920 channels put a
+    group across the source boundary), plus the bf16 raw copy that replaces the concat + cast kernels."""
+    torch.manual_seed(N * HW + Ca)
+    td = torch.bfloat16 if dtype == "bf16" else torch.float32
+    xa = (torch.randn(N, HW, Ca) * 1.5 + 0.3).to(td).to(DEV)
+    xb = (torch.randn(N, HW, Cb) * 0.7 - 1.0).to(td).to(DEV) if Cb else None
+    Cc = Ca + Cb
+    w, b = torch.randn(Cc, device=DEV), torch.randn(Cc, device=DEV)
+    assert C.lib().sdod_group_norm_nhwc2_supported(N, Ca, Cb, HW, 32, C.F32 if dtype == "f32" else C.BF16) == 1
+    cat = xa if xb is None else torch.cat([xa, xb], -1)
+    side = int(HW ** 0.5)
+    want = F.silu(L.group_norm_f64(cat.float().cpu().permute(0, 2, 1).reshape(N, Cc, side, side), 32, w.cpu(), b.cpu(), 1e-5).float())
+    want = want.reshape(N, Cc, HW).permute(0, 2, 1)
+    y, raw = ops.group_norm_nhwc2(xa, xb, 32, w, b, 1e-5, True, True, torch.bfloat16)
+    assert rel_err(y, want) < TOL_BF16
+    assert torch.equal(raw, cat.to(torch.bfloat16))
+    if dtype == "f32":
+        y32 = ops.group_norm_nhwc2(xa, xb, 32, w, b, 1e-5, True, False, torch.float32)
+        assert rel_err(y32, want) < TOL_F32
+    for _ in range(3):      # the arrive / depart counters re-arm themselves; the fold order is fixed -> same bits
+        y2 = ops.group_norm_nhwc2(xa, xb, 32, w, b, 1e-5, True, False, torch.bfloat16)
+        assert torch.equal(y2, y)
+
+
+def test_gn_two_kernel_path_for_large_tensors():
+    torch.manual_seed(3)
+    x = (torch.randn(16, 4096, 320) * 1.5 + 0.3).to(DEV)          # 84 MB fp32: not L2-resident -> stats + apply kernels
+    assert C.lib().sdod_group_norm_nhwc2_supported(16, 320, 0, 4096, 32, C.F32) == 0
+    w, b = torch.randn(320, device=DEV), torch.randn(320, device=DEV)
+    want = F.silu(F.group_norm(x.permute(0, 2, 1).reshape(16, 320, 64, 64), 32, w, b, 1e-5)).reshape(16, 320, 4096).permute(0, 2, 1)
+    got = ops.group_norm_nhwc(x, 32, w, b, 1e-5, True, None, torch.bfloat16)
+    assert rel_err(got, want) < TOL_BF16
+
+
 def test_gn_fused_temb_add_and_parameterless():
     torch.manual_seed(2)
     x = torch.randn(2, 640, 32, 32)
@@ -432,6 +470,67 @@ def test_gemm_split_k(M, N, K):
     finally:
         ops.enable_splitk(False)
     assert rel_err(got, want) < TOL_F32 and torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("splitk", [False, True])
+@pytest.mark.parametrize("M,N,K,K2", [(128, 1280, 2560, 1280), (512, 640, 1280, 640), (8192, 320, 640, 320), (200, 320, 128, 64)])
+def test_gemm_second_operand_k_concat(M, N, K, K2, splitk):
+    """C = [A | A2] W^T: the second operand's K blocks are loaded through its own tensor map into the same accumulator."""
+    torch.manual_seed(M + K2)
+    a, a2 = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(M, K2)).to(DEV)
+    w = bf(torch.randn(N, K + K2) / (K + K2) ** 0.5).to(DEV)
+    bias = torch.randn(N, device=DEV)
+    want = torch.cat([a, a2], 1).float() @ w.float().t() + bias
+    ops.enable_splitk(splitk)
+    try:
+        got = torch.ops.sdod.linear(a, w, bias, None, 0, 1.0, True, None, 0, 0, a2)
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want) < TOL_F32
+    assert rel_err(got, torch.ops.sdod.linear(torch.cat([a, a2], 1), w, bias, None, 0, 1.0, True)) < 1e-5
+
+
+@pytest.mark.parametrize("splitk", [False, True])
+@pytest.mark.parametrize("B,H,Cin,Cskip,Cout", [(2, 8, 1280, 2560, 1280), (2, 16, 1280, 1920, 1280), (2, 32, 640, 960, 640), (2, 64, 320, 640, 320),
+                                                (1, 16, 64, 128, 64)])
+def test_conv3x3_with_fused_skip_projection(B, H, Cin, Cskip, Cout, splitk):
+    """ResBlock tail in one launch: out_layers.3 (3x3) + skip_connection (1x1) + both biases, one TMEM accumulator."""
+    torch.manual_seed(H + Cskip)
+    x, xs = bf(torch.randn(B, H, H, Cin)).to(DEV), bf(torch.randn(B, H, H, Cskip)).to(DEV)
+    w = bf(torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    ws = bf(torch.randn(Cout, Cskip) / Cskip ** 0.5).to(DEV)
+    bias = torch.randn(Cout, device=DEV)
+    want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1) + xs.float() @ ws.float().t()
+    wt = torch.cat([ops.pack_conv3x3_weight(w.float()), ws], 1).contiguous()
+    ops.enable_splitk(splitk)
+    try:
+        got = torch.ops.sdod.conv3x3(x, wt, bias, None, None, 0, 0, xs)
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want) < TOL_BF16
+
+
+def test_split_k_cluster_epilogue_variants():
+    """In-kernel split-K (cluster reduce) runs the generic epilogue: row bias + SiLU + bf16 residual, and the attention head layouts."""
+    torch.manual_seed(77)
+    M, N, K = 128, 1280, 5120
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias, rb, res = torch.randn(N, device=DEV), torch.randn(2, N, device=DEV), bf(torch.randn(M, N)).to(DEV)
+    want = F.silu(a.float() @ w.float().t() + bias + rb.repeat_interleave(64, 0)) + res.float()
+    ops.enable_splitk(True)
+    try:
+        got = torch.ops.sdod.linear(a, w, bias, res, C.ACT_SILU, 1.0, False, rb, 64)
+        heads, dh, tokens, B = 8, 160, 64, 2
+        x = bf(torch.randn(B * tokens, heads * dh)).to(DEV)
+        wq = bf(torch.randn(3 * heads * dh, heads * dh) / (heads * dh) ** 0.5).to(DEV)
+        qh, kh, vt = ops.qkv_project(x, wq, heads, dh, tokens)
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want) < TOL_BF16
+    qkv = bf(x.float() @ wq.float().t()).view(B, tokens, 3, heads * dh)
+    for g_, want_ in ((qh, ops.pack_heads(qkv[:, :, 0], heads, dh)), (kh, ops.pack_heads(qkv[:, :, 1], heads, dh)),
+                      (vt, ops.pack_heads(qkv[:, :, 2], heads, dh, True))):
+        assert rel_err(g_, want_) < TOL_BF16
 
 
 def test_conv_split_k_small_spatial():
