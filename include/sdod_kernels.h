@@ -142,6 +142,12 @@ typedef struct sdod_epilogue {
     int heads, head_dim, tokens, dpad, tok_pad;   /* HEADS / HEADS_T / QKV modes                   */
     int vt_rows;             /* HEADS_T / QKV: rows allocated per head in the V^T buffer           */
     int residual_f32;        /* residual is fp32 (fp32 residual stream) instead of bf16            */
+    /* Fused LayerNorm of the output rows (SpatialTransformer norm1/2/3 folded into the GEMM that produces their input):
+     * with out_mode F32 and N a multiple of the tile width, ln_out receives bf16 LayerNorm(C[m,:]) * ln_weight + ln_bias
+     * (row stride ld_ln) next to the fp32 output.  The N tiles of a row block run as one thread-block cluster and
+     * exchange their row moments over distributed shared memory (two-pass mean / variance).  Returns an error status
+     * when the shape does not allow it (N / tile width > 8, split-K, batched, multi-wave grid); NULL = off. */
+    void* ln_out; long long ld_ln; const float* ln_weight; const float* ln_bias; float ln_eps;
 } sdod_epilogue;
 
 typedef struct sdod_gemm_desc {
@@ -160,6 +166,11 @@ SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d);
  * order (deterministic) and runs the epilogue on it — one launch).  ws: fp32 scratch; counters: reserved (n_counters
  * zero-initialised uint32).  Pass NULLs to disable. */
 SDOD_API int sdod_set_splitk_workspace(float* ws, size_t ws_bytes, unsigned int* counters, int n_counters);
+/* Profiling hook for the calling thread's subsequent GEMM / conv launches: every CTA records globaltimer stamps of its phases
+ * (16 x uint64 per CTA: 0 start, 1 set-up done, 2 predecessor complete, 3 first operands landed, 4 last MMA issued, 5 accumulator
+ * complete, 6 epilogue done, 7 split-K partials published, 8 all roles done, 9 residual landed, 10 tile staged) into buf
+ * (device memory, >= 16 * 8 * #CTAs bytes).  Results are unaffected.  NULL turns it off.  tools/gemm_timeline.py. */
+SDOD_API int sdod_set_gemm_timeline(unsigned long long* buf);
 
 /* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC:  Y[B,H,W,Cout] = epilogue( X (*) Wt )
  * X bf16 [B,H,W,Cin] (Cin % 64 == 0), Wt bf16 [Cout, 9*Cin] with k = (ky*3+kx)*Cin + c.

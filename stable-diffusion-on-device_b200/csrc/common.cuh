@@ -132,6 +132,19 @@ SDOD_DEVICE void cluster_sync_all() {     // every thread of every CTA in the cl
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+SDOD_DEVICE void cluster_sync_unaligned() {     // same barrier, callable from diverged warps (each thread arrives on its own)
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+SDOD_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// fp32 load from the shared memory of CTA `rank` of this cluster, at the address `local_ptr` has in this CTA (distributed shared memory)
+SDOD_DEVICE float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
 // shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the cluster
 SDOD_DEVICE uint32_t mapa_shared(const void* p, uint32_t rank) {
     uint32_t r;

@@ -63,6 +63,16 @@ struct GemmCfg {
     static_assert(kSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
 };
 
+// Profiling hook: one thread stamps phase `slot` of this CTA with the global nanosecond timer (results are unaffected).
+SDOD_DEVICE void tstamp(const MainloopParams& mp, int slot) {
+    if (mp.tlog) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long cta = (static_cast<unsigned long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        mp.tlog[cta * 16 + slot] = t;
+    }
+}
+
 SDOD_DEVICE float apply_act(float v, int act) {
     if (act == SDOD_ACT_SILU) return silu_f(v);
     if (act == SDOD_ACT_GELU) return gelu_f(v);
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) tstamp(mp, 0);                                   // CTA started
     // Tile coordinates come from SDOD_TILE_COORDS inside each role's tile loop (one trip unless PERSIST).  Pair grids put M on
     // x: the two CTAs of a cluster (dims 2x1x1, as cta_group::2 kernels must be launched) are consecutive M tiles.
     const int zs = (!PERSIST && mp.split > 1) ? blockIdx.z : 0;            // split index (split-K only when batch == 1)
@@ -419,10 +430,12 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     // PDL: everything above overlapped the previous kernel's tail; its outputs are visible from here.  CTA-pair kernels stay out of
     // it (ordinary launch, no early trigger): a cta_group::2 TMEM allocation racing the neighbour kernel's allocation on the same
     // SM pair deadlocked the step (B200, r1).
+    if (threadIdx.x == 0) tstamp(mp, 1);                                   // barriers + TMEM ready
     if (!PAIR) {
         griddep_wait();
         griddep_launch();
     }
+    if (threadIdx.x == 0) tstamp(mp, 2);                                   // predecessor complete
 
     if (warp == 0) {
         if (lane == 0) {
@@ -500,6 +513,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 const int s = g % STAGES;
                 const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
+                if (g == 0) tstamp(mp, 3);                                 // first operand stage landed
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kABytes);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
@@ -515,6 +529,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             }
             if (PAIR) tc_commit_pair(&tmem_full_bar[ab]);       // accumulator complete (each CTA holds its own 128 rows)
             else tc_commit(&tmem_full_bar[ab]);
+            if (iter == 0) tstamp(mp, 4);                                  // last MMA issued
             }   // tile loop
         }
     } else {
@@ -540,6 +555,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }
         mbar_wait(&tmem_full_bar[ab], PERSIST ? ((iter >> 1) & 1) : 0);
         tc_fence_after();
+        if (threadIdx.x == 64 && iter == 0) tstamp(mp, 5);                 // accumulator complete
         const uint32_t res_parity = PERSIST ? (iter & 1) : 0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;             // which of the quarter's NPART warps
@@ -683,6 +699,133 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 if (dbuf) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
                 else bulk_wait_read_all();
             }
+        } else if (mp.ln_fuse) {
+            // fp32 TMA epilogue + LayerNorm of the finished rows (SpatialTransformer norm1/2/3 folded into the GEMM that produces
+            // their input; removes a kernel and a read of the fp32 stream per norm).  The N tiles of this row block are the CTAs of one
+            // thread-block cluster (n_tiles,1,1).  Each thread owns one output row x half of the tile's columns: the final values
+            // (alpha, bias, row bias, residual) are staged in the fp32 boxes as in the plain TMA epilogue; row sums, then sums of
+            // squared deviations (two-pass: no cancellation), are combined across the two column halves through shared memory and
+            // across the cluster through distributed shared memory; the normalised bf16 rows go out through a second set of boxes.
+            constexpr int NB = BN / 32;
+            uint8_t* qbase = stage + q * (NB * 4096);                       // fp32 boxes of this lane quarter
+            uint8_t* hbase = stage + 4 * NB * 4096 + q * (NB * 2048);       // bf16 boxes (LayerNorm output)
+            float* s_gamma = reinterpret_cast<float*>(stage + 4 * NB * 6144);
+            float* s_beta = s_gamma + BN;
+            float* s_halfsum = s_beta + BN;                                 // [NPART][128] partial row moments of the column parts
+            float* ln_part = s_halfsum + NPART * kBlockM;                   // [2][128] this CTA's row sum / row sum of squared deviations
+            if (mp.tma_epi == 2 && half == 0 && lane == 0) {
+                mbar_arrive_expect_tx(&res_bar[q], NB * 4096);
+                for (int bx = 0; bx < NB; ++bx) tma_load_3d(qbase + bx * 4096, &tmR, &res_bar[q], n0 + bx * 32, m0 + q * 32, bz);
+            }
+            for (int i = te; i < BN; i += 32 * EW) {
+                s_gamma[i] = ep.ln_weight ? __ldg(ep.ln_weight + n0 + i) : 1.f;
+                s_beta[i] = ep.ln_bias ? __ldg(ep.ln_bias + n0 + i) : 0.f;
+            }
+            const float* rb = (ep.row_bias && m < mp.M) ? ep.row_bias + static_cast<long long>(m / ep.rows_per_group) * (ep.ld_row_bias ? ep.ld_row_bias : mp.N) : nullptr;
+            bool res_waited = (mp.tma_epi != 2);
+            float part = 0.f;
+#pragma unroll 1
+            for (int j = j_lo; j < j_hi; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j + 4 * q4);
+                    v[4 * q4] = fmaf(__uint_as_float(acc[4 * q4]), ep.alpha, b4.x);
+                    v[4 * q4 + 1] = fmaf(__uint_as_float(acc[4 * q4 + 1]), ep.alpha, b4.y);
+                    v[4 * q4 + 2] = fmaf(__uint_as_float(acc[4 * q4 + 2]), ep.alpha, b4.z);
+                    v[4 * q4 + 3] = fmaf(__uint_as_float(acc[4 * q4 + 3]), ep.alpha, b4.w);
+                }
+                if (rb) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += __ldg(rb + n0 + j + i);
+                }
+                if (!res_waited) { mbar_wait(&res_bar[q], res_parity); res_waited = true; }
+                uint8_t* rowp = qbase + (j >> 5) * 4096 + lane * 128;
+                const int u0 = (j & 31) >> 2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float4* cell = reinterpret_cast<float4*>(rowp + (((u0 + k) ^ (lane & 7)) << 4));
+                    float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    if (mp.tma_epi == 2) { const float4 r4 = *cell; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                    *cell = o;
+                    part += (o.x + o.y) + (o.z + o.w);
+                }
+            }
+            auto epi_sync = [&]() { asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory"); };
+            const uint32_t n_cta = cluster_nctarank();
+            const float inv_n = 1.0f / static_cast<float>(mp.N);
+            // ---- mean
+            s_halfsum[half * kBlockM + row] = part;
+            epi_sync();
+            if (half == 0) {
+                float t = 0.f;
+#pragma unroll
+                for (int h = 0; h < NPART; ++h) t += s_halfsum[h * kBlockM + row];
+                ln_part[row] = t;
+            }
+            cluster_sync_unaligned();
+            float mean = 0.f;
+            for (uint32_t r = 0; r < n_cta; ++r) mean += ld_dsmem_f32(ln_part + row, r);
+            mean *= inv_n;
+            // ---- variance (second pass over the staged row)
+            part = 0.f;
+#pragma unroll 1
+            for (int j = j_lo; j < j_hi; j += 16) {
+                const uint8_t* rowp = qbase + (j >> 5) * 4096 + lane * 128;
+                const int u0 = (j & 31) >> 2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 o = *reinterpret_cast<const float4*>(rowp + (((u0 + k) ^ (lane & 7)) << 4));
+                    const float d0 = o.x - mean, d1 = o.y - mean, d2 = o.z - mean, d3 = o.w - mean;
+                    part += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+                }
+            }
+            epi_sync();                                   // every reader of s_halfsum (mean pass) is done
+            s_halfsum[half * kBlockM + row] = part;
+            epi_sync();
+            if (half == 0) {
+                float t = 0.f;
+#pragma unroll
+                for (int h = 0; h < NPART; ++h) t += s_halfsum[h * kBlockM + row];
+                ln_part[kBlockM + row] = t;
+            }
+            cluster_sync_unaligned();
+            float var = 0.f;
+            for (uint32_t r = 0; r < n_cta; ++r) var += ld_dsmem_f32(ln_part + kBlockM + row, r);
+            const float rstd = rsqrtf(var * inv_n + ep.ln_eps);
+            // ---- normalised bf16 rows into the second set of boxes (64-B swizzled 32x32 bf16)
+#pragma unroll 1
+            for (int j = j_lo; j < j_hi; j += 16) {
+                const uint8_t* rowp = qbase + (j >> 5) * 4096 + lane * 128;
+                uint8_t* hrow = hbase + (j >> 5) * 2048 + lane * 64;
+                const int u0 = (j & 31) >> 2, h0 = (j & 31) >> 3;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float4 a = *reinterpret_cast<const float4*>(rowp + (((u0 + 2 * k) ^ (lane & 7)) << 4));
+                    const float4 b = *reinterpret_cast<const float4*>(rowp + (((u0 + 2 * k + 1) ^ (lane & 7)) << 4));
+                    const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + j + 8 * k), g1 = *reinterpret_cast<const float4*>(s_gamma + j + 8 * k + 4);
+                    const float4 e0 = *reinterpret_cast<const float4*>(s_beta + j + 8 * k), e1 = *reinterpret_cast<const float4*>(s_beta + j + 8 * k + 4);
+                    uint4 w;
+                    w.x = pack_bf16x2(fmaf((a.x - mean) * rstd, g0.x, e0.x), fmaf((a.y - mean) * rstd, g0.y, e0.y));
+                    w.y = pack_bf16x2(fmaf((a.z - mean) * rstd, g0.z, e0.z), fmaf((a.w - mean) * rstd, g0.w, e0.w));
+                    w.z = pack_bf16x2(fmaf((b.x - mean) * rstd, g1.x, e1.x), fmaf((b.y - mean) * rstd, g1.y, e1.y));
+                    w.w = pack_bf16x2(fmaf((b.z - mean) * rstd, g1.z, e1.z), fmaf((b.w - mean) * rstd, g1.w, e1.w));
+                    *reinterpret_cast<uint4*>(hrow + (((h0 + k) ^ ((lane >> 1) & 3)) << 4)) = w;
+                }
+            }
+            fence_proxy_async_smem();
+            quarter_sync();
+            if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
+                for (int bx = 0; bx < NB; ++bx) {
+                    tma_store_3d(&tmC, qbase + bx * 4096, n0 + bx * 32, m0 + q * 32, bz);
+                    tma_store_3d(&tmC2, hbase + bx * 2048, n0 + bx * 32, m0 + q * 32, bz);
+                }
+                bulk_commit();
+                bulk_wait_read_all();
+            }
         } else if (mp.tma_epi) {
             // TMA epilogue.  The idle TMA ring becomes a staging area of 32x32-element boxes (128-B or 64-B swizzled rows).
             // If there is a residual of the output's dtype it is TMA-loaded straight into those boxes while the accumulator
@@ -727,7 +870,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
                 }
-                if (!res_waited) { mbar_wait(&res_bar[q], res_parity); res_waited = true; }
+                if (!res_waited) { mbar_wait(&res_bar[q], res_parity); res_waited = true; if (threadIdx.x == 64 && iter == 0) tstamp(mp, 9); }
                 uint8_t* box = qbase + (j >> 5) * bstr;
                 if (f32) {
                     uint8_t* rowp = box + lane * 128;
@@ -762,6 +905,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     }
                 }
             }
+            if (threadIdx.x == 64 && iter == 0) tstamp(mp, 10);       // tile staged
             fence_proxy_async_smem();                  // staged tile (generic-proxy writes) -> visible to the TMA engine
             quarter_sync();
             if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
@@ -936,11 +1080,16 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 epilogue_plain16(ep, mp, bz, m, n0 + j, acc);
             }
         }
+        if (threadIdx.x == 64 && iter == 0) tstamp(mp, 6);                 // epilogue of the first tile done (stores issued and read)
         tc_fence_before();
         if (stage_next) s_bias_base[(ab ^ 1) * BN + te] = bias_next;
         if (PERSIST) mbar_arrive(&tmem_empty_bar[ab]);     // every TMEM read of this buffer has completed (tcgen05.wait::ld above)
         }   // tile loop
         if (PERSIST) bulk_wait_read_all();                 // (storing threads) shared memory stays valid until the last store has read it
+    }
+    if (!PAIR && !PERSIST && mp.ln_fuse && warp < 2) {      // the producer / MMA warps take part in the epilogue's two cluster barriers
+        cluster_sync_unaligned();
+        cluster_sync_unaligned();
     }
     if (!PAIR && !PERSIST && mp.split_cluster) {
         // Split-K inside one launch: the `split` CTAs of this output tile are one thread-block cluster (1,1,split).  Each has published its
@@ -949,6 +1098,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         // z order (deterministic, independent of arrival order) and runs the shared epilogue on it.
         asm volatile("barrier.cluster.arrive.release;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+        if (threadIdx.x == 64) tstamp(mp, 7);                              // split-K: all partials published
         if (warp >= 2) {
             const int n_tile = static_cast<int>(blockIdx.x), m_tile = static_cast<int>(blockIdx.y);
             const long long tile_id = static_cast<long long>(m_tile) * gridDim.x + n_tile;
@@ -965,7 +1115,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }
     }
     __syncthreads();
-    if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the pair may still touch it
+    if (threadIdx.x == 0) tstamp(mp, 8);                                   // all roles done
+    if (PAIR || (!PERSIST && mp.ln_fuse)) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while a peer may still touch it
     if (warp == 2) {
         tc_fence_after();
         if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
@@ -983,18 +1134,22 @@ static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) 
                             "cudaFuncSetAttribute(gemm)"));
         configured = true;
     }
-    if (!PAIR && !(g.mp.split > 1 && g.mp.split_cluster)) {
+    if (!PAIR && !(g.mp.split > 1 && g.mp.split_cluster) && !g.mp.ln_fuse) {
         return check_cuda(launch_pdl(gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, grid, dim3(PERSIST ? kGemmThreadsPersist : kGemmThreads),
                                      Cfg::kSmemBytes, stream, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.tmA2, g.mp, g.ep),
                           "launch gemm_tcgen05_kernel");
     }
     if (!PAIR) {
-        // split-K cluster: the `split` CTAs of a tile (grid.z) are co-scheduled as one cluster and reduce in-kernel
+        // split-K cluster: the `split` CTAs of a tile (grid.z) are co-scheduled as one cluster and reduce in-kernel;
+        // LayerNorm epilogue: the N tiles of a row block form the cluster
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = static_cast<unsigned>(g.mp.split);
+        if (g.mp.ln_fuse) {   // LayerNorm epilogue: the N tiles of a row block (grid.x) are one cluster
+            attr[0].val.clusterDim.x = static_cast<unsigned>(g.n_tiles); attr[0].val.clusterDim.z = 1;
+        }
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
@@ -1187,6 +1342,26 @@ static int setup_heads_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M,
     return kOk;
 }
 
+// LayerNorm fused into the epilogue (see the kernel's ln_fuse branch): fp32 TMA-store output, every N tile full, the N tiles of a row
+// block small enough for one portable cluster, a single-wave grid (the DEEP variant, whose idle ring holds both staging areas).
+static int setup_ln_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, int N, int batch, bool pair) {
+    MainloopParams& mp = out->mp;
+    mp.ln_fuse = 0;
+    if (!ep.ln_out) return kOk;
+    const int bn = out->bn, n_tiles = N / bn;
+    const long long ctas = static_cast<long long>((M + kBlockM - 1) / kBlockM) * n_tiles;
+    if (pair || batch != 1 || mp.split > 1 || (mp.tma_epi != 1 && mp.tma_epi != 2) || mp.c_bytes != 4 || ep.act != SDOD_ACT_NONE || N % bn != 0 ||
+        n_tiles > 8 || ctas > 148 || (bn != 128 && bn != 160) || M % kBlockM != 0)
+        return fail(kUnsupported, "gemm: this shape cannot take the fused LayerNorm epilogue");
+    if ((reinterpret_cast<uintptr_t>(ep.ln_out) & 15) || (ep.ld_ln * 2) % 16) return fail(kInvalidArgument, "gemm: ln_out must be 16-byte aligned");
+    const uint32_t box[3] = {32, 32, 1};
+    uint64_t dims[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 1};
+    uint64_t strides[2] = {static_cast<uint64_t>(ep.ld_ln) * 2, static_cast<uint64_t>(M) * ep.ld_ln * 2};
+    SDOD_TRY(encode_tmap(&out->tmC2, ep.ln_out, 2, 3, dims, strides, box, 64));
+    mp.ln_fuse = 1;
+    return kOk;
+}
+
 // Persistent scheduling for short-K, multi-wave GEMMs with a TMA epilogue: the per-tile fill/drain chain dominates there.
 // SDOD_GEMM_PERSIST=0 disables it, =2 uses it wherever legal (A/B measurements).
 static void choose_persist(GemmLaunch* out) {
@@ -1210,6 +1385,8 @@ static int k_rotation(int k_blocks) {
 
 static thread_local SplitKWorkspace g_splitk;
 void set_splitk_workspace(const SplitKWorkspace& w) { g_splitk = w; }
+static thread_local unsigned long long* g_tlog = nullptr;
+void set_gemm_timeline(unsigned long long* buf) { g_tlog = buf; }
 
 // Split-K factor: small-M layers (8x8 / 16x16 levels at batch 2) have too few output tiles to fill 148 SMs and
 // are bound by streaming the weights; splitting K spreads that stream over the whole chip.
@@ -1278,6 +1455,7 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     SDOD_TRY(validate_epilogue(d.epi, d.N));
     int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, Ktot / kBlockK);
     if (!d.block_n && d.N % 160 == 0 && heads_tma_eligible(d.epi, d.M, d.N, d.batch)) bn = 160;   // four 40-column head boxes per tile
+    if (!d.block_n && d.epi.ln_out) bn = d.N % 160 == 0 ? 160 : 128;                              // whole tiles only (fused LayerNorm)
     const bool pair = use_pair(bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, false);
 
     CUtensorMap& tmA = out->tmA;
@@ -1300,16 +1478,20 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     mp.M = d.M; mp.N = d.N; mp.k_blocks = Ktot / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
     mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
+    if (d.epi.ln_out) { mp.split = 1; mp.kb_per_split = mp.k_blocks; }      // the LayerNorm epilogue needs the finished rows in one CTA row
     mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
+    out->mp.tlog = g_tlog;
     SDOD_TRY(setup_second_operand(out, d.A2, d.lda2, K2, d.M, d.K / kBlockK));
     out->w_ptr = d.W; out->w_bytes = static_cast<long long>(d.N) * d.ldw * 2 * (wb ? d.batch : 1);
     SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
     SDOD_TRY(setup_heads_epilogue(out, d.epi, d.M, d.N, d.batch));
+    SDOD_TRY(setup_ln_epilogue(out, d.epi, d.M, d.N, d.batch, pair));
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.N + bn - 1) / bn;
     out->batch = d.batch;
     choose_persist(out);
+    if (out->mp.ln_fuse) out->persist = 0;
     return kOk;
 }
 
@@ -1335,6 +1517,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     const int bb = 128 / (bw * bh);
     const int M = d.B * d.H * d.W;
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
+    if (d.epi.ln_out) return fail(kUnsupported, "conv3x3: no fused LayerNorm epilogue");
     const int Cin2 = d.X2 ? d.Cin2 : 0;
     const int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, (9 * d.Cin + Cin2) / kBlockK);
     const bool pair = use_pair(bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, true);
@@ -1363,6 +1546,7 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
     mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
+    out->mp.tlog = g_tlog;
     SDOD_TRY(setup_second_operand(out, d.X2, d.ldx2, Cin2, M, 9 * d.Cin / kBlockK));
     out->w_ptr = d.Wt; out->w_bytes = static_cast<long long>(d.Cout) * K * 2;
     SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));
@@ -1387,6 +1571,10 @@ SDOD_API int sdod_set_splitk_workspace(float* ws, size_t ws_bytes, unsigned int*
     sdod::SplitKWorkspace w;
     if (ws && counters && n_counters > 0) { w.ws = ws; w.ws_bytes = ws_bytes; w.counters = counters; w.n_counters = n_counters; }
     sdod::set_splitk_workspace(w);
+    return sdod::kOk;
+}
+SDOD_API int sdod_set_gemm_timeline(unsigned long long* buf) {
+    sdod::set_gemm_timeline(buf);
     return sdod::kOk;
 }
 SDOD_API int sdod_gemm_bf16(sdod_stream_t stream, const sdod_gemm_desc* d) {

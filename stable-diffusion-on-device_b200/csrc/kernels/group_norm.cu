@@ -61,14 +61,6 @@ template <typename T> SDOD_DEVICE T from_f(float v);
 template <> SDOD_DEVICE float from_f<float>(float v) { return v; }
 template <> SDOD_DEVICE bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
 
-SDOD_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-SDOD_DEVICE float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
-    uint32_t a = smem_u32(local_ptr), ra;
-    float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-    return v;
-}
 
 // Chan et al. parallel Welford merge of (n, mean, M2)
 SDOD_DEVICE void welford_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {

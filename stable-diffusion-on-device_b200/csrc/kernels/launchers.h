@@ -26,6 +26,8 @@ struct MainloopParams {
                        //    cluster barrier; 0: partials are folded by splitk_reduce_kernel (a second launch)
     int kb_a2;         // first K block served by the second A operand (tmA2: plain [K2, M] rows, the K-concatenated skip / concat
                        //    source); >= k_blocks when there is none
+    int ln_fuse;       // 1: LayerNorm of the output rows fused into the epilogue (cluster over the N tiles, see the kernel); tmC2 = bf16 LN output
+    unsigned long long* tlog; // profiling hook (tools/gemm_timeline.py): per-CTA globaltimer stamps of the kernel's phases, 16 slots per CTA; NULL = off
     const char* pf_ptr;       // L2 prefetch of the NEXT layer's weights (constant data, issued before griddepcontrol.wait); NULL = none
     long long pf_bytes;
     int k_rot;         // K-loop start rotation per M tile (in K blocks); 0 = every tile starts at block 0
@@ -56,6 +58,7 @@ int pick_block_n_k(int M, int N, int batch, int act, int k_blocks);
 // Split-K scratch shared by all GEMM/conv launches on one stream (launches are serialised by stream order).
 struct SplitKWorkspace { float* ws = nullptr; size_t ws_bytes = 0; unsigned int* counters = nullptr; int n_counters = 0; };
 void set_splitk_workspace(const SplitKWorkspace& w);     // thread-local "current" workspace used by *_prepare
+void set_gemm_timeline(unsigned long long* buf);          // thread-local: launches prepared afterwards record their phase stamps into buf
 int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out);
 int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);

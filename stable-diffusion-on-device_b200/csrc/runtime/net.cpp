@@ -408,16 +408,17 @@ Act NetBase::ln(const Act& x, const std::string& prefix) {
     return y;
 }
 
-int NetBase::gemm_into(const sdod_gemm_desc& d) {
+int NetBase::gemm_into(const sdod_gemm_desc& d, bool may_fail) {
     auto g = std::make_shared<GemmLaunch>();
     set_splitk_workspace(skw_);
     const int st_prep = gemm_prepare(d, g.get());
     set_splitk_workspace(SplitKWorkspace{});              // never leave a pointer to this net's scratch behind
+    if (may_fail && st_prep != kOk) return st_prep;
     check(st_prep);
     note_gemm(g);
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
                 "gemm M" + std::to_string(d.M) + " N" + std::to_string(d.N) + " K" + std::to_string(d.K) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split) +
-                    (d.batch > 1 ? " batch" + std::to_string(d.batch) : ""));
+                    (d.batch > 1 ? " batch" + std::to_string(d.batch) : "") + (g->mp.ln_fuse ? " +ln" : ""));
     return kOk;
 }
 
@@ -433,6 +434,21 @@ Act NetBase::linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o
     d.epi.bias = o.bias;
     if (o.residual) { d.epi.residual = o.residual->p; d.epi.ldr = o.residual->C; d.epi.residual_f32 = o.residual->f32 ? 1 : 0; }
     d.epi.alpha = o.alpha; d.epi.act = o.act; d.epi.out_mode = o.out_f32 ? SDOD_OUT_F32 : SDOD_OUT_BF16;
+    if (o.ln_out) {
+        static const int env = [] { const char* e = std::getenv("SDOD_LN_FUSE"); return e ? std::atoi(e) : 1; }();
+        if (!o.out_f32) throw std::runtime_error("linear: a LayerNorm output needs the fp32 stream output");
+        *o.ln_out = new_act(x.B, x.H, x.W, n_out, false);
+        sdod_gemm_desc dl = d;
+        dl.epi.ln_out = o.ln_out->p; dl.epi.ld_ln = n_out; dl.epi.ln_weight = o.ln_w; dl.epi.ln_bias = o.ln_b; dl.epi.ln_eps = 1e-5f;
+        if (env && gemm_into(dl, true) == kOk) return y;
+        gemm_into(d);                                        // shape not eligible: plain GEMM + a LayerNorm launch
+        const void* yp = y.p;
+        void* lp = o.ln_out->p;
+        const float *w = o.ln_w, *b = o.ln_b;
+        const int rows = y.M(), C = n_out;
+        plan_->push([=](cudaStream_t st) { return sdod_layer_norm(st, yp, SDOD_F32, lp, w, b, rows, C, 1e-5f); }, 1, "ln rows" + std::to_string(rows) + " C" + std::to_string(C));
+        return y;
+    }
     gemm_into(d);
     return y;
 }

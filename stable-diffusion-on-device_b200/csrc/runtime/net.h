@@ -117,9 +117,14 @@ protected:
         float alpha = 1.0f;
         int block_n = 0;
         bool out_f32 = false;    // write the fp32 residual stream
+        // LayerNorm of the output rows (fp32 stream outputs only): *ln_out receives bf16 LN(y) * ln_w + ln_b — fused into the GEMM's
+        // epilogue where the shape allows (gemm_tcgen05.cu, ln_fuse), else a separate layer_norm launch
+        Act* ln_out = nullptr;
+        const float* ln_w = nullptr;
+        const float* ln_b = nullptr;
     };
     Act linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o);          // out [M, N or N/2 (GEGLU)]
-    int gemm_into(const sdod_gemm_desc& d);                                           // fully custom epilogue
+    int gemm_into(const sdod_gemm_desc& d, bool may_fail = false);                    // fully custom epilogue; may_fail: return the status instead of throwing
     Act conv3(const Act& x, const std::string& prefix, int cout, const float* row_bias, long long ld_row_bias, const Act* residual,
               bool stream_out = false, float* out_f32 = nullptr);
     // out = conv3x3(x) + conv1x1(x_skip) + biases, one launch (skip weights K-concatenated); fp32 stream output

@@ -130,12 +130,18 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     const HeadGeom g = head_geom(C);
     const LevelBufs& lb = level_bufs_[level];
     Act hn = gn(x, prefix + ".norm", 1e-6f, false);
-    Act h = conv1x1(hn, prefix + ".proj_in", C, nullptr, true);     // fp32 token stream
-    release(hn);
     const std::string tb = prefix + ".transformer_blocks.0";
+    // proj_in writes the fp32 token stream and, from the same epilogue, norm1 of it (the three LayerNorms of the block ride on the
+    // GEMMs that produce their inputs: proj_in, attn1.to_out, attn2.to_out)
+    Act n1;
+    LinearOpts oi;
+    oi.bias = w32(prefix + ".proj_in.bias", {C}, kInitBias);
+    oi.out_f32 = true;
+    oi.ln_out = &n1; oi.ln_w = w32(tb + ".norm1.weight", {C}, kInitOnes); oi.ln_b = w32(tb + ".norm1.bias", {C}, kInitZeros);
+    Act h = linear(hn, pack_linear(prefix + ".proj_in.weight", C, C), C, oi);     // fp32 token stream
+    release(hn);
 
     // ---- self-attention: fused q/k/v projection straight into the attention operand layouts
-    Act n1 = ln(h, tb + ".norm1");
     {
         void* wqkv = pack_concat(tb + ".attn1.qkv", {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, {C, C, C}, C);
         sdod_gemm_desc d{};
@@ -152,12 +158,13 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     o1.bias = w32(tb + ".attn1.to_out.0.bias", {C}, kInitBias);
     o1.residual = &h;
     o1.out_f32 = true;
+    Act n2;
+    o1.ln_out = &n2; o1.ln_w = w32(tb + ".norm2.weight", {C}, kInitOnes); o1.ln_b = w32(tb + ".norm2.bias", {C}, kInitZeros);
     Act h2 = linear(a1, pack_linear(tb + ".attn1.to_out.0.weight", C, C), C, o1);
     release(a1);
     release(h);
 
     // ---- cross-attention against the cached prompt K / V^T
-    Act n2 = ln(h2, tb + ".norm2");
     {
         sdod_gemm_desc d{};
         d.A = n2.p; d.lda = C; d.W = pack_linear(tb + ".attn2.to_q.weight", C, C); d.ldw = C; d.M = n2.M(); d.N = C; d.K = C; d.batch = 1;
@@ -173,12 +180,13 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     o2.bias = w32(tb + ".attn2.to_out.0.bias", {C}, kInitBias);
     o2.residual = &h2;
     o2.out_f32 = true;
+    Act n3;
+    o2.ln_out = &n3; o2.ln_w = w32(tb + ".norm3.weight", {C}, kInitOnes); o2.ln_b = w32(tb + ".norm3.bias", {C}, kInitZeros);
     Act h3 = linear(a2, pack_linear(tb + ".attn2.to_out.0.weight", C, C), C, o2);
     release(a2);
     release(h2);
 
     // ---- GEGLU feed-forward (gate fused in the projection's epilogue)
-    Act n3 = ln(h3, tb + ".norm3");
     std::vector<int> rowmap(8 * C);
     {
         const int half = 64, n = 4 * C;    // block_n 128: [64 value rows | 64 gate rows] per tile (2 CTAs/SM: epilogues overlap mainloops)

@@ -26,7 +26,8 @@ class SdodError(RuntimeError):
 class Epilogue(ctypes.Structure):
     _fields_ = [("C", c_vp), ("C2", c_vp), ("C3", c_vp), ("ldc", c_ll), ("strideC", c_ll), ("bias", c_vp), ("row_bias", c_vp),
                 ("rows_per_group", c_int), ("ld_row_bias", c_ll), ("residual", c_vp), ("ldr", c_ll), ("strideR", c_ll), ("alpha", c_f), ("act", c_int),
-                ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int), ("vt_rows", c_int), ("residual_f32", c_int)]
+                ("out_mode", c_int), ("heads", c_int), ("head_dim", c_int), ("tokens", c_int), ("dpad", c_int), ("tok_pad", c_int), ("vt_rows", c_int), ("residual_f32", c_int),
+                ("ln_out", c_vp), ("ld_ln", c_ll), ("ln_weight", c_vp), ("ln_bias", c_vp), ("ln_eps", c_f)]
 
 
 class GemmDesc(ctypes.Structure):
@@ -60,6 +61,7 @@ _SIGS = {
     "sdod_image_to_u8": (c_int, [c_vp, c_vp, c_int, c_vp, c_sz]),
     "sdod_gemm_bf16": (c_int, [c_vp, ctypes.POINTER(GemmDesc)]),
     "sdod_set_splitk_workspace": (c_int, [c_vp, c_sz, c_vp, c_int]),
+    "sdod_set_gemm_timeline": (c_int, [c_vp]),
     "sdod_conv3x3_bf16": (c_int, [c_vp, ctypes.POINTER(ConvDesc)]),
     "sdod_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f]),
     "sdod_softmax_rows": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_ll, c_f]),

@@ -247,6 +247,28 @@ def _(a, w, bias=None, residual=None, act=0, alpha=1.0, out_f32=False, row_bias=
     return a.new_empty(a.shape[:-1] + (n,), dtype=torch.float32 if out_f32 else torch.bfloat16)
 
 
+def linear_ln(a, w, bias, residual, ln_weight, ln_bias, eps=1e-5):
+    """(y fp32, LayerNorm(y) bf16) with y = a @ w^T + bias + residual: the LayerNorm runs in the GEMM's epilogue (N tiles of a row
+    block = one thread-block cluster).  Raises SdodError when the shape does not allow the fusion."""
+    _need_cuda(a, w, bias, residual, ln_weight, ln_bias)
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    ln = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    bias, ln_weight, ln_bias = _f32(bias), _f32(ln_weight), _f32(ln_bias)
+    residual = None if residual is None else residual.contiguous()
+    d = C.GemmDesc()
+    d.A, d.lda, d.strideA = _p(a), K, M * K
+    d.W, d.ldw, d.strideW = _p(w), K, 0
+    d.M, d.N, d.K, d.batch, d.block_n = M, N, K, 1, 0
+    e = _epilogue(y, bias, None, 0, residual, 1.0, 0)
+    e.ln_out, e.ld_ln, e.ln_weight, e.ln_bias, e.ln_eps = _p(ln), N, _p(ln_weight), _p(ln_bias), eps
+    d.epi = e
+    C.check(C.lib().sdod_gemm_bf16(_stream(), d), "sdod_gemm_bf16 (+LayerNorm)")
+    return y, ln
+
+
 @torch.library.custom_op("sdod::conv3x3", mutates_args=(), device_types="cuda")
 def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
             row_bias: Optional[torch.Tensor] = None, act: int = 0, block_n: int = 0, x2: Optional[torch.Tensor] = None) -> torch.Tensor:

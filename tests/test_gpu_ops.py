@@ -533,6 +533,33 @@ def test_split_k_cluster_epilogue_variants():
         assert rel_err(g_, want_) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 320, 320), (2048, 640, 640), (512, 1280, 1280), (128, 1280, 1280), (256, 256, 128)])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_gemm_fused_layer_norm_epilogue(M, N, K, with_res):
+    """LayerNorm of the finished rows inside the GEMM epilogue: row moments exchanged over distributed shared memory between the
+    N-tile CTAs of a cluster (2 / 4 / 8 CTAs), two-pass variance; fp32 stream output and bf16 normalised output from one launch."""
+    torch.manual_seed(M + N)
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, device=DEV)
+    res = (torch.randn(M, N, device=DEV) * 2 + 0.7) if with_res else None
+    g, b = torch.randn(N, device=DEV), torch.randn(N, device=DEV)
+    want = a.float() @ w.float().t() + bias + (res if with_res else 0)
+    y, ln = ops.linear_ln(a, w, bias, res, g, b)
+    assert rel_err(y, want) < TOL_F32
+    assert rel_err(ln, F.layer_norm(want, (N,), g, b, 1e-5)) < TOL_BF16
+    y2, ln2 = ops.linear_ln(a, w, bias, res, g, b)
+    assert torch.equal(y, y2) and torch.equal(ln, ln2)
+    # same bits as the unfused pair (GEMM, then the LayerNorm kernel on its fp32 output)
+    y3 = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)
+    assert rel_err(y, y3) < 1e-6
+
+
+def test_gemm_fused_layer_norm_rejects_ineligible_shapes():
+    a, w = bf(torch.randn(8192, 320)).to(DEV), bf(torch.randn(2560, 320)).to(DEV)      # 16 N tiles > one portable cluster
+    with pytest.raises(C.SdodError):
+        ops.linear_ln(a, w, None, None, None, None)
+
+
 def test_conv_split_k_small_spatial():
     torch.manual_seed(5)
     x = bf(torch.randn(2, 8, 8, 2560)).to(DEV)
