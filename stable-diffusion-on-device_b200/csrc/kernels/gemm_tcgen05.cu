@@ -345,10 +345,49 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const MainloopParams
 // persistent CTAs take every gridDim.x-th tile (N fastest).  (Contiguous chunks per CTA, which would let the producer keep the A rows
 // resident across the N tiles of one M tile, measured 10 % slower on the 64x64 GEGLU projection: the CTAs of a wave then touch
 // 148 different A tiles at once instead of ~8, and the layer is epilogue-bound, not L2-bound — profiles/r01_gemm_load_vs_mma.txt.)
+// Stream-K (persistent CTAs only, mp.streamk): instead of whole tiles each CTA takes a contiguous, equal share [u, u_end) of the linearised
+// (tile, K block) space and walks it as per-tile segments [seg_lo, seg_hi).  Layers with few tiles and long K (every conv and most linear
+// layers of the batch-2 step) otherwise leave SMs idle or run a second, mostly empty wave; here all CTAs finish together.  A segment that does
+// not start at K block 0 publishes its fp32 partial tile (each CTA publishes at most one: the head of its share) and raises a flag; the CTA
+// whose segment starts the tile — always the LAST segment of its own share, so the partials of the later K ranges were published at the very
+// start of their owners' shares — folds them into its accumulator reads, in fixed order (deterministic), and runs the epilogue.
+struct WorkWalk {
+    int t, iter, seg_lo, seg_hi, t_step, t_end, kblocks;
+    long long u, u_end;
+    bool live, sk;
+    __device__ WorkWalk(const MainloopParams& mp, bool persist, int kb0, int kb1) {
+        iter = 0; kblocks = mp.k_blocks; sk = persist && mp.streamk; u = u_end = 0;
+        if (!persist) { t = 0; t_step = 1; t_end = 1; seg_lo = kb0; seg_hi = kb1; live = true; }
+        else if (!sk) { t = blockIdx.x; t_step = gridDim.x; t_end = mp.tiles_total; seg_lo = 0; seg_hi = kblocks; live = t < t_end; }
+        else {
+            const long long total = static_cast<long long>(mp.tiles_total) * kblocks;
+            t_step = 0; t_end = mp.tiles_total;
+            u = total * blockIdx.x / gridDim.x;
+            u_end = total * (blockIdx.x + 1) / gridDim.x;
+            live = u < u_end;
+            if (live) cut();
+        }
+    }
+    __device__ void cut() {
+        t = static_cast<int>(u / kblocks);
+        seg_lo = static_cast<int>(u - static_cast<long long>(t) * kblocks);
+        const long long hi = seg_lo + (u_end - u);
+        seg_hi = hi < kblocks ? static_cast<int>(hi) : kblocks;
+    }
+    __device__ void next() {
+        ++iter;
+        if (!sk) { t += t_step; live = t < t_end; }
+        else { u += seg_hi - seg_lo; live = u < u_end; if (live) cut(); }
+    }
+    // first unit of CTA c's share (stream-K)
+    static __device__ long long share_begin(const MainloopParams& mp, int c) {
+        return static_cast<long long>(mp.tiles_total) * mp.k_blocks * c / gridDim.x;
+    }
+};
 #define SDOD_TILE_LOOP                                                                                                               \
-    for (int t = PERSIST ? static_cast<int>(blockIdx.x) : 0, iter = 0, t_end = PERSIST ? mp.tiles_total : 1; t < t_end;                \
-         t += (PERSIST ? static_cast<int>(gridDim.x) : 1), ++iter)
+    for (WorkWalk wk(mp, PERSIST, kb0, kb1); wk.live; wk.next())
 #define SDOD_TILE_COORDS                                                                                               \
+    const int t = wk.t, iter = wk.iter; (void)t; (void)iter;                                                           \
     const int n_tile = PERSIST ? t % mp.n_tiles : static_cast<int>(PAIR ? blockIdx.y : blockIdx.x);                    \
     const int m_tile = PERSIST ? (t / mp.n_tiles) % mp.m_tiles : static_cast<int>(PAIR ? blockIdx.x : blockIdx.y);     \
     const int bz = PERSIST ? t / (mp.n_tiles * mp.m_tiles) : (mp.split > 1 ? 0 : static_cast<int>(blockIdx.z));        \
@@ -459,9 +498,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             // K rotation: M tile i starts its K loop i*rot blocks in, so the CTAs of a wave do not all pull the same weight
             // tile out of the same few L2 slices at the same moment (the sum over K is order-independent up to fp32 rounding,
             // and the order is fixed per tile, so results stay deterministic).
-            const int nkb = kb1 - kb0;
-            int kb = kb0 + (mp.k_rot ? static_cast<int>((static_cast<long long>(PAIR ? m_tile >> 1 : m_tile) * mp.k_rot) % nkb) : 0);
-            for (int it = 0; it < nkb; ++it, ++g, kb = (kb + 1 == kb1 ? kb0 : kb + 1)) {
+            const int seg_lo = wk.seg_lo, seg_hi = wk.seg_hi, nkb = seg_hi - seg_lo;
+            int kb = seg_lo + (mp.k_rot ? static_cast<int>((static_cast<long long>(PAIR ? m_tile >> 1 : m_tile) * mp.k_rot) % nkb) : 0);
+            for (int it = 0; it < nkb; ++it, ++g, kb = (kb + 1 == seg_hi ? seg_lo : kb + 1)) {
                 const int s = g % STAGES;
                 const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -502,14 +541,15 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BN);
             int g = 0;
             SDOD_TILE_LOOP {
+            const int iter = wk.iter;
             const int ab = PERSIST ? (iter & 1) : 0;                 // TMEM accumulator buffer of this tile
             const uint32_t tmem_acc = tmem_base + ab * BN;
             if (PERSIST && iter >= 2) {                               // the epilogue of tile iter-2 has drained this buffer
                 mbar_wait(&tmem_empty_bar[ab], ((iter >> 1) - 1) & 1);
                 tc_fence_after();
             }
-            for (int kb = kb0; kb < kb1; ++kb, ++g) {
-                const int it = kb - kb0;
+            for (int kb = wk.seg_lo; kb < wk.seg_hi; ++kb, ++g) {
+                const int it = kb - wk.seg_lo;
                 const int s = g % STAGES;
                 const uint32_t ph = (g / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
@@ -534,6 +574,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }
     } else {
         // -------------------------------------------------------------------- epilogue
+        int res_uses = 0;                              // residual-barrier phases consumed so far (stream-K head segments load no residual)
         SDOD_TILE_LOOP {
         SDOD_TILE_COORDS
         const int ab = PERSIST ? (iter & 1) : 0;
@@ -543,9 +584,18 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         // with an exposed L2 round trip.
         const int te = static_cast<int>(threadIdx.x) - 64;
         float bias_next = 0.f;
-        const bool stage_next = PERSIST && mp.tma_epi && t + static_cast<int>(gridDim.x) < t_end && te < BN;
+        const bool stage_next = PERSIST && !wk.sk && mp.tma_epi && t + static_cast<int>(gridDim.x) < wk.t_end && te < BN;
+        // stream-K role of this segment: a head segment (starts inside the tile) only publishes its partial; the segment that starts the tile
+        // folds the partials of the CTAs that follow it (their shares begin inside this tile) and runs the epilogue
+        const bool sk_publish = PERSIST && wk.sk && wk.seg_lo > 0;
+        int sk_parts = 0;
+        if (PERSIST && wk.sk && wk.seg_lo == 0 && wk.seg_hi < wk.kblocks) {
+            const long long tile_end = static_cast<long long>(t + 1) * wk.kblocks;
+            while (static_cast<int>(blockIdx.x) + sk_parts + 1 < static_cast<int>(gridDim.x) &&
+                   WorkWalk::share_begin(mp, blockIdx.x + sk_parts + 1) < tile_end) ++sk_parts;
+        }
         if (mp.tma_epi) {
-            if (!PERSIST || iter == 0)
+            if (!PERSIST || iter == 0 || wk.sk)
                 for (int i = te; i < BN; i += 32 * EW) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
             asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");   // (persistent: also orders the previous tile's staging reads/stores)
             if (stage_next) {
@@ -556,7 +606,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         mbar_wait(&tmem_full_bar[ab], PERSIST ? ((iter >> 1) & 1) : 0);
         tc_fence_after();
         if (threadIdx.x == 64 && iter == 0) tstamp(mp, 5);                 // accumulator complete
-        const uint32_t res_parity = PERSIST ? (iter & 1) : 0;
+        const uint32_t res_parity = PERSIST ? (res_uses & 1) : 0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;             // which of the quarter's NPART warps
         // this warp's columns, in 16-column units: [j_lo, j_hi) of the BN-wide tile, [g_lo, g_hi) of a GEGLU half tile
@@ -566,7 +616,58 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         const int row = q * 32 + lane;
         const int m = m0 + row;
         const uint32_t taddr = tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16);
-        if (mp.split > 1) {
+        if (PERSIST && sk_parts) {
+            // the CTAs whose shares begin inside this tile published their partials at the very start of their walks; the check is a formality
+            if (threadIdx.x == 64) {
+                for (int c = 1; c <= sk_parts; ++c) {
+                    unsigned int seen = 0, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(mp.counters + blockIdx.x + c) : "memory");
+                        if (!seen && ++spins > (1u << 22)) __trap();
+                    } while (!seen);
+                }
+            }
+            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");
+        }
+        // 16 accumulator columns [j, j+16) of this thread's row: TMEM, plus (stream-K) the published partials of the later K ranges
+        auto acc_ld16 = [&](int j, uint32_t (&acc)[16]) {
+            tmem_ld16(taddr + j, acc);
+            tmem_ld_wait();
+            if (PERSIST && sk_parts) {
+                const float4* p = reinterpret_cast<const float4*>(mp.ws + static_cast<long long>(blockIdx.x + 1) * (BN * kBlockM) + ((j >> 4) * kBlockM + row) * 16);
+                for (int c = 0; c < sk_parts; ++c, p += BN * kBlockM / 4) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const float4 v = __ldcg(p + q4);
+                        acc[4 * q4] = __float_as_uint(__uint_as_float(acc[4 * q4]) + v.x);
+                        acc[4 * q4 + 1] = __float_as_uint(__uint_as_float(acc[4 * q4 + 1]) + v.y);
+                        acc[4 * q4 + 2] = __float_as_uint(__uint_as_float(acc[4 * q4 + 2]) + v.z);
+                        acc[4 * q4 + 3] = __float_as_uint(__uint_as_float(acc[4 * q4 + 3]) + v.w);
+                    }
+                }
+            }
+        };
+        if (PERSIST && sk_publish) {
+            // stream-K head segment: publish the fp32 partial tile ([chunk16][row][16]) in this CTA's slot, then raise its flag
+            float* mine = mp.ws + static_cast<long long>(blockIdx.x) * (BN * kBlockM);
+#pragma unroll 1
+            for (int j = j_lo; j < j_hi; j += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + j, acc);
+                tmem_ld_wait();
+                float4* dst = reinterpret_cast<float4*>(mine + ((j >> 4) * kBlockM + row) * 16);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    dst[q4] = make_float4(__uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]), __uint_as_float(acc[4 * q4 + 2]),
+                                          __uint_as_float(acc[4 * q4 + 3]));
+            }
+            __threadfence();
+            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");
+            if (threadIdx.x == 64) {
+                const unsigned int one = 1u;
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mp.counters + blockIdx.x), "r"(one) : "memory");
+            }
+        } else if (mp.split > 1) {
             // split-K: publish this CTA's fp32 partial tile ([chunk16][row][16], coalesced); splitk_reduce_kernel folds
             // the partials in fixed order (deterministic) and applies the epilogue.
             const long long tile_id = static_cast<long long>(m_tile) * (PAIR ? gridDim.y : gridDim.x) + n_tile;
@@ -593,9 +694,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = g_lo; j < g_hi; j += 16) {
                 uint32_t a[16], g[16];
-                tmem_ld16(taddr + j, a);
-                tmem_ld16(taddr + HALF + j, g);
-                tmem_ld_wait();
+                acc_ld16(j, a);
+                acc_ld16(HALF + j, g);
                 float v[16];
                 const uint64_t alpha2 = pack_f32x2(ep.alpha, ep.alpha);
 #pragma unroll
@@ -634,9 +734,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = g_lo; j < g_hi; j += 16) {
                 uint32_t a[16], g[16];
-                tmem_ld16(taddr + j, a);
-                tmem_ld16(taddr + HALF + j, g);
-                tmem_ld_wait();
+                acc_ld16(j, a);
+                acc_ld16(HALF + j, g);
                 epilogue_geglu16<BN>(ep, mp, bz, m, n_tile, j, a, g);
             }
         } else if (BN == 160 && mp.tma_epi == 3) {
@@ -652,8 +751,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
-                tmem_ld16(taddr + j, acc);
-                tmem_ld_wait();
+                acc_ld16(j, acc);
                 float v[16];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -727,8 +825,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
-                tmem_ld16(taddr + j, acc);
-                tmem_ld_wait();
+                acc_ld16(j, acc);
                 float v[16];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -847,8 +944,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
-                tmem_ld16(taddr + j, acc);
-                tmem_ld_wait();
+                acc_ld16(j, acc);
                 float v[16];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -925,8 +1021,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
-                tmem_ld16(taddr + j, acc);
-                tmem_ld_wait();
+                acc_ld16(j, acc);
                 float4* dst = reinterpret_cast<float4*>(stg + lane * LDS + j);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
@@ -1075,12 +1170,17 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 #pragma unroll 1
             for (int j = j_lo; j < j_hi; j += 16) {
                 uint32_t acc[16];
-                tmem_ld16(taddr + j, acc);
-                tmem_ld_wait();
+                acc_ld16(j, acc);
                 epilogue_plain16(ep, mp, bz, m, n0 + j, acc);
             }
         }
         if (threadIdx.x == 64 && iter == 0) tstamp(mp, 6);                 // epilogue of the first tile done (stores issued and read)
+        if (mp.tma_epi == 2 && !(PERSIST && sk_publish)) ++res_uses;
+        if (PERSIST && sk_parts) {                                         // every thread has folded the partials: re-arm their flags
+            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");
+            if (threadIdx.x == 64)
+                for (int c = 1; c <= sk_parts; ++c) mp.counters[blockIdx.x + c] = 0u;
+        }
         tc_fence_before();
         if (stage_next) s_bias_base[(ab ^ 1) * BN + te] = bias_next;
         if (PERSIST) mbar_arrive(&tmem_empty_bar[ab]);     // every TMEM read of this buffer has completed (tcgen05.wait::ld above)
@@ -1183,7 +1283,7 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     if constexpr (BN == 128 || BN == 160) {
         if (g.persist) {
             const int sms = device_sm_count();
-            SDOD_TRY((launch_gemm_cfg<BN, true, false, true>(stream, g, dim3(mp.tiles_total < sms ? mp.tiles_total : sms))));
+            SDOD_TRY((launch_gemm_cfg<BN, true, false, true>(stream, g, dim3(mp.streamk ? g.sk_grid : (mp.tiles_total < sms ? mp.tiles_total : sms)))));
             count_launch();
             return check_launch("gemm_tcgen05_kernel (persistent)");
         }
@@ -1370,6 +1470,7 @@ static void choose_persist(GemmLaunch* out) {
     mp.n_tiles = out->n_tiles; mp.m_tiles = out->m_tiles;
     mp.tiles_total = out->n_tiles * out->m_tiles * out->batch;
     out->persist = 0;
+    if (mp.streamk) { out->persist = 1; return; }     // stream-K runs on the persistent variant, grid = out->sk_grid
     if (!env || out->pair || mp.split > 1 || !mp.tma_epi || (out->bn != 128 && out->bn != 160)) return;
     const int sms = device_sm_count();
     if (env == 2) { out->persist = mp.tiles_total > sms; return; }
@@ -1409,6 +1510,24 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
     mp->split = split; mp->kb_per_split = kbps; mp->ws = g_splitk.ws; mp->counters = g_splitk.counters;
 }
 
+// Stream-K decision (see WorkWalk): worthwhile when whole-tile scheduling would leave the chip badly quantised — few tiles, long K — i.e.
+// when an equal share of the (tile, K block) space per SM is clearly shorter than ceil(tiles / SMs) full K loops.  SDOD_STREAMK=0 disables it.
+// Returns the grid size (0 = do not use stream-K).
+static int streamk_grid(int bn, long long tiles, int k_blocks, int batch, bool pair) {
+    static const int env = [] { const char* e = std::getenv("SDOD_STREAMK"); return e ? std::atoi(e) : 1; }();
+    if (!env || pair || batch != 1 || (bn != 128 && bn != 160) || !g_splitk.ws || k_blocks < 16) return 0;
+    const int sms = device_sm_count();
+    const long long total = tiles * k_blocks;
+    if (tiles > 4LL * sms || total < 8LL * 16) return 0;
+    int grid = static_cast<int>(std::min<long long>(sms, total / 8));                 // at least 8 K blocks per CTA
+    if (grid < 2) return 0;
+    if (static_cast<size_t>(grid) * bn * kBlockM * sizeof(float) > g_splitk.ws_bytes || grid > g_splitk.n_counters) return 0;
+    const long long sk_blocks = (total + grid - 1) / grid + 2;                          // + publish / fold overhead
+    const long long classic = ((tiles + sms - 1) / sms) * k_blocks;
+    if (env != 2 && sk_blocks * 5 > classic * 4) return 0;                              // needs a >= 20 % shorter critical path
+    return grid;
+}
+
 // In-kernel reduction over a (1,1,split) cluster (one launch) unless SDOD_SPLITK_CLUSTER=0 (A/B measurements: separate reduce kernel).
 static int split_cluster_mode(const MainloopParams& mp, bool pair, int act) {
     static const int env = [] { const char* e = std::getenv("SDOD_SPLITK_CLUSTER"); return e ? std::atoi(e) : 1; }();
@@ -1444,7 +1563,14 @@ static int validate_epilogue(const sdod_epilogue& ep, int N) {
     return kOk;
 }
 
+static int gemm_prepare_impl(const sdod_gemm_desc& d, GemmLaunch* out, bool try_streamk, bool* used_streamk);
 int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
+    bool sk = false;
+    SDOD_TRY(gemm_prepare_impl(d, out, true, &sk));
+    if (sk && !out->mp.tma_epi) return gemm_prepare_impl(d, out, false, &sk);    // this epilogue has no persistent form: classic scheduling
+    return kOk;
+}
+static int gemm_prepare_impl(const sdod_gemm_desc& d, GemmLaunch* out, bool try_streamk, bool* used_streamk) {
     if (!d.A || !d.W) return fail(kInvalidArgument, "gemm: NULL operand");
     if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.batch <= 0) return fail(kInvalidArgument, "gemm: non-positive extent");
     if (d.K % kBlockK != 0) return fail(kInvalidArgument, "gemm: K must be a multiple of 64 (pad the operand)");
@@ -1456,7 +1582,15 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     int bn = d.block_n ? d.block_n : pick_block_n_k(d.M, d.N, d.batch, d.epi.act, Ktot / kBlockK);
     if (!d.block_n && d.N % 160 == 0 && heads_tma_eligible(d.epi, d.M, d.N, d.batch)) bn = 160;   // four 40-column head boxes per tile
     if (!d.block_n && d.epi.ln_out) bn = d.N % 160 == 0 ? 160 : 128;                              // whole tiles only (fused LayerNorm)
-    const bool pair = use_pair(bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, false);
+    int sk_grid = 0;
+    *used_streamk = false;
+    if (try_streamk && !d.epi.ln_out) {
+        const int bn_sk = d.block_n ? d.block_n : pick_block_n(d.M, d.N, d.batch, d.epi.act);      // the widest well-fitting tile: tile count is no concern
+        const long long tiles_sk = static_cast<long long>((d.M + kBlockM - 1) / kBlockM) * ((d.N + bn_sk - 1) / bn_sk);
+        sk_grid = streamk_grid(bn_sk, tiles_sk, Ktot / kBlockK, d.batch, false);
+        if (sk_grid) { bn = bn_sk; *used_streamk = true; }
+    }
+    const bool pair = !sk_grid && use_pair(bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, false);
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;
@@ -1478,7 +1612,9 @@ int gemm_prepare(const sdod_gemm_desc& d, GemmLaunch* out) {
     mp.M = d.M; mp.N = d.N; mp.k_blocks = Ktot / kBlockK; mp.conv = 0; mp.w_batched = wb ? 1 : 0;
     mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, d.batch);
-    if (d.epi.ln_out) { mp.split = 1; mp.kb_per_split = mp.k_blocks; }      // the LayerNorm epilogue needs the finished rows in one CTA row
+    if (d.epi.ln_out || sk_grid) { mp.split = 1; mp.kb_per_split = mp.k_blocks; }      // the LayerNorm epilogue needs the finished rows in one CTA row
+    if (sk_grid) { mp.streamk = 1; mp.ws = g_splitk.ws; mp.counters = g_splitk.counters; }
+    out->sk_grid = sk_grid;
     mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     out->mp.tlog = g_tlog;
@@ -1505,7 +1641,14 @@ int gemm_bf16(cudaStream_t stream, const sdod_gemm_desc& d) {
     return gemm_launch(g, stream);
 }
 
+static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool try_streamk, bool* used_streamk);
 int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
+    bool sk = false;
+    SDOD_TRY(conv3x3_prepare_impl(d, out, true, &sk));
+    if (sk && !out->mp.tma_epi) return conv3x3_prepare_impl(d, out, false, &sk);
+    return kOk;
+}
+static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool try_streamk, bool* used_streamk) {
     if (!d.X || !d.Wt) return fail(kInvalidArgument, "conv3x3: NULL operand");
     if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.Cin <= 0 || d.Cout <= 0) return fail(kInvalidArgument, "conv3x3: non-positive extent");
     if (d.Cin % kBlockK != 0) return fail(kInvalidArgument, "conv3x3: Cin must be a multiple of 64 (use im2col + gemm otherwise)");
@@ -1519,8 +1662,16 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
     if (d.epi.ln_out) return fail(kUnsupported, "conv3x3: no fused LayerNorm epilogue");
     const int Cin2 = d.X2 ? d.Cin2 : 0;
-    const int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, (9 * d.Cin + Cin2) / kBlockK);
-    const bool pair = use_pair(bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, true);
+    int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, (9 * d.Cin + Cin2) / kBlockK);
+    int sk_grid = 0;
+    *used_streamk = false;
+    if (try_streamk) {
+        const int bn_sk = d.block_n ? d.block_n : pick_block_n(M, d.Cout, 1, d.epi.act);
+        const long long tiles_sk = static_cast<long long>((M + kBlockM - 1) / kBlockM) * ((d.Cout + bn_sk - 1) / bn_sk);
+        sk_grid = streamk_grid(bn_sk, tiles_sk, (9 * d.Cin + Cin2) / kBlockK, 1, false);
+        if (sk_grid) { bn = bn_sk; *used_streamk = true; }
+    }
+    const bool pair = !sk_grid && use_pair(bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, true);
 
     CUtensorMap& tmA = out->tmA;
     CUtensorMap& tmW = out->tmW;
@@ -1544,6 +1695,8 @@ int conv3x3_prepare(const sdod_conv_desc& d, GemmLaunch* out) {
     mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
     mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
+    if (sk_grid) { mp.split = 1; mp.kb_per_split = mp.k_blocks; mp.streamk = 1; mp.ws = g_splitk.ws; mp.counters = g_splitk.counters; }
+    out->sk_grid = sk_grid;
     mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     out->mp.tlog = g_tlog;

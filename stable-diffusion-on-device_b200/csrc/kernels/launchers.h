@@ -26,6 +26,8 @@ struct MainloopParams {
                        //    cluster barrier; 0: partials are folded by splitk_reduce_kernel (a second launch)
     int kb_a2;         // first K block served by the second A operand (tmA2: plain [K2, M] rows, the K-concatenated skip / concat
                        //    source); >= k_blocks when there is none
+    int streamk;       // persistent variant only: CTAs take equal contiguous shares of the (tile, K block) space (see WorkWalk); partial tiles go
+                       //    through `ws` (one slot per CTA), `counters` are the per-CTA "partial published" flags
     int ln_fuse;       // 1: LayerNorm of the output rows fused into the epilogue (cluster over the N tiles, see the kernel); tmC2 = bf16 LN output
     unsigned long long* tlog; // profiling hook (tools/gemm_timeline.py): per-CTA globaltimer stamps of the kernel's phases, 16 slots per CTA; NULL = off
     const char* pf_ptr;       // L2 prefetch of the NEXT layer's weights (constant data, issued before griddepcontrol.wait); NULL = none
@@ -44,6 +46,7 @@ struct GemmLaunch {
     int bn, m_tiles, n_tiles, batch;
     int pair;   // 1: launched as 2-CTA clusters running tcgen05 cta_group::2
     int persist;   // 1: one CTA per SM walks the tile list (TMEM double-buffered accumulator)
+    int sk_grid;   // stream-K: number of persistent CTAs (0 = off)
 };
 
 struct AttnLaunch {

@@ -417,7 +417,7 @@ int NetBase::gemm_into(const sdod_gemm_desc& d, bool may_fail) {
     check(st_prep);
     note_gemm(g);
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
-                "gemm M" + std::to_string(d.M) + " N" + std::to_string(d.N) + " K" + std::to_string(d.K) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split) +
+                "gemm M" + std::to_string(d.M) + " N" + std::to_string(d.N) + " K" + std::to_string(d.K) + " bn" + std::to_string(g->bn) + (g->mp.streamk ? " sk" + std::to_string(g->sk_grid) : " split" + std::to_string(g->mp.split)) +
                     (d.batch > 1 ? " batch" + std::to_string(d.batch) : "") + (g->mp.ln_fuse ? " +ln" : ""));
     return kOk;
 }
@@ -475,7 +475,7 @@ Act NetBase::conv3(const Act& x, const std::string& prefix, int cout, const floa
     check(st_prep);
     note_gemm(g);
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
-                "conv3 HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) + " split" + std::to_string(g->mp.split));
+                "conv3 HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) + (g->mp.streamk ? " sk" + std::to_string(g->sk_grid) : " split" + std::to_string(g->mp.split)));
     return y;
 }
 
@@ -497,7 +497,7 @@ Act NetBase::conv3_skip(const Act& x, const std::string& prefix, const std::stri
     note_gemm(g);
     plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
                 "conv3+skip HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + "+" + std::to_string(x_skip.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) +
-                    " split" + std::to_string(g->mp.split));
+                    (g->mp.streamk ? " sk" + std::to_string(g->sk_grid) : " split" + std::to_string(g->mp.split)));
     return y;
 }
 

@@ -560,6 +560,59 @@ def test_gemm_fused_layer_norm_rejects_ineligible_shapes():
         ops.linear_ln(a, w, None, None, None, None)
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 640, 2560), (512, 1280, 5120), (512, 1280, 1280), (128, 1280, 1280), (512, 3840, 1280), (300, 640, 2048)])
+def test_gemm_stream_k(M, N, K):
+    """Stream-K on the persistent kernel: CTAs take equal shares of the (tile, K block) space; head segments publish fp32 partials that the
+    tile's first segment folds into its accumulator reads in fixed order.  Epilogues: fp32 residual (TMA), bf16 + SiLU, GEGLU, QKV head layouts."""
+    torch.manual_seed(M + N + K)
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+    want = a.float() @ w.float().t() + bias
+    ops.enable_splitk(True)
+    try:
+        got = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)
+        got2 = torch.ops.sdod.linear(a, w, bias, res, 0, 1.0, True)
+        act = torch.ops.sdod.linear(a, w, bias, None, C.ACT_SILU)
+        if N == 1280 and K == 1280 and M == 512:
+            wg = bf(torch.randn(8 * N, K) / K ** 0.5).to(DEV)          # GEGLU projection of the 16x16 level: 320 tiles x 20 K blocks
+            bg = torch.randn(8 * N, device=DEV)
+            wp, bp = ops.pack_geglu_weight(wg, bg)
+            gg = torch.ops.sdod.linear(a, wp, bp, None, C.ACT_GEGLU)
+            h = a.float() @ wg.float().t() + bg
+            assert rel_err(gg, h[:, :4 * N] * F.gelu(h[:, 4 * N:])) < TOL_BF16
+        if N == 3840:
+            heads, dh, tokens = 8, 160, 256
+            qh, kh, vt = ops.qkv_project(a, w, heads, dh, tokens)
+            qkv = bf(a.float() @ w.float().t()).view(2, tokens, 3, heads * dh)
+            for g_, want_ in ((qh, ops.pack_heads(qkv[:, :, 0], heads, dh)), (kh, ops.pack_heads(qkv[:, :, 1], heads, dh)),
+                              (vt, ops.pack_heads(qkv[:, :, 2], heads, dh, True))):
+                assert rel_err(g_, want_) < TOL_BF16
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want + res) < TOL_F32 and torch.equal(got, got2)
+    assert rel_err(act, F.silu(want)) < TOL_BF16
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 32, 640, 640), (2, 16, 1280, 1280), (2, 8, 1280, 1280), (2, 32, 1280, 640), (1, 16, 320, 1280)])
+def test_conv3x3_stream_k(B, H, Cin, Cout):
+    torch.manual_seed(H + Cin)
+    x = bf(torch.randn(B, H, H, Cin)).to(DEV)
+    w = bf(torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    bias, rb = torch.randn(Cout, device=DEV), torch.randn(B, Cout, device=DEV)
+    res = torch.randn(B, H, H, Cout, device=DEV)
+    want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1) + rb[:, None, None, :]
+    wt = ops.pack_conv3x3_weight(w.float())
+    ops.enable_splitk(True)
+    try:
+        got = torch.ops.sdod.conv3x3(x, wt, bias, None, rb)
+        got_r = torch.ops.sdod.conv3x3(x, wt, bias, bf(res), rb)
+        again = torch.ops.sdod.conv3x3(x, wt, bias, None, rb)
+    finally:
+        ops.enable_splitk(False)
+    assert rel_err(got, want) < TOL_BF16 and torch.equal(got, again)
+    assert rel_err(got_r, want + bf(res).float()) < TOL_BF16
+
+
 def test_conv_split_k_small_spatial():
     torch.manual_seed(5)
     x = bf(torch.randn(2, 8, 8, 2560)).to(DEV)

@@ -73,6 +73,8 @@ cases = [
     ("gemm M512 N1280 K1280 f32res split", lambda: gemm(512, 1280, 1280, True, True, True)),
     ("gemm M512 N1280 K5120 f32res split", lambda: gemm(512, 1280, 5120, True, True, True)),
     ("gemm M128 N1280 K1280 f32res split", lambda: gemm(128, 1280, 1280, True, True, True)),
+    ("gemm M2048 N640 K2560 f32res split", lambda: gemm(2048, 640, 2560, True, True, True)),
+    ("gemm M512 N10240 K1280 geglu split", lambda: gemm(512, 10240, 1280, False, False, True, 0, 3)),
     ("conv B2 64x64 320->320 bf16", lambda: conv(2, 64, 320, 320)),
     ("conv B2 32x32 640->640 split", lambda: conv(2, 32, 640, 640, False, True)),
     ("conv B2 16x16 1280->1280 split", lambda: conv(2, 16, 1280, 1280, False, True)),
