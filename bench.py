@@ -9,9 +9,15 @@ GPUs (one process per GPU, no data-path collective; weak scaling).  Prints ONE J
   value    : images/s, device-event timed, inputs/outputs resident in HBM (libsdod_b200_generate_device)
   e2e      : images/s through the reference-facing C API with HOST buffers (libsdod_b200_generate: pinned H2D of
              conditioning + latents, D2H of the uint8 images inside the timed region)
-  roofline : the UNet denoising step (one CUDA-graph replay = all its kernels) against the measured bf16 peak
+  roofline : the dominant kernel (gemm_tcgen05_kernel: every linear layer and 3x3 conv) over one UNet pass at the
+             benchmarked batch (2 x images per step), per-launch CUDA events, against the measured sustained bf16 peak
+  step_roofline : BASELINE.json's second metric, "UNet step p50 ms" = config C2 (batch 2: one image's cond + uncond),
+             one CUDA-graph replay of the whole step, 1.6065 TFLOP, against the same peak
+  parity   : the GPU UNet on the CPU leg's own inputs and weights (seeds 0/1/2) at batch 2 AND inside the benchmarked
+             batch — eps relative L2 vs the fp32 oracle, asserted <= 1e-2 (BASELINE.json north star)
   cpu_baseline : the oracle (fp32 PyTorch restatement + C sampler) on the host cores, bounded sample
---impl reference times that CPU path as its own arm.
+--impl reference times that CPU path as its own arm: there one "step" = one CFG UNet step (cond + uncond) on the
+host, ms_per_step is its mean time, and images/s = 1 / (20 steps + 1 VAE decode).
 """
 import argparse
 import json
@@ -71,9 +77,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_oracle_times(n_unet_steps=1):
+def cpu_oracle_times(n_unet_steps=1, keep=None):
     """Bounded CPU sample of the same workload: one CFG UNet step (cond + uncond, as context.cpp:352,366) and one VAE
-    decode at full size, fp32, all host threads -> extrapolated images/s = 1 / (20 * t_step + t_vae)."""
+    decode at full size, fp32, all host threads -> extrapolated images/s = 1 / (20 * t_step + t_vae).
+    keep (dict, optional) receives the first step's inputs, outputs and the oracle module for the GPU parity check."""
     import torch
     from oracle import ldm_oracle as L
     from oracle import sampler as S
@@ -91,8 +98,10 @@ def cpu_oracle_times(n_unet_steps=1):
         xs = x.numpy().copy().ravel()
         for i in range(n_unet_steps):
             t0 = time.perf_counter()
-            e_c = unet(x, emb, cond).numpy().ravel()
-            e_u = unet(x, emb, uncond).numpy().ravel()
+            e_c_t, e_u_t = unet(x, emb, cond), unet(x, emb, uncond)
+            e_c, e_u = e_c_t.numpy().ravel(), e_u_t.numpy().ravel()
+            if keep is not None and i == 0:
+                keep.update(unet=unet, x=x, emb=emb, cond=cond, uncond=uncond, eps_c=e_c_t.clone(), eps_u=e_u_t.clone())
             e = S.cfg_combine(e_c, e_u, 7.5)
             solver.update(0 if i == 0 else 1, xs, e)
             ts.append(time.perf_counter() - t0)
@@ -112,8 +121,10 @@ def run_reference(args, rank):
     sample = "%d timed CFG UNet steps (cond+uncond, 64x64 latent) + 1 VAE decode, fp32 PyTorch oracle; images/s = 1/(20*t_step + t_vae)" % len(ts)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * (20 * t_step + t_vae), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sampled": sample},
+        "ms_per_step": 1000.0 * t_step, "ms_per_image_extrapolated": 1000.0 * (20 * t_step + t_vae),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sampled": sample,
+                                        "step": "one CFG UNet step (cond + uncond) on the host; steps x ms_per_step = the timed region"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "unet_cfg_step_s": t_step, "vae_decode_s": t_vae},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -256,12 +267,16 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
-            ts, t_vae, cores = cpu_oracle_times(1)
-            v = 1.0 / (20 * ts[0] + t_vae)
+            keep = {}
+            ts, t_vae, cores = cpu_oracle_times(2, keep)             # the first step is the warm-up (and the parity vector), the second is timed
+            v = 1.0 / (20 * ts[1] + t_vae)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "1 CFG UNet step (cond+uncond) + 1 VAE decode, fp32 PyTorch oracle on host; images/s = 1/(20*t_step + t_vae)",
-                                    "unet_cfg_step_s": ts[0], "vae_decode_s": t_vae}
+                                    "sample": "1 warm-up + 1 timed CFG UNet step (cond+uncond) + 1 VAE decode, fp32 PyTorch oracle on host; images/s = 1/(20*t_step + t_vae)",
+                                    "unet_cfg_step_s": ts[1], "vae_decode_s": t_vae}
+            line["parity"] = gpu_parity(keep, dev, Bk)
         print(json.dumps(line))
+        if line.get("parity") and not line["parity"]["ok"]:
+            raise SystemExit("bench.py: GPU eps differs from the oracle beyond tolerance: %s" % line["parity"])
     ctx.release()
     if world > 1:
         dist.destroy_process_group()
@@ -312,6 +327,36 @@ def run_cfg_split(args, rank, world, local_rank):
     dist.destroy_process_group()
 
 
+def gpu_parity(keep, dev, big_batch):
+    """The product UNet on the CPU leg's inputs and weights: eps relative L2 vs the fp32 oracle at batch 2 (config C2) and inside
+    the benchmarked batch (every slot of the batch carries one of the two oracle-checked samples, so every tile of the
+    large-batch plan — CTA-pair and persistent GEMM variants included — has a known answer)."""
+    import torch
+    from sdod import model as M
+    tol = 1e-2
+    want = torch.cat([keep["eps_c"], keep["eps_u"]], 0).to(dev)
+    weights = M.Weights(keep["unet"].state_dict())
+    x2 = torch.cat([keep["x"], keep["x"]], 0)
+    emb2 = torch.cat([keep["emb"], keep["emb"]], 0)
+    ctx2 = torch.cat([keep["cond"], keep["uncond"]], 0)
+
+    def rel(got, ref):
+        return ((got.double() - ref.double()).norm() / ref.double().norm()).item()
+
+    net = M.UNet(weights, latent_hw=64, max_batch=2)
+    e2 = rel(net(x2, emb2, ctx2), want)
+    del net
+    reps = big_batch // 2
+    net = M.UNet(weights, latent_hw=64, max_batch=big_batch)
+    got = net(x2.repeat(reps, 1, 1, 1), emb2.repeat(reps, 1), ctx2.repeat(reps, 1, 1))
+    per_slot = [rel(got[i:i + 1], want[i % 2:i % 2 + 1]) for i in range(big_batch)]
+    del net
+    torch.cuda.synchronize()
+    worst = max(per_slot)
+    return {"eps_rel_l2_batch2": e2, "eps_rel_l2_bench_batch_worst_slot": worst, "bench_batch": big_batch, "tol": tol,
+            "ok": bool(e2 <= tol and worst <= tol), "oracle": "oracle/ldm_oracle.py fp32 on the host (seeds 0/1/2: weights / latent / prompts)"}
+
+
 def op_flops(name, batch):
     """Algorithmic FLOPs of one op of the UNet plan from its profile name (None for non-GEMM ops)."""
     import re
@@ -321,6 +366,9 @@ def op_flops(name, batch):
     m = re.match(r"conv3 HW(\d+) Cin(\d+) Cout(\d+)", name)
     if m:
         return 2.0 * batch * int(m.group(1)) * int(m.group(3)) * 9 * int(m.group(2))
+    m = re.match(r"conv3\+skip HW(\d+) Cin(\d+)\+(\d+) Cout(\d+)", name)     # 3x3 conv + the ResBlock's 1x1 skip projection in one launch
+    if m:
+        return 2.0 * batch * int(m.group(1)) * int(m.group(4)) * (9 * int(m.group(2)) + int(m.group(3)))
     return None
 
 
@@ -334,8 +382,9 @@ def traffic_from_profiles():
 
 
 def main():
-    if os.environ.get("SDOD_GEMM_DBG"):
-        raise SystemExit("SDOD_GEMM_DBG (timing experiments that skip loads or MMAs) must not be set for a benchmark run")
+    knobs = sorted(k for k in os.environ if k.startswith("SDOD_"))
+    if knobs:
+        print("bench.py: note — A/B knobs set in the environment: %s" % knobs, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -400,6 +400,92 @@ __global__ void gn_nhwc_apply_kernel(const TI* __restrict__ x, TO* __restrict__ 
     }
 }
 
+// Group-owned NHWC GroupNorm: one CTA (or a cluster of `cs` CTAs splitting the rows) owns one (sample, group) — its rows x (C/G) channels
+// slab — stages it in shared memory as fp32 while accumulating pivot-shifted moments, reduces within the block (+ across the cluster over
+// distributed shared memory, fixed rank order), and normalises out of shared memory.  x is read once, y written once, there is no grid-wide
+// synchronisation and no workspace: at the batch-2 UNet step a GroupNorm costs one short dependent kernel instead of a cooperative two-pass one
+// (the grid barrier + partial-sum round trips of gn_nhwc_fused_kernel put ~9 us of pure L2 latency on the step's critical path, x61).
+// x is the channel concatenation [xa | xb] (xb may be NULL); `raw` optionally receives the bf16 copy of the un-normalised concatenation.
+// Thread layout: a thread owns one 2-channel unit (column) of the slab and walks the rows with a fixed stride, so its affine
+// coefficients are loop constants; 8-byte (fp32) / 4-byte (bf16) accesses, adjacent groups (adjacent CTAs) complete each 32-byte sector.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict__ xa, int Ca, const TI* __restrict__ xb, int Cb,
+                                                            TO* __restrict__ y, bf16* __restrict__ raw, const float* __restrict__ weight,
+                                                            const float* __restrict__ bias, int HW, int G, int cs, int rows_per_cta, float eps,
+                                                            int fuse_silu) {
+    extern __shared__ float2 slab[];            // [rows_per_cta][upr]
+    __shared__ float red[2][16];
+    __shared__ float cta_tot[2];
+    const int C = Ca + Cb, cpg = C / G, upr = cpg / 2;
+    const int g = blockIdx.x / cs, rank = blockIdx.x - g * cs, n = blockIdx.y;
+    const int rpb = blockDim.x / upr;                       // rows per pass
+    const int u = threadIdx.x % upr, r0 = threadIdx.x / upr;
+    const bool active = r0 < rpb;
+    const int c = g * cpg + 2 * u;                          // this thread's first channel (of the concatenation)
+    const bool from_b = c >= Ca;
+    const int ldx = from_b ? Cb : Ca;
+    const int p0 = rank * rows_per_cta, p1 = min(HW, p0 + rows_per_cta);
+    griddep_wait();
+    griddep_launch();
+    const TI* xcol = from_b ? xb + static_cast<long long>(n) * HW * Cb + (c - Ca) : xa + static_cast<long long>(n) * HW * Ca + c;
+    const int cg0 = g * cpg;                                // pivot: the group's first element of row 0 (identical in every CTA of the cluster)
+    const float K = cg0 < Ca ? to_f<TI>(xa[static_cast<long long>(n) * HW * Ca + cg0]) : to_f<TI>(xb[static_cast<long long>(n) * HW * Cb + (cg0 - Ca)]);
+    float s = 0.f, ss = 0.f;
+    if (active) {
+        for (int p = p0 + r0; p < p1; p += rpb) {
+            float2 v;
+            if (sizeof(TI) == 4) {
+                v = *reinterpret_cast<const float2*>(xcol + static_cast<long long>(p) * ldx);
+            } else {
+                v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xcol + static_cast<long long>(p) * ldx));
+            }
+            slab[(p - p0) * upr + u] = v;
+            const float d0 = v.x - K, d1 = v.y - K;
+            s += d0 + d1;
+            ss += d0 * d0 + d1 * d1;
+        }
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < nwarps; ++w) { a += red[0][w]; b += red[1][w]; }
+        cta_tot[0] = a; cta_tot[1] = b;
+    }
+    float ts, tss;
+    if (cs > 1) {
+        cluster_sync_all();                                 // (also a block barrier) every CTA's totals are visible cluster-wide
+        ts = 0.f; tss = 0.f;
+        for (int r = 0; r < cs; ++r) { ts += ld_dsmem_f32(&cta_tot[0], r); tss += ld_dsmem_f32(&cta_tot[1], r); }
+    } else {
+        __syncthreads();
+        ts = cta_tot[0]; tss = cta_tot[1];
+    }
+    const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+    const float m = ts / cnt;
+    const float var = fmaxf(tss / cnt - m * m, 0.f);
+    const float mean = K + m, rstd = rsqrtf(var + eps);
+    if (active) {
+        const float w0 = weight ? weight[c] : 1.f, w1 = weight ? weight[c + 1] : 1.f;
+        const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
+        const float A0 = rstd * w0, A1 = rstd * w1, B0 = -mean * A0 + b0, B1 = -mean * A1 + b1;
+        TO* ycol = y + static_cast<long long>(n) * HW * C + c;
+        bf16* rcol = raw ? raw + static_cast<long long>(n) * HW * C + c : nullptr;
+        for (int p = p0 + r0; p < p1; p += rpb) {
+            const float2 v = slab[(p - p0) * upr + u];
+            if (rcol) *reinterpret_cast<uint32_t*>(rcol + static_cast<long long>(p) * C) = pack_bf16x2(v.x, v.y);
+            float o0 = fmaf(v.x, A0, B0), o1 = fmaf(v.y, A1, B1);
+            if (fuse_silu) { o0 = silu_f(o0); o1 = silu_f(o1); }
+            if (sizeof(TO) == 4) *reinterpret_cast<float2*>(ycol + static_cast<long long>(p) * C) = make_float2(o0, o1);
+            else *reinterpret_cast<uint32_t*>(ycol + static_cast<long long>(p) * C) = pack_bf16x2(o0, o1);
+        }
+    }
+    if (cs > 1) cluster_sync_all();                         // peers may still be reading this CTA's totals
+}
+
 // Single-launch NHWC GroupNorm for tensors that live in L2 (the batch-2 UNet step: every tensor is <= 31 MB).
 // One grid of <= 148 CTAs, all co-resident: each CTA (sample n, row slab) accumulates pivot-shifted sums of its slab, publishes its per-group
 // partials, arrives on the sample's counter and waits until the sample's S slabs have arrived; then EVERY CTA folds the S partials in
@@ -498,7 +584,13 @@ __global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict
             const int gg = threadIdx.x / lanes, l = threadIdx.x - gg * lanes;
             float a = 0.f, b = 0.f;
             const float2* src = reinterpret_cast<const float2*>(partials + (static_cast<long long>(n) * S * G + gg) * 2);
-            for (int q = l; q < S; q += lanes) { const float2 v = __ldcg(src + static_cast<long long>(q) * G); a += v.x; b += v.y; }
+            int q = l;
+            for (; q + 3 * lanes < S; q += 4 * lanes) {        // four L2 loads in flight per thread; the summation order stays fixed
+                const float2 v0 = __ldcg(src + static_cast<long long>(q) * G), v1 = __ldcg(src + static_cast<long long>(q + lanes) * G);
+                const float2 v2 = __ldcg(src + static_cast<long long>(q + 2 * lanes) * G), v3 = __ldcg(src + static_cast<long long>(q + 3 * lanes) * G);
+                a += v0.x; b += v0.y; a += v1.x; b += v1.y; a += v2.x; b += v2.y; a += v3.x; b += v3.y;
+            }
+            for (; q < S; q += lanes) { const float2 v = __ldcg(src + static_cast<long long>(q) * G); a += v.x; b += v.y; }
             fold[(gg * lanes + l) * 2] = a; fold[(gg * lanes + l) * 2 + 1] = b;
         }
         __syncthreads();
@@ -643,8 +735,73 @@ static int group_norm_fused_typed(cudaStream_t stream, const TI* xa, int Ca, con
     return check_launch("gn_nhwc_fused_kernel");
 }
 
+// Geometry of the group-owned kernel: cluster size (rows split) and rows per CTA; cs == 0 -> not eligible.
+static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int* rows_per_cta) {
+    static const int env = [] { const char* e = std::getenv("SDOD_GN_GROUP"); return e ? std::atoi(e) : 1; }();
+    const int C = Ca + Cb;
+    if (!env || G <= 0 || C % G != 0) return 0;
+    const int cpg = C / G;
+    if (cpg % 2 != 0 || Ca % 2 != 0 || cpg / 2 > 512 || N > 65535) return 0;
+    const size_t slab = static_cast<size_t>(HW) * cpg * sizeof(float);
+    int cs = 1;
+    while (cs < 8 && (slab / cs > (static_cast<size_t>(100) << 10) || HW % cs != 0)) cs *= 2;          // <= 100 KB: two CTAs per SM
+    while (cs < 8 && static_cast<long long>(N) * G * cs < 128 && HW / (cs * 2) >= 32 && HW % (cs * 2) == 0) cs *= 2;   // fill the chip at small batch
+    if (HW % cs != 0 || slab / cs > (static_cast<size_t>(200) << 10)) return 0;
+    *rows_per_cta = HW / cs;
+    return cs;
+}
+
+template <typename TI, typename TO>
+static int group_norm_group_typed(cudaStream_t stream, const TI* xa, int Ca, const TI* xb, int Cb, TO* y, bf16* raw, const float* weight,
+                                  const float* bias, int N, int HW, int G, float eps, int fuse_silu, int cs, int rows_per_cta) {
+    const int C = Ca + Cb, upr = (C / G) / 2;
+    int rpb = std::max(1, std::min(512 / upr, rows_per_cta));
+    const int threads = std::min(512, ((upr * rpb + 31) / 32) * 32);      // whole warps; threads beyond upr*rpb idle (r0 >= rpb)
+    const size_t smem = static_cast<size_t>(rows_per_cta) * upr * sizeof(float2);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_group_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                            "cudaFuncSetAttribute(gn group)"));
+        configured = 200 * 1024;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(G) * cs, N); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cs > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cs; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled() && static_cast<long long>(G) * cs * N <= 296) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    SDOD_TRY(check_cuda(cudaLaunchKernelEx(&cfg, gn_nhwc_group_kernel<TI, TO>, xa, Ca, xb, Cb, y, raw, weight, bias, HW, G, cs, rows_per_cta, eps, fuse_silu),
+                        "launch gn_nhwc_group_kernel"));
+    count_launch();
+    return check_launch("gn_nhwc_group_kernel");
+}
+
 int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y, int out_dtype, void* raw_bf16,
                      const float* weight, const float* bias, int N, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
+    {
+        int rpc = 0;
+        const int cs = (xa && y && (Cb == 0 || xb)) ? group_kernel_geometry(N, Ca, xb ? Cb : 0, HW, G, &rpc) : 0;
+        if (cs && N > 0 && HW > 0 && ((weight == nullptr) == (bias == nullptr)) && group_norm_fused_eligible(N, Ca, xb ? Cb : 0, HW, G, in_dtype)) {
+            if (!xb) Cb = 0;
+#define SDOD_GNG_CASE(TI, TO) \
+    return group_norm_group_typed<TI, TO>(stream, static_cast<const TI*>(xa), Ca, static_cast<const TI*>(xb), Cb, static_cast<TO*>(y), \
+                                          static_cast<bf16*>(raw_bf16), weight, bias, N, HW, G, eps, fuse_silu, cs, rpc)
+            if (in_dtype == SDOD_F32 && out_dtype == SDOD_F32) SDOD_GNG_CASE(float, float);
+            if (in_dtype == SDOD_F32 && out_dtype == SDOD_BF16) SDOD_GNG_CASE(float, bf16);
+            if (in_dtype == SDOD_BF16 && out_dtype == SDOD_BF16) SDOD_GNG_CASE(bf16, bf16);
+            if (in_dtype == SDOD_BF16 && out_dtype == SDOD_F32) SDOD_GNG_CASE(bf16, float);
+#undef SDOD_GNG_CASE
+        }
+    }
     if (!xa || !y || (Cb > 0 && !xb)) return fail(kInvalidArgument, "group_norm: NULL tensor");
     if (!xb) Cb = 0;
     if (N <= 0 || Ca <= 0 || Cb < 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");

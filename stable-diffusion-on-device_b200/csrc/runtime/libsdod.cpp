@@ -96,14 +96,26 @@ unsigned long long fnv1a(const char* s) {
 
 class Engine {
 public:
+    // Like the reference's Context (context.cpp:24-47) the constructor only records its arguments and cannot fail; everything that can
+    // (device, weights, plans) happens in init(), which libsdod_setup runs AFTER publishing the handle (libsdod.cpp:77-87), so a failed
+    // setup leaves a context whose error table can be queried and which must be released.
     Engine(const std::string& models_dir, unsigned latent_spatial, unsigned log_level, unsigned max_images, int device)
-        : log_(log_level), S_(static_cast<int>(latent_spatial)), max_images_(static_cast<int>(max_images)), device_(device), sched_(1000, 0.00085f, 0.0120f), ddim_(1000, 0.00085f, 0.0120f) {   // context.cpp:196
+        : log_(log_level), S_(static_cast<int>(latent_spatial)), max_images_(static_cast<int>(max_images)), device_(device), sched_(1000, 0.00085f, 0.0120f), ddim_(1000, 0.00085f, 0.0120f),   // context.cpp:196
+          models_dir_(models_dir) {}
+
+    void init() {
+        std::string models_dir = models_dir_;
+        if (const char* over = std::getenv("LIBSDOD_B200_MODELS_DIR")) {      // deployment override: the reference's callers hard-code a relative path (simple_app.cpp:11)
+            models_dir = over;
+            log_.log(LIBSDOD_LOG_INFO, "models_dir overridden by LIBSDOD_B200_MODELS_DIR: %s", over);
+        }
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
             cudaGetLastError();
             API_THROW(LIBSDOD_RUNTIME_ERROR, "no CUDA device available (libsdod_b200 has no CPU fallback)");
         }
         if (device_ >= 0) CU(cudaSetDevice(device_));
+        else CU(cudaGetDevice(&device_));                                 // libsdod_setup: pin the caller's current device for every later entry
         CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (auto& e : ev_) CU(cudaEventCreate(&e));
         seed_ = std::random_device{}();                                   // context.cpp:16
@@ -141,18 +153,25 @@ public:
         // cached empty-prompt conditioning (context.cpp:233-239)
         uncond_default_.resize(77 * 768);
         prompt_embedding("", uncond_default_.data());
+        ready_ = true;
         log_.log(LIBSDOD_LOG_INFO, "Models and buffers prepared!");
     }
 
-    ~Engine() {
+    ~Engine() {                                                           // safe on a partially initialised engine (failed init)
         if (device_ >= 0) cudaSetDevice(device_);
-        cudaStreamSynchronize(stream_);
+        if (stream_) cudaStreamSynchronize(stream_);
         unet_.reset();
         vae_.reset();
         cudaFree(y_prev_); cudaFree(ctx_dev_); cudaFree(temb_); cudaFree(plms_buf_);
-        cudaFreeHost(pin_ctx_); cudaFreeHost(pin_lat_); cudaFreeHost(pin_img_);
-        for (auto& e : ev_) cudaEventDestroy(e);
-        cudaStreamDestroy(stream_);
+        if (pin_ctx_) cudaFreeHost(pin_ctx_);
+        if (pin_lat_) cudaFreeHost(pin_lat_);
+        if (pin_img_) cudaFreeHost(pin_img_);
+        for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        if (stream_) cudaStreamDestroy(stream_);
+        cudaGetLastError();
+    }
+    void require_ready() const {
+        if (!ready_) API_THROW(LIBSDOD_RUNTIME_ERROR, "context is not initialised (libsdod_setup failed; query its error and release the context)");
     }
 
     size_t image_bytes() const { return static_cast<size_t>(3) * S_ * 8 * S_ * 8; }     // context.cpp:406-409
@@ -161,6 +180,7 @@ public:
     void set_sampler(int sampler) {
         if (sampler != LIBSDOD_B200_SAMPLER_DPM && sampler != LIBSDOD_B200_SAMPLER_DDIM && sampler != LIBSDOD_B200_SAMPLER_PLMS)
             API_THROW(LIBSDOD_INVALID_ARGUMENT, "unknown sampler id: " + std::to_string(sampler));
+        require_ready();
         sampler_ = sampler;
         if (steps_) prepare_schedule(steps_);
         log_.log(LIBSDOD_LOG_INFO, "Sampler: %s", sampler == LIBSDOD_B200_SAMPLER_DDIM ? "DDIM (eta 0)" : sampler == LIBSDOD_B200_SAMPLER_PLMS ? "PLMS" : "DPM-Solver++(2M)");
@@ -170,6 +190,7 @@ public:
     int max_images() const { return max_images_; }
 
     void prepare_schedule(unsigned steps) {                               // context.cpp:245-282
+        require_ready();
         if (steps < 1 || steps > 1000) API_THROW(LIBSDOD_INVALID_ARGUMENT, "steps must be in [1, 1000], got: " + std::to_string(steps));
         if (device_ >= 0) CU(cudaSetDevice(device_));
         sched_.prepare(steps);
@@ -202,6 +223,7 @@ public:
     }
 
     void generate_prompt(const char* prompt, float guidance, unsigned char* out) {
+        require_ready();
         log_.log(LIBSDOD_LOG_INFO, "Starting image generation for prompt: \"%s\" and guidance %g", prompt, guidance);
         std::vector<float> cond(77 * 768);
         prompt_embedding(prompt, cond.data());
@@ -257,6 +279,7 @@ public:
     // context.cpp:292-403, batched over n images
     void generate(unsigned n, const float* cond, const float* uncond, const float* latents, float guidance, unsigned char* images_out,
                   float* latents_out, bool device_ptrs = false) {
+        require_ready();
         if (n < 1 || static_cast<int>(n) > max_images_) API_THROW(LIBSDOD_INVALID_ARGUMENT, "n_images out of range (max_images = " + std::to_string(max_images_) + ")");
         if (!cond) API_THROW(LIBSDOD_INVALID_ARGUMENT, "cond is nullptr");
         if (!images_out) API_THROW(LIBSDOD_INVALID_ARGUMENT, "images_out is nullptr");
@@ -348,6 +371,8 @@ private:
     std::vector<float> uncond_default_;
     unsigned long long seed_ = 0, rng_offset_ = 0;
     float timings_[4] = {0, 0, 0, 0};
+    std::string models_dir_;
+    bool ready_ = false;
 };
 
 struct Handle {                                  // reference libsdod.cpp:22-27
@@ -407,15 +432,16 @@ int setup_common(void** context, const char* models_dir, unsigned latent_spatial
     Handle* hnd = new (std::nothrow) Handle;
     if (hnd == nullptr) return record(nullptr, LIBSDOD_FAILED_ALLOCATION, "Could not create a new CAPI_Context_Handler object", func, __FILE__, __LINE__);
     hnd->ref_count += 1;
-    // As in the reference (libsdod.cpp:77-87) the handle is published before initialisation can fail, so the
-    // caller can query the error and must release it.  The engine constructor itself may throw -> contextless table.
-    int st = guarded(nullptr, func, [&] { hnd->cptr = new Engine(models_dir, latent_spatial, log_level, max_images, device); });
-    if (st != LIBSDOD_NO_ERROR) {
+    hnd->cptr = new (std::nothrow) Engine(models_dir, latent_spatial, log_level, max_images, device);     // records its arguments only
+    if (hnd->cptr == nullptr) {
         delete hnd;
-        return st;
+        return record(nullptr, LIBSDOD_FAILED_ALLOCATION, "Could not create a new Context object", func, __FILE__, __LINE__);
     }
+    // As in the reference (libsdod.cpp:77-87) the handle is published before initialisation can fail: on error *context is
+    // non-NULL, the message sits in the context's own table (libsdod_get_last_error_extra_info(code, ctx)) and the caller must
+    // still release the context (libsdod.h:42-45).
     *context = hnd;
-    return guarded(&hnd->cptr->errors(), func, [&] { hnd->cptr->prepare_schedule(steps); });
+    return guarded(&hnd->cptr->errors(), func, [&] { hnd->cptr->init(); hnd->cptr->prepare_schedule(steps); });
 }
 
 }  // namespace

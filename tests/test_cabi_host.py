@@ -108,7 +108,16 @@ def test_libsdod_api_argument_and_context_errors_without_gpu():
     assert b"magic header mismatch" in lib.libsdod_get_last_error_extra_info(A.INVALID_CONTEXT, None)
     if not torch.cuda.is_available():
         assert lib.libsdod_setup(ctypes.byref(ctx), b"random-init", 4, 64, 8, 20, 0, 1) == A.RUNTIME_ERROR    # no CPU fallback
-        assert b"no CUDA device" in lib.libsdod_get_last_error_extra_info(A.RUNTIME_ERROR, None)
+        # as in the reference (libsdod.cpp:77-87, libsdod.h:42-45) the handle is published before initialisation can fail: the context is
+        # non-NULL, holds the error, rejects work and must still be released
+        assert ctx
+        assert b"no CUDA device" in lib.libsdod_get_last_error_extra_info(A.RUNTIME_ERROR, ctx)
+        assert lib.libsdod_set_steps(ctx, 20) == A.RUNTIME_ERROR
+        assert b"not initialised" in lib.libsdod_get_last_error_extra_info(A.RUNTIME_ERROR, ctx)
+        img, n = ctypes.POINTER(ctypes.c_ubyte)(), ctypes.c_uint(0)
+        assert lib.libsdod_generate_image(ctx, b"x", 7.5, ctypes.byref(img), ctypes.byref(n)) == A.RUNTIME_ERROR and not img
+        assert lib.libsdod_release(ctx) == A.NO_ERROR
+        assert lib.libsdod_release(ctx) == A.INVALID_CONTEXT                 # released handles are detected, not dereferenced
 
 
 def test_checkpoint_conversion_roundtrip(tmp_path):

@@ -134,3 +134,27 @@ def test_ddim_sampler_vs_oracle_loop(models_dir):
           % (rel, psnr_u8(imgs, want_u8), rel_dpm, np.linalg.norm(want_lat - dpm_lat) / np.linalg.norm(dpm_lat)))
     assert psnr_u8(imgs, want_u8) >= 35.0 and rel < 5e-2
     assert psnr_u8(imgs_dpm, dpm_u8) >= 35.0 and rel_dpm < 5e-2
+
+
+def test_reference_simple_app_runs_unmodified(models_dir, tmp_path):
+    """The reference's own caller (csrc/libsdod/test/simple_app.cpp, compiled UNMODIFIED against include/libsdod.h and linked to
+    libsdod_b200.so by oracle/Makefile) sets up, generates 'A photograph of an astronaut riding a horse' at 7.5 and writes output.bin:
+    786,432 bytes of RGB [H,W,C] (libsdod.h:89, simple_app.cpp:31-33).  Its hard-coded models path is redirected with LIBSDOD_B200_MODELS_DIR."""
+    import subprocess
+    root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    app = os.path.join(root, "oracle", "_ref", "simple_app")
+    if not os.path.exists(app):
+        pytest.skip("oracle/_ref/simple_app not built (needs /root/reference at build time)")
+    d, _, _ = models_dir
+    env = dict(os.environ, LIBSDOD_B200_MODELS_DIR=d)
+    r = subprocess.run([app], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = tmp_path / "output.bin"
+    assert out.exists() and out.stat().st_size == 3 * 512 * 512
+    img = np.frombuffer(out.read_bytes(), dtype=np.uint8).reshape(512, 512, 3)
+    assert img.std() > 1.0
+    assert "Image generation took" in r.stdout                      # the reference's timer lines (context.cpp:402) at LOG_DEBUG
+    # a failing setup through the same binary: error text comes from the published context, exit code 1 (simple_app.cpp:13-18)
+    r = subprocess.run([app], cwd=str(tmp_path), env=dict(os.environ, LIBSDOD_B200_MODELS_DIR=str(tmp_path / "missing")),
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Initialization error" in r.stdout and "cannot open" in r.stdout

@@ -14,10 +14,11 @@ from sdod import model as M  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 tag = sys.argv[2] if len(sys.argv) > 2 else "b%d" % B
+HW = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 dev = torch.device("cuda")
-net = M.UNet(None, seed=0, latent_hw=64, max_batch=B)
+net = M.UNet(None, seed=0, latent_hw=HW, max_batch=B)
 net.set_context(torch.randn(B, 77, 768, device=dev))
-x, emb = torch.randn(B, 64, 64, 4, device=dev), torch.randn(B, 1280, device=dev)
+x, emb = torch.randn(B, HW, HW, 4, device=dev), torch.randn(B, 1280, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 s = torch.cuda.Stream()
 cold, warm = [], []
@@ -35,7 +36,7 @@ with torch.cuda.stream(s):
         (cold if it < 20 else warm).append(a.elapsed_time(b))
     rows = net.profile(B, 5)
 out = []
-out.append("B=%d launches/forward %d  ops %d  env %s" % (B, net.launches_per_forward(B), len(rows),
+out.append("B=%d hw=%d launches/forward %d  ops %d  env %s" % (B, HW, net.launches_per_forward(B), len(rows),
                                                       {k: v for k, v in os.environ.items() if k.startswith("SDOD_")}))
 out.append("graph replay: p50 %.3f ms (L2 flushed before each replay), %.3f ms back-to-back; min %.3f" % (statistics.median(cold), statistics.median(warm), min(cold + warm)))
 tot = sum(r[0] for r in rows)
