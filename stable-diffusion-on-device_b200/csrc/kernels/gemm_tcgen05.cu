@@ -1497,10 +1497,17 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
     if (tiles >= 120) return;
     if (tiles >= 60 && mp->k_blocks <= 24) return;             // short K: one kernel with the TMA epilogue beats split + reduce
-    int split = static_cast<int>((2 * 148 + tiles - 1) / tiles);
+    // One CTA per SM with the deep ring (tiles x split <= #SMs) rather than two shallow-ring CTAs per SM with twice the split: the mainloop is
+    // bound by each SM's operand ingest either way (timeline, profiles/r02_*), half the partial tiles go through L2, and a grid that
+    // overshoots the resident slots (64 tiles x 5 = 320 CTAs on 296 slots) no longer pays a second, nearly empty wave.
+    // SDOD_SPLIT_POLICY=0 restores the round-1 rule (A/B measurements).
+    static const int policy = [] { const char* e = std::getenv("SDOD_SPLIT_POLICY"); return e ? std::atoi(e) : 1; }();
+    const int sms = device_sm_count();
+    int split = policy ? static_cast<int>(sms / tiles) : static_cast<int>((2 * 148 + tiles - 1) / tiles);
     const int max_by_k = mp->k_blocks / 4;                    // at least 4 K blocks (256 deep) per split
     if (split > max_by_k) split = max_by_k;
-    if (split > 8) split = 8;                                 // bounds the partial-tile traffic (L2-resident)
+    const int cap = (policy && m_tiles == 1) ? 16 : 8;        // bounds the partial-tile traffic (L2-resident); single-row-block layers are pure weight streams
+    if (split > cap) split = cap;
     const size_t per_tile = static_cast<size_t>(bn) * kBlockM * sizeof(float);
     while (split > 1 && static_cast<size_t>(tiles) * split * per_tile > g_splitk.ws_bytes) --split;
     if (split < 2) return;
@@ -1514,7 +1521,9 @@ static void choose_split(MainloopParams* mp, int bn, int m_tiles, int n_tiles, i
 // when an equal share of the (tile, K block) space per SM is clearly shorter than ceil(tiles / SMs) full K loops.  SDOD_STREAMK=0 disables it.
 // Returns the grid size (0 = do not use stream-K).
 static int streamk_grid(int bn, long long tiles, int k_blocks, int batch, bool pair) {
-    static const int env = [] { const char* e = std::getenv("SDOD_STREAMK"); return e ? std::atoi(e) : 1; }();
+    // Off by default: measured on B200 (r2, profiles/r02_streamk_notes.txt) the batch-2 step ran 6.8 ms with stream-K against 5.7 ms with split-K —
+    // the single owner folding up to 18 published partials serialises what the separate reduce kernel does with 300 CTAs.  SDOD_STREAMK=1 enables it.
+    static const int env = [] { const char* e = std::getenv("SDOD_STREAMK"); return e ? std::atoi(e) : 0; }();
     if (!env || pair || batch != 1 || (bn != 128 && bn != 160) || !g_splitk.ws || k_blocks < 16) return 0;
     const int sms = device_sm_count();
     const long long total = tiles * k_blocks;
@@ -1528,9 +1537,11 @@ static int streamk_grid(int bn, long long tiles, int k_blocks, int batch, bool p
     return grid;
 }
 
-// In-kernel reduction over a (1,1,split) cluster (one launch) unless SDOD_SPLITK_CLUSTER=0 (A/B measurements: separate reduce kernel).
+// In-kernel reduction over a (1,1,split) cluster (one launch instead of two) with SDOD_SPLITK_CLUSTER=1.  Off by default: measured on B200 (r2) the
+// batch-2 step is 0.2 ms faster with the separate reduce kernel (5.28 vs 5.49 ms) — its 80 x tiles CTAs fold the partials with far more loads
+// in flight than the 8 epilogue warps of each cluster CTA, and 8-CTA clusters wait for 8 simultaneously free SMs of one GPC.
 static int split_cluster_mode(const MainloopParams& mp, bool pair, int act) {
-    static const int env = [] { const char* e = std::getenv("SDOD_SPLITK_CLUSTER"); return e ? std::atoi(e) : 1; }();
+    static const int env = [] { const char* e = std::getenv("SDOD_SPLITK_CLUSTER"); return e ? std::atoi(e) : 0; }();
     return (env && mp.split > 1 && mp.split <= 8 && !pair && act != SDOD_ACT_GEGLU) ? 1 : 0;
 }
 

@@ -432,17 +432,29 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
     const float K = cg0 < Ca ? to_f<TI>(xa[static_cast<long long>(n) * HW * Ca + cg0]) : to_f<TI>(xb[static_cast<long long>(n) * HW * Cb + (cg0 - Ca)]);
     float s = 0.f, ss = 0.f;
     if (active) {
-        for (int p = p0 + r0; p < p1; p += rpb) {
-            float2 v;
-            if (sizeof(TI) == 4) {
-                v = *reinterpret_cast<const float2*>(xcol + static_cast<long long>(p) * ldx);
-            } else {
-                v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xcol + static_cast<long long>(p) * ldx));
+        // eight rows per trip, all loads issued before the first use: the slab is L2-resident and each access is only 8 (4) bytes, so the
+        // kernel lives on memory-level parallelism (one load in flight per thread ran this phase at ~0.4 us per row)
+        constexpr int UN = 8;
+        for (int pb = p0 + r0; pb < p1; pb += UN * rpb) {
+            float2 v[UN];
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                const int p = pb + k * rpb;
+                if (p < p1) {
+                    if (sizeof(TI) == 4) v[k] = *reinterpret_cast<const float2*>(xcol + static_cast<long long>(p) * ldx);
+                    else v[k] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xcol + static_cast<long long>(p) * ldx));
+                }
             }
-            slab[(p - p0) * upr + u] = v;
-            const float d0 = v.x - K, d1 = v.y - K;
-            s += d0 + d1;
-            ss += d0 * d0 + d1 * d1;
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                const int p = pb + k * rpb;
+                if (p < p1) {
+                    slab[(p - p0) * upr + u] = v[k];
+                    const float d0 = v[k].x - K, d1 = v[k].y - K;
+                    s += d0 + d1;
+                    ss += d0 * d0 + d1 * d1;
+                }
+            }
         }
     }
     s = warp_sum(s);
@@ -486,26 +498,26 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
     if (cs > 1) cluster_sync_all();                         // peers may still be reading this CTA's totals
 }
 
-// Single-launch NHWC GroupNorm for tensors that live in L2 (the batch-2 UNet step: every tensor is <= 31 MB).
-// One grid of <= 148 CTAs, all co-resident: each CTA (sample n, row slab) accumulates pivot-shifted sums of its slab, publishes its per-group
-// partials, arrives on the sample's counter and waits until the sample's S slabs have arrived; then EVERY CTA folds the S partials in
-// the same fixed order (deterministic, bit-identical statistics in all CTAs) and normalises its own slab, which it re-reads from L1/L2.
+// Single-launch cooperative NHWC GroupNorm for L2-resident tensors (the batch-2 UNet step), register-resident:
+// one grid of <= #SMs CTAs, all co-resident.  Each CTA (sample n, row slab) loads its rows ONCE — every thread keeps its <= MAXR rows x 8
+// channels in registers — accumulates moments about a pivot taken from its own slab, converts them to a Welford partial (mean, M2) per group,
+// publishes it and joins the sample's arrive counter; once the sample's S slabs have arrived EVERY CTA merges the S partials with Chan's
+// update in the same fixed order (deterministic, bit-identical statistics everywhere) and normalises straight out of its registers.
+// Critical path: one row-load round trip, one publish + arrive, the spin, one fold round trip, the stores (the first version re-read the rows
+// and used a shared pivot from global memory: ~10 dependent L2 round trips, 13 us per GroupNorm in the step's timeline).
 // x is the channel concatenation [xa | xb] (xb may be NULL): the UNet's skip concat never exists in memory, and `raw` (optional) receives
-// the bf16 copy of the un-normalised concatenation that the ResBlock's 1x1 skip convolution consumes — the former concat and cast
-// kernels.  Replaces 2 (+2) launches per GroupNorm by one.
-// Co-residency: the grid is sized <= #SMs with one CTA per SM's worth of resources, the predecessor kernel has completed when
-// griddepcontrol.wait returns and a PDL successor can only be launched once every CTA of this grid runs, so every CTA a spinning CTA
-// waits for is resident or about to be; the spin is bounded and traps instead of hanging the GPU.
-template <typename TI, typename TO>
-__global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict__ xa, int Ca, const TI* __restrict__ xb, int Cb,
-                                                            TO* __restrict__ y, bf16* __restrict__ raw, const float* __restrict__ weight,
-                                                            const float* __restrict__ bias, float* __restrict__ partials,
-                                                            unsigned int* __restrict__ counters, int HW, int G, int rows_per_slab, float eps,
-                                                            int fuse_silu) {
+// the bf16 copy of the un-normalised concatenation that the ResBlock's 1x1 skip convolution consumes.
+// Co-residency: the grid is sized <= #SMs at one CTA per SM, the predecessor kernel has completed when griddepcontrol.wait returns and a PDL
+// successor can only be launched once every CTA of this grid runs, so every CTA a spinning CTA waits for is resident or about to be; the
+// spin is bounded and traps instead of hanging the GPU.
+template <typename TI, typename TO, int MAXR>
+__global__ void __launch_bounds__(512, 1) gn_nhwc_fused_kernel(const TI* __restrict__ xa, int Ca, const TI* __restrict__ xb, int Cb,
+                                                               TO* __restrict__ y, bf16* __restrict__ raw, const float* __restrict__ weight,
+                                                               const float* __restrict__ bias, float* __restrict__ partials,
+                                                               unsigned int* __restrict__ counters, int HW, int G, int rows_per_slab, float eps,
+                                                               int fuse_silu) {
     constexpr int VEC = kNhwcVec;
-    griddep_wait();
-    griddep_launch();
-    extern __shared__ float gsm[];          // [r][C][2], then [G][lanes][2]
+    extern __shared__ float gsm[];          // [r][C][2], then [G][lanes][3]
     __shared__ float pivots[64], s_mean[64], s_rstd[64];
     const int C = Ca + Cb;
     const int n = blockIdx.y, slab = blockIdx.x, S = gridDim.x;
@@ -514,43 +526,43 @@ __global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict
     const int col = threadIdx.x % cvec, rr = threadIdx.x / cvec;
     const bool active = rr < r;
     const int cpg = C / G;
-    // this thread's 8 channels live in one of the two sources (Ca % 8 == 0)
-    const int c0 = col * VEC;
+    const int c0 = col * VEC;                                  // this thread's 8 channels live in one of the two sources (Ca % 8 == 0)
     const bool from_b = c0 >= Ca;
     const int ldx = from_b ? Cb : Ca;
-    const TI* xcol = (from_b ? xb + static_cast<long long>(n) * HW * Cb + (c0 - Ca) : xa + static_cast<long long>(n) * HW * Ca + c0);
-    for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
-        const int c = gg * cpg;
-        pivots[gg] = c < Ca ? to_f<TI>(xa[static_cast<long long>(n) * HW * Ca + c]) : to_f<TI>(xb[static_cast<long long>(n) * HW * Cb + (c - Ca)]);
-    }
-    __syncthreads();
-    float K[VEC], s[VEC], ss[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { K[i] = pivots[(c0 + i) / cpg]; s[i] = 0.f; ss[i] = 0.f; }
     const int p0 = slab * rows_per_slab;
     const int p1 = min(HW, p0 + rows_per_slab);
+    griddep_wait();
+    griddep_launch();
+    const TI* xcol = (from_b ? xb + static_cast<long long>(n) * HW * Cb + (c0 - Ca) : xa + static_cast<long long>(n) * HW * Ca + c0);
+    float e[MAXR][VEC];
+#pragma unroll
+    for (int k = 0; k < MAXR; ++k) {
+        const int p = p0 + rr + k * r;
+        if (active && p < p1) {
+            load8<TI>(xcol + static_cast<long long>(p) * ldx, e[k]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) e[k][i] = 0.f;
+        }
+    }
+    // pivot of group g = its first channel in this slab's first row (held by a thread of row 0)
+    if (active && rr == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            if ((c0 + i) % cpg == 0) pivots[(c0 + i) / cpg] = e[0][i];
+    }
+    __syncthreads();
     if (active) {
-        int p = p0 + rr;
-        for (; p + 3 * r < p1; p += 4 * r) {
-            float e[4][VEC];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) load8<TI>(xcol + static_cast<long long>(p + u * r) * ldx, e[u]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) { float d = e[u][i] - K[i]; s[i] += d; ss[i] += d * d; }
-            }
-        }
-        for (; p < p1; p += r) {
-            float e[VEC];
-            load8<TI>(xcol + static_cast<long long>(p) * ldx, e);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) { float d = e[i] - K[i]; s[i] += d; ss[i] += d * d; }
-        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            gsm[(rr * C + c0 + i) * 2 + 0] = s[i];
-            gsm[(rr * C + c0 + i) * 2 + 1] = ss[i];
+            const float K = pivots[(c0 + i) / cpg];
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+                if (p0 + rr + k * r < p1) { const float d = e[k][i] - K; s += d; ss += d * d; }
+            }
+            gsm[(rr * C + c0 + i) * 2 + 0] = s;
+            gsm[(rr * C + c0 + i) * 2 + 1] = ss;
         }
     }
     __syncthreads();
@@ -563,12 +575,14 @@ __global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict
     for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
         float a = 0.f, b = 0.f;
         for (int c = gg * cpg; c < (gg + 1) * cpg; ++c) { a += gsm[c * 2]; b += gsm[c * 2 + 1]; }
+        const float cnt = static_cast<float>(cpg) * static_cast<float>(p1 - p0);
         float* dst = partials + ((static_cast<long long>(n) * S + slab) * G + gg) * 2;
-        dst[0] = a; dst[1] = b;
+        dst[0] = pivots[gg] + a / cnt;                         // slab mean
+        dst[1] = fmaxf(b - a * a / cnt, 0.f);                  // slab M2
     }
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         atomicAdd(&counters[n], 1u);
         unsigned int seen = 0, spins = 0;
         do {
@@ -578,30 +592,37 @@ __global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict
     }
     __syncthreads();
     {
+        // fold: `lanes` threads per group take a strided subset of the S slab partials (all loads in flight), Chan-merge them in order,
+        // then one thread per group merges the lane results in lane order
         const int lanes = max(1, min(static_cast<int>(blockDim.x) / G, 16));
-        float* fold = gsm;                                    // [G][lanes][2]
+        float* fold = gsm;                                    // [G][lanes][3] = (count, mean, M2)
         if (static_cast<int>(threadIdx.x) < G * lanes) {
             const int gg = threadIdx.x / lanes, l = threadIdx.x - gg * lanes;
-            float a = 0.f, b = 0.f;
             const float2* src = reinterpret_cast<const float2*>(partials + (static_cast<long long>(n) * S * G + gg) * 2);
-            int q = l;
-            for (; q + 3 * lanes < S; q += 4 * lanes) {        // four L2 loads in flight per thread; the summation order stays fixed
-                const float2 v0 = __ldcg(src + static_cast<long long>(q) * G), v1 = __ldcg(src + static_cast<long long>(q + lanes) * G);
-                const float2 v2 = __ldcg(src + static_cast<long long>(q + 2 * lanes) * G), v3 = __ldcg(src + static_cast<long long>(q + 3 * lanes) * G);
-                a += v0.x; b += v0.y; a += v1.x; b += v1.y; a += v2.x; b += v2.y; a += v3.x; b += v3.y;
+            constexpr int kMaxPer = 16;                        // S <= 148 and lanes >= 10 at the block sizes used (checked by the host)
+            float2 v[kMaxPer];
+#pragma unroll
+            for (int j = 0; j < kMaxPer; ++j) {
+                const int q = l + j * lanes;
+                v[j] = q < S ? __ldcg(src + static_cast<long long>(q) * G) : make_float2(0.f, 0.f);
             }
-            for (; q < S; q += lanes) { const float2 v = __ldcg(src + static_cast<long long>(q) * G); a += v.x; b += v.y; }
-            fold[(gg * lanes + l) * 2] = a; fold[(gg * lanes + l) * 2 + 1] = b;
+            float cn = 0.f, cm = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMaxPer; ++j) {
+                const int q = l + j * lanes;
+                if (q < S) {
+                    const float nb = static_cast<float>(cpg) * static_cast<float>(min(HW, (q + 1) * rows_per_slab) - q * rows_per_slab);
+                    welford_merge(cn, cm, c2, nb, v[j].x, v[j].y);
+                }
+            }
+            fold[(gg * lanes + l) * 3] = cn; fold[(gg * lanes + l) * 3 + 1] = cm; fold[(gg * lanes + l) * 3 + 2] = c2;
         }
         __syncthreads();
         for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
-            float a = 0.f, b = 0.f;
-            for (int l = 0; l < lanes; ++l) { a += fold[(gg * lanes + l) * 2]; b += fold[(gg * lanes + l) * 2 + 1]; }
-            const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
-            const float m = a / cnt;
-            const float var = fmaxf(b / cnt - m * m, 0.f);
-            s_mean[gg] = pivots[gg] + m;
-            s_rstd[gg] = rsqrtf(var + eps);
+            float cn = 0.f, cm = 0.f, c2 = 0.f;
+            for (int l = 0; l < lanes; ++l) welford_merge(cn, cm, c2, fold[(gg * lanes + l) * 3], fold[(gg * lanes + l) * 3 + 1], fold[(gg * lanes + l) * 3 + 2]);
+            s_mean[gg] = cm;
+            s_rstd[gg] = rsqrtf(fmaxf(c2 / cn, 0.f) + eps);
         }
     }
     __syncthreads();
@@ -624,32 +645,18 @@ __global__ void __launch_bounds__(512) gn_nhwc_fused_kernel(const TI* __restrict
     }
     TO* ycol = y + static_cast<long long>(n) * HW * C + c0;
     bf16* rcol = raw ? raw + static_cast<long long>(n) * HW * C + c0 : nullptr;
-    int p = p0 + rr;
-    for (; p + 3 * r < p1; p += 4 * r) {
-        float e[4][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load8<TI>(xcol + static_cast<long long>(p + u * r) * ldx, e[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (rcol) store8v<bf16>(rcol + static_cast<long long>(p + u * r) * C, e[u]);
+    for (int k = 0; k < MAXR; ++k) {
+        const int p = p0 + rr + k * r;
+        if (p < p1) {
+            if (rcol) store8v<bf16>(rcol + static_cast<long long>(p) * C, e[k]);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                float o = fmaf(e[u][i], A[i], B[i]);
-                e[u][i] = fuse_silu ? silu_f(o) : o;
+                float o = fmaf(e[k][i], A[i], B[i]);
+                e[k][i] = fuse_silu ? silu_f(o) : o;
             }
-            store8v<TO>(ycol + static_cast<long long>(p + u * r) * C, e[u]);
+            store8v<TO>(ycol + static_cast<long long>(p) * C, e[k]);
         }
-    }
-    for (; p < p1; p += r) {
-        float e[VEC];
-        load8<TI>(xcol + static_cast<long long>(p) * ldx, e);
-        if (rcol) store8v<bf16>(rcol + static_cast<long long>(p) * C, e);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float o = fmaf(e[i], A[i], B[i]);
-            e[i] = fuse_silu ? silu_f(o) : o;
-        }
-        store8v<TO>(ycol + static_cast<long long>(p) * C, e);
     }
 }
 
@@ -703,7 +710,7 @@ static bool fused_env() {
     static const int env = [] { const char* e = std::getenv("SDOD_GN_FUSED"); return e ? std::atoi(e) : 1; }();
     return env != 0;
 }
-bool group_norm_fused_eligible(int N, int Ca, int Cb, int HW, int G, int in_dtype) {
+static bool fused_size_ok(int N, int Ca, int Cb, int HW, int G, int in_dtype) {
     const int C = Ca + Cb;
     if (!fused_env() || N < 1 || N > kGnCounterInts / 2 || N > device_sm_count()) return false;
     if (C % kNhwcVec != 0 || Ca % kNhwcVec != 0 || C / kNhwcVec > 512 || G > 64 || C % G != 0) return false;
@@ -711,26 +718,42 @@ bool group_norm_fused_eligible(int N, int Ca, int Cb, int HW, int G, int in_dtyp
     return bytes <= (static_cast<size_t>(48) << 20);
 }
 
+constexpr int kGnCoopMaxRows = 8;
+// Geometry of the cooperative kernel: threads per CTA, slabs per sample, rows per slab; false when the rows do not fit the registers.
+static bool coop_geometry(int N, int C, int HW, int G, int* threads, int* slabs, int* rows_per_slab) {
+    static const int env = [] { const char* e = std::getenv("SDOD_GN_COOP"); return e ? std::atoi(e) : 1; }();
+    if (!env) return false;
+    const int cvec = C / kNhwcVec;
+    if (cvec < 1 || cvec > 512) return false;
+    int r = std::max(1, 512 / cvec);
+    if (r > HW) r = HW;
+    int S = std::max(1, std::min(device_sm_count() / N, (HW + r - 1) / r));
+    const int rps = (HW + S - 1) / S;
+    S = (HW + rps - 1) / rps;
+    if ((rps + r - 1) / r > kGnCoopMaxRows) return false;
+    const int lanes = std::max(1, std::min((cvec * r) / G, 16));        // fold lanes per group, as the kernel computes them
+    if (S > 16 * lanes) return false;
+    *threads = cvec * r; *slabs = S; *rows_per_slab = rps;
+    return true;
+}
+
 template <typename TI, typename TO>
 static int group_norm_fused_typed(cudaStream_t stream, const TI* xa, int Ca, const TI* xb, int Cb, TO* y, bf16* raw, const float* weight,
                                   const float* bias, int N, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
-    const int C = Ca + Cb, cvec = C / kNhwcVec;
-    int r = std::max(1, 512 / cvec);
-    if (r > HW) r = HW;
-    const int threads = cvec * r;
-    int S = std::max(1, std::min(device_sm_count() / N, std::max(1, HW / (2 * r))));
-    const int rps = (HW + S - 1) / S;
-    S = (HW + rps - 1) / rps;
+    const int C = Ca + Cb;
+    int threads = 0, S = 0, rps = 0;
+    if (!coop_geometry(N, C, HW, G, &threads, &S, &rps)) return fail(kUnsupported, "group_norm (cooperative): rows per thread exceed the register budget");
+    const int r = threads / (C / kNhwcVec);
     const size_t need = kGnCounterInts * sizeof(unsigned int) + static_cast<size_t>(N) * G * 2 * sizeof(float) * (1 + S);
     if (!ws || ws_bytes < need) return fail(kInvalidArgument, "group_norm (fused): workspace too small (need " + std::to_string(need) + " bytes)");
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float* partials = reinterpret_cast<float*>(counters + kGnCounterInts) + static_cast<size_t>(N) * G * 2;
-    const size_t smem = std::max(static_cast<size_t>(r) * C * 2 * sizeof(float), static_cast<size_t>(G) * 16 * 2 * sizeof(float));
+    const size_t smem = std::max(static_cast<size_t>(r) * C * 2 * sizeof(float), static_cast<size_t>(G) * 16 * 3 * sizeof(float));
     if (smem > 48 * 1024)
-        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_fused_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nhwc_fused_kernel<TI, TO, kGnCoopMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                             "cudaFuncSetAttribute(gn fused)"));
-    SDOD_TRY(check_cuda(launch_pdl(gn_nhwc_fused_kernel<TI, TO>, dim3(S, N), dim3(threads), smem, stream, xa, Ca, xb, Cb, y, raw, weight, bias, partials,
-                                   counters, HW, G, rps, eps, fuse_silu), "launch gn_nhwc_fused_kernel"));
+    SDOD_TRY(check_cuda(launch_pdl(gn_nhwc_fused_kernel<TI, TO, kGnCoopMaxRows>, dim3(S, N), dim3(threads), smem, stream, xa, Ca, xb, Cb, y, raw, weight, bias,
+                                   partials, counters, HW, G, rps, eps, fuse_silu), "launch gn_nhwc_fused_kernel"));
     count_launch();
     return check_launch("gn_nhwc_fused_kernel");
 }
@@ -745,7 +768,9 @@ static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int* rows
     const size_t slab = static_cast<size_t>(HW) * cpg * sizeof(float);
     int cs = 1;
     while (cs < 8 && (slab / cs > (static_cast<size_t>(100) << 10) || HW % cs != 0)) cs *= 2;          // <= 100 KB: two CTAs per SM
-    while (cs < 8 && static_cast<long long>(N) * G * cs < 128 && HW / (cs * 2) >= 32 && HW % (cs * 2) == 0) cs *= 2;   // fill the chip at small batch
+    // small batch: spread each group over more CTAs (two 512-thread CTAs per SM) while a thread still walks >= 8 rows
+    const int rpb = std::max(1, 512 / (cpg / 2));
+    while (cs < 8 && static_cast<long long>(N) * G * cs < 256 && HW / (cs * 2) >= 8 * rpb && HW % (cs * 2) == 0) cs *= 2;
     if (HW % cs != 0 || slab / cs > (static_cast<size_t>(200) << 10)) return 0;
     *rows_per_cta = HW / cs;
     return cs;
@@ -785,12 +810,23 @@ static int group_norm_group_typed(cudaStream_t stream, const TI* xa, int Ca, con
     return check_launch("gn_nhwc_group_kernel");
 }
 
+// Can the single-launch forms (cooperative register-resident kernel, else the group-owned kernel) take this shape?
+bool group_norm_fused_eligible(int N, int Ca, int Cb, int HW, int G, int in_dtype) {
+    if (N <= 0 || HW <= 0 || G <= 0 || !fused_size_ok(N, Ca, Cb, HW, G, in_dtype)) return false;
+    int a = 0, b = 0, c = 0;
+    return coop_geometry(N, Ca + Cb, HW, G, &a, &b, &c) || group_kernel_geometry(N, Ca, Cb, HW, G, &a) != 0;
+}
+
 int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y, int out_dtype, void* raw_bf16,
                      const float* weight, const float* bias, int N, int HW, int G, float eps, int fuse_silu, void* ws, size_t ws_bytes) {
-    {
+    int ct = 0, cS = 0, crps = 0;
+    const bool coop_ok = xa && y && N > 0 && HW > 0 && G > 0 && fused_size_ok(N, Ca, xb ? Cb : 0, HW, G, in_dtype) &&
+                         coop_geometry(N, Ca + (xb ? Cb : 0), HW, G, &ct, &cS, &crps);
+    {   // the group-owned kernel first (measured B200 r2: batch-2 step 5.42 ms vs 5.67 ms with the cooperative kernel, whose 128 registers x
+        // 512 threads own the whole SM and so forfeit the PDL overlap with its neighbours); the cooperative kernel serves odd channels-per-group
         int rpc = 0;
         const int cs = (xa && y && (Cb == 0 || xb)) ? group_kernel_geometry(N, Ca, xb ? Cb : 0, HW, G, &rpc) : 0;
-        if (cs && N > 0 && HW > 0 && ((weight == nullptr) == (bias == nullptr)) && group_norm_fused_eligible(N, Ca, xb ? Cb : 0, HW, G, in_dtype)) {
+        if (cs && N > 0 && HW > 0 && ((weight == nullptr) == (bias == nullptr)) && fused_size_ok(N, Ca, xb ? Cb : 0, HW, G, in_dtype)) {
             if (!xb) Cb = 0;
 #define SDOD_GNG_CASE(TI, TO) \
     return group_norm_group_typed<TI, TO>(stream, static_cast<const TI*>(xa), Ca, static_cast<const TI*>(xb), Cb, static_cast<TO*>(y), \
@@ -807,7 +843,7 @@ int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb
     if (N <= 0 || Ca <= 0 || Cb < 0 || HW <= 0 || G <= 0) return fail(kInvalidArgument, "group_norm: non-positive extent");
     if ((Ca + Cb) % G != 0) return fail(kInvalidArgument, "num_channels must be divisible by num_groups");
     if ((weight == nullptr) != (bias == nullptr)) return fail(kInvalidArgument, "group_norm: weight and bias must both be given or both be NULL");
-    if (!group_norm_fused_eligible(N, Ca, Cb, HW, G, in_dtype))
+    if (!coop_ok)
         return fail(kUnsupported, "group_norm (two-source / single-launch form): tensor too large for the L2-resident kernel or unsupported shape");
 #define SDOD_GN2_CASE(TI, TO) \
     return group_norm_fused_typed<TI, TO>(stream, static_cast<const TI*>(xa), Ca, static_cast<const TI*>(xb), Cb, static_cast<TO*>(y), \

@@ -654,3 +654,15 @@ def test_onnx_export_emits_the_reference_nodes(tmp_path):
     except Exception as e:
         pytest.skip("neither torch.onnx.export nor the graph conversion is usable without the onnx package: %r" % (e,))
     assert "sdod::GroupNorm" in text and "sdod::ParameterlessGroupNorm" in text and "num_groups" in text and "eps" in text
+
+
+def test_optional_scheduling_variants_in_subprocess():
+    """Stream-K and the in-kernel (cluster) split-K reduction are opt-in (measured slower than split-K + reduce kernel on the batch-2 step);
+    their env switches are read once per process, so their parity tests run in a child process with the switches on."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SDOD_STREAMK="1", SDOD_SPLITK_CLUSTER="1")
+    root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "stream_k or split_k or second_operand or fused_skip"], env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
