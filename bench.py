@@ -235,6 +235,10 @@ def run_ours(args, rank, world, local_rank):
             gemm_n += 1
     del unet_b
 
+    ctx.release()
+    ctx = None
+    multi = multi_gpu_records(args, rank, world, local_rank, dev, barrier) if (world >= 2 and not args.no_c5) else {}
+
     tot_dev_s = sum(dev_ms) / 1000.0
     t_dev = torch.tensor([tot_dev_s, wall_e2e, wall_dev], dtype=torch.float64, device=dev)
     if world > 1:
@@ -266,6 +270,7 @@ def run_ours(args, rank, world, local_rank):
                               "frac_of_burst_peak": achieved / pk["bf16_tflops"], "algorithmic_tflop_per_launch": UNET_STEP_TFLOP},
             "clocks": clocks,
         }
+        line.update(multi)
         if not args.no_cpu_baseline:
             keep = {}
             ts, t_vae, cores = cpu_oracle_times(2, keep)             # the first step is the warm-up (and the parity vector), the second is timed
@@ -277,54 +282,68 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line))
         if line.get("parity") and not line["parity"]["ok"]:
             raise SystemExit("bench.py: GPU eps differs from the oracle beyond tolerance: %s" % line["parity"])
-    ctx.release()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_cfg_split(args, rank, world, local_rank):
-    """CFG split over GPU pairs: rank 2k = cond half, rank 2k+1 = uncond half, one NCCL all-gather of eps per step."""
+def multi_gpu_records(args, rank, world, local_rank, dev, barrier):
+    """N >= 2 only: (1) `cfg_split` — the second partitioning of SURVEY §8e through the library (libsdod_b200_generate_pair: rank 2k runs the
+    conditional half, rank 2k+1 the unconditional half, per-step eps exchange = peer stores inside the fused sampler kernel), at the same
+    images per GPU as the headline, plus the single-image latency of a pair; (2) `c5` — BASELINE config C5: total batches of 8 / 32 / 128
+    images over the N GPUs in both partitionings.  Wall clock around the calls (host buffers), barrier on both sides, max over ranks."""
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from sdod import model as M
-    from sdod import ops
+    from sdod import libsdod as A
     from sdod import parallel as P
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
-    groups = P.make_pair_groups(world)
-    pair, role = P.pair_layout(rank, world)
     n = args.images_per_step
-    unet = M.UNet(None, seed=0, latent_hw=64, max_batch=n)
-    vae = M.VaeDecoder(None, seed=1, latent_hw=64, max_batch=max(1, (n + 1) // 2))
+    pairs = world // 2
+    totals = [t for t in (8, 32, 128) if t % world == 0 and t // world <= 64 and t // pairs <= 64]
+    cap = max([2 * n] + [t // pairs for t in totals])
+    pair, role = P.pair_layout(rank, world)
+    groups = P.make_pair_groups(world)
+    ctx = A.Context("random-init:0", latent_spatial=64, steps=20, log_level=A.LOG_ERROR, max_images=cap, device=local_rank)
+    ctx.set_seed(1234 + pair)                                # both ranks of a pair draw the same x_T
+    P.connect_pair(ctx, groups[pair], role)
     g = torch.Generator().manual_seed(2 + pair)
-    cond, uncond = torch.randn(n, 77, 768, generator=g), torch.randn(n, 77, 768, generator=g)
-    unet.set_context((cond if role == 0 else uncond).to(dev))
-    emb_all = unet.time_embed(torch.tensor(ops.dpm_schedule(20)["model_ts"][:20], device=dev))
-    lat = torch.randn(n, 64, 64, 4, generator=torch.Generator().manual_seed(1 + pair)).to(dev)
-    s = torch.cuda.Stream(device=dev)
-    times = []
-    with torch.cuda.stream(s):
-        for it in range(max(args.warmup, 3) + args.steps):
-            torch.cuda.synchronize()
-            dist.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(s)
-            x, imgs, nbytes = P.gpu_cfg_split_generate(unet, vae, emb_all, lat, 7.5, groups[pair], role, 20)
-            b.record(s)
-            s.synchronize()
-            if it >= max(args.warmup, 3):
-                times.append(a.elapsed_time(b))
-    t = torch.tensor([sum(times) / 1000.0], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        images = args.steps * n * (world // 2)
-        print(json.dumps({"metric": METRIC, "value": images / t.item(), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": 1000.0 * t.item() / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                          "data": "synthetic", "config": {"workload": WORKLOAD, "images_per_step_per_pair": n, "parallelism": "cfg-split x%d pairs" % (world // 2),
-                                                          "exchange": "2-rank NCCL all-gather of eps per step, %d bytes per rank per image-step" % (64 * 64 * 4 * 4)},
-                          "eps_bytes_exchanged_per_generate": nbytes}))
-    dist.destroy_process_group()
+    cond = torch.randn(cap, 77, 768, generator=g).numpy()
+    uncond = torch.randn(cap, 77, 768, generator=g).numpy()
+    lat = torch.randn(cap, 4, 64, 64, generator=torch.Generator().manual_seed(1 + pair)).numpy()
+    half = cond if role == 0 else uncond
+
+    def timed(fn, reps):
+        fn()                                                 # builds the plan / graph of this batch size
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / reps
+
+    out = {}
+    m = 2 * n                                                # images per pair per call = the headline's images per GPU
+    t_pair = timed(lambda: ctx.generate_pair(half[:m], lat[:m], 7.5), max(2, args.steps // 2))
+    it_ms = ctx.last_timings()["iteration_ms"]
+    t_one = timed(lambda: ctx.generate_pair(half[:1], lat[:1], 7.5), 3)
+    out["cfg_split"] = {"images_per_s": pairs * m / t_pair, "unit": UNIT, "pairs": pairs, "images_per_pair_per_call": m, "unet_batch_per_gpu": m,
+                        "iteration_ms_in_loop": it_ms, "single_image_latency_ms_on_a_pair": 1000.0 * t_one,
+                        "eps_bytes_per_step_per_rank": m * 64 * 64 * 4 * 4,
+                        "comm": "peer stores into the other GPU's IPC-mapped exchange buffer + flag, fused with the CFG + DPM update (cfg_dpm_step_pair_kernel); no NCCL on the data path",
+                        "timing": "wall clock around libsdod_b200_generate_pair with host buffers; barrier both sides; max over ranks"}
+    rows = []
+    for total in totals:
+        k = total // world                                   # sample-parallel: k images per GPU per call
+        t_sp = timed(lambda: ctx.generate(cond[:k], uncond[:k], lat[:k], 7.5), 2)
+        rows.append({"total_batch": total, "partition": "sample-parallel", "images_per_gpu_per_call": k, "images_per_s": total / t_sp})
+        kp = total // pairs                                  # CFG split: kp images per pair per call
+        t_cs = timed(lambda: ctx.generate_pair(half[:kp], lat[:kp], 7.5), 2)
+        rows.append({"total_batch": total, "partition": "cfg-split", "images_per_pair_per_call": kp, "images_per_s": total / t_cs})
+    out["c5"] = {"n_gpus": world, "rows": rows, "skipped_totals": [t for t in (8, 32, 128) if t not in totals],
+                 "note": "BASELINE.json config C5; one generate call per measurement, 2 timed calls after 1 warm-up, host buffers"}
+    ctx.release()
+    return out
 
 
 def gpu_parity(keep, dev, big_batch):
@@ -392,13 +411,11 @@ def main():
     ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="sample-parallel", choices=["sample-parallel", "cfg-split"])
+    ap.add_argument("--no-c5", action="store_true", help="N >= 2: skip the cfg_split record and the C5 sweep")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
-    elif args.mode == "cfg-split":
-        run_cfg_split(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

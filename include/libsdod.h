@@ -109,6 +109,22 @@ LIBSDOD_API int libsdod_b200_generate_device(void* context, unsigned int n_image
 LIBSDOD_API int libsdod_b200_setup(void** context, const char* models_dir, unsigned int latent_spatial, unsigned int steps,
                                    unsigned int log_level, unsigned int max_images, int device);
 
+/* ---- CFG split over a GPU pair (one process per GPU).  The reference runs the conditional and the unconditional UNet pass one
+ * after the other on one device (context.cpp:352,366); here two contexts on two GPUs each run ONE of them per step and exchange the noise
+ * prediction over NVLink: libsdod_b200_pair_export() returns a 64-byte CUDA IPC handle of this context's exchange buffer; the application
+ * hands it to the peer process (any transport: a torch.distributed all_gather, a pipe, ...); libsdod_b200_pair_connect() maps the peer's buffer
+ * and fixes this context's role (0 = conditional half, 1 = unconditional half).  libsdod_b200_generate_pair() then runs the same loop as
+ * libsdod_b200_generate with a UNet batch of n_images instead of 2*n_images; per step one fused kernel stores this half's eps into the peer's
+ * buffer, waits for the peer's and applies the identical CFG + solver update on both ranks (the sampler state stays replicated bit for bit).
+ * The VAE decode is split by image: this rank decodes and returns images [*first_image, *first_image + *n_decoded) of images_out
+ * ([n_images, 8S, 8S, 3] on both ranks; the rest of the buffer is left untouched).  Both contexts must be set up alike (steps, sampler, seed when
+ * latents == NULL) and call generate_pair the same number of times.  DPM-Solver++ and DDIM only; guidance must differ from 1. */
+LIBSDOD_API int libsdod_b200_pair_export(void* context, unsigned char handle_out[64]);
+LIBSDOD_API int libsdod_b200_pair_connect(void* context, const unsigned char peer_handle[64], int role);
+LIBSDOD_API int libsdod_b200_generate_pair(void* context, unsigned int n_images, const float* conditioning_half, const float* latents,
+                                           float guidance_scale, unsigned char* images_out, unsigned int* first_image, unsigned int* n_decoded,
+                                           float* latents_out);
+
 /* Milliseconds of the last generate call as the reference logs them (context.cpp:309-314,331,381,398,402):
  * out[0] conditioning, out[1] mean single iteration, out[2] decoding, out[3] total.  Device-event timed. */
 LIBSDOD_API int libsdod_b200_last_timings(void* context, float out[4]);

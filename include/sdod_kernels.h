@@ -89,6 +89,15 @@ SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, co
                                int eps_dtype, size_t n, float guidance, float sigma_s, float alpha_s, float c_x,
                                float c_prev, float c_y0, int order, float* x_copy);
 
+/* CFG split over a GPU pair (the reference evaluates cond and uncond as two sequential graph executions, context.cpp:352,366):
+ * this rank holds eps of ONE guidance half (role 0 = cond, 1 = uncond).  One kernel stores it into the peer's exchange slot (peer_slot / peer_flag
+ * are IPC-mapped pointers into the other GPU's memory: plain remote stores over NVLink), raises the peer's flag to `seq`, waits for its own
+ * flag to reach `seq`, then applies the same fused CFG + DPM update as sdod_cfg_dpm_step on both ranks, so x / y_prev stay replicated bit for
+ * bit.  done_counter: one zero-initialised uint32 in local memory.  Callers alternate two slots / flags with the parity of seq. */
+SDOD_API int sdod_cfg_dpm_step_pair(sdod_stream_t stream, float* x, float* y_prev, const float* eps_local, float* peer_slot, const float* recv_slot,
+                                    unsigned int* peer_flag, const unsigned int* my_flag, unsigned int* done_counter, unsigned int seq, int role,
+                                    size_t n, float guidance, float sigma_s, float alpha_s, float c_x, float c_prev, float c_y0, int order);
+
 /* Host-side schedule tables. Replaces DPMSolver::DPMSolver / ::prepare, dpm_solver.cpp:84-131.
  * Each out array has steps+1 floats (may be NULL). Returns 0 or a negative status. */
 SDOD_API int sdod_dpm_schedule(unsigned timesteps, float lin_start, float lin_end, unsigned steps, float* ts,

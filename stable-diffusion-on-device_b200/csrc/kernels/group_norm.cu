@@ -758,11 +758,14 @@ static int group_norm_fused_typed(cudaStream_t stream, const TI* xa, int Ca, con
     return check_launch("gn_nhwc_fused_kernel");
 }
 
-// Geometry of the group-owned kernel: cluster size (rows split) and rows per CTA; cs == 0 -> not eligible.
-static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int* rows_per_cta) {
+// Geometry of the group-owned kernel: cluster size (rows split) and rows per CTA; cs == 0 -> not eligible.  It needs neither workspace nor
+// co-residency, so large batches qualify too (SDOD_GN_GROUP_MAXMB bounds the input size, default 48 MB = L2-resident tensors only).
+static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int in_dtype, int* rows_per_cta) {
     static const int env = [] { const char* e = std::getenv("SDOD_GN_GROUP"); return e ? std::atoi(e) : 1; }();
+    static const long long max_mb = [] { const char* e = std::getenv("SDOD_GN_GROUP_MAXMB"); return e ? std::atoll(e) : 48LL; }();
     const int C = Ca + Cb;
-    if (!env || G <= 0 || C % G != 0) return 0;
+    if (!env || !fused_env() || G <= 0 || C % G != 0 || N < 1 || HW < 1) return 0;
+    if (static_cast<long long>(N) * HW * C * (in_dtype == SDOD_F32 ? 4 : 2) > (max_mb << 20)) return 0;
     const int cpg = C / G;
     if (cpg % 2 != 0 || Ca % 2 != 0 || cpg / 2 > 512 || N > 65535) return 0;
     const size_t slab = static_cast<size_t>(HW) * cpg * sizeof(float);
@@ -812,9 +815,9 @@ static int group_norm_group_typed(cudaStream_t stream, const TI* xa, int Ca, con
 
 // Can the single-launch forms (cooperative register-resident kernel, else the group-owned kernel) take this shape?
 bool group_norm_fused_eligible(int N, int Ca, int Cb, int HW, int G, int in_dtype) {
-    if (N <= 0 || HW <= 0 || G <= 0 || !fused_size_ok(N, Ca, Cb, HW, G, in_dtype)) return false;
+    if (N <= 0 || HW <= 0 || G <= 0) return false;
     int a = 0, b = 0, c = 0;
-    return coop_geometry(N, Ca + Cb, HW, G, &a, &b, &c) || group_kernel_geometry(N, Ca, Cb, HW, G, &a) != 0;
+    return group_kernel_geometry(N, Ca, Cb, HW, G, in_dtype, &a) != 0 || (fused_size_ok(N, Ca, Cb, HW, G, in_dtype) && coop_geometry(N, Ca + Cb, HW, G, &a, &b, &c));
 }
 
 int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb, int Cb, int in_dtype, void* y, int out_dtype, void* raw_bf16,
@@ -825,8 +828,8 @@ int group_norm_nhwc2(cudaStream_t stream, const void* xa, int Ca, const void* xb
     {   // the group-owned kernel first (measured B200 r2: batch-2 step 5.42 ms vs 5.67 ms with the cooperative kernel, whose 128 registers x
         // 512 threads own the whole SM and so forfeit the PDL overlap with its neighbours); the cooperative kernel serves odd channels-per-group
         int rpc = 0;
-        const int cs = (xa && y && (Cb == 0 || xb)) ? group_kernel_geometry(N, Ca, xb ? Cb : 0, HW, G, &rpc) : 0;
-        if (cs && N > 0 && HW > 0 && ((weight == nullptr) == (bias == nullptr)) && fused_size_ok(N, Ca, xb ? Cb : 0, HW, G, in_dtype)) {
+        const int cs = (xa && y && (Cb == 0 || xb)) ? group_kernel_geometry(N, Ca, xb ? Cb : 0, HW, G, in_dtype, &rpc) : 0;
+        if (cs && ((weight == nullptr) == (bias == nullptr))) {
             if (!xb) Cb = 0;
 #define SDOD_GNG_CASE(TI, TO) \
     return group_norm_group_typed<TI, TO>(stream, static_cast<const TI*>(xa), Ca, static_cast<const TI*>(xb), Cb, static_cast<TO*>(y), \

@@ -55,6 +55,45 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(float* __restrict__ x
     }
 }
 
+// CFG split over a GPU pair: this rank evaluated ONE half of classifier-free guidance (role 0: cond, role 1: uncond) and the
+// peer the other.  One kernel does the whole per-step exchange + update: (1) every CTA stores its part of the local eps straight into the
+// PEER's exchange slot (remote stores over NVLink through an IPC-mapped pointer); the last CTA to finish, after a system-scope fence,
+// raises the peer's flag to this step's sequence number; (2) every CTA waits until the peer has done the same for us, then applies the
+// identical fused CFG + DPM update on both ranks (same inputs, same roundings as cfg_dpm_step_kernel), so x / y_prev stay replicated
+// bit for bit and no second exchange is needed.  The grid is capped at one CTA per SM so that every CTA is resident before any of
+// them waits; the wait is bounded and traps instead of hanging.  Slots and flags alternate with the sequence number's parity.
+__global__ void __launch_bounds__(256) cfg_dpm_step_pair_kernel(float* __restrict__ x, float* __restrict__ y_prev, const float* __restrict__ eps_local,
+                                                                float* peer_slot, const float* recv_slot, unsigned int* peer_flag,
+                                                                const unsigned int* my_flag, unsigned int* done_counter, unsigned int seq, int role,
+                                                                size_t n, StepCoef k) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (size_t i = first; i < n; i += stride) peer_slot[i] = eps_local[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+            *done_counter = 0;                                           // re-armed for the next step (stream order)
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag), "r"(seq) : "memory");
+        }
+        unsigned int seen = 0, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flag) : "memory");
+            if (static_cast<int>(seen - seq) < 0 && ++spins > (1u << 24)) __trap();      // the peer never arrived: fail the launch, do not hang
+        } while (static_cast<int>(seen - seq) < 0);
+    }
+    __syncthreads();
+    const float* eps_c = role == 0 ? eps_local : recv_slot;
+    const float* eps_u = role == 0 ? recv_slot : eps_local;
+    for (size_t i = first; i < n; i += stride) {
+        float yp = (k.order == 2) ? y_prev[i] : 0.f;
+        const float xn = dpm_one(x[i], __ldcg(eps_c + i), __ldcg(eps_u + i), yp, k);
+        x[i] = xn;
+        y_prev[i] = yp;
+    }
+}
+
 // PLMS / linear-multistep form of the same fusion (public CompVis plms.py, parity unpinned): CFG combine, optional store of the
 // combined eps into the history ring, e' = w0 e + w1 h1 + w2 h2 + w3 h3, x0 = (x_from - s_t e') / a_t, x = a_prev x0 + s_prev e'.
 // DDIM is w = (1,0,0,0); the first PLMS step calls it twice (second call: x_from = the saved x_t, h1 = the first eps, w = (1/2, 1/2)).
@@ -159,6 +198,32 @@ static inline int grid_for(size_t n, int block, int per_thread = 1) {
 using namespace sdod;
 
 extern "C" {
+
+SDOD_API int sdod_cfg_dpm_step_pair(sdod_stream_t stream, float* x, float* y_prev, const float* eps_local, float* peer_slot, const float* recv_slot,
+                                    unsigned int* peer_flag, const unsigned int* my_flag, unsigned int* done_counter, unsigned int seq, int role,
+                                    size_t n, float guidance, float sigma_s, float alpha_s, float c_x, float c_prev, float c_y0, int order) {
+    if (!x || !y_prev || !eps_local || !peer_slot || !recv_slot || !peer_flag || !my_flag || !done_counter)
+        return fail(kInvalidArgument, "cfg_dpm_step_pair: NULL pointer");
+    if (order != 1 && order != 2) return fail(kInvalidArgument, "cfg_dpm_step_pair: order must be 1 or 2");
+    if (role != 0 && role != 1) return fail(kInvalidArgument, "cfg_dpm_step_pair: role must be 0 (cond) or 1 (uncond)");
+    if (guidance == 1.0f) return fail(kInvalidArgument, "cfg_dpm_step_pair: guidance 1 has no unconditional half to split off");
+    StepCoef k;
+    k.g = guidance;
+    k.one_minus_g = 1 - guidance;
+    k.neg_sigma = -sigma_s;
+    k.alpha = alpha_s;
+    k.c_x = c_x; k.c_prev = c_prev; k.c_y0 = c_y0;
+    k.order = order;
+    k.cfg = 1;
+    if (n == 0) return kOk;
+    int grid = grid_for(n, 256);
+    const int sms = device_sm_count();
+    if (grid > sms) grid = sms;                     // every CTA resident before any of them waits for the peer
+    cfg_dpm_step_pair_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y_prev, eps_local, peer_slot, recv_slot, peer_flag, my_flag, done_counter,
+                                                                                 seq, role, n, k);
+    count_launch();
+    return check_launch("cfg_dpm_step_pair_kernel");
+}
 
 SDOD_API int sdod_cfg_dpm_step(sdod_stream_t stream, float* x, float* y_prev, const void* eps_c, const void* eps_u, int eps_dtype,
                                size_t n, float guidance, float sigma_s, float alpha_s, float c_x, float c_prev, float c_y0, int order,

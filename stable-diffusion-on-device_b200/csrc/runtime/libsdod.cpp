@@ -163,6 +163,8 @@ public:
         unet_.reset();
         vae_.reset();
         cudaFree(y_prev_); cudaFree(ctx_dev_); cudaFree(temb_); cudaFree(plms_buf_);
+        if (peer_exch_) cudaIpcCloseMemHandle(peer_exch_);
+        cudaFree(exch_); cudaFree(pair_done_);
         if (pin_ctx_) cudaFreeHost(pin_ctx_);
         if (pin_lat_) cudaFreeHost(pin_lat_);
         if (pin_img_) cudaFreeHost(pin_img_);
@@ -276,6 +278,99 @@ public:
         }
     }
 
+    // ---- CFG split over a GPU pair (libsdod.h: libsdod_b200_pair_*)
+    // exchange buffer: [2 flags, padded to 256 B][slot 0][slot 1], a slot = max_images latents (fp32); the peer writes into it over NVLink
+    size_t slot_floats() const { return static_cast<size_t>(max_images_) * S_ * S_ * 4; }
+    void pair_export(unsigned char out[64]) {
+        require_ready();
+        if (device_ >= 0) CU(cudaSetDevice(device_));
+        if (!exch_) {
+            const size_t bytes = 256 + 2 * slot_floats() * sizeof(float);
+            CU(cudaMalloc(reinterpret_cast<void**>(&exch_), bytes));
+            CU(cudaMemset(exch_, 0, bytes));
+            CU(cudaMalloc(reinterpret_cast<void**>(&pair_done_), sizeof(unsigned int)));
+            CU(cudaMemset(pair_done_, 0, sizeof(unsigned int)));
+            CU(cudaDeviceSynchronize());
+        }
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, exch_));
+        static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+        std::memcpy(out, &h, 64);
+    }
+    void pair_connect(const unsigned char peer[64], int role) {
+        require_ready();
+        if (role != 0 && role != 1) API_THROW(LIBSDOD_INVALID_ARGUMENT, "role must be 0 (conditional half) or 1 (unconditional half)");
+        if (!exch_) API_THROW(LIBSDOD_INVALID_ARGUMENT, "call libsdod_b200_pair_export first (the peer needs this context's handle too)");
+        if (device_ >= 0) CU(cudaSetDevice(device_));
+        if (peer_exch_) { cudaIpcCloseMemHandle(peer_exch_); peer_exch_ = nullptr; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, peer, 64);
+        CU(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&peer_exch_), h, cudaIpcMemLazyEnablePeerAccess));
+        pair_role_ = role;
+        pair_seq_ = 0;
+        log_.log(LIBSDOD_LOG_INFO, "CFG split: this context runs the %s half; eps exchange over a peer-mapped buffer", role == 0 ? "conditional" : "unconditional");
+    }
+    void generate_pair(unsigned n, const float* cond_half, const float* latents, float guidance, unsigned char* images_out, unsigned* first_image,
+                       unsigned* n_decoded, float* latents_out) {
+        require_ready();
+        if (!peer_exch_) API_THROW(LIBSDOD_INVALID_ARGUMENT, "pair not connected (libsdod_b200_pair_export / _connect)");
+        if (n < 1 || static_cast<int>(n) > max_images_) API_THROW(LIBSDOD_INVALID_ARGUMENT, "n_images out of range (max_images = " + std::to_string(max_images_) + ")");
+        if (!cond_half || !images_out || !first_image || !n_decoded) API_THROW(LIBSDOD_INVALID_ARGUMENT, "nullptr argument");
+        if (guidance == 1.0f) API_THROW(LIBSDOD_INVALID_ARGUMENT, "guidance 1 skips the unconditional pass (context.cpp:359): nothing to split");
+        if (sampler_ == LIBSDOD_B200_SAMPLER_PLMS) API_THROW(LIBSDOD_INVALID_ARGUMENT, "the pair loop supports DPM-Solver++ and DDIM");
+        if (steps_ == 0) API_THROW(LIBSDOD_RUNTIME_ERROR, "schedule not prepared");
+        if (device_ >= 0) CU(cudaSetDevice(device_));
+        const int B = static_cast<int>(n);
+        const size_t per = static_cast<size_t>(S_) * S_ * 4, lat = per * n, ctx1 = static_cast<size_t>(77) * 768;
+        float* x = unet_->x_in();
+        float* eps = unet_->eps_out();
+        unsigned int* my_flags = reinterpret_cast<unsigned int*>(exch_);
+        unsigned int* peer_flags = reinterpret_cast<unsigned int*>(peer_exch_);
+        float* my_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(exch_) + 256);
+        float* peer_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(peer_exch_) + 256);
+        CU(cudaEventRecord(ev_[0], stream_));
+        std::memcpy(pin_ctx_, cond_half, n * ctx1 * sizeof(float));
+        CU(cudaMemcpyAsync(ctx_dev_, pin_ctx_, n * ctx1 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        SD(unet_->set_context(stream_, ctx_dev_, SDOD_F32, B));
+        CU(cudaEventRecord(ev_[1], stream_));
+        if (latents) {
+            for (unsigned i = 0; i < n; ++i)
+                for (int c = 0; c < 4; ++c)
+                    for (int p = 0; p < S_ * S_; ++p) pin_lat_[i * per + static_cast<size_t>(p) * 4 + c] = latents[i * per + static_cast<size_t>(c) * S_ * S_ + p];
+            CU(cudaMemcpyAsync(x, pin_lat_, lat * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        } else {
+            SD(sdod_randn(stream_, x, lat, seed_, rng_offset_));            // both ranks: same seed, same offsets -> same x_T
+            rng_offset_ += (lat + 3) / 4;
+        }
+        for (unsigned step = 0; step < steps_; ++step) {
+            SD(sdod::broadcast_rows(stream_, unet_->emb_in(), temb_ + static_cast<size_t>(step) * 1280, B, 1280));
+            SD(unet_->forward(stream_, x, unet_->emb_in(), eps, B, true));
+            const sdod::DpmStep k = sampler_ == LIBSDOD_B200_SAMPLER_DDIM ? ddim_.step(step) : sched_.step(step);
+            ++pair_seq_;
+            const unsigned par = pair_seq_ & 1u;
+            SD(sdod_cfg_dpm_step_pair(stream_, x, y_prev_, eps, peer_slots + par * slot_floats(), my_slots + par * slot_floats(), peer_flags + par,
+                                      my_flags + par, pair_done_, pair_seq_, pair_role_, lat, guidance, k.sigma_s, k.alpha_s, k.c_x, k.c_prev, k.c_y0, k.order));
+        }
+        CU(cudaEventRecord(ev_[2], stream_));
+        // decode split by image: role 0 takes the first ceil(n/2) images, role 1 the rest
+        const unsigned first = pair_role_ == 0 ? 0u : (n + 1) / 2, cnt = pair_role_ == 0 ? (n + 1) / 2 : n / 2;
+        if (cnt) SD(vae_->decode(stream_, x + first * per, reinterpret_cast<uint8_t*>(pin_img_), nullptr, static_cast<int>(cnt), true));
+        if (latents_out) CU(cudaMemcpyAsync(pin_lat_, x, lat * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        CU(cudaEventRecord(ev_[3], stream_));
+        CU(cudaStreamSynchronize(stream_));
+        if (cnt) std::memcpy(images_out + first * image_bytes(), pin_img_, cnt * image_bytes());
+        *first_image = first; *n_decoded = cnt;
+        if (latents_out) {
+            for (unsigned i = 0; i < n; ++i)
+                for (int c = 0; c < 4; ++c)
+                    for (int p = 0; p < S_ * S_; ++p) latents_out[i * per + static_cast<size_t>(c) * S_ * S_ + p] = pin_lat_[i * per + static_cast<size_t>(p) * 4 + c];
+        }
+        float ms[3];
+        for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]);
+        timings_[0] = ms[0]; timings_[1] = ms[1] / steps_; timings_[2] = ms[2]; timings_[3] = ms[0] + ms[1] + ms[2];
+        log_.log(LIBSDOD_LOG_INFO, "CFG-split generate: %u images, iteration %.3fms, decode of %u images %.3fms, total %.3fms", n, timings_[1], cnt, timings_[2], timings_[3]);
+    }
+
     // context.cpp:292-403, batched over n images
     void generate(unsigned n, const float* cond, const float* uncond, const float* latents, float guidance, unsigned char* images_out,
                   float* latents_out, bool device_ptrs = false) {
@@ -373,6 +468,11 @@ private:
     float timings_[4] = {0, 0, 0, 0};
     std::string models_dir_;
     bool ready_ = false;
+    void* exch_ = nullptr;            // this context's exchange buffer (exported over CUDA IPC)
+    void* peer_exch_ = nullptr;       // the peer's, mapped into this process
+    unsigned int* pair_done_ = nullptr;
+    int pair_role_ = 0;
+    unsigned int pair_seq_ = 0;
 };
 
 struct Handle {                                  // reference libsdod.cpp:22-27
@@ -565,6 +665,31 @@ LIBSDOD_API int libsdod_b200_generate_device(void* context, unsigned int n_image
     if (int st = retrieve(context, &hnd, __func__)) return st;
     Engine* e = hnd->cptr;
     return guarded(&e->errors(), __func__, [&] { e->generate(n_images, cond_dev, uncond_dev, latents_nhwc_dev, guidance_scale, images_out_dev, nullptr, true); });
+}
+
+LIBSDOD_API int libsdod_b200_pair_export(void* context, unsigned char handle_out[64]) {
+    Handle* hnd = nullptr;
+    if (int st = retrieve(context, &hnd, __func__)) return st;
+    Engine* e = hnd->cptr;
+    if (!handle_out) return ERR(&e->errors(), LIBSDOD_INVALID_ARGUMENT, "handle_out is nullptr");
+    return guarded(&e->errors(), __func__, [&] { e->pair_export(handle_out); });
+}
+
+LIBSDOD_API int libsdod_b200_pair_connect(void* context, const unsigned char peer_handle[64], int role) {
+    Handle* hnd = nullptr;
+    if (int st = retrieve(context, &hnd, __func__)) return st;
+    Engine* e = hnd->cptr;
+    if (!peer_handle) return ERR(&e->errors(), LIBSDOD_INVALID_ARGUMENT, "peer_handle is nullptr");
+    return guarded(&e->errors(), __func__, [&] { e->pair_connect(peer_handle, role); });
+}
+
+LIBSDOD_API int libsdod_b200_generate_pair(void* context, unsigned int n_images, const float* conditioning_half, const float* latents,
+                                           float guidance_scale, unsigned char* images_out, unsigned int* first_image, unsigned int* n_decoded,
+                                           float* latents_out) {
+    Handle* hnd = nullptr;
+    if (int st = retrieve(context, &hnd, __func__)) return st;
+    Engine* e = hnd->cptr;
+    return guarded(&e->errors(), __func__, [&] { e->generate_pair(n_images, conditioning_half, latents, guidance_scale, images_out, first_image, n_decoded, latents_out); });
 }
 
 LIBSDOD_API int libsdod_b200_last_timings(void* context, float out[4]) {

@@ -52,6 +52,7 @@ _SIGS = {
     "sdod_group_norm_nhwc2_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "sdod_layer_norm": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f]),
     "sdod_cfg_dpm_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_sz, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_vp]),
+    "sdod_cfg_dpm_step_pair": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u, c_int, c_sz, c_f, c_f, c_f, c_f, c_f, c_f, c_int]),
     "sdod_dpm_schedule": (c_int, [c_u, c_f, c_f, c_u] + [c_vp] * 8),
     "sdod_dpm_coeffs": (c_int, [c_u, c_f, c_f, c_u, c_u] + [c_vp] * 6),
     "sdod_ddim_schedule": (c_int, [c_u, c_f, c_f, c_u, c_vp, c_vp]),

@@ -26,6 +26,9 @@ _SIGS = {
     "libsdod_b200_generate_device": (_i, [_vp, _u, _vp, _vp, _vp, _f, _vp]),
     "libsdod_b200_setup": (_i, [ctypes.POINTER(_vp), ctypes.c_char_p, _u, _u, _u, _u, _i]),
     "libsdod_b200_last_timings": (_i, [_vp, ctypes.POINTER(_f * 4)]),
+    "libsdod_b200_pair_export": (_i, [_vp, _vp]),
+    "libsdod_b200_pair_connect": (_i, [_vp, _vp, _i]),
+    "libsdod_b200_generate_pair": (_i, [_vp, _u, _vp, _vp, _f, _vp, ctypes.POINTER(_u), ctypes.POINTER(_u), _vp]),
 }
 _bound = False
 
@@ -113,6 +116,32 @@ class Context:
         p = lambda a: None if a is None else a.data_ptr()
         self._ok(api().libsdod_b200_generate_device(self._h, cond.shape[0], p(cond), p(uncond), p(latents_nhwc), guidance_scale, p(images_out)))
         return images_out
+
+    # ---- CFG split over a GPU pair (include/libsdod.h: libsdod_b200_pair_*)
+    def pair_export(self):
+        """64-byte CUDA IPC handle of this context's eps exchange buffer; hand it to the peer process."""
+        h = (ctypes.c_ubyte * 64)()
+        self._ok(api().libsdod_b200_pair_export(self._h, ctypes.addressof(h)))
+        return bytes(h)
+
+    def pair_connect(self, peer_handle, role):
+        """Map the peer's exchange buffer; role 0 = this context runs the conditional half, 1 = the unconditional half."""
+        h = (ctypes.c_ubyte * 64).from_buffer_copy(peer_handle)
+        self._ok(api().libsdod_b200_pair_connect(self._h, ctypes.addressof(h), int(role)))
+
+    def generate_pair(self, conditioning_half, latents=None, guidance_scale=7.5, return_latents=False):
+        """This rank's half of classifier-free guidance (cond for role 0, uncond for role 1), [n,77,768]; the peer context must make the
+        same call.  Returns (images [n,8S,8S,3] with this rank's decoded share filled in, first_image, n_decoded[, final latents])."""
+        c = np.ascontiguousarray(conditioning_half, dtype=np.float32)
+        n = c.shape[0]
+        latents = None if latents is None else np.ascontiguousarray(latents, dtype=np.float32)
+        side = self.latent_spatial * 8
+        imgs = np.zeros((n, side, side, 3), dtype=np.uint8)
+        lat_out = np.empty((n, 4, self.latent_spatial, self.latent_spatial), dtype=np.float32) if return_latents else None
+        first, cnt = _u(0), _u(0)
+        p = lambda a: None if a is None else a.ctypes.data
+        self._ok(api().libsdod_b200_generate_pair(self._h, n, p(c), p(latents), guidance_scale, p(imgs), ctypes.byref(first), ctypes.byref(cnt), p(lat_out)))
+        return (imgs, first.value, cnt.value, lat_out) if return_latents else (imgs, first.value, cnt.value)
 
     def last_timings(self):
         t = (_f * 4)()

@@ -58,6 +58,16 @@ class CfgSplitLoop:
         return x
 
 
+def connect_pair(ctx, group, role):
+    """Wire two libsdod contexts (one per process / GPU) into a CFG-split pair: exchange the 64-byte CUDA IPC handles of their eps
+    exchange buffers over `group` (any backend: this is set-up plumbing, the per-step exchange itself is peer stores inside the fused
+    sampler kernel — csrc/kernels/sampler.cu: cfg_dpm_step_pair_kernel) and map the peer's buffer."""
+    mine = ctx.pair_export()
+    both = [None, None]
+    dist.all_gather_object(both, mine, group=group)
+    ctx.pair_connect(both[1 - role], role)
+
+
 def gpu_cfg_split_generate(unet, vae, emb_all, latents_nhwc, guidance, group, role, steps=20):
     """CFG-split generation on GPUs: `unet` already holds this rank's context (cond or uncond), batch = images."""
     from . import ops

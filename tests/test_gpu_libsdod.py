@@ -66,6 +66,24 @@ def test_full_size_512_generate(models_dir):
     assert np.array_equal(imgs, imgs2)           # deterministic; y_prev persistence never leaks into step 0
 
 
+def test_generate_16_images_per_call_as_benchmarked(models_dir):
+    """bench.py's workload: one generate call for 16 images (UNet batch 32 x 20 steps + a batch-16 decode), every image against the oracle loop."""
+    d, unet, vae = models_dir
+    n = 16
+    lat = torch.randn(n, 4, 64, 64, generator=torch.Generator().manual_seed(31))
+    g2 = torch.Generator().manual_seed(32)
+    cond, uncond = torch.randn(n, 77, 768, generator=g2), torch.randn(n, 77, 768, generator=g2)
+    want = [P.generate(unet, vae, cond[i:i + 4], uncond[i:i + 4], lat[i:i + 4], 7.5, 20, device="cuda") for i in range(0, n, 4)]
+    want_u8 = np.concatenate([w[0] for w in want], 0)
+    want_lat = np.concatenate([w[2] for w in want], 0)
+    with A.Context(d, latent_spatial=64, steps=20, max_images=n, device=0) as ctx:
+        imgs, lat_out = ctx.generate(cond.numpy(), uncond.numpy(), lat.numpy(), 7.5, return_latents=True)
+    ps = [psnr_u8(imgs[i], want_u8[i]) for i in range(n)]
+    rel = np.linalg.norm(lat_out - want_lat) / np.linalg.norm(want_lat)
+    print("16 images per call, 512x512, 20 steps: worst PSNR %.1f dB (mean %.1f), final-latent rel-L2 %.3e" % (min(ps), sum(ps) / n, rel))
+    assert min(ps) >= 35.0 and rel < 5e-2
+
+
 def test_reference_style_app_flow():
     """csrc/libsdod/test/simple_app.cpp:7-37 through the same eight symbols."""
     lib = A.api()

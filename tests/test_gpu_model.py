@@ -79,13 +79,38 @@ def test_unet_step_eps_parity(unet_pair, hw, B):
     assert torch.equal(a, got) and torch.equal(b, got) and torch.equal(c, got)
 
 
-@pytest.mark.parametrize("hw,B", [(16, 2), (64, 1)])
+@pytest.mark.parametrize("B", [8, 32])
+def test_unet_step_eps_parity_at_benchmarked_batches(unet_pair, B):
+    """The configurations bench.py actually times: UNet batch 32 (16 images per call; selects the CTA-pair and persistent GEMM variants,
+    M = 131072) and batch 8 (4 images per call).  Every sample has its own latent, prompt and timestep."""
+    oracle, weights = unet_pair
+    net = M.UNet(weights, latent_hw=64, max_batch=B)
+    x = torch.randn(B, 4, 64, 64, generator=torch.Generator().manual_seed(11)).to(DEV)
+    ctx = torch.randn(B, 77, 768, generator=torch.Generator().manual_seed(12)).to(DEV)
+    t = torch.linspace(999.0, 49.95, B, device=DEV)
+    with torch.no_grad():
+        emb = oracle.embed_time(t)
+        want = torch.cat([oracle(x[i:i + 4], emb[i:i + 4], ctx[i:i + 4]) for i in range(0, B, 4)], 0)
+    got = net(x, emb, ctx)
+    assert torch.isfinite(got).all()
+    per = [rel_l2(got[i], want[i]) for i in range(B)]
+    print("unet hw=64 B=%d eps rel-L2 = %.3e (worst sample %.3e), launches/forward = %d" % (B, rel_l2(got, want), max(per), net.launches_per_forward(B)))
+    assert rel_l2(got, want) < 1e-2 and max(per) < 1e-2
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        a = net(x, emb, None, use_graph=True)
+        b = net(x, emb, None, use_graph=True)
+    s.synchronize()
+    assert torch.equal(a, got) and torch.equal(b, got)
+
+
+@pytest.mark.parametrize("hw,B", [(16, 2), (64, 1), (64, 8), (64, 16)])
 def test_vae_decode_parity(fp32_exact, hw, B):
     oracle = L.make_vae(seed=0).to(DEV)
     net = M.VaeDecoder(M.Weights(oracle.state_dict()), latent_hw=hw, max_batch=B)
     z = torch.randn(B, 4, hw, hw, generator=torch.Generator().manual_seed(3)).to(DEV) * 0.18215 * 2
     with torch.no_grad():
-        want = oracle(z).permute(0, 2, 3, 1)
+        want = torch.cat([oracle(z[i:i + 2]) for i in range(0, B, 2)], 0).permute(0, 2, 3, 1)      # (64,8) = BASELINE config C4; (64,16) = bench.py's batch
     u8, img = net(z)
     p = psnr(img, want)
     print("vae hw=%d B=%d PSNR = %.1f dB" % (hw, B, p))
