@@ -52,10 +52,34 @@ for i, e in enumerate(last):
 out.append("%10s %6s %5s %8s %10s  %s" % ("dur us", "share", "n", "avg us", "gap-after", "kernel"))
 for k, (c, d, g) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("%10.1f %5.1f%% %5d %8.2f %10.1f  %s" % (d, 100 * d / busy, c, d / c, g, k))
+# label every kernel with its plan op (ops are recorded in launch order; a split-K op without the in-cluster reduction and the two-kernel
+# GroupNorm are two launches each) and attribute the span by end-to-end deltas: the time an op adds to the step once overlap is accounted for
+with torch.cuda.stream(s):
+    names = [n for _, n in net.profile(B, 1)]
+labels = []
+for n in names:
+    m = re.search(r" split(\d+)", n)
+    k = 2 if ((m and int(m.group(1)) > 1) or n.startswith("gn ")) else 1
+    labels += [n] * k
+if len(labels) == len(last):
+    byop = collections.OrderedDict()
+    prev_end = last[0].time_range.start
+    for e, n in zip(last, labels):
+        a = byop.setdefault(n, [0, 0.0])
+        a[0] += 1
+        a[1] += e.time_range.end - prev_end
+        prev_end = e.time_range.end
+    out.append("---- in-graph cost by plan op (end-to-end deltas; sums to the span)")
+    for n, (c, d) in sorted(byop.items(), key=lambda kv: -kv[1][1]):
+        out.append("%9.1f us %5.1f%%  x%-3d avg %7.2f us  %s" % (d, 100 * d / span, c, d / c, n))
+else:
+    out.append("---- (op labels not aligned: %d labels vs %d kernels)" % (len(labels), len(last)))
+    labels = [""] * len(last)
 out.append("---- timeline (start us, dur us, gap to next us, kernel)")
 for i, e in enumerate(last):
     g = last[i + 1].time_range.start - e.time_range.end if i + 1 < len(last) else 0.0
-    out.append("%9.1f %7.2f %6.2f  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, g, re.sub(r"\(.*", "", e.name).replace("void ", "").replace("sdod::", "")[:60]))
-print("\n".join(out[:28]))
+    out.append("%9.1f %7.2f %6.2f  %-52s %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, g, re.sub(r"\(.*", "", e.name).replace("void ", "").replace("sdod::", "")[:52], labels[i]))
+cut = [i for i, l in enumerate(out) if l.startswith("---- timeline")][0]
+print("\n".join(out[:min(cut, 90)]))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "graph_trace_%s.txt" % tag), "w").write("\n".join(out) + "\n")
