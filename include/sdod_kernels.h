@@ -27,7 +27,7 @@ typedef void* sdod_stream_t; /* cudaStream_t */
 
 enum sdod_dtype { SDOD_F32 = 0, SDOD_BF16 = 1 };
 enum sdod_layout { SDOD_NCHW = 0, SDOD_NHWC = 1 };
-enum sdod_act { SDOD_ACT_NONE = 0, SDOD_ACT_SILU = 1, SDOD_ACT_GELU = 2, SDOD_ACT_GEGLU = 3 };
+enum sdod_act { SDOD_ACT_NONE = 0, SDOD_ACT_SILU = 1, SDOD_ACT_GELU = 2, SDOD_ACT_GEGLU = 3, SDOD_ACT_QUICK_GELU = 4 /* x*sigmoid(1.702x): CLIP */ };
 /* GEMM/conv output placement */
 enum sdod_out_mode {
     SDOD_OUT_BF16 = 0,      /* C[m*ldc + n] bf16                                                     */
@@ -195,12 +195,15 @@ typedef struct sdod_conv_desc {
 } sdod_conv_desc;
 SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d);
 
-/* Fused flash-style attention on tcgen05 (S and O accumulators in TMEM, online softmax, P through
- * swizzled shared memory).  SpatialTransformer attn1/attn2 (analyze_results.py:60-75).
+/* Fused flash-style attention on tcgen05 (S and O accumulators in TMEM, online softmax, P written back to
+ * TMEM and consumed as the A operand of the PV MMA).  SpatialTransformer attn1/attn2 (analyze_results.py:60-75).
  * Qh [BH, Nq, dpad], Kh [BH, Nkv, dpad] (HEADS layout, dpad = 64*ceil(head_dim/64), zero padded),
  * Vt [BH, vt_rows, kv_pad] (HEADS_T layout, vt_rows = 16*ceil(head_dim/16), kv_pad % 8 == 0, zero padded).
  * O bf16 [B, Nq, heads*head_dim] (token-major, heads concatenated).  softmax(scale * Q K^T) V. */
 SDOD_API int sdod_attention_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O,
+                                 int B, int heads, int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale);
+/* The same with a causal mask (key k visible to query q iff k <= q): the CLIP text encoder's self-attention (head_dim 64). */
+SDOD_API int sdod_attention_causal_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O,
                                  int B, int heads, int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale);
 
 /* Row softmax (unfused attention for the VAE mid block, d=512). x,y bf16 [rows, cols], ld in elements. */

@@ -50,6 +50,27 @@ SDOD_API void sdod_vae_destroy(sdod_vae* v);
 /* z [B,H,W,4] fp32 NHWC latent -> image_u8 [B,8H,8W,3] (may be NULL) and image_f32 [B,8H,8W,3] in [0,1] (may be NULL) */
 SDOD_API int sdod_vae_decode(sdod_vae* v, sdod_stream_t stream, const float* z, uint8_t* image_u8, float* image_f32, int B, int use_graph);
 
+/* ---- prompt path: CLIP byte-pair tokenizer + CLIP ViT-L/14 text encoder.
+ * Replaces libsdod::Tokenizer (csrc/libsdod/src/tokenizer.{h,cpp}; loaded at context.cpp:180-187, called at context.cpp:235,325) and the
+ * `cond_model` graph ("text_encoder.serialized", context.cpp:143,170; executed at context.cpp:237,327). */
+typedef struct sdod_tokenizer sdod_tokenizer;
+typedef struct sdod_text_encoder sdod_text_encoder;
+
+/* bpe_file: a ctokenizer.txt in the reference's format (gen_tokenizer_file.py:27-42).  NULL: byte-level vocabulary without merges
+ * (the 512 byte symbols in the same id order) — what random-init contexts use. */
+SDOD_API int sdod_tokenizer_create(sdod_tokenizer** out, const char* bpe_file);
+SDOD_API void sdod_tokenizer_destroy(sdod_tokenizer* t);
+/* tokens_out[context_len] = [start, ids..., end padding]; context_len = 77 for SD (tokenizer.h:24).  Invalid UTF-8 -> status -1 (invalid argument). */
+SDOD_API int sdod_tokenizer_encode(const sdod_tokenizer* t, const char* utf8, unsigned short* tokens_out, unsigned context_len);
+SDOD_API int sdod_tokenizer_vocab_size(const sdod_tokenizer* t);
+
+/* weights == NULL: random-init with `seed`.  Weight names: the HuggingFace CLIPTextModel state_dict keys under "text_model."
+ * (ldm checkpoints: "cond_stage_model.transformer.text_model.", stripped by sdod/checkpoint.py). */
+SDOD_API int sdod_text_encoder_create(sdod_text_encoder** out, const sdod_weights* weights, unsigned long long seed, int max_batch);
+SDOD_API void sdod_text_encoder_destroy(sdod_text_encoder* e);
+/* tokens [B,77] int32 (device) -> context_out [B,77,768] (device; dtype SDOD_F32 or SDOD_BF16): last_hidden_state after final_layer_norm */
+SDOD_API int sdod_text_encoder_forward(sdod_text_encoder* e, sdod_stream_t stream, const int* tokens, int B, void* context_out, int out_dtype);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,6 +234,13 @@ SDOD_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+SDOD_DEVICE void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
 SDOD_DEVICE void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -282,6 +289,7 @@ SDOD_DEVICE float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 SDOD_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+SDOD_DEVICE float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }     // CLIP's QuickGELU: x * sigmoid(1.702 x)
 // exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): a handful of FMAs + one MUFU exp + one rcp
 // instead of erff's long polynomial — the GEGLU epilogue evaluates it on 21 M elements per 64x64 transformer block.
 SDOD_DEVICE float erf_fast(float x) {

@@ -12,6 +12,7 @@
 //                O = (O_0 w_0 + O_1 w_1) -> bf16 [B, Nq, heads*head_dim].
 // TMEM columns: S at [0,128) (two 64-key buffers), O_0 at [128, 128+dv), O_1 at [128+dv, 128+2dv).  Everything is K-major + SWIZZLE_128B: K^T comes
 // for free from the HEADS layout, V is stored transposed (HEADS_T) by the producing GEMM epilogue.
+#include <cstdlib>
 #include "../common.cuh"
 #include "../host_common.h"
 #include "../launch_count.h"
@@ -24,20 +25,30 @@ constexpr int kAttThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 constexpr int kBQ = 128;    // query rows per CTA
 constexpr int kBKV = 64;    // keys per tile: one thread holds a whole S row (64 fp32) in registers -> S is read from TMEM once
 
-template <int DH>
+// MODE 0: P through shared memory (round 1).  MODE 1: P in TMEM (TS-form PV).  MODE 2 (head dims with a spare V^T row, i.e. d = 40):
+// MODE 1 plus row sums on the tensor pipe — row DH of every V^T tile in shared memory is a row of ones (written once per CTA; the TMA box
+// covers rows [0, DH) only), so column DH of the O accumulator is sum_k P[q,k] of exactly the rounded P that multiplied V, and the 16
+// packed adds per tile disappear.  Tried on top and dropped (B200 r2, B8 x 8 heads x 4096^2, d = 40; profiles/r02_attention_notes.txt):
+// ex2.approx.ftz.bf16x2 for the exponentials (ptxas splits it into two MUFU.EX2.BF16 plus a PRMT: no MUFU slots saved, precision lost);
+// fetching S_{j+1} from TMEM in the middle of tile j's exponentials (444 us against 376: a warp then needs S_{j+1} half a tile earlier, and
+// S_{j+1} is only issued once EVERY warp has handed over P_{j-1} — the slack between fast and slow warps halves).
+template <int DH, int MODE = 1>
 struct AttCfg {
+    static constexpr bool PT = MODE >= 1;
+    static constexpr bool kOnes = MODE == 2;                  // ones row at V^T row DH
+    static constexpr int kVBoxRows = kOnes ? DH : ((DH + 15) / 16) * 16;
     static constexpr int kNK = (DH + 63) / 64;            // 64-wide d chunks of Q / K
     static constexpr int kKSteps = (DH + 15) / 16;        // UMMA K steps for S = Q K^T
     static constexpr int kDV = ((DH + 15) / 16) * 16;     // N of the PV MMA (rows of the V^T tile)
     static constexpr int kStages = DH > 80 ? 3 : 4;
     static constexpr int kQBytes = kNK * kBQ * 128;
     static constexpr int kKBytes = kNK * kBKV * 128;
-    static constexpr int kVBytes = kDV * 128;             // one 64-key chunk, kDV rows of 128 B
+    static constexpr int kVBytes = kVBoxRows * 128;       // one 64-key chunk: the TMA box, kVBoxRows rows of 128 B
     static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;
     static constexpr int kStageBytes = kKBytes + kVChunk;
     static constexpr int kPBytes = kBQ * 128;             // one P buffer: 128 rows x 64 keys bf16
     static constexpr int kTmemCols = (128 + 2 * kDV) <= 256 ? 256 : 512;   // S double buffer + two O accumulators
-    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBytes + 1024 + 256 + 3 * 256 * 4;   // + row-max / row-sum exchange
+    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + (PT ? 0 : 2 * kPBytes) + 1024 + 256 + 3 * 256 * 4;   // + row-max / row-sum exchange
 };
 
 SDOD_DEVICE float ex2(float x) {
@@ -62,19 +73,27 @@ SDOD_DEVICE float ex2_poly(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int DH>
+// PT = true: P never touches shared memory.  Each softmax thread writes its 32 probabilities (bf16 pairs, 16 columns) over the first half of
+// the S columns it has just read (tcgen05.st) and the PV MMAs take A from TMEM (tcgen05.mma TS form).  Per 128x64 tile that removes 16 KB of
+// shared-memory stores, 16 KB of UMMA operand reads and the generic->async proxy fence; shared-memory bandwidth (~70 KB per tile at
+// 128 B/clk) was what bound the d=40 kernel (profiles/r01_attention_notes.txt: neither removing the exponentials nor the TMEM reads helped).
+// S_{j+2} overwrites the buffer that holds P_j: it is issued after PV_j and tcgen05.mma instructions execute in issue order, so the separate
+// "S buffer drained" barrier goes away too (p_full(j) already says every thread has read S_j).
+template <int DH, int MODE>
 __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O,
-                                                                 int heads, int Nq, int Nkv, float scale_log2) {
-    using Cfg = AttCfg<DH>;
+                                                                 int heads, int Nq, int Nkv, float scale_log2, int causal) {
+    using Cfg = AttCfg<DH, MODE>;
+    constexpr bool PT = Cfg::PT;
     constexpr int STAGES = Cfg::kStages;
+    static_assert(!Cfg::kOnes || (DH % 8 == 0 && Cfg::kDV >= DH + 8), "the ones row needs a spare 8-row group in the V^T tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned shared-space pointer
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Cfg::kQBytes;
     uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PT ? 0 : 2 * Cfg::kPBytes));
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;                 // [STAGES]
     uint64_t* kv_empty = kv_full + STAGES;        // [STAGES]
@@ -90,7 +109,8 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, bh = blockIdx.y;
     const int q0 = q_tile * kBQ;
-    const int n_tiles = (Nkv + kBKV - 1) / kBKV;
+    // causal (the CLIP text encoder): key k is visible to query q iff k <= q, so this query tile needs the key tiles up to its last row only
+    const int n_tiles = causal ? (min(Nkv, q0 + kBQ) + kBKV - 1) / kBKV : (Nkv + kBKV - 1) / kBKV;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -104,6 +124,16 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (Cfg::kOnes && warp >= 3) {
+        // rows [DH, DH+8) of every stage's V^T tile are never written by TMA: row DH = ones (row sums on the tensor pipe), the rest zeros.
+        // A row of equal 16-byte chunks is invariant under the 128-byte swizzle.
+        for (int i = static_cast<int>(threadIdx.x) - 96; i < STAGES * 8 * 8; i += kAttThreads - 96) {
+            const int st = i >> 6, r = (i >> 3) & 7, ch = i & 7;
+            const uint32_t w = r == 0 ? 0x3F803F80u : 0u;      // bf16 1.0 pairs
+            *reinterpret_cast<uint4*>(sKV + st * Cfg::kStageBytes + Cfg::kKBytes + (DH + r) * 128 + ch * 16) = make_uint4(w, w, w, w);
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -139,7 +169,7 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                 if (j < n_tiles) {                                   // S_j = Q K_j^T -> S buffer j&1
                     const int st = j % STAGES;
                     mbar_wait(&kv_full[st], (j / STAGES) & 1);
-                    if (j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
+                    if (!PT && j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
                     tc_fence_after();
                     const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
 #pragma unroll
@@ -157,11 +187,13 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                     const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
                     const uint32_t pb = p_addr + (i & 1) * Cfg::kPBytes;
 #pragma unroll
-                    for (int k = 0; k < kBKV / 16; ++k)    // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
-                        tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
-                                    (i | (k & 1)) != 0);
+                    for (int k = 0; k < kBKV / 16; ++k) {  // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
+                        if (PT) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
+                                               make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | (k & 1)) != 0);
+                        else tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
+                                         (i | (k & 1)) != 0);
+                    }
                     tc_commit(&kv_empty[st]);
-                    tc_commit(&p_free[i & 1]);
                     tc_commit(o_ready);
                 }
             }
@@ -189,12 +221,22 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             uint32_t sv[32];
             tmem_ld32(tmem_base + lane_off + b * 64 + half * 32, sv);
             tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&s_free[b]);                 // S buffer b may be overwritten by S_{j+2}
+            if (!PT) {
+                tc_fence_before();
+                mbar_arrive(&s_free[b]);             // S buffer b may be overwritten by S_{j+2}
+            }
             if (kv_valid < 32) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (i >= kv_valid) sv[i] = 0xff800000u;          // -inf
+            }
+            if (causal) {
+                const int visible = q0 + row - (j * kBKV + half * 32);      // keys [0, visible] of this thread's 32 may be attended
+                if (visible < 31) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i > visible) sv[i] = 0xff800000u;
+                }
             }
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -210,6 +252,14 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             const uint64_t negm2 = pack_f32x2(-m_new, -m_new);
             uint64_t ls2[2] = {0ull, 0ull};
             uint32_t pk[16];
+            if (Cfg::kOnes) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float x0, x1;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), scale2, negm2), x0, x1);
+                    pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
+                }
+            } else
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 // x = s * scale - m for two keys in one FFMA2 (sm_100 packed fp32), then MUFU.EX2 each
@@ -221,7 +271,7 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                 ls2[i & 1] = add_f32x2(ls2[i & 1], pack_f32x2(p0, p1));
                 pk[i] = pack_bf16x2(p0, p1);
             }
-            {
+            if (!Cfg::kOnes) {
                 float a0, a1, a2, a3;
                 unpack_f32x2(ls2[0], a0, a1);
                 unpack_f32x2(ls2[1], a2, a3);
@@ -231,10 +281,15 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             // P buffer b is free: the MMA thread issues S_j after PV_{j-2}, and a tcgen05.commit covers every MMA issued before it, so
             // having seen s_full for tile j already implies PV_{j-2} has consumed this buffer.  (A satisfied mbarrier wait still costs
             // ~200 clk here — clock64 phase timing, profiles/r01_attention_notes.txt — so the loop keeps exactly one per tile.)
-            uint8_t* prow = sP + b * Cfg::kPBytes + row * 128;
+            if (PT) {
+                // keys (2i, 2i+1) of this thread's 32 -> column i of its own S half: lane = query row, 32-bit column = two consecutive K elements
+                tmem_st16(tmem_base + lane_off + b * 64 + half * 32, pk);
+            } else {
+                uint8_t* prow = sP + b * Cfg::kPBytes + row * 128;
 #pragma unroll
-            for (int un = 0; un < 4; ++un)
-                *reinterpret_cast<uint4*>(prow + (((half * 4 + un) ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
+                for (int un = 0; un < 4; ++un)
+                    *reinterpret_cast<uint4*>(prow + (((half * 4 + un) ^ sw) << 4)) = make_uint4(pk[4 * un], pk[4 * un + 1], pk[4 * un + 2], pk[4 * un + 3]);
+            }
             if (j > 0 && __any_sync(0xffffffffu, need)) {            // rare: this warp's accumulator must be rescaled
                 // PV_{j-1} must have completed.  s_full(j) above proves PV_{j-2} has, so o_ready is either in phase j-1 (pending) or
                 // already past it: the parity test is unambiguous even though this wait is not taken every tile.
@@ -249,25 +304,35 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                     for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                     tmem_st16(tmem_mine + c * 16, o);
                 }
-                tmem_st_wait();
             }
+            if (PT) tmem_st_wait();              // P (and a rescaled O) have landed in TMEM
+            else if (j > 0) tmem_st_wait();
             tc_fence_before();
-            fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the UMMA async proxy
+            if (!PT) fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the UMMA async proxy
             mbar_arrive(&p_full[b]);
         }
         // epilogue: merge the two halves of each row
         xch[half * 128 + row] = m_run;
         xch[(2 + half) * 128 + row] = l_run;
         asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-        const float m_o = xch[(half ^ 1) * 128 + row], l_o = xch[(2 + (half ^ 1)) * 128 + row];
+        const float m_o = xch[(half ^ 1) * 128 + row];
+        float l_o = xch[(2 + (half ^ 1)) * 128 + row];
         const float m_all = fmaxf(m_run, m_o);
         const float f_me = ex2(m_run - m_all), f_ot = ex2(m_o - m_all);
-        const float inv_l = 1.0f / fmaf(l_run, f_me, l_o * f_ot);
-        const float w_me = f_me * inv_l, w_ot = f_ot * inv_l;
         // All PVs retired: a barrier of its own, committed once after the last PV.  (o_ready flips every tile and is no longer waited in
         // lockstep, so its parity cannot tell "all done" from "two behind" here.)
         mbar_wait(o_final, 0);
         tc_fence_after();
+        if (Cfg::kOnes) {                                   // the row sums are column DH of the two accumulators
+            uint32_t a[8], b[8];
+            tmem_ld8(tmem_O + lane_off + half * Cfg::kDV + DH, a);
+            tmem_ld8(tmem_O + lane_off + (half ^ 1) * Cfg::kDV + DH, b);
+            tmem_ld_wait();
+            l_run = __uint_as_float(a[0]);
+            l_o = __uint_as_float(b[0]);
+        }
+        const float inv_l = 1.0f / fmaf(l_run, f_me, l_o * f_ot);
+        const float w_me = f_me * inv_l, w_ot = f_ot * inv_l;
         const int bb = bh / heads, h = bh - bb * heads;
         const int qi = q0 + row;
         bf16* orow = O + (static_cast<long long>(bb) * Nq + qi) * (heads * DH) + h * DH;
@@ -303,6 +368,13 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     }
 }
 
+static int attention_mode(int DH) {
+    // SDOD_ATTN_MODE = 0 | 1 | 2 overrides the default (A/B measurements); MODE 2 exists for head dims with a spare V^T row group only
+    static const int env = [] { const char* e = std::getenv("SDOD_ATTN_MODE"); return e ? std::atoi(e) : -1; }();
+    const int best = DH == 40 ? 2 : 1;
+    return env < 0 ? best : (env > best ? best : env);
+}
+
 template <int DH>
 static int prepare_attention(AttnLaunch* out, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq,
                              int Nkv, int dpad, int kv_pad, float scale) {
@@ -328,28 +400,37 @@ static int prepare_attention(AttnLaunch* out, const void* Qh, const void* Kh, co
     {
         uint64_t dims[3] = {static_cast<uint64_t>(kv_pad), static_cast<uint64_t>(Cfg::kDV), static_cast<uint64_t>(BH)};
         uint64_t strides[2] = {static_cast<uint64_t>(kv_pad) * 2, static_cast<uint64_t>(Cfg::kDV) * kv_pad * 2};
-        uint32_t box[3] = {64, static_cast<uint32_t>(Cfg::kDV), 1};
+        uint32_t box[3] = {64, static_cast<uint32_t>(attention_mode(DH) == 2 ? DH : Cfg::kDV), 1};
         SDOD_TRY(encode_tmap_bf16(&tmV, Vt, 3, dims, strides, box, true));
     }
-    out->O = O; out->heads = heads; out->Nq = Nq; out->Nkv = Nkv; out->head_dim = DH; out->BH = BH;
+    out->O = O; out->heads = heads; out->Nq = Nq; out->Nkv = Nkv; out->head_dim = DH; out->BH = BH; out->causal = 0;
     out->scale_log2 = scale * 1.4426950408889634f;
     return kOk;
 }
 
-template <int DH>
-static int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
-    using Cfg = AttCfg<DH>;
+template <int DH, int MODE>
+static int launch_attention_v(const AttnLaunch& a, cudaStream_t stream) {
+    using Cfg = AttCfg<DH, MODE>;
     static bool configured = false;
     if (!configured) {
-        SDOD_TRY(check_cuda(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+        SDOD_TRY(check_cuda(cudaFuncSetAttribute(attention_kernel<DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
                             "cudaFuncSetAttribute(attention)"));
         configured = true;
     }
     dim3 grid((a.Nq + kBQ - 1) / kBQ, a.BH);
-    SDOD_TRY(check_cuda(launch_pdl(attention_kernel<DH>, grid, dim3(kAttThreads), Cfg::kSmemBytes, stream, a.tmQ, a.tmK, a.tmV,
-                                   static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv, a.scale_log2), "launch attention_kernel"));
+    SDOD_TRY(check_cuda(launch_pdl(attention_kernel<DH, MODE>, grid, dim3(kAttThreads), Cfg::kSmemBytes, stream, a.tmQ, a.tmK, a.tmV,
+                                   static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv, a.scale_log2, a.causal), "launch attention_kernel"));
     count_launch();
     return check_launch("attention_kernel");
+}
+
+template <int DH>
+static int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
+    const int mode = attention_mode(DH);
+    if constexpr (DH == 40) {
+        if (mode == 2) return launch_attention_v<DH, 2>(a, stream);
+    }
+    return mode ? launch_attention_v<DH, 1>(a, stream) : launch_attention_v<DH, 0>(a, stream);
 }
 
 int attention_prepare(AttnLaunch* out, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
@@ -376,9 +457,10 @@ int attention_launch(const AttnLaunch& a, cudaStream_t stream) {
 }
 
 int attention_bf16(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
-                   int head_dim, int dpad, int kv_pad, float scale) {
+                   int head_dim, int dpad, int kv_pad, float scale, int causal) {
     AttnLaunch a;
     SDOD_TRY(attention_prepare(&a, Qh, Kh, Vt, O, B, heads, Nq, Nkv, head_dim, dpad, kv_pad, scale));
+    a.causal = causal ? 1 : 0;
     return attention_launch(a, stream);
 }
 
@@ -386,5 +468,9 @@ int attention_bf16(cudaStream_t stream, const void* Qh, const void* Kh, const vo
 
 extern "C" SDOD_API int sdod_attention_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads,
                                             int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale) {
-    return sdod::attention_bf16(static_cast<cudaStream_t>(stream), Qh, Kh, Vt, O, B, heads, Nq, Nkv, head_dim, dpad, kv_pad, scale);
+    return sdod::attention_bf16(static_cast<cudaStream_t>(stream), Qh, Kh, Vt, O, B, heads, Nq, Nkv, head_dim, dpad, kv_pad, scale, 0);
+}
+extern "C" SDOD_API int sdod_attention_causal_bf16(sdod_stream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads,
+                                                   int Nq, int Nkv, int head_dim, int dpad, int kv_pad, float scale) {
+    return sdod::attention_bf16(static_cast<cudaStream_t>(stream), Qh, Kh, Vt, O, B, heads, Nq, Nkv, head_dim, dpad, kv_pad, scale, 1);
 }

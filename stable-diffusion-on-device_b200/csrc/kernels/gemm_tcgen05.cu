@@ -76,6 +76,7 @@ SDOD_DEVICE void tstamp(const MainloopParams& mp, int slot) {
 SDOD_DEVICE float apply_act(float v, int act) {
     if (act == SDOD_ACT_SILU) return silu_f(v);
     if (act == SDOD_ACT_GELU) return gelu_f(v);
+    if (act == SDOD_ACT_QUICK_GELU) return quick_gelu_f(v);
     return v;
 }
 
@@ -213,6 +214,9 @@ SDOD_DEVICE void bias_act(float (&v)[NV], const sdod_epilogue& ep, const float* 
     } else if (ep.act == SDOD_ACT_GELU) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = gelu_f(v[i]);
+    } else if (ep.act == SDOD_ACT_QUICK_GELU) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = quick_gelu_f(v[i]);
     }
 }
 
@@ -965,6 +969,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 } else if (ep.act == SDOD_ACT_GELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+                } else if (ep.act == SDOD_ACT_QUICK_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = quick_gelu_f(v[i]);
                 }
                 if (!res_waited) { mbar_wait(&res_bar[q], res_parity); res_waited = true; if (threadIdx.x == 64 && iter == 0) tstamp(mp, 9); }
                 uint8_t* box = qbase + (j >> 5) * bstr;
@@ -1131,6 +1138,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                                     } else if (ACT == SDOD_ACT_GELU) {
 #pragma unroll
                                         for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+                                    } else if (ACT == SDOD_ACT_QUICK_GELU) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) v[i] = quick_gelu_f(v[i]);
                                     }
                                     const float4 o = make_float4(v[0] + add[rr][ci].x, v[1] + add[rr][ci].y, v[2] + add[rr][ci].z, v[3] + add[rr][ci].w);
                                     if (out32) {
@@ -1147,6 +1157,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 };
                 if (ep.act == SDOD_ACT_SILU) run_rows(std::integral_constant<int, SDOD_ACT_SILU>{});
                 else if (ep.act == SDOD_ACT_GELU) run_rows(std::integral_constant<int, SDOD_ACT_GELU>{});
+                else if (ep.act == SDOD_ACT_QUICK_GELU) run_rows(std::integral_constant<int, SDOD_ACT_QUICK_GELU>{});
                 else run_rows(std::integral_constant<int, SDOD_ACT_NONE>{});
             } else {
                 for (int r = r_lo; r < r_hi; ++r) {

@@ -13,4 +13,7 @@ int vae_post(cudaStream_t s, const float* x, uint8_t* u8, float* img, size_t n);
 int broadcast_rows(cudaStream_t s, float* dst, const float* src, int rows, int width);
 int fill_f32(cudaStream_t s, float* x, size_t n, float v);
 int scale_f32(cudaStream_t s, float* x, size_t n, float v);
+// out[r, :] = tok_emb[tokens[r], :] + pos_emb[r % T, :]   (CLIP text embeddings; ids clamped to the table)
+int clip_embed(cudaStream_t s, const int* tokens, const float* tok_emb, const float* pos_emb, float* out, int rows, int T, int D, int vocab);
+int cast_bf16_to_f32(cudaStream_t s, const void* x_bf16, float* y, size_t n);
 }  // namespace sdod

@@ -54,6 +54,7 @@ struct AttnLaunch {
     void* O;
     int heads, Nq, Nkv, head_dim, BH;
     float scale_log2;
+    int causal;      // 1: key k is visible to query q iff k <= q (CLIP text encoder); set after attention_prepare
 };
 
 int pick_block_n(int M, int N, int batch, int act);
@@ -71,6 +72,8 @@ int conv3x3_bf16(cudaStream_t stream, const sdod_conv_desc& d);
 int attention_prepare(AttnLaunch* out, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
                       int head_dim, int dpad, int kv_pad, float scale);
 int attention_launch(const AttnLaunch& a, cudaStream_t stream);
+int attention_bf16(cudaStream_t stream, const void* Qh, const void* Kh, const void* Vt, void* O, int B, int heads, int Nq, int Nkv,
+                   int head_dim, int dpad, int kv_pad, float scale, int causal);
 
 int group_norm(cudaStream_t stream, const void* x, void* y, const float* weight, const float* bias, const float* add_nc, int N, int C,
                int HW, int G, float eps, int dtype, int layout, int fuse_silu, void* ws, size_t ws_bytes);

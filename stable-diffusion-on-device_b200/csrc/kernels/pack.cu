@@ -81,6 +81,24 @@ __global__ void broadcast_rows_kernel(float* __restrict__ dst, const float* __re
         dst[i] = src[i % width];
 }
 
+__global__ void clip_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                                  float* __restrict__ out, int rows, int T, int D, int vocab) {
+    const int d4 = D / 4;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<size_t>(rows) * d4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / d4), c = static_cast<int>(i - static_cast<size_t>(r) * d4);
+        int id = tokens[r];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const float4 a = reinterpret_cast<const float4*>(tok_emb + static_cast<size_t>(id) * D)[c];
+        const float4 b = reinterpret_cast<const float4*>(pos_emb + static_cast<size_t>(r % T) * D)[c];
+        reinterpret_cast<float4*>(out + static_cast<size_t>(r) * D)[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
+__global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, size_t n) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        y[i] = __bfloat162float(x[i]);
+}
+
 static inline int g1(size_t n) {
     size_t g = (n + 255) / 256;
     if (g > 148 * 32) g = 148 * 32;
@@ -127,6 +145,17 @@ int broadcast_rows(cudaStream_t s, float* dst, const float* src, int rows, int w
     broadcast_rows_kernel<<<g1(static_cast<size_t>(rows) * width), 256, 0, s>>>(dst, src, rows, width);
     count_launch();
     return check_launch("broadcast_rows_kernel");
+}
+int clip_embed(cudaStream_t s, const int* tokens, const float* tok_emb, const float* pos_emb, float* out, int rows, int T, int D, int vocab) {
+    if (D % 4 != 0) return fail(kInvalidArgument, "clip_embed: width must be a multiple of 4");
+    clip_embed_kernel<<<g1(static_cast<size_t>(rows) * (D / 4)), 256, 0, s>>>(tokens, tok_emb, pos_emb, out, rows, T, D, vocab);
+    count_launch();
+    return check_launch("clip_embed_kernel");
+}
+int cast_bf16_to_f32(cudaStream_t s, const void* x, float* y, size_t n) {
+    cast_bf16_to_f32_kernel<<<g1(n), 256, 0, s>>>(static_cast<const bf16*>(x), y, n);
+    count_launch();
+    return check_launch("cast_bf16_to_f32_kernel");
 }
 int fill_f32(cudaStream_t s, float* x, size_t n, float v) {
     fill_f32_kernel<<<g1(n), 256, 0, s>>>(x, n, v);

@@ -5,12 +5,16 @@
 #include <vector>
 
 #include "sdod_model.h"
+#include "clip_text.h"
+#include "tokenizer.h"
 #include "unet.h"
 #include "vae.h"
 
 struct sdod_weights { sdod::WeightStore store; };
 struct sdod_unet { sdod::UNet* net; };
 struct sdod_vae { sdod::VaeDecoder* net; };
+struct sdod_tokenizer { sdod::Tokenizer tok; };
+struct sdod_text_encoder { sdod::ClipTextEncoder* net; };
 
 using sdod::fail;
 using sdod::kCudaError;
@@ -106,5 +110,47 @@ SDOD_API void sdod_vae_destroy(sdod_vae* v) {
 SDOD_API int sdod_vae_decode(sdod_vae* v, sdod_stream_t stream, const float* z, uint8_t* image_u8, float* image_f32, int B, int use_graph) {
     if (!v || !z) return fail(kInvalidArgument, "vae_decode: bad arguments");
     return v->net->decode(static_cast<cudaStream_t>(stream), z, image_u8, image_f32, B, use_graph != 0);
+}
+
+SDOD_API int sdod_tokenizer_create(sdod_tokenizer** out, const char* bpe_file) {
+    if (!out) return fail(kInvalidArgument, "tokenizer_create: out is NULL");
+    *out = nullptr;
+    try {
+        *out = bpe_file ? new sdod_tokenizer{sdod::Tokenizer(std::string(bpe_file))} : new sdod_tokenizer{sdod::Tokenizer()};
+    } catch (const std::exception& e) {
+        return fail(kInvalidArgument, std::string("tokenizer_create: ") + e.what());
+    }
+    return kOk;
+}
+SDOD_API void sdod_tokenizer_destroy(sdod_tokenizer* t) { delete t; }
+SDOD_API int sdod_tokenizer_encode(const sdod_tokenizer* t, const char* utf8, unsigned short* tokens_out, unsigned context_len) {
+    if (!t || !utf8 || !tokens_out || context_len < 2) return fail(kInvalidArgument, "tokenizer_encode: bad arguments");
+    try {
+        const std::vector<sdod::Tokenizer::token_type> ids = t->tok.encode(utf8, context_len);
+        std::memcpy(tokens_out, ids.data(), sizeof(unsigned short) * context_len);
+    } catch (const std::exception& e) {
+        return fail(kInvalidArgument, std::string("tokenizer_encode: ") + e.what());
+    }
+    return kOk;
+}
+SDOD_API int sdod_tokenizer_vocab_size(const sdod_tokenizer* t) { return t ? static_cast<int>(t->tok.vocab_size()) : -1; }
+
+SDOD_API int sdod_text_encoder_create(sdod_text_encoder** out, const sdod_weights* weights, unsigned long long seed, int max_batch) {
+    if (!out) return fail(kInvalidArgument, "text_encoder_create: out is NULL");
+    *out = nullptr;
+    SDOD_TRY(have_device());
+    try {
+        *out = new sdod_text_encoder{new sdod::ClipTextEncoder(weights ? &weights->store : nullptr, seed, max_batch)};
+    } catch (const std::exception& e) {
+        return fail(kCudaError, std::string("text_encoder_create: ") + e.what());
+    }
+    return kOk;
+}
+SDOD_API void sdod_text_encoder_destroy(sdod_text_encoder* e) {
+    if (e) { delete e->net; delete e; }
+}
+SDOD_API int sdod_text_encoder_forward(sdod_text_encoder* e, sdod_stream_t stream, const int* tokens, int B, void* context_out, int out_dtype) {
+    if (!e) return fail(kInvalidArgument, "text_encoder_forward: bad arguments");
+    return e->net->forward(static_cast<cudaStream_t>(stream), tokens, B, context_out, out_dtype);
 }
 }

@@ -90,6 +90,13 @@ _SIGS = {
     "sdod_vae_create": (c_int, [ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_int, c_int]),
     "sdod_vae_destroy": (None, [c_vp]),
     "sdod_vae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
+    "sdod_tokenizer_create": (c_int, [ctypes.POINTER(c_vp), ctypes.c_char_p]),
+    "sdod_tokenizer_destroy": (None, [c_vp]),
+    "sdod_tokenizer_encode": (c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_ushort), c_u]),
+    "sdod_tokenizer_vocab_size": (c_int, [c_vp]),
+    "sdod_text_encoder_create": (c_int, [ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_int]),
+    "sdod_text_encoder_destroy": (None, [c_vp]),
+    "sdod_text_encoder_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int]),
 }
 
 _lib = None
