@@ -125,6 +125,12 @@ LIBSDOD_API int libsdod_b200_generate_pair(void* context, unsigned int n_images,
                                            float guidance_scale, unsigned char* images_out, unsigned int* first_image, unsigned int* n_decoded,
                                            float* latents_out);
 
+/* The prompt path on its own (context.cpp:325-329: tokenizer -> cond_model): embedding_out[77*768] (host, fp32) = last_hidden_state of the CLIP text
+ * encoder for `prompt` — what libsdod_generate_image feeds the UNet as conditioning, and what libsdod_b200_generate takes as cond / uncond.
+ * tokens_out (may be NULL) receives the 77 token ids.  Fails with LIBSDOD_RUNTIME_ERROR when the context has no tokenizer / text encoder
+ * (a models_dir without ctokenizer.txt + text_encoder.sdodw), LIBSDOD_INVALID_ARGUMENT on invalid UTF-8 (tokenizer.cpp:77). */
+LIBSDOD_API int libsdod_b200_encode_prompt(void* context, const char* prompt, float* embedding_out, unsigned short* tokens_out);
+
 /* Milliseconds of the last generate call as the reference logs them (context.cpp:309-314,331,381,398,402):
  * out[0] conditioning, out[1] mean single iteration, out[2] decoding, out[3] total.  Device-event timed. */
 LIBSDOD_API int libsdod_b200_last_timings(void* context, float out[4]);

@@ -60,8 +60,11 @@ typedef struct sdod_text_encoder sdod_text_encoder;
  * (the 512 byte symbols in the same id order) — what random-init contexts use. */
 SDOD_API int sdod_tokenizer_create(sdod_tokenizer** out, const char* bpe_file);
 SDOD_API void sdod_tokenizer_destroy(sdod_tokenizer* t);
-/* tokens_out[context_len] = [start, ids..., end padding]; context_len = 77 for SD (tokenizer.h:24).  Invalid UTF-8 -> status -1 (invalid argument). */
-SDOD_API int sdod_tokenizer_encode(const sdod_tokenizer* t, const char* utf8, unsigned short* tokens_out, unsigned context_len);
+/* tokens_out[context_len] = [start, ids..., end padding]; context_len = 77 for SD (tokenizer.h:24).  Invalid UTF-8 -> status -1 (invalid argument).
+ * The ids equal the reference's for every prompt on which the reference terminates.  *deviated (may be NULL) is set to 1 for the prompts on which
+ * it does not: its merge pass (tokenizer.cpp:339-356) repeats for ever when the best-ranked pair (a, b) only occurs as "a a b"; there the
+ * textbook BPE merge is applied instead. */
+SDOD_API int sdod_tokenizer_encode(const sdod_tokenizer* t, const char* utf8, unsigned short* tokens_out, unsigned context_len, int* deviated);
 SDOD_API int sdod_tokenizer_vocab_size(const sdod_tokenizer* t);
 
 /* weights == NULL: random-init with `seed`.  Weight names: the HuggingFace CLIPTextModel state_dict keys under "text_model."

@@ -6,6 +6,7 @@
 #include "tokenizer.h"
 
 #include <clocale>
+#include <cstdlib>
 #include <cstring>
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -17,6 +18,7 @@ EXPORT void tok_ref_destroy(void* h) { delete static_cast<libsdod::Tokenizer*>(h
 // returns the number of ids written (== context_len), or -1 when the reference throws (invalid UTF-8)
 EXPORT int tok_ref_tokenize(void* h, const char* utf8, unsigned short* out, unsigned context_len) {
     std::setlocale(LC_ALL, "C.utf8");
+    std::mbtowc(nullptr, nullptr, 0);      // reset mbtowc's internal state: after one invalid sequence it would reject every later prompt
     try {
         auto v = static_cast<libsdod::Tokenizer*>(h)->tokenize(std::string(utf8), context_len);
         std::memcpy(out, v.data(), v.size() * sizeof(unsigned short));

@@ -1306,7 +1306,7 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
         }
     }
     if (!g.pair) {
-        if (ctas <= 148) SDOD_TRY((launch_gemm_cfg<BN, true, false>(stream, g, grid)));
+        if (ctas <= 148 || mp.ln_fuse) SDOD_TRY((launch_gemm_cfg<BN, true, false>(stream, g, grid)));    // (the LayerNorm epilogue stages in the deep ring)
         else SDOD_TRY((launch_gemm_cfg<BN, false, false>(stream, g, grid)));
     }
     count_launch();
@@ -1461,8 +1461,10 @@ static int setup_ln_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, in
     if (!ep.ln_out) return kOk;
     const int bn = out->bn, n_tiles = N / bn;
     const long long ctas = static_cast<long long>((M + kBlockM - 1) / kBlockM) * n_tiles;
+    // single-wave grids only: a multi-wave attempt (one DEEP CTA per SM, B200 r2) faulted and would forfeit the two-CTA overlap anyway
+    const long long max_ctas = 148;
     if (pair || batch != 1 || mp.split > 1 || (mp.tma_epi != 1 && mp.tma_epi != 2) || mp.c_bytes != 4 || ep.act != SDOD_ACT_NONE || N % bn != 0 ||
-        n_tiles > 8 || ctas > 148 || (bn != 128 && bn != 160) || M % kBlockM != 0)
+        n_tiles > 8 || ctas > max_ctas || (bn != 128 && bn != 160) || M % kBlockM != 0)
         return fail(kUnsupported, "gemm: this shape cannot take the fused LayerNorm epilogue");
     if ((reinterpret_cast<uintptr_t>(ep.ln_out) & 15) || (ep.ld_ln * 2) % 16) return fail(kInvalidArgument, "gemm: ln_out must be 16-byte aligned");
     const uint32_t box[3] = {32, 32, 1};

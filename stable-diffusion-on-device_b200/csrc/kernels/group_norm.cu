@@ -76,18 +76,28 @@ SDOD_DEVICE void welford_merge(float& n, float& mean, float& m2, float nb, float
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxChunks = 4;
 
+constexpr int kGnClusterThreads = 512;
+constexpr int kGnMaxCpgSmem = 256;      // per-channel scale / shift staged in shared memory up to this many channels per group
+
+// Round 2: the round-1 form of this kernel spent its time on address arithmetic, not on memory — a 64-bit division per vector to find the
+// channel, per-element weight / bias loads, 16-byte global stores from 256 threads (13.4 us warm for the 21 MB of config C1).  Now: 512
+// threads, the channel walked incrementally, per-channel scale / shift folded with mean / rstd once into shared memory, the normalised slab
+// written back IN PLACE and handed to TMA bulk stores (cp.async.bulk shared -> global, one per chunk), the second cluster barrier moved to the
+// end of the kernel (it only protects the peers' DSMEM reads), and programmatic dependent launch.
 template <typename T>
-__global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
-                                                                      const float* __restrict__ weight, const float* __restrict__ bias,
-                                                                      const float* __restrict__ add_nc, int C, int HW, int G, float eps,
-                                                                      int fuse_silu, int slab_elems) {
+__global__ void __launch_bounds__(kGnClusterThreads) gn_nchw_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                             const float* __restrict__ weight, const float* __restrict__ bias,
+                                                                             const float* __restrict__ add_nc, int C, int HW, int G, float eps,
+                                                                             int fuse_silu, int slab_elems) {
     constexpr int VEC = VecOf<T>::N;
+    constexpr int NT = kGnClusterThreads;
     extern __shared__ __align__(128) uint8_t gn_smem[];
     T* slab = reinterpret_cast<T*>(gn_smem);
     __shared__ __align__(8) uint64_t bars[kGnMaxChunks];
-    __shared__ float red_s[kGnThreads / 32], red_ss[kGnThreads / 32];
+    __shared__ float red_s[NT / 32], red_ss[NT / 32];
     __shared__ float cta_stats[4];   // n, mean, M2
     __shared__ float pivot_sh;
+    __shared__ float sc_sh[kGnMaxCpgSmem], sh_sh[kGnMaxCpgSmem];
 
     const uint32_t cs = cluster_nctarank(), rank = cluster_ctarank();
     const int group = blockIdx.x / cs;
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __
     const int cpg = C / G;
     const long long L = static_cast<long long>(cpg) * HW;
     const long long gbase = (static_cast<long long>(n) * C + static_cast<long long>(g) * cpg) * HW;
-    const long long my_off = static_cast<long long>(rank) * slab_elems;
+    const uint32_t my_off = rank * static_cast<uint32_t>(slab_elems);      // < cpg * HW, which the launcher keeps below 2^31
     const T* src = x + gbase + my_off;
     const uint32_t slab_bytes = static_cast<uint32_t>(slab_elems) * sizeof(T);
     const int nch = slab_bytes >= 16384 ? kGnMaxChunks : 1;
@@ -107,6 +117,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __
         fence_mbar_init();
     }
     __syncthreads();
+    griddep_wait();                       // PDL: x may be the previous kernel's output
     if (threadIdx.x == 0) {
         for (int c = 0; c < nch; ++c) {
             uint32_t off = c * chunk_bytes;
@@ -115,25 +126,24 @@ __global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __
             bulk_load_1d(reinterpret_cast<uint8_t*>(slab) + off, reinterpret_cast<const uint8_t*>(src) + off, bytes, &bars[c]);
         }
     }
+    griddep_launch();
     // ---- pass A (smem): pivot-shifted moments
     mbar_wait(&bars[0], 0);
-    if (threadIdx.x == 0) pivot_sh = to_f<T>(slab[0]) + (addp ? addp[static_cast<int>(my_off / HW)] : 0.f);
+    if (threadIdx.x == 0) pivot_sh = to_f<T>(slab[0]) + (addp ? addp[my_off / static_cast<uint32_t>(HW)] : 0.f);
     __syncthreads();
     const float K = pivot_sh;
     float s = 0.f, ss = 0.f;
     const int nvec = slab_elems / VEC;
     const int chunk_vecs = chunk_bytes / 16;
     int ready = 1;
-    for (int v = threadIdx.x; v < nvec; v += kGnThreads) {
-        int need = v / chunk_vecs;
-        if (need >= nch) need = nch - 1;
-        while (ready <= need) { mbar_wait(&bars[ready], 0); ++ready; }
+    for (int v = threadIdx.x; v < nvec; v += NT) {
+        while (ready < nch && v >= ready * chunk_vecs) { mbar_wait(&bars[ready], 0); ++ready; }
         float e[VEC];
         load_vec<T>(slab + v * VEC, e);
         if (addp) {
-            const long long gi = my_off + static_cast<long long>(v) * VEC;
+            const uint32_t gi = my_off + static_cast<uint32_t>(v) * VEC;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) e[i] += addp[static_cast<int>((gi + i) / HW)];
+            for (int i = 0; i < VEC; ++i) e[i] += addp[(gi + i) / static_cast<uint32_t>(HW)];
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { float d = e[i] - K; s += d; ss += d * d; }
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __
     __syncthreads();
     if (threadIdx.x == 0) {
         float S = 0.f, SS = 0.f;
-        for (int w = 0; w < kGnThreads / 32; ++w) { S += red_s[w]; SS += red_ss[w]; }
+        for (int w = 0; w < NT / 32; ++w) { S += red_s[w]; SS += red_ss[w]; }
         const float cnt = static_cast<float>(slab_elems);
         cta_stats[0] = cnt;
         cta_stats[1] = K + S / cnt;
@@ -158,30 +168,73 @@ __global__ void __launch_bounds__(kGnThreads) gn_nchw_cluster_kernel(const T* __
         if (r == 0) { cn = nb; cmean = mb; cm2 = qb; }
         else welford_merge(cn, cmean, cm2, nb, mb, qb);
     }
-    cluster_sync_all();   // peers have finished reading my cta_stats
     const float mean = cmean;
     const float rstd = rsqrtf(cm2 / static_cast<float>(L) + eps);
 
-    // ---- pass B (smem -> HBM): normalise, affine, SiLU
-    T* dst = y + gbase + my_off;
-    for (int v = threadIdx.x; v < nvec; v += kGnThreads) {
-        float e[VEC];
-        load_vec<T>(slab + v * VEC, e);
-        const long long gi = my_off + static_cast<long long>(v) * VEC;
-        const int ch0 = static_cast<int>(gi / HW);
-        const bool one_ch = (gi - static_cast<long long>(ch0) * HW) + VEC <= HW;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const int ch = one_ch ? ch0 : static_cast<int>((gi + i) / HW);
+    // ---- pass B (in place in smem): y = x * scale[ch] + shift[ch] with scale = rstd * w, shift = b + (add - mean) * scale
+    const bool staged = cpg <= kGnMaxCpgSmem;
+    if (staged) {
+        for (int ch = threadIdx.x; ch < cpg; ch += NT) {
             const int c = g * cpg + ch;
-            float xv = e[i] + (addp ? addp[ch] : 0.f);
-            float o = (xv - mean) * rstd;
-            if (weight) o *= weight[c];
-            if (bias) o += bias[c];
-            e[i] = fuse_silu ? silu_f(o) : o;
+            const float sc = rstd * (weight ? weight[c] : 1.f);
+            sc_sh[ch] = sc;
+            sh_sh[ch] = (bias ? bias[c] : 0.f) + ((addp ? addp[ch] : 0.f) - mean) * sc;
         }
-        store_vec<T>(dst + v * VEC, e);
+        __syncthreads();
     }
+    auto scale_of = [&](int ch) { return staged ? sc_sh[ch] : rstd * (weight ? weight[g * cpg + ch] : 1.f); };
+    auto shift_of = [&](int ch, float sc) { return staged ? sh_sh[ch] : (bias ? bias[g * cpg + ch] : 0.f) + ((addp ? addp[ch] : 0.f) - mean) * sc; };
+    const uint32_t uHW = static_cast<uint32_t>(HW);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(y + gbase + my_off);
+    // chunk by chunk: normalise chunk c in place, then one thread hands it to a TMA bulk store while the others start on chunk c+1
+    for (int c = 0; c < nch; ++c) {
+        const int v_lo = c * chunk_vecs, v_hi = (c == nch - 1) ? nvec : min(nvec, v_lo + chunk_vecs);
+        if (uHW % VEC == 0) {
+            // a vector never straddles channels: walk (channel, vector-in-channel) incrementally, no divisions in the loop
+            const uint32_t vpc = uHW / VEC;
+            const uint32_t v0 = my_off / VEC + v_lo + threadIdx.x;
+            uint32_t ch = v0 / vpc, rem = v0 - ch * vpc;
+            const uint32_t step_ch = NT / vpc, step_rem = NT - step_ch * vpc;
+            for (int v = v_lo + threadIdx.x; v < v_hi; v += NT) {
+                float e[VEC];
+                load_vec<T>(slab + v * VEC, e);
+                const float sc = scale_of(static_cast<int>(ch));
+                const float sh = shift_of(static_cast<int>(ch), sc);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float o = fmaf(e[i], sc, sh);
+                    e[i] = fuse_silu ? silu_f(o) : o;
+                }
+                store_vec<T>(slab + v * VEC, e);
+                ch += step_ch; rem += step_rem;
+                if (rem >= vpc) { rem -= vpc; ++ch; }
+            }
+        } else {
+            for (int v = v_lo + threadIdx.x; v < v_hi; v += NT) {
+                float e[VEC];
+                load_vec<T>(slab + v * VEC, e);
+                const uint32_t gi = my_off + static_cast<uint32_t>(v) * VEC;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const int ch = static_cast<int>((gi + i) / uHW);
+                    const float sc = scale_of(ch);
+                    const float o = fmaf(e[i], sc, shift_of(ch, sc));
+                    e[i] = fuse_silu ? silu_f(o) : o;
+                }
+                store_vec<T>(slab + v * VEC, e);
+            }
+        }
+        fence_proxy_async_smem();         // this thread's generic-proxy writes -> visible to the bulk-copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t off = c * chunk_bytes;
+            const uint32_t bytes = (c == nch - 1) ? slab_bytes - off : chunk_bytes;
+            bulk_store_1d(dst + off, reinterpret_cast<const uint8_t*>(slab) + off, bytes);
+            bulk_commit();
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_read_all();      // shared memory may go away once the stores have read it
+    cluster_sync_all();                   // peers have finished reading my cta_stats (DSMEM) before any CTA of the cluster exits
 }
 
 // Any shape: one CTA per (n,g), exact two-pass statistics straight from global memory.
@@ -759,10 +812,13 @@ static int group_norm_fused_typed(cudaStream_t stream, const TI* xa, int Ca, con
 }
 
 // Geometry of the group-owned kernel: cluster size (rows split) and rows per CTA; cs == 0 -> not eligible.  It needs neither workspace nor
-// co-residency, so large batches qualify too (SDOD_GN_GROUP_MAXMB bounds the input size, default 48 MB = L2-resident tensors only).
+// co-residency, so large batches qualify too.  Measured at UNet batch 32 (B200 r2, profiles/r02_unet_step_b32_per_op_*.txt): serving every
+// in-network GroupNorm with it (no size bound) instead of the stats + apply pair above 48 MB removes the materialised concat / cast launches
+// (374 -> 328 per pass) and takes the pass from 42.40 to 42.08 ms; the CTAs of one image's 32 groups run together, so the 40-byte-per-row
+// slices they read share their DRAM sectors in L2.  SDOD_GN_GROUP_MAXMB bounds the input size for A/B runs (default: unbounded).
 static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int in_dtype, int* rows_per_cta) {
     static const int env = [] { const char* e = std::getenv("SDOD_GN_GROUP"); return e ? std::atoi(e) : 1; }();
-    static const long long max_mb = [] { const char* e = std::getenv("SDOD_GN_GROUP_MAXMB"); return e ? std::atoll(e) : 48LL; }();
+    static const long long max_mb = [] { const char* e = std::getenv("SDOD_GN_GROUP_MAXMB"); return e ? std::atoll(e) : (1LL << 40); }();
     const int C = Ca + Cb;
     if (!env || !fused_env() || G <= 0 || C % G != 0 || N < 1 || HW < 1) return 0;
     if (static_cast<long long>(N) * HW * C * (in_dtype == SDOD_F32 ? 4 : 2) > (max_mb << 20)) return 0;
@@ -888,14 +944,14 @@ static int group_norm_typed(cudaStream_t stream, const T* x, T* y, const float* 
         const bool aligned = (Lb % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
         int cs = 1;
         while (Lb / cs > 49152 && cs < 8) cs *= 2;
-        while (static_cast<long long>(N) * G * cs < 2 * 148 && cs < 8 && Lb / (cs * 2) >= 8192) cs *= 2;
+        while (static_cast<long long>(N) * G * cs < 148 && cs < 8 && Lb / (cs * 2) >= 8192) cs *= 2;     // (C1: 4 beats 8, 9.6 vs 14.2 us, B200 r2)
         {
             static const int env_cs = [] { const char* e = std::getenv("SDOD_GN_CS"); return e ? std::atoi(e) : 0; }();   // experiment knob
             if (env_cs >= 1 && env_cs <= 8 && (env_cs & (env_cs - 1)) == 0 && Lb / env_cs <= 200 * 1024) cs = env_cs;
         }
         while (cs > 1 && ((L % cs) != 0 || ((Lb / cs) % 16) != 0)) cs /= 2;
         const long long slab_bytes = Lb / cs;
-        if (aligned && slab_bytes <= 200 * 1024 && slab_bytes >= 16 && (L / cs) % VEC == 0) {
+        if (aligned && slab_bytes <= 200 * 1024 && slab_bytes >= 16 && (L / cs) % VEC == 0 && L < (1LL << 31)) {
             static bool configured = false;
             if (!configured) {
                 SDOD_TRY(check_cuda(cudaFuncSetAttribute(gn_nchw_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
@@ -904,13 +960,15 @@ static int group_norm_typed(cudaStream_t stream, const T* x, T* y, const float* 
             }
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(static_cast<unsigned>(N) * G * cs);
-            cfg.blockDim = dim3(kGnThreads);
+            cfg.blockDim = dim3(kGnClusterThreads);
             cfg.dynamicSmemBytes = static_cast<size_t>(slab_bytes);
             cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
             int slab_elems = static_cast<int>(L / cs);
             SDOD_TRY(check_cuda(cudaLaunchKernelEx(&cfg, gn_nchw_cluster_kernel<T>, x, y, weight, bias, add_nc, C, HW, G, eps, fuse_silu, slab_elems),
                                 "gn_nchw_cluster_kernel"));

@@ -26,8 +26,10 @@
 #include <vector>
 
 #include "../kernels/glue.h"
+#include "clip_text.h"
 #include "dpm_schedule.h"
 #include "sdod_kernels.h"
+#include "tokenizer.h"
 #include "unet.h"
 #include "vae.h"
 
@@ -88,12 +90,6 @@ private:
     std::chrono::steady_clock::time_point t0_;
 };
 
-unsigned long long fnv1a(const char* s) {
-    unsigned long long h = 1469598103934665603ull;
-    for (; *s; ++s) { h ^= static_cast<unsigned char>(*s); h *= 1099511628211ull; }
-    return h;
-}
-
 class Engine {
 public:
     // Like the reference's Context (context.cpp:24-47) the constructor only records its arguments and cannot fail; everything that can
@@ -126,6 +122,8 @@ public:
             const auto pos = models_dir.find(':');
             if (pos != std::string::npos) wseed = std::strtoull(models_dir.c_str() + pos + 1, nullptr, 10);
             log_.log(LIBSDOD_LOG_INFO, "Using random-init weights (seed %llu)", wseed);
+            tokenizer_ = std::make_unique<sdod::Tokenizer>();             // byte-level vocabulary: there is no vocabulary file to read
+            have_text_ = true;
         } else {
             std::string dir = models_dir.empty() ? "." : models_dir;          // context.cpp:19-22
             if (dir.back() == '/') dir.pop_back();
@@ -136,10 +134,39 @@ public:
             uw = unet_w_.get();
             vw = vae_w_.get();
             log_.log(LIBSDOD_LOG_INFO, "Loaded %zu UNet and %zu decoder tensors from %s", unet_w_->size(), vae_w_->size(), dir.c_str());
+            // prompt path (context.cpp:180-187 tokenizer, :143,170 cond_model): <models_dir>/ctokenizer.txt + text_encoder.sdodw.  Deviation: the
+            // reference fails setup without them; here a models_dir without the text model still serves libsdod_b200_generate (conditioning
+            // supplied by the caller) and libsdod_generate_image reports the missing files when it is called.
+            const std::string tok_path = dir + "/ctokenizer.txt", te_path = dir + "/text_encoder.sdodw";
+            FILE* tf = std::fopen(tok_path.c_str(), "rb");
+            FILE* ef = std::fopen(te_path.c_str(), "rb");
+            if (tf) std::fclose(tf);
+            if (ef) std::fclose(ef);
+            if (tf && ef) {
+                try {
+                    tokenizer_ = std::make_unique<sdod::Tokenizer>(tok_path);
+                } catch (const std::exception& e) {
+                    API_THROW(LIBSDOD_INVALID_ARGUMENT, e.what());
+                }
+                text_w_ = std::make_unique<sdod::WeightStore>();
+                SD(text_w_->load_file(te_path));
+                have_text_ = true;
+                log_.log(LIBSDOD_LOG_INFO, "Loaded the tokenizer (%zu tokens, %zu merges) and %zu text-encoder tensors", tokenizer_->vocab_size(), tokenizer_->merges(), text_w_->size());
+            } else {
+                log_.log(LIBSDOD_LOG_INFO, "No %s in %s: prompts cannot be encoded (libsdod_generate_image will fail; libsdod_b200_generate takes embeddings)",
+                         tf ? "text_encoder.sdodw" : "ctokenizer.txt", dir.c_str());
+            }
         }
         try {
             unet_ = std::make_unique<sdod::UNet>(uw, wseed, S_, 2 * max_images_);
             vae_ = std::make_unique<sdod::VaeDecoder>(vw, wseed + 1, S_, max_images_);
+            if (have_text_) {
+                text_ = std::make_unique<sdod::ClipTextEncoder>(text_w_.get(), wseed + 2, 1);
+                if (tokenizer_->vocab_size() > static_cast<size_t>(sdod::ClipTextEncoder::kVocab))
+                    API_THROW(LIBSDOD_INVALID_ARGUMENT, "ctokenizer.txt defines more tokens than the text encoder's embedding table holds");
+            }
+        } catch (const ApiError&) {
+            throw;
         } catch (const std::exception& e) {
             API_THROW(LIBSDOD_RUNTIME_ERROR, e.what());
         }
@@ -151,8 +178,11 @@ public:
         CU(cudaMallocHost(reinterpret_cast<void**>(&pin_lat_), lat * sizeof(float)));
         CU(cudaMallocHost(reinterpret_cast<void**>(&pin_img_), static_cast<size_t>(max_images_) * image_bytes()));
         // cached empty-prompt conditioning (context.cpp:233-239)
-        uncond_default_.resize(77 * 768);
-        prompt_embedding("", uncond_default_.data());
+        if (have_text_) {
+            CU(cudaMalloc(reinterpret_cast<void**>(&tok_dev_), 77 * sizeof(int)));
+            uncond_default_.resize(77 * 768);
+            prompt_embedding("", uncond_default_.data());
+        }
         ready_ = true;
         log_.log(LIBSDOD_LOG_INFO, "Models and buffers prepared!");
     }
@@ -162,6 +192,8 @@ public:
         if (stream_) cudaStreamSynchronize(stream_);
         unet_.reset();
         vae_.reset();
+        text_.reset();
+        cudaFree(tok_dev_);
         cudaFree(y_prev_); cudaFree(ctx_dev_); cudaFree(temb_); cudaFree(plms_buf_);
         if (peer_exch_) cudaIpcCloseMemHandle(peer_exch_);
         cudaFree(exch_); cudaFree(pair_done_);
@@ -212,12 +244,24 @@ public:
         log_.log(LIBSDOD_LOG_INFO, "Time schedule prepared for %u steps!", steps);
     }
 
-    // Deterministic stand-in for the CLIP text encoder (outside this hot path): N(0,1) [77,768] seeded by the prompt bytes.
-    void prompt_embedding(const char* prompt, float* out_host) {
+    // context.cpp:325-329: tokenize -> cond_model -> p_cond.  77 ids go up, the [77,768] last_hidden_state comes back to the host buffer the
+    // generate loop stages from (a prompt is encoded once per image, not per step).
+    void prompt_embedding(const char* prompt, float* out_host, unsigned short* tokens_out = nullptr) {
+        if (!have_text_) API_THROW(LIBSDOD_RUNTIME_ERROR, "this context has no tokenizer / text encoder (models_dir lacks ctokenizer.txt or text_encoder.sdodw)");
+        std::vector<sdod::Tokenizer::token_type> ids;
+        try {
+            ids = tokenizer_->encode(prompt, 77);
+        } catch (const sdod::TokenizerError& e) {
+            API_THROW(LIBSDOD_INVALID_ARGUMENT, e.what());                  // tokenizer.cpp:77
+        }
+        int tok[77];
+        for (int i = 0; i < 77; ++i) tok[i] = ids[static_cast<size_t>(i)];
+        if (tokens_out) std::memcpy(tokens_out, ids.data(), 77 * sizeof(unsigned short));
         float* d = nullptr;
         CU(cudaMalloc(reinterpret_cast<void**>(&d), 77 * 768 * sizeof(float)));
-        int st = sdod_randn(stream_, d, 77 * 768, fnv1a(prompt) ^ 0x5D0D5D0Dull, 0);
-        cudaError_t e = cudaMemcpyAsync(out_host, d, 77 * 768 * sizeof(float), cudaMemcpyDeviceToHost, stream_);
+        cudaError_t e = cudaMemcpyAsync(tok_dev_, tok, sizeof(tok), cudaMemcpyHostToDevice, stream_);
+        int st = e == cudaSuccess ? text_->forward(stream_, tok_dev_, 1, d, SDOD_F32) : 0;
+        if (e == cudaSuccess && st == 0) e = cudaMemcpyAsync(out_host, d, 77 * 768 * sizeof(float), cudaMemcpyDeviceToHost, stream_);
         cudaStreamSynchronize(stream_);
         cudaFree(d);
         if (st != 0) API_THROW(LIBSDOD_RUNTIME_ERROR, std::string(sdod::last_error()));
@@ -455,7 +499,11 @@ private:
     size_t plms_cap_ = 0;
     int sampler_ = LIBSDOD_B200_SAMPLER_DPM;
     unsigned steps_ = 0;
-    std::unique_ptr<sdod::WeightStore> unet_w_, vae_w_;
+    std::unique_ptr<sdod::WeightStore> unet_w_, vae_w_, text_w_;
+    std::unique_ptr<sdod::Tokenizer> tokenizer_;
+    std::unique_ptr<sdod::ClipTextEncoder> text_;
+    bool have_text_ = false;
+    int* tok_dev_ = nullptr;
     std::unique_ptr<sdod::UNet> unet_;
     std::unique_ptr<sdod::VaeDecoder> vae_;
     cudaStream_t stream_ = nullptr;
@@ -642,6 +690,18 @@ LIBSDOD_API int libsdod_b200_set_seed(void* context, unsigned long long seed) {
     if (int st = retrieve(context, &hnd, __func__)) return st;
     hnd->cptr->set_seed(seed);
     return LIBSDOD_NO_ERROR;
+}
+
+LIBSDOD_API int libsdod_b200_encode_prompt(void* context, const char* prompt, float* embedding_out, unsigned short* tokens_out) {
+    Handle* hnd = nullptr;
+    if (int st = retrieve(context, &hnd, __func__)) return st;
+    Engine* e = hnd->cptr;
+    return guarded(&e->errors(), __func__, [&] {
+        if (!prompt) API_THROW(LIBSDOD_INVALID_ARGUMENT, "prompt is nullptr");
+        if (!embedding_out) API_THROW(LIBSDOD_INVALID_ARGUMENT, "embedding_out is nullptr");
+        e->require_ready();
+        e->prompt_embedding(prompt, embedding_out, tokens_out);
+    });
 }
 
 LIBSDOD_API int libsdod_b200_set_sampler(void* context, int sampler) {

@@ -123,11 +123,13 @@ SDOD_API int sdod_tokenizer_create(sdod_tokenizer** out, const char* bpe_file) {
     return kOk;
 }
 SDOD_API void sdod_tokenizer_destroy(sdod_tokenizer* t) { delete t; }
-SDOD_API int sdod_tokenizer_encode(const sdod_tokenizer* t, const char* utf8, unsigned short* tokens_out, unsigned context_len) {
+SDOD_API int sdod_tokenizer_encode(const sdod_tokenizer* t, const char* utf8, unsigned short* tokens_out, unsigned context_len, int* deviated) {
     if (!t || !utf8 || !tokens_out || context_len < 2) return fail(kInvalidArgument, "tokenizer_encode: bad arguments");
     try {
-        const std::vector<sdod::Tokenizer::token_type> ids = t->tok.encode(utf8, context_len);
+        bool dev = false;
+        const std::vector<sdod::Tokenizer::token_type> ids = t->tok.encode(utf8, context_len, &dev);
         std::memcpy(tokens_out, ids.data(), sizeof(unsigned short) * context_len);
+        if (deviated) *deviated = dev ? 1 : 0;
     } catch (const std::exception& e) {
         return fail(kInvalidArgument, std::string("tokenizer_encode: ") + e.what());
     }

@@ -27,8 +27,9 @@ bool is_blank(uint32_t cp) { return in_ranges(kBlankRanges, cp); }     // iswbla
 bool is_letter(uint32_t cp) { return in_ranges(kAlphaRanges, cp); }    // iswalpha (glibc counts non-ASCII digits as letters)
 bool is_digit(uint32_t cp) { return in_ranges(kDigitRanges, cp); }     // iswdigit: ASCII 0-9 only
 
-// One UTF-8 sequence at s[0..n): its length, or -1 when mbtowc would fail (stray / truncated / overlong sequences, surrogates,
-// code points above U+10FFFF).
+// One UTF-8 sequence at s[0..n): its length, or -1 when glibc's mbtowc fails under a UTF-8 locale — stray / truncated / overlong sequences
+// and surrogates.  Like glibc (probed in this image, 2.39) it still accepts the pre-RFC-3629 forms: lead bytes 0xF5..0xFD, i.e. 4- to 6-byte
+// sequences up to 0x7FFFFFFF; such code points belong to no character class and tokenize as "other" symbols, byte by byte.
 int utf8_decode(const unsigned char* s, size_t n, uint32_t* cp) {
     if (n == 0) return -1;
     const unsigned char c = s[0];
@@ -37,14 +38,16 @@ int utf8_decode(const unsigned char* s, size_t n, uint32_t* cp) {
     uint32_t v, min;
     if (c >= 0xC2 && c <= 0xDF) { len = 2; v = c & 0x1F; min = 0x80; }
     else if (c >= 0xE0 && c <= 0xEF) { len = 3; v = c & 0x0F; min = 0x800; }
-    else if (c >= 0xF0 && c <= 0xF4) { len = 4; v = c & 0x07; min = 0x10000; }
+    else if (c >= 0xF0 && c <= 0xF7) { len = 4; v = c & 0x07; min = 0x10000; }
+    else if (c >= 0xF8 && c <= 0xFB) { len = 5; v = c & 0x03; min = 0x200000; }
+    else if (c >= 0xFC && c <= 0xFD) { len = 6; v = c & 0x01; min = 0x4000000; }
     else return -1;
     if (n < static_cast<size_t>(len)) return -1;
     for (int i = 1; i < len; ++i) {
         if ((s[i] & 0xC0) != 0x80) return -1;
         v = (v << 6) | (s[i] & 0x3F);
     }
-    if (v < min || v > 0x10FFFF || (v >= 0xD800 && v <= 0xDFFF)) return -1;
+    if (v < min || (v >= 0xD800 && v <= 0xDFFF)) return -1;
     *cp = v;
     return len;
 }
@@ -195,17 +198,18 @@ void Tokenizer::finish(unsigned next_token) {
 }
 
 // ------------------------------------------------------------------------------------------------ encode
-std::vector<Tokenizer::token_type> Tokenizer::encode(const std::string& utf8, unsigned context_len) const {
+std::vector<Tokenizer::token_type> Tokenizer::encode(const std::string& utf8, unsigned context_len, bool* deviated) const {
+    if (deviated) *deviated = false;
     std::vector<token_type> out;
     out.reserve(context_len);
     out.push_back(start_);
     const std::string clean = sanitize(utf8);
-    for (const std::string& w : split_words(clean)) bpe(out, byte_symbols(w), context_len - 1);
+    for (const std::string& w : split_words(clean)) bpe(out, byte_symbols(w), context_len - 1, deviated);
     while (out.size() < context_len) out.push_back(end_);
     return out;
 }
 
-void Tokenizer::bpe(std::vector<token_type>& out, const std::string& symbols, unsigned max_len) const {
+void Tokenizer::bpe(std::vector<token_type>& out, const std::string& symbols, unsigned max_len, bool* deviated) const {
     if (out.size() >= max_len) return;
     auto id_of = [&](const std::string& sym) {
         auto it = ids_.find(sym);
@@ -259,6 +263,7 @@ void Tokenizer::bpe(std::vector<token_type>& out, const std::string& symbols, un
         if (next == word) {
             // The pass changed nothing although the pair occurs (e.g. [a, a, b] with pair (a, b)): the reference repeats the same pass for ever.
             // Documented deviation: merge every non-overlapping occurrence left to right (the textbook BPE step) and carry on.
+            if (deviated) *deviated = true;
             next.clear();
             for (size_t i = 0; i < word.size();) {
                 if (i + 1 < word.size() && word[i] == first && word[i + 1] == second) { next.push_back(first + second); i += 2; }

@@ -30,7 +30,9 @@ public:
     Tokenizer();
 
     // [start, ids..., end, end, ...] of exactly context_len entries
-    std::vector<token_type> encode(const std::string& utf8, unsigned context_len = 77) const;
+    // *deviated (optional) is set when a merge pass of the reference would not terminate on this prompt (see bpe()) and the textbook merge was
+    // used instead; for every other prompt the ids equal the reference's.
+    std::vector<token_type> encode(const std::string& utf8, unsigned context_len = 77, bool* deviated = nullptr) const;
 
     token_type start_token() const { return start_; }
     token_type end_token() const { return end_; }
@@ -48,7 +50,7 @@ private:
     token_type start_ = 0, end_ = 0;
 
     void finish(unsigned next_token);
-    void bpe(std::vector<token_type>& out, const std::string& symbols, unsigned max_len) const;    // tokenizer.cpp:279-369
+    void bpe(std::vector<token_type>& out, const std::string& symbols, unsigned max_len, bool* deviated) const;    // tokenizer.cpp:279-369
 };
 
 }  // namespace sdod

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsdod_b200.so")
 
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
-ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 OUT_BF16, OUT_F32, OUT_HEADS, OUT_HEADS_T, OUT_QKV = 0, 1, 2, 3, 4
 
 c_vp, c_int, c_ll, c_f, c_sz, c_u = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint
@@ -65,6 +65,7 @@ _SIGS = {
     "sdod_set_gemm_timeline": (c_int, [c_vp]),
     "sdod_conv3x3_bf16": (c_int, [c_vp, ctypes.POINTER(ConvDesc)]),
     "sdod_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f]),
+    "sdod_attention_causal_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f]),
     "sdod_softmax_rows": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_ll, c_f]),
     "sdod_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),
     "sdod_nhwc_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int]),
@@ -92,7 +93,7 @@ _SIGS = {
     "sdod_vae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
     "sdod_tokenizer_create": (c_int, [ctypes.POINTER(c_vp), ctypes.c_char_p]),
     "sdod_tokenizer_destroy": (None, [c_vp]),
-    "sdod_tokenizer_encode": (c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_ushort), c_u]),
+    "sdod_tokenizer_encode": (c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_ushort), c_u, ctypes.POINTER(c_int)]),
     "sdod_tokenizer_vocab_size": (c_int, [c_vp]),
     "sdod_text_encoder_create": (c_int, [ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_int]),
     "sdod_text_encoder_destroy": (None, [c_vp]),

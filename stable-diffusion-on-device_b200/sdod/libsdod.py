@@ -26,6 +26,7 @@ _SIGS = {
     "libsdod_b200_generate_device": (_i, [_vp, _u, _vp, _vp, _vp, _f, _vp]),
     "libsdod_b200_setup": (_i, [ctypes.POINTER(_vp), ctypes.c_char_p, _u, _u, _u, _u, _i]),
     "libsdod_b200_last_timings": (_i, [_vp, ctypes.POINTER(_f * 4)]),
+    "libsdod_b200_encode_prompt": (_i, [_vp, ctypes.c_char_p, _vp, _vp]),
     "libsdod_b200_pair_export": (_i, [_vp, _vp]),
     "libsdod_b200_pair_connect": (_i, [_vp, _vp, _i]),
     "libsdod_b200_generate_pair": (_i, [_vp, _u, _vp, _vp, _f, _vp, ctypes.POINTER(_u), ctypes.POINTER(_u), _vp]),
@@ -98,6 +99,14 @@ class Context:
         self._ok(api().libsdod_generate_image(self._h, prompt.encode(), guidance_scale, ctypes.byref(buf), ctypes.byref(n)))
         assert n.value == side * side * 3
         return out
+
+    def encode_prompt(self, prompt, return_tokens=False):
+        """The prompt path alone: tokenizer + CLIP text encoder -> [77,768] fp32 (and the 77 token ids)."""
+        emb = np.empty((77, 768), dtype=np.float32)
+        tok = np.empty(77, dtype=np.uint16)
+        raw = prompt if isinstance(prompt, (bytes, bytearray)) else prompt.encode("utf-8")
+        self._ok(api().libsdod_b200_encode_prompt(self._h, bytes(raw), emb.ctypes.data, tok.ctypes.data))
+        return (emb, tok) if return_tokens else emb
 
     def generate(self, cond, uncond=None, latents=None, guidance_scale=7.5, return_latents=False):
         cond = np.ascontiguousarray(cond, dtype=np.float32)

@@ -459,6 +459,17 @@ def attention(qh: torch.Tensor, kh: torch.Tensor, vt: torch.Tensor, batch: int, 
     return out
 
 
+def attention_causal(qh, kh, vt, batch, heads, head_dim, n_kv, scale):
+    """attention() with a causal mask (key k visible to query q iff k <= q): the CLIP text encoder's self-attention."""
+    _need_cuda(qh, kh, vt)
+    qh, kh, vt = qh.contiguous(), kh.contiguous(), vt.contiguous()
+    nq, dpad = qh.shape[1], qh.shape[2]
+    out = torch.empty(batch, nq, heads * head_dim, dtype=torch.bfloat16, device=qh.device)
+    C.check(C.lib().sdod_attention_causal_bf16(_stream(), _p(qh), _p(kh), _p(vt), _p(out), batch, heads, nq, n_kv, head_dim, dpad,
+                                               vt.shape[2], scale), "sdod_attention_causal_bf16")
+    return out
+
+
 @attention.register_fake
 def _(qh, kh, vt, batch, heads, head_dim, n_kv, scale):
     return qh.new_empty(batch, qh.shape[1], heads * head_dim)

@@ -21,17 +21,22 @@ class Tokenizer:
     def vocab_size(self):
         return int(C.lib().sdod_tokenizer_vocab_size(self._h))
 
-    def encode(self, prompt, context_len=77):
-        """-> list of context_len token ids: [start, ..., end padding] (tokenizer.cpp:258-276).  Invalid UTF-8 raises SdodError."""
+    def encode(self, prompt, context_len=77, return_deviated=False):
+        """-> list of context_len token ids: [start, ..., end padding] (tokenizer.cpp:258-276).  Invalid UTF-8 raises SdodError.
+        return_deviated: also return whether the reference's merge loop would not have terminated on this prompt (see sdod_model.h)."""
         raw = prompt if isinstance(prompt, (bytes, bytearray)) else prompt.encode("utf-8")
         out = (ctypes.c_ushort * context_len)()
-        C.check(C.lib().sdod_tokenizer_encode(self._h, bytes(raw), out, context_len), "sdod_tokenizer_encode")
-        return list(out)
+        dev = ctypes.c_int(0)
+        C.check(C.lib().sdod_tokenizer_encode(self._h, bytes(raw), out, context_len, ctypes.byref(dev)), "sdod_tokenizer_encode")
+        return (list(out), bool(dev.value)) if return_deviated else list(out)
 
     def __del__(self):
-        if getattr(self, "_h", None) and C is not None:
-            C.lib().sdod_tokenizer_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                C.lib().sdod_tokenizer_destroy(self._h)
+                self._h = None
+        except Exception:          # interpreter shutdown: the module globals may already be gone
+            pass
 
 
 class TextEncoder:
@@ -55,6 +60,9 @@ class TextEncoder:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None) and C is not None:
-            C.lib().sdod_text_encoder_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                C.lib().sdod_text_encoder_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -176,3 +176,47 @@ def test_reference_simple_app_runs_unmodified(models_dir, tmp_path):
     r = subprocess.run([app], cwd=str(tmp_path), env=dict(os.environ, LIBSDOD_B200_MODELS_DIR=str(tmp_path / "missing")),
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Initialization error" in r.stdout and "cannot open" in r.stdout
+
+
+def test_models_dir_without_text_model_reports_it(models_dir):
+    """A models_dir holding only the UNet / decoder still serves libsdod_b200_generate; the prompt entry point fails loudly
+    (round 1 silently returned an image unrelated to the prompt)."""
+    d, _, _ = models_dir
+    assert not os.path.exists(os.path.join(d, "text_encoder.sdodw"))
+    with A.Context(d, latent_spatial=16, steps=2, max_images=1, device=0) as ctx:
+        with pytest.raises(A.LibsdodError) as ei:
+            ctx.generate_image("a cat", 7.5)
+        assert ei.value.status == A.RUNTIME_ERROR and "text encoder" in str(ei.value)
+
+
+def test_prompt_path_from_files_vs_reference_tokenizer_and_clip(models_dir, golden_dir):
+    """Row f1 end to end through the C API: <models_dir>/ctokenizer.txt (the reference's file format) + text_encoder.sdodw (CLIPTextModel keys) ->
+    token ids equal to the ones the reference's compiled tokenizer produced (golden), embedding within the bf16 per-op tolerance of HuggingFace's
+    CLIPTextModel on the same weights, and libsdod_generate_image == encode -> libsdod_b200_generate."""
+    import json
+    import shutil
+    from sdod import checkpoint as K
+    from _clip_ref import clip_text_model, rel_err
+    d, _, _ = models_dir
+    shutil.copy(os.path.join(golden_dir, "ctokenizer_synth.txt"), os.path.join(d, "ctokenizer.txt"))
+    m = clip_text_model(5)
+    K.convert({"cond_stage_model.transformer." + k: v for k, v in m.state_dict().items()}, d)
+    try:
+        prompt = "a photograph of an astronaut riding a horse on mars, highly detailed, 8k"
+        gold = {bytes.fromhex(c["utf8_hex"]): c["ids"] for c in json.load(open(os.path.join(golden_dir, "tokenizer_golden.json")))["cases"]}
+        with A.Context(d, latent_spatial=16, steps=4, max_images=1, device=0) as ctx:
+            emb, tok = ctx.encode_prompt(prompt, return_tokens=True)
+            assert list(tok) == gold[prompt.encode()]
+            with torch.no_grad():
+                want = m(input_ids=torch.from_numpy(tok.astype(np.int64))[None]).last_hidden_state[0]
+            e = rel_err(torch.from_numpy(emb), want)
+            print("prompt embedding vs CLIPTextModel: max rel err %.3e" % e)
+            assert e < 2e-2
+            ctx.set_seed(5)
+            img = ctx.generate_image(prompt, 7.5)
+            ctx.set_seed(5)
+            img2 = ctx.generate(emb[None], ctx.encode_prompt("")[None], None, 7.5)[0]
+            assert np.array_equal(img, img2) and img.std() > 1
+    finally:
+        os.remove(os.path.join(d, "ctokenizer.txt"))
+        os.remove(os.path.join(d, "text_encoder.sdodw"))

@@ -109,11 +109,23 @@ def test_gn_single_launch_two_sources(N, HW, Ca, Cb, dtype):
 
 
 def test_gn_two_kernel_path_for_large_tensors():
+    """Odd channels per group (288 / 32 = 9) on a tensor beyond the cooperative kernel's L2 bound -> the stats + apply kernel pair."""
     torch.manual_seed(3)
-    x = (torch.randn(16, 4096, 320) * 1.5 + 0.3).to(DEV)          # 84 MB fp32: not L2-resident -> stats + apply kernels
-    assert C.lib().sdod_group_norm_nhwc2_supported(16, 320, 0, 4096, 32, C.F32) == 0
+    x = (torch.randn(16, 4096, 288) * 1.5 + 0.3).to(DEV)          # 75 MB fp32
+    assert C.lib().sdod_group_norm_nhwc2_supported(16, 288, 0, 4096, 32, C.F32) == 0
+    w, b = torch.randn(288, device=DEV), torch.randn(288, device=DEV)
+    want = F.silu(F.group_norm(x.permute(0, 2, 1).reshape(16, 288, 64, 64), 32, w, b, 1e-5)).reshape(16, 288, 4096).permute(0, 2, 1)
+    got = ops.group_norm_nhwc(x, 32, w, b, 1e-5, True, None, torch.bfloat16)
+    assert rel_err(got, want) < TOL_BF16
+
+
+def test_gn_group_owned_kernel_on_a_tensor_larger_than_l2():
+    """UNet batch 32, level 0: 168 MB fp32 through the single-launch group-owned kernel (no size bound since round 2)."""
+    torch.manual_seed(4)
+    x = (torch.randn(32, 4096, 320) * 1.5 + 0.3).to(DEV)
+    assert C.lib().sdod_group_norm_nhwc2_supported(32, 320, 0, 4096, 32, C.F32) == 1
     w, b = torch.randn(320, device=DEV), torch.randn(320, device=DEV)
-    want = F.silu(F.group_norm(x.permute(0, 2, 1).reshape(16, 320, 64, 64), 32, w, b, 1e-5)).reshape(16, 320, 4096).permute(0, 2, 1)
+    want = F.silu(F.group_norm(x.permute(0, 2, 1).reshape(32, 320, 64, 64), 32, w, b, 1e-5)).reshape(32, 320, 4096).permute(0, 2, 1)
     got = ops.group_norm_nhwc(x, 32, w, b, 1e-5, True, None, torch.bfloat16)
     assert rel_err(got, want) < TOL_BF16
 
