@@ -185,55 +185,55 @@ __global__ void __launch_bounds__(kGnClusterThreads) gn_nchw_cluster_kernel(cons
     auto scale_of = [&](int ch) { return staged ? sc_sh[ch] : rstd * (weight ? weight[g * cpg + ch] : 1.f); };
     auto shift_of = [&](int ch, float sc) { return staged ? sh_sh[ch] : (bias ? bias[g * cpg + ch] : 0.f) + ((addp ? addp[ch] : 0.f) - mean) * sc; };
     const uint32_t uHW = static_cast<uint32_t>(HW);
-    uint8_t* dst = reinterpret_cast<uint8_t*>(y + gbase + my_off);
-    // chunk by chunk: normalise chunk c in place, then one thread hands it to a TMA bulk store while the others start on chunk c+1
-    for (int c = 0; c < nch; ++c) {
-        const int v_lo = c * chunk_vecs, v_hi = (c == nch - 1) ? nvec : min(nvec, v_lo + chunk_vecs);
-        if (uHW % VEC == 0) {
-            // a vector never straddles channels: walk (channel, vector-in-channel) incrementally, no divisions in the loop
-            const uint32_t vpc = uHW / VEC;
-            const uint32_t v0 = my_off / VEC + v_lo + threadIdx.x;
-            uint32_t ch = v0 / vpc, rem = v0 - ch * vpc;
-            const uint32_t step_ch = NT / vpc, step_rem = NT - step_ch * vpc;
-            for (int v = v_lo + threadIdx.x; v < v_hi; v += NT) {
-                float e[VEC];
-                load_vec<T>(slab + v * VEC, e);
-                const float sc = scale_of(static_cast<int>(ch));
-                const float sh = shift_of(static_cast<int>(ch), sc);
+    if (uHW % VEC == 0) {
+        // a vector never straddles channels: walk (channel, vector-in-channel) incrementally, no divisions in the loop
+        const uint32_t vpc = uHW / VEC;
+        const uint32_t v0 = my_off / VEC + threadIdx.x;
+        uint32_t ch = v0 / vpc, rem = v0 - ch * vpc;
+        const uint32_t step_ch = NT / vpc, step_rem = NT - step_ch * vpc;
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            float e[VEC];
+            load_vec<T>(slab + v * VEC, e);
+            const float sc = scale_of(static_cast<int>(ch));
+            const float sh = shift_of(static_cast<int>(ch), sc);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float o = fmaf(e[i], sc, sh);
-                    e[i] = fuse_silu ? silu_f(o) : o;
-                }
-                store_vec<T>(slab + v * VEC, e);
-                ch += step_ch; rem += step_rem;
-                if (rem >= vpc) { rem -= vpc; ++ch; }
+            for (int i = 0; i < VEC; ++i) {
+                const float o = fmaf(e[i], sc, sh);
+                e[i] = fuse_silu ? silu_f(o) : o;
             }
-        } else {
-            for (int v = v_lo + threadIdx.x; v < v_hi; v += NT) {
-                float e[VEC];
-                load_vec<T>(slab + v * VEC, e);
-                const uint32_t gi = my_off + static_cast<uint32_t>(v) * VEC;
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const int ch = static_cast<int>((gi + i) / uHW);
-                    const float sc = scale_of(ch);
-                    const float o = fmaf(e[i], sc, shift_of(ch, sc));
-                    e[i] = fuse_silu ? silu_f(o) : o;
-                }
-                store_vec<T>(slab + v * VEC, e);
-            }
+            store_vec<T>(slab + v * VEC, e);
+            ch += step_ch; rem += step_rem;
+            if (rem >= vpc) { rem -= vpc; ++ch; }
         }
-        fence_proxy_async_smem();         // this thread's generic-proxy writes -> visible to the bulk-copy engine
-        __syncthreads();
-        if (threadIdx.x == 0) {
+    } else {
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            float e[VEC];
+            load_vec<T>(slab + v * VEC, e);
+            const uint32_t gi = my_off + static_cast<uint32_t>(v) * VEC;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int ch = static_cast<int>((gi + i) / uHW);
+                const float sc = scale_of(ch);
+                const float o = fmaf(e[i], sc, shift_of(ch, sc));
+                e[i] = fuse_silu ? silu_f(o) : o;
+            }
+            store_vec<T>(slab + v * VEC, e);
+        }
+    }
+    // ---- smem -> HBM: TMA bulk stores, one per chunk, issued together (handing each chunk over as soon as it is normalised — a barrier and a
+    // bulk group per chunk — measured slower: 11.2 vs 9.6 us on config C1)
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(y + gbase + my_off);
+        for (int c = 0; c < nch; ++c) {
             const uint32_t off = c * chunk_bytes;
             const uint32_t bytes = (c == nch - 1) ? slab_bytes - off : chunk_bytes;
             bulk_store_1d(dst + off, reinterpret_cast<const uint8_t*>(slab) + off, bytes);
-            bulk_commit();
         }
+        bulk_commit();
+        bulk_wait_read_all();             // shared memory may go away once the stores have read it
     }
-    if (threadIdx.x == 0) bulk_wait_read_all();      // shared memory may go away once the stores have read it
     cluster_sync_all();                   // peers have finished reading my cta_stats (DSMEM) before any CTA of the cluster exits
 }
 

@@ -25,7 +25,7 @@ def _free_port():
 def test_cfg_split_pair_matches_oracle(tmp_path):
     out = tmp_path / "pair.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "pair_check.py"), "--S", "16", "--n", "3", "--out", str(out)]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "pair_check.py"), "--S", "16", "--images", "3", "--out", str(out)]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.loads(out.read_text())

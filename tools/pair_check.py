@@ -1,5 +1,5 @@
 """CFG split over a GPU pair through the libsdod C API (libsdod_b200_pair_export / _connect / _generate_pair), launched as
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tools/pair_check.py [--S 16] [--n 2] [--perf]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tools/pair_check.py [--S 16] [--images 2] [--perf]
 Each rank owns one GPU and one context; rank 0 = conditional half, rank 1 = unconditional half.  Checks (rank 0 prints one JSON line):
   * both ranks end with bit-identical sampler state (the update is replicated, not exchanged),
   * final latents / images vs the ORACLE generate loop (oracle/pipeline.py) on the same weights, latents and prompts,
@@ -32,7 +32,7 @@ def psnr_u8(a, b):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--S", type=int, default=16)
-    ap.add_argument("--n", type=int, default=2)
+    ap.add_argument("--images", dest="n", type=int, default=2)   # (not "--n": torchrun's argparse rejects it as an ambiguous abbreviation of its own options)
     ap.add_argument("--perf", action="store_true")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
