@@ -131,6 +131,12 @@ LIBSDOD_API int libsdod_b200_generate_pair(void* context, unsigned int n_images,
  * (a models_dir without ctokenizer.txt + text_encoder.sdodw), LIBSDOD_INVALID_ARGUMENT on invalid UTF-8 (tokenizer.cpp:77). */
 LIBSDOD_API int libsdod_b200_encode_prompt(void* context, const char* prompt, float* embedding_out, unsigned short* tokens_out);
 
+/* libsdod_generate_image for n prompts in one call (n <= max_images): the prompts go through the tokenizer and ONE text-encoder batch, every image's
+ * unconditional half is the cached empty prompt (context.cpp:233-239), the latents are drawn from the context's generator, and images_out
+ * ([n_images, 8S, 8S, 3] uint8, HOST) receives the images.  Same status codes as libsdod_generate_image. */
+LIBSDOD_API int libsdod_b200_generate_images(void* context, unsigned int n_images, const char* const* prompts, float guidance_scale,
+                                             unsigned char* images_out);
+
 /* Milliseconds of the last generate call as the reference logs them (context.cpp:309-314,331,381,398,402):
  * out[0] conditioning, out[1] mean single iteration, out[2] decoding, out[3] total.  Device-event timed. */
 LIBSDOD_API int libsdod_b200_last_timings(void* context, float out[4]);

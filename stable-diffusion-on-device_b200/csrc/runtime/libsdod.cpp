@@ -161,7 +161,7 @@ public:
             unet_ = std::make_unique<sdod::UNet>(uw, wseed, S_, 2 * max_images_);
             vae_ = std::make_unique<sdod::VaeDecoder>(vw, wseed + 1, S_, max_images_);
             if (have_text_) {
-                text_ = std::make_unique<sdod::ClipTextEncoder>(text_w_.get(), wseed + 2, 1);
+                text_ = std::make_unique<sdod::ClipTextEncoder>(text_w_.get(), wseed + 2, max_images_);
                 if (tokenizer_->vocab_size() > static_cast<size_t>(sdod::ClipTextEncoder::kVocab))
                     API_THROW(LIBSDOD_INVALID_ARGUMENT, "ctokenizer.txt defines more tokens than the text encoder's embedding table holds");
             }
@@ -179,7 +179,7 @@ public:
         CU(cudaMallocHost(reinterpret_cast<void**>(&pin_img_), static_cast<size_t>(max_images_) * image_bytes()));
         // cached empty-prompt conditioning (context.cpp:233-239)
         if (have_text_) {
-            CU(cudaMalloc(reinterpret_cast<void**>(&tok_dev_), 77 * sizeof(int)));
+            CU(cudaMalloc(reinterpret_cast<void**>(&tok_dev_), static_cast<size_t>(max_images_) * 77 * sizeof(int)));
             uncond_default_.resize(77 * 768);
             prompt_embedding("", uncond_default_.data());
         }
@@ -247,25 +247,46 @@ public:
     // context.cpp:325-329: tokenize -> cond_model -> p_cond.  77 ids go up, the [77,768] last_hidden_state comes back to the host buffer the
     // generate loop stages from (a prompt is encoded once per image, not per step).
     void prompt_embedding(const char* prompt, float* out_host, unsigned short* tokens_out = nullptr) {
+        prompt_embeddings(1, &prompt, out_host, tokens_out);
+    }
+    // n prompts as ONE text-encoder batch: out_host [n, 77, 768] fp32
+    void prompt_embeddings(unsigned n, const char* const* prompts, float* out_host, unsigned short* tokens_out = nullptr) {
         if (!have_text_) API_THROW(LIBSDOD_RUNTIME_ERROR, "this context has no tokenizer / text encoder (models_dir lacks ctokenizer.txt or text_encoder.sdodw)");
-        std::vector<sdod::Tokenizer::token_type> ids;
-        try {
-            ids = tokenizer_->encode(prompt, 77);
-        } catch (const sdod::TokenizerError& e) {
-            API_THROW(LIBSDOD_INVALID_ARGUMENT, e.what());                  // tokenizer.cpp:77
+        if (n < 1 || static_cast<int>(n) > max_images_) API_THROW(LIBSDOD_INVALID_ARGUMENT, "number of prompts out of range (max_images = " + std::to_string(max_images_) + ")");
+        std::vector<int> tok(static_cast<size_t>(n) * 77);
+        for (unsigned i = 0; i < n; ++i) {
+            if (!prompts[i]) API_THROW(LIBSDOD_INVALID_ARGUMENT, "prompt is nullptr");
+            std::vector<sdod::Tokenizer::token_type> ids;
+            try {
+                ids = tokenizer_->encode(prompts[i], 77);
+            } catch (const sdod::TokenizerError& e) {
+                API_THROW(LIBSDOD_INVALID_ARGUMENT, e.what());              // tokenizer.cpp:77
+            }
+            for (int j = 0; j < 77; ++j) tok[i * 77 + static_cast<size_t>(j)] = ids[static_cast<size_t>(j)];
+            if (tokens_out) std::memcpy(tokens_out + i * 77, ids.data(), 77 * sizeof(unsigned short));
         }
-        int tok[77];
-        for (int i = 0; i < 77; ++i) tok[i] = ids[static_cast<size_t>(i)];
-        if (tokens_out) std::memcpy(tokens_out, ids.data(), 77 * sizeof(unsigned short));
+        const size_t count = static_cast<size_t>(n) * 77 * 768;
         float* d = nullptr;
-        CU(cudaMalloc(reinterpret_cast<void**>(&d), 77 * 768 * sizeof(float)));
-        cudaError_t e = cudaMemcpyAsync(tok_dev_, tok, sizeof(tok), cudaMemcpyHostToDevice, stream_);
-        int st = e == cudaSuccess ? text_->forward(stream_, tok_dev_, 1, d, SDOD_F32) : 0;
-        if (e == cudaSuccess && st == 0) e = cudaMemcpyAsync(out_host, d, 77 * 768 * sizeof(float), cudaMemcpyDeviceToHost, stream_);
+        CU(cudaMalloc(reinterpret_cast<void**>(&d), count * sizeof(float)));
+        cudaError_t e = cudaMemcpyAsync(tok_dev_, tok.data(), tok.size() * sizeof(int), cudaMemcpyHostToDevice, stream_);
+        int st = e == cudaSuccess ? text_->forward(stream_, tok_dev_, static_cast<int>(n), d, SDOD_F32) : 0;
+        if (e == cudaSuccess && st == 0) e = cudaMemcpyAsync(out_host, d, count * sizeof(float), cudaMemcpyDeviceToHost, stream_);
         cudaStreamSynchronize(stream_);
         cudaFree(d);
         if (st != 0) API_THROW(LIBSDOD_RUNTIME_ERROR, std::string(sdod::last_error()));
         CU(e);
+    }
+
+    // context.cpp:292-403 for n prompts in one call: one text-encoder batch, the cached empty prompt as every image's unconditional half
+    void generate_prompts(unsigned n, const char* const* prompts, float guidance, unsigned char* images_out) {
+        require_ready();
+        if (!prompts) API_THROW(LIBSDOD_INVALID_ARGUMENT, "prompts is nullptr");
+        if (device_ >= 0) CU(cudaSetDevice(device_));
+        std::vector<float> cond(static_cast<size_t>(n ? n : 1) * 77 * 768), uncond;
+        prompt_embeddings(n, prompts, cond.data());
+        uncond.reserve(cond.size());
+        for (unsigned i = 0; i < n; ++i) uncond.insert(uncond.end(), uncond_default_.begin(), uncond_default_.end());
+        generate(n, cond.data(), uncond.data(), nullptr, guidance, images_out, nullptr);
     }
 
     void generate_prompt(const char* prompt, float guidance, unsigned char* out) {
@@ -701,6 +722,16 @@ LIBSDOD_API int libsdod_b200_encode_prompt(void* context, const char* prompt, fl
         if (!embedding_out) API_THROW(LIBSDOD_INVALID_ARGUMENT, "embedding_out is nullptr");
         e->require_ready();
         e->prompt_embedding(prompt, embedding_out, tokens_out);
+    });
+}
+
+LIBSDOD_API int libsdod_b200_generate_images(void* context, unsigned int n_images, const char* const* prompts, float guidance_scale, unsigned char* images_out) {
+    Handle* hnd = nullptr;
+    if (int st = retrieve(context, &hnd, __func__)) return st;
+    Engine* e = hnd->cptr;
+    return guarded(&e->errors(), __func__, [&] {
+        if (!images_out) API_THROW(LIBSDOD_INVALID_ARGUMENT, "images_out is nullptr");
+        e->generate_prompts(n_images, prompts, guidance_scale, images_out);
     });
 }
 

@@ -27,6 +27,7 @@ _SIGS = {
     "libsdod_b200_setup": (_i, [ctypes.POINTER(_vp), ctypes.c_char_p, _u, _u, _u, _u, _i]),
     "libsdod_b200_last_timings": (_i, [_vp, ctypes.POINTER(_f * 4)]),
     "libsdod_b200_encode_prompt": (_i, [_vp, ctypes.c_char_p, _vp, _vp]),
+    "libsdod_b200_generate_images": (_i, [_vp, _u, ctypes.POINTER(ctypes.c_char_p), _f, _vp]),
     "libsdod_b200_pair_export": (_i, [_vp, _vp]),
     "libsdod_b200_pair_connect": (_i, [_vp, _vp, _i]),
     "libsdod_b200_generate_pair": (_i, [_vp, _u, _vp, _vp, _f, _vp, ctypes.POINTER(_u), ctypes.POINTER(_u), _vp]),
@@ -107,6 +108,15 @@ class Context:
         raw = prompt if isinstance(prompt, (bytes, bytearray)) else prompt.encode("utf-8")
         self._ok(api().libsdod_b200_encode_prompt(self._h, bytes(raw), emb.ctypes.data, tok.ctypes.data))
         return (emb, tok) if return_tokens else emb
+
+    def generate_images(self, prompts, guidance_scale=7.5):
+        """libsdod_generate_image for a list of prompts in one call -> uint8 [n, 8S, 8S, 3]."""
+        n = len(prompts)
+        arr = (ctypes.c_char_p * n)(*[p if isinstance(p, (bytes, bytearray)) else p.encode("utf-8") for p in prompts])
+        side = self.latent_spatial * 8
+        imgs = np.empty((n, side, side, 3), dtype=np.uint8)
+        self._ok(api().libsdod_b200_generate_images(self._h, n, arr, guidance_scale, imgs.ctypes.data))
+        return imgs
 
     def generate(self, cond, uncond=None, latents=None, guidance_scale=7.5, return_latents=False):
         cond = np.ascontiguousarray(cond, dtype=np.float32)

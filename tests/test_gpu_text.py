@@ -98,5 +98,23 @@ def test_random_init_context_encodes_prompts():
         imgs = ctx.generate(e1[None], ctx.encode_prompt("")[None], None, 7.5)
         assert np.array_equal(img, imgs[0])                           # generate_image == encode(prompt) / cached encode("") -> generate
         with pytest.raises(A.LibsdodError) as ei:
+            ctx.generate_images(["a cat", "a dog"], 7.5)              # max_images = 1
+        assert ei.value.status == A.INVALID_ARGUMENT
+        with pytest.raises(A.LibsdodError) as ei:
             ctx.encode_prompt(b"bad \xff utf8")
         assert ei.value.status == A.INVALID_ARGUMENT and "Invalid UTF-8" in str(ei.value)
+
+
+def test_generate_images_batches_the_prompts():
+    """libsdod_b200_generate_images: n prompts -> one text-encoder batch -> one generate call; equals the per-prompt path image by image."""
+    prompts = ["a cat", "a photograph of an astronaut riding a horse", ""]
+    with A.Context("random-init:4", latent_spatial=16, steps=3, max_images=3, device=0) as ctx:
+        embs = np.stack([ctx.encode_prompt(p) for p in prompts])
+        ctx.set_seed(21)
+        imgs = ctx.generate_images(prompts, 7.5)
+        ctx.set_seed(21)
+        want = ctx.generate(embs, np.stack([ctx.encode_prompt("")] * 3), None, 7.5)
+        # (a batch of 3 may pick other split-K factors than three batches of 1: equal up to fp32 summation order)
+        mse = ((imgs.astype(np.float64) - want.astype(np.float64)) ** 2).mean()
+        assert imgs.shape == (3, 128, 128, 3) and 10 * np.log10(255.0 ** 2 / max(mse, 1e-12)) >= 40.0
+        assert np.abs(imgs[0].astype(np.int32) - imgs[1].astype(np.int32)).mean() > 1.0
