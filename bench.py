@@ -264,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": pk["source"] + " (sustained: the launches are timed inside a long step)",
                          "algorithmic_gflop_per_launch": gemm_flop / gemm_n * 1e-9, "avg_launch_us": 1e3 * gemm_ms / gemm_n,
                          "share_of_unet_pass": gemm_ms / all_ms, "traffic": traffic_from_profiles(),
-                         "traffic_note": "mean dram__bytes_read+write per gemm_tcgen05 launch, ncu capture of the same pass (profiles/r01_gemm_traffic.json)"},
+                         "traffic_note": "mean dram__bytes_read+write per gemm_tcgen05 launch, ncu capture of the same pass (profiles/r02_gemm_traffic.json)"},
             "step_roofline": {"bound": "tensor", "kernel": "whole UNet denoising step, batch 2 (one CUDA-graph replay of %d kernels)" % unet_launches,
                               "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                               "frac_of_burst_peak": achieved / pk["bf16_tflops"], "algorithmic_tflop_per_launch": UNET_STEP_TFLOP},
@@ -393,7 +393,7 @@ def op_flops(name, batch):
 
 def traffic_from_profiles():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if absent)."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     try:
         return json.load(open(path))["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):

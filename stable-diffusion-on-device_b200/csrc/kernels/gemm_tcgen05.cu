@@ -1463,8 +1463,10 @@ static int setup_ln_epilogue(GemmLaunch* out, const sdod_epilogue& ep, int M, in
     const long long ctas = static_cast<long long>((M + kBlockM - 1) / kBlockM) * n_tiles;
     // single-wave grids only: a multi-wave attempt (one DEEP CTA per SM, B200 r2) faulted and would forfeit the two-CTA overlap anyway
     const long long max_ctas = 148;
+    // few-CTA layers (16x16 / 8x8 levels at batch 2) are better served by split-K + a LayerNorm launch than by a fused epilogue that rules split-K out
+    static const long long min_ctas = [] { const char* e = std::getenv("SDOD_LN_FUSE_MINCTAS"); return e ? std::atoll(e) : 0LL; }();
     if (pair || batch != 1 || mp.split > 1 || (mp.tma_epi != 1 && mp.tma_epi != 2) || mp.c_bytes != 4 || ep.act != SDOD_ACT_NONE || N % bn != 0 ||
-        n_tiles > 8 || ctas > max_ctas || (bn != 128 && bn != 160) || M % kBlockM != 0)
+        n_tiles > 8 || ctas > max_ctas || ctas < min_ctas || (bn != 128 && bn != 160) || M % kBlockM != 0)
         return fail(kUnsupported, "gemm: this shape cannot take the fused LayerNorm epilogue");
     if ((reinterpret_cast<uintptr_t>(ep.ln_out) & 15) || (ep.ld_ln * 2) % 16) return fail(kInvalidArgument, "gemm: ln_out must be 16-byte aligned");
     const uint32_t box[3] = {32, 32, 1};

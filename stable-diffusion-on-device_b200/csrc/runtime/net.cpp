@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 
 #include "../kernels/glue.h"
@@ -32,30 +33,41 @@ int WeightStore::set(const std::string& name, const float* host, const std::vect
 }
 
 int WeightStore::load_file(const std::string& path) {
-    FILE* f = std::fopen(path.c_str(), "rb");
+    struct Closer { void operator()(FILE* f) const { if (f) std::fclose(f); } };
+    std::unique_ptr<FILE, Closer> f(std::fopen(path.c_str(), "rb"));
     if (!f) return fail(kInvalidArgument, "weights: cannot open " + path);
-    auto bail = [&](const std::string& m) { std::fclose(f); return fail(kInvalidArgument, "weights: " + m + " in " + path); };
+    auto bail = [&](const std::string& m) { return fail(kInvalidArgument, "weights: " + m + " in " + path); };
+    std::fseek(f.get(), 0, SEEK_END);
+    const long long file_bytes = std::ftell(f.get());
+    std::fseek(f.get(), 0, SEEK_SET);
     char magic[8];
     uint32_t count = 0;
-    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "SDODW001", 8) != 0) return bail("bad magic");
-    if (std::fread(&count, 4, 1, f) != 1) return bail("truncated header");
+    if (std::fread(magic, 1, 8, f.get()) != 8 || std::memcmp(magic, "SDODW001", 8) != 0) return bail("bad magic");
+    if (std::fread(&count, 4, 1, f.get()) != 1) return bail("truncated header");
     std::vector<float> buf;
-    for (uint32_t i = 0; i < count; ++i) {
-        uint32_t nl = 0, nd = 0;
-        if (std::fread(&nl, 4, 1, f) != 1 || nl == 0 || nl > 4096) return bail("bad name length");
-        std::string name(nl, '\0');
-        if (std::fread(&name[0], 1, nl, f) != nl) return bail("truncated name");
-        if (std::fread(&nd, 4, 1, f) != 1 || nd > 8) return bail("bad rank");
-        std::vector<long long> shape(nd);
-        if (nd && std::fread(shape.data(), 8, nd, f) != nd) return bail("truncated shape");
-        size_t n = 1;
-        for (long long s : shape) n *= static_cast<size_t>(s);
-        buf.resize(n);
-        if (std::fread(buf.data(), 4, n, f) != n) return bail("truncated data for " + name);
-        int st = set(name, buf.data(), shape);
-        if (st != kOk) { std::fclose(f); return st; }
+    try {
+        for (uint32_t i = 0; i < count; ++i) {
+            uint32_t nl = 0, nd = 0;
+            if (std::fread(&nl, 4, 1, f.get()) != 1 || nl == 0 || nl > 4096) return bail("bad name length");
+            std::string name(nl, '\0');
+            if (std::fread(&name[0], 1, nl, f.get()) != nl) return bail("truncated name");
+            if (std::fread(&nd, 4, 1, f.get()) != 1 || nd > 8) return bail("bad rank");
+            std::vector<long long> shape(nd);
+            if (nd && std::fread(shape.data(), 8, nd, f.get()) != nd) return bail("truncated shape");
+            // every dimension positive, and the element count bounded by what is left of the file (no overflow, no huge resize)
+            const long long left = (file_bytes - std::ftell(f.get())) / 4;
+            long long n = 1;
+            for (long long d : shape) {
+                if (d <= 0 || d > left || n > left / d) return bail("bad shape for " + name);
+                n *= d;
+            }
+            buf.resize(static_cast<size_t>(n));
+            if (std::fread(buf.data(), 4, static_cast<size_t>(n), f.get()) != static_cast<size_t>(n)) return bail("truncated data for " + name);
+            SDOD_TRY(set(name, buf.data(), shape));
+        }
+    } catch (const std::exception& e) {
+        return bail(std::string("exception while reading: ") + e.what());
     }
-    std::fclose(f);
     return kOk;
 }
 
@@ -192,6 +204,10 @@ const float* NetBase::w32(const std::string& name, const std::vector<long long>&
         const DevTensor* t = ws_->find(name);
         if (!t) throw std::runtime_error("missing weight tensor '" + name + "'");
         if (t->numel != n) throw std::runtime_error("weight tensor '" + name + "' has " + std::to_string(t->numel) + " elements, expected " + std::to_string(n));
+        // same element count is not enough: a transposed tensor would load silently.  Singleton dimensions may differ (ldm stores 1x1 convs as
+        // [Cout, Cin, 1, 1] where a linear layer says [Cout, Cin]).
+        auto squeeze = [](const std::vector<long long>& v) { std::vector<long long> o; for (long long d : v) if (d != 1) o.push_back(d); return o; };
+        if (squeeze(t->shape) != squeeze(shape)) throw std::runtime_error("weight tensor '" + name + "' has an unexpected shape");
         return t->p;
     }
     auto hit = cache_.find("r|" + name);

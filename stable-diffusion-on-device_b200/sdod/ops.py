@@ -50,10 +50,16 @@ def _gn_workspace(device, nbytes):
     return ws
 
 
+class SdodTypeError(TypeError):
+    pass
+
+
 @torch.library.custom_op("sdod::group_norm", mutates_args=(), device_types="cuda")
 def group_norm(x: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float,
                silu: bool = False, add_nc: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(+SiLU)(+x+add_nc[n,c]) on [N,C,*spatial]; NCHW-contiguous or channels_last input."""
+    """GroupNorm(+SiLU)(+x+add_nc[n,c]) on [N,C,*spatial].  Kernels: fp32 / bf16, NCHW-contiguous (any shape) or channels_last (C % 8 == 0,
+    num_groups <= 64, N <= 256).  Like the reference's F.group_norm every other floating input is still served: fp16 / fp64 are computed in
+    fp32 and cast back, channels_last tensors outside the NHWC kernels' constraints go through the NCHW kernel on a contiguous copy."""
     _need_cuda(x, weight, bias, add_nc)
     n, c = x.shape[0], x.shape[1]
     hw = 1
@@ -61,7 +67,13 @@ def group_norm(x: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor],
         hw *= s
     if c % num_groups != 0:
         raise ValueError("num_channels must be divisible by num_groups")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        if not x.is_floating_point():
+            raise SdodTypeError("group_norm: floating-point input required, got %s" % x.dtype)
+        return group_norm(x.float(), num_groups, weight, bias, eps, silu, add_nc).to(x.dtype)
     nhwc = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+    if nhwc and (c % 8 != 0 or num_groups > 64 or n > 256):
+        nhwc = False
     if not nhwc:
         x = x.contiguous()
     y = torch.empty_like(x)

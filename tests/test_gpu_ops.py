@@ -130,6 +130,18 @@ def test_gn_group_owned_kernel_on_a_tensor_larger_than_l2():
     assert rel_err(got, want) < TOL_BF16
 
 
+def test_gn_inputs_outside_the_nhwc_kernels_constraints():
+    """A drop-in user may hand EfficientGN what F.group_norm accepts: channels_last with C % 8 != 0, fp16."""
+    torch.manual_seed(5)
+    x = torch.randn(2, 12, 9, 7)
+    w, b = torch.randn(12), torch.randn(12)
+    want = F.group_norm(x, 4, w, b, 1e-5)
+    got = torch.ops.sdod.group_norm(x.to(DEV).contiguous(memory_format=torch.channels_last), 4, w.to(DEV), b.to(DEV), 1e-5)
+    assert rel_err(got.cpu(), want) < TOL_F32
+    got16 = torch.ops.sdod.group_norm(x.half().to(DEV), 4, w.to(DEV), b.to(DEV), 1e-5)
+    assert got16.dtype == torch.float16 and rel_err(got16.cpu(), want) < 5e-3
+
+
 def test_gn_fused_temb_add_and_parameterless():
     torch.manual_seed(2)
     x = torch.randn(2, 640, 32, 32)

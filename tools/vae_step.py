@@ -16,4 +16,5 @@ torch.cuda.synchronize()
 for _ in range(n):
     img = vae(z)
 torch.cuda.synchronize()
+img = img[0] if isinstance(img, (tuple, list)) else img
 print("ok", img.float().mean().item())
