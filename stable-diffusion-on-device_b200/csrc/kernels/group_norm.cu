@@ -826,7 +826,8 @@ static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int in_dt
     if (cpg % 2 != 0 || Ca % 2 != 0 || cpg / 2 > 512 || N > 65535) return 0;
     const size_t slab = static_cast<size_t>(HW) * cpg * sizeof(float);
     int cs = 1;
-    while (cs < 8 && (slab / cs > (static_cast<size_t>(100) << 10) || HW % cs != 0)) cs *= 2;          // <= 100 KB: two CTAs per SM
+    static const long long slab_kb = [] { const char* e = std::getenv("SDOD_GN_GROUP_SLABKB"); return e ? std::atoll(e) : 100LL; }();     // A/B knob
+    while (cs < 8 && (slab / cs > (static_cast<size_t>(slab_kb) << 10) || HW % cs != 0)) cs *= 2;      // <= 100 KB: two CTAs per SM
     // small batch: spread each group over more CTAs (two 512-thread CTAs per SM) while a thread still walks >= 8 rows
     const int rpb = std::max(1, 512 / (cpg / 2));
     while (cs < 8 && static_cast<long long>(N) * G * cs < 256 && HW / (cs * 2) >= 8 * rpb && HW % (cs * 2) == 0) cs *= 2;

@@ -33,6 +33,27 @@ def models_dir(tmp_path_factory):
     return str(d), unet, vae
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def text_model_files(d, golden_dir, seed=5):
+    """Adds the prompt path's files to a models_dir for the duration of one test: ctokenizer.txt (the synthetic vocabulary in the reference's
+    format) and text_encoder.sdodw (a seeded random-init CLIPTextModel, written through sdod.checkpoint like a real SD checkpoint's
+    cond_stage_model); yields that CLIPTextModel."""
+    import shutil
+    from sdod import checkpoint as K
+    from _clip_ref import clip_text_model
+    shutil.copy(os.path.join(golden_dir, "ctokenizer_synth.txt"), os.path.join(d, "ctokenizer.txt"))
+    m = clip_text_model(seed)
+    K.convert({"cond_stage_model.transformer." + k: v for k, v in m.state_dict().items()}, d)
+    try:
+        yield m
+    finally:
+        os.remove(os.path.join(d, "ctokenizer.txt"))
+        os.remove(os.path.join(d, "text_encoder.sdodw"))
+
+
 @pytest.mark.parametrize("S,n,guidance", [(16, 2, 7.5), (32, 1, 7.5), (16, 1, 1.0)])
 def test_generate_20_steps_vs_oracle_loop(models_dir, S, n, guidance):
     d, unet, vae = models_dir
@@ -154,7 +175,7 @@ def test_ddim_sampler_vs_oracle_loop(models_dir):
     assert psnr_u8(imgs_dpm, dpm_u8) >= 35.0 and rel_dpm < 5e-2
 
 
-def test_reference_simple_app_runs_unmodified(models_dir, tmp_path):
+def test_reference_simple_app_runs_unmodified(models_dir, tmp_path, golden_dir):
     """The reference's own caller (csrc/libsdod/test/simple_app.cpp, compiled UNMODIFIED against include/libsdod.h and linked to
     libsdod_b200.so by oracle/Makefile) sets up, generates 'A photograph of an astronaut riding a horse' at 7.5 and writes output.bin:
     786,432 bytes of RGB [H,W,C] (libsdod.h:89, simple_app.cpp:31-33).  Its hard-coded models path is redirected with LIBSDOD_B200_MODELS_DIR."""
@@ -165,7 +186,8 @@ def test_reference_simple_app_runs_unmodified(models_dir, tmp_path):
         pytest.skip("oracle/_ref/simple_app not built (needs /root/reference at build time)")
     d, _, _ = models_dir
     env = dict(os.environ, LIBSDOD_B200_MODELS_DIR=d)
-    r = subprocess.run([app], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    with text_model_files(d, golden_dir):                            # the app generates from a prompt: tokenizer + text encoder needed
+        r = subprocess.run([app], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = tmp_path / "output.bin"
     assert out.exists() and out.stat().st_size == 3 * 512 * 512
@@ -194,29 +216,20 @@ def test_prompt_path_from_files_vs_reference_tokenizer_and_clip(models_dir, gold
     token ids equal to the ones the reference's compiled tokenizer produced (golden), embedding within the bf16 per-op tolerance of HuggingFace's
     CLIPTextModel on the same weights, and libsdod_generate_image == encode -> libsdod_b200_generate."""
     import json
-    import shutil
-    from sdod import checkpoint as K
-    from _clip_ref import clip_text_model, rel_err
+    from _clip_ref import rel_err
     d, _, _ = models_dir
-    shutil.copy(os.path.join(golden_dir, "ctokenizer_synth.txt"), os.path.join(d, "ctokenizer.txt"))
-    m = clip_text_model(5)
-    K.convert({"cond_stage_model.transformer." + k: v for k, v in m.state_dict().items()}, d)
-    try:
-        prompt = "a photograph of an astronaut riding a horse on mars, highly detailed, 8k"
-        gold = {bytes.fromhex(c["utf8_hex"]): c["ids"] for c in json.load(open(os.path.join(golden_dir, "tokenizer_golden.json")))["cases"]}
-        with A.Context(d, latent_spatial=16, steps=4, max_images=1, device=0) as ctx:
-            emb, tok = ctx.encode_prompt(prompt, return_tokens=True)
-            assert list(tok) == gold[prompt.encode()]
-            with torch.no_grad():
-                want = m(input_ids=torch.from_numpy(tok.astype(np.int64))[None]).last_hidden_state[0]
-            e = rel_err(torch.from_numpy(emb), want)
-            print("prompt embedding vs CLIPTextModel: max rel err %.3e" % e)
-            assert e < 2e-2
-            ctx.set_seed(5)
-            img = ctx.generate_image(prompt, 7.5)
-            ctx.set_seed(5)
-            img2 = ctx.generate(emb[None], ctx.encode_prompt("")[None], None, 7.5)[0]
-            assert np.array_equal(img, img2) and img.std() > 1
-    finally:
-        os.remove(os.path.join(d, "ctokenizer.txt"))
-        os.remove(os.path.join(d, "text_encoder.sdodw"))
+    prompt = "a photograph of an astronaut riding a horse on mars, highly detailed, 8k"
+    gold = {bytes.fromhex(c["utf8_hex"]): c["ids"] for c in json.load(open(os.path.join(golden_dir, "tokenizer_golden.json")))["cases"]}
+    with text_model_files(d, golden_dir) as m, A.Context(d, latent_spatial=16, steps=4, max_images=1, device=0) as ctx:
+        emb, tok = ctx.encode_prompt(prompt, return_tokens=True)
+        assert list(tok) == gold[prompt.encode()]
+        with torch.no_grad():
+            want = m(input_ids=torch.from_numpy(tok.astype(np.int64))[None]).last_hidden_state[0]
+        e = rel_err(torch.from_numpy(emb), want)
+        print("prompt embedding vs CLIPTextModel: max rel err %.3e" % e)
+        assert e < 2e-2
+        ctx.set_seed(5)
+        img = ctx.generate_image(prompt, 7.5)
+        ctx.set_seed(5)
+        img2 = ctx.generate(emb[None], ctx.encode_prompt("")[None], None, 7.5)[0]
+        assert np.array_equal(img, img2) and img.std() > 1
