@@ -388,6 +388,9 @@ def op_flops(name, batch):
     m = re.match(r"conv3\+skip HW(\d+) Cin(\d+)\+(\d+) Cout(\d+)", name)     # 3x3 conv + the ResBlock's 1x1 skip projection in one launch
     if m:
         return 2.0 * batch * int(m.group(1)) * int(m.group(4)) * (9 * int(m.group(2)) + int(m.group(3)))
+    m = re.match(r"conv3up2 HW(\d+) Cin(\d+) Cout(\d+)", name)               # upsample + conv3x3 in sub-pixel form: the EXECUTED math, 4 taps per output pixel
+    if m:
+        return 2.0 * batch * 4 * int(m.group(1)) * int(m.group(3)) * 4 * int(m.group(2))
     return None
 
 

@@ -192,8 +192,15 @@ typedef struct sdod_conv_desc {
     int block_n;
     sdod_epilogue epi;       /* M = B*H*W rows, N = Cout                                            */
     const void* X2; long long ldx2; int Cin2;
+    /* != 0: Y = conv3x3(nearest_upsample_2x(X)) without materialising the upsampled tensor (UNet / VAE Upsample blocks).  Sub-pixel form: each of
+     * the four output parities (y%2, x%2) is a 2x2 convolution over X with pre-summed weights — 4/9 of the multiply-adds.  Wt is then
+     * [4 parities][Cout][4*Cin] as packed by sdod_pack_conv3x3_up2_weight; epi.C is [B, 2H, 2W, Cout]; no residual / row_bias / X2. */
+    int upsample2x;
 } sdod_conv_desc;
 SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d);
+/* OIHW fp32 [Cout,Cin,3,3] -> bf16 [4][Cout][4*Cin] for sdod_conv_desc.upsample2x: parity p = 2*py+px, k = (2a+b)*Cin + c, weight = sum of the
+ * 3x3 taps (ky,kx) that read source pixel (i+a-1+py, j+b-1+px) (fp32 sums, rounded once). */
+SDOD_API int sdod_pack_conv3x3_up2_weight(sdod_stream_t stream, const float* w_oihw, void* out, int Cout, int Cin);
 
 /* Fused flash-style attention on tcgen05 (S and O accumulators in TMEM, online softmax, P written back to
  * TMEM and consumed as the A operand of the PV MMA).  SpatialTransformer attn1/attn2 (analyze_results.py:60-75).

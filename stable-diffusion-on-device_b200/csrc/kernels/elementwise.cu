@@ -276,6 +276,25 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, bf16* __restric
     }
 }
 
+// OIHW fp32 -> [parity][O][2a+b][I] bf16: the sub-pixel form of conv3x3 after a nearest 2x upsample.  Output row 2i+py reads source rows
+// i-1+py (a=0) and i+py (a=1); the 3x3 rows ky that land on them are {0} | {1,2} for py=0 and {0,1} | {2} for py=1 (same for columns).
+__global__ void pack_conv3x3_up2_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+    const size_t per = static_cast<size_t>(Cout) * 4 * Cin, total = 4 * per;
+    for (size_t o = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int par = static_cast<int>(o / per);
+        const size_t r = o - par * per;
+        const int co = static_cast<int>(r / (4 * Cin)), k = static_cast<int>(r - static_cast<size_t>(co) * 4 * Cin);
+        const int tap = k / Cin, ci = k - tap * Cin;
+        const int py = par >> 1, px = par & 1, a = tap >> 1, b = tap & 1;
+        const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        float v = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) v += w[(static_cast<size_t>(co) * Cin + ci) * 9 + ky * 3 + kx];
+        out[o] = __float2bfloat16(v);
+    }
+}
+
 }  // namespace sdod
 
 using namespace sdod;
@@ -396,6 +415,14 @@ SDOD_API int sdod_pack_conv3x3_weight(sdod_stream_t stream, const float* w_oihw,
     pack_conv3x3_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(w_oihw, static_cast<bf16*>(out), Cout, Cin, Kpad);
     count_launch();
     return check_launch("pack_conv3x3_kernel");
+}
+
+SDOD_API int sdod_pack_conv3x3_up2_weight(sdod_stream_t stream, const float* w_oihw, void* out, int Cout, int Cin) {
+    if (!w_oihw || !out || Cout <= 0 || Cin <= 0) return fail(kInvalidArgument, "pack_conv3x3_up2_weight: bad arguments");
+    const size_t n = static_cast<size_t>(4) * Cout * 4 * Cin;
+    pack_conv3x3_up2_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(w_oihw, static_cast<bf16*>(out), Cout, Cin);
+    count_launch();
+    return check_launch("pack_conv3x3_up2_kernel");
 }
 
 }  // extern "C"

@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     } else if (mp.conv) {
                         const int tap = kb / mp.cin_blocks;
                         const int cb = kb - tap * mp.cin_blocks;
-                        const int ky = tap / 3, kx = tap - ky * 3;
+                        // 3x3 taps, or (sub-pixel form of upsample + conv) the 2x2 source taps of output parity bz = 2*py + px
+                        const int ky = mp.up2 ? (tap >> 1) + (bz >> 1) : tap / 3, kx = mp.up2 ? (tap & 1) + (bz & 1) : tap - ky * 3;
                         tma_load_4d_pair(sA + s * kABytes, &tmA, fb, cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
                     } else {
                         tma_load_3d_pair(sA + s * kABytes, &tmA, fb, kb * kBlockK, m0, bz);
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 } else if (mp.conv) {
                     const int tap = kb / mp.cin_blocks;
                     const int cb = kb - tap * mp.cin_blocks;
-                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const int ky = mp.up2 ? (tap >> 1) + (bz >> 1) : tap / 3, kx = mp.up2 ? (tap & 1) + (bz & 1) : tap - ky * 3;
                     tma_load_4d(sA + s * kABytes, &tmA, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
                 } else {
                     tma_load_3d(sA + s * kABytes, &tmA, &full_bar[s], kb * kBlockK, m0, bz);
@@ -1012,8 +1013,20 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             fence_proxy_async_smem();                  // staged tile (generic-proxy writes) -> visible to the TMA engine
             quarter_sync();
             if (half == 0 && lane == 0 && m0 + q * 32 < mp.M) {
-                for (int bx = 0; bx < NB; ++bx)
-                    if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
+                if (mp.up2) {
+                    // sub-pixel form: the quarter's 32 source pixels (x fastest, then y, then image) go to output pixels (2y+py, 2x+px): one
+                    // 5-D box {32 ch, px, min(bw,32) x's, py, 32/min(bw,32) merged (image, y) rows} per 32-column box
+                    const int rq = q * 32, hw = mp.H * mp.W;
+                    int b0 = 0, y0 = 0, x0 = 0;
+                    if (mp.bb > 1) { b0 = m_tile * mp.bb; } else { b0 = m0 / hw; const int rem = m0 - b0 * hw; y0 = rem / mp.W; x0 = rem - y0 * mp.W; }
+                    const int xq = x0 + (mp.bw >= 32 ? rq % mp.bw : 0);
+                    const int biq = (b0 + rq / (mp.bw * mp.bh)) * mp.H + y0 + (rq / mp.bw) % mp.bh;
+                    for (int bx = 0; bx < NB; ++bx)
+                        if (n0 + bx * 32 < mp.N) tma_store_5d(&tmC, qbase + bx * bstr, n0 + bx * 32, bz & 1, xq, bz >> 1, biq);
+                } else {
+                    for (int bx = 0; bx < NB; ++bx)
+                        if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
+                }
                 bulk_commit();
                 if (dbuf) bulk_wait_read_but_last();
                 else bulk_wait_read_all();             // smem may be released once the stores have read it
@@ -1688,13 +1701,21 @@ static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool t
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
     if (d.epi.ln_out) return fail(kUnsupported, "conv3x3: no fused LayerNorm epilogue");
     const int Cin2 = d.X2 ? d.Cin2 : 0;
-    int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, 1, d.epi.act, (9 * d.Cin + Cin2) / kBlockK);
+    const bool up2 = d.upsample2x != 0;                 // sub-pixel form of conv3x3(nearest_upsample_2x(X)): 4 output parities x 2x2 source taps
+    const int taps = up2 ? 4 : 9;
+    if (up2) {
+        try_streamk = false;
+        if (d.X2 || d.epi.residual || d.epi.row_bias || d.epi.act == SDOD_ACT_GEGLU || (d.epi.out_mode != SDOD_OUT_BF16 && d.epi.out_mode != SDOD_OUT_F32))
+            return fail(kUnsupported, "conv3x3 (upsample2x): no second operand, residual, row bias, GEGLU or head layouts");
+        if (d.Cout % 8 != 0 || (reinterpret_cast<uintptr_t>(d.epi.C) & 15)) return fail(kInvalidArgument, "conv3x3 (upsample2x): Cout % 8 and a 16-byte aligned output required");
+    }
+    int bn = d.block_n ? d.block_n : pick_block_n_k(M, d.Cout, up2 ? 4 : 1, d.epi.act, (taps * d.Cin + Cin2) / kBlockK);
     int sk_grid = 0;
     *used_streamk = false;
     if (try_streamk) {
         const int bn_sk = d.block_n ? d.block_n : pick_block_n(M, d.Cout, 1, d.epi.act);
         const long long tiles_sk = static_cast<long long>((M + kBlockM - 1) / kBlockM) * ((d.Cout + bn_sk - 1) / bn_sk);
-        sk_grid = streamk_grid(bn_sk, tiles_sk, (9 * d.Cin + Cin2) / kBlockK, 1, false);
+        sk_grid = streamk_grid(bn_sk, tiles_sk, (taps * d.Cin + Cin2) / kBlockK, 1, false);
         if (sk_grid) { bn = bn_sk; *used_streamk = true; }
     }
     const bool pair = !sk_grid && use_pair(bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, true);
@@ -1708,9 +1729,9 @@ static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool t
         uint32_t box[4] = {kBlockK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
         SDOD_TRY(encode_tmap_bf16(&tmA, d.X, 4, dims, strides, box, true));
     }
-    const int K = 9 * d.Cin + Cin2;
+    const int K = taps * d.Cin + Cin2;
     {
-        uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(d.Cout), 1};
+        uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(d.Cout), static_cast<uint64_t>(up2 ? 4 : 1)};
         uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * d.Cout * 2};
         uint32_t box[3] = {kBlockK, static_cast<uint32_t>(pair ? bn / 2 : bn), 1};
         SDOD_TRY(encode_tmap_bf16(&tmW, d.Wt, 3, dims, strides, box, true));
@@ -1718,22 +1739,36 @@ static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool t
     out->pair = pair ? 1 : 0;
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
-    mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = 0;
+    mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = up2 ? 1 : 0; mp.up2 = up2 ? 1 : 0;
     mp.k_rot = k_rotation(mp.k_blocks);
-    choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, 1);
+    choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, up2 ? 4 : 1);      // (batch != 1: grid.z is taken by the parities)
     if (sk_grid) { mp.split = 1; mp.kb_per_split = mp.k_blocks; mp.streamk = 1; mp.ws = g_splitk.ws; mp.counters = g_splitk.counters; }
     out->sk_grid = sk_grid;
     mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     out->mp.tlog = g_tlog;
-    SDOD_TRY(setup_second_operand(out, d.X2, d.ldx2, Cin2, M, 9 * d.Cin / kBlockK));
-    out->w_ptr = d.Wt; out->w_bytes = static_cast<long long>(d.Cout) * K * 2;
-    SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));
+    SDOD_TRY(setup_second_operand(out, d.X2, d.ldx2, Cin2, M, taps * d.Cin / kBlockK));
+    out->w_ptr = d.Wt; out->w_bytes = static_cast<long long>(d.Cout) * K * 2 * (up2 ? 4 : 1);
+    if (!up2) {
+        SDOD_TRY(setup_tma_epilogue(out, d.epi, M, d.Cout, 1));
+    } else {
+        // output [B, 2H, 2W, Cout] seen as (c, px, x, py, (b, y)): a tile row = source pixel (b, y, x) lands at output pixel (2y+py, 2x+px)
+        out->mp.tma_epi = 1;
+        out->mp.c_bytes = d.epi.out_mode == SDOD_OUT_F32 ? 4 : 2;
+        std::memset(&out->tmR, 0, sizeof(CUtensorMap));
+        const uint64_t es = static_cast<uint64_t>(out->mp.c_bytes), C = static_cast<uint64_t>(d.Cout);
+        uint64_t dims[5] = {C, 2, static_cast<uint64_t>(d.W), 2, static_cast<uint64_t>(d.B) * d.H};
+        uint64_t strides[4] = {C * es, 2 * C * es, 2 * static_cast<uint64_t>(d.W) * C * es, 4 * static_cast<uint64_t>(d.W) * C * es};
+        const uint32_t bwq = static_cast<uint32_t>(bw < 32 ? bw : 32);
+        const uint32_t box[5] = {32, 1, bwq, 1, 32 / bwq};
+        SDOD_TRY(encode_tmap(&out->tmC, d.epi.C, static_cast<int>(es), 5, dims, strides, box, es == 4 ? 128 : 64));
+    }
     std::memset(&out->tmC2, 0, sizeof(CUtensorMap));
     out->m_tiles = (M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.Cout + bn - 1) / bn;
-    out->batch = 1;
+    out->batch = up2 ? 4 : 1;
     choose_persist(out);
+    if (up2) out->persist = 0;
     return kOk;
 }
 

@@ -517,6 +517,46 @@ Act NetBase::conv3_skip(const Act& x, const std::string& prefix, const std::stri
     return y;
 }
 
+void* NetBase::pack_conv3_up2(const std::string& wname, int Cout, int Cin) {
+    const std::string key = "cu|" + wname;
+    auto hit = cache_.find(key);
+    if (hit != cache_.end()) return hit->second;
+    const float* src = w32(wname, {Cout, Cin, 3, 3}, kInitWeight);
+    void* dst = dev_alloc(static_cast<size_t>(4) * Cout * 4 * Cin * 2, false);
+    cache_[key] = dst;
+    check(sdod_pack_conv3x3_up2_weight(nullptr, src, dst, Cout, Cin));
+    return dst;
+}
+
+Act NetBase::conv3_up2(const Act& x, const std::string& prefix, int cout, bool stream_out) {
+    static const int env = [] { const char* e = std::getenv("SDOD_CONV_UP2"); return e ? std::atoi(e) : 1; }();     // 0: upsample kernel + 3x3 conv (A/B)
+    if (!env || x.C % 64 != 0 || cout % 8 != 0) {
+        Act u = upsample(x);
+        Act c = conv3(u, prefix, cout, nullptr, 0, nullptr, stream_out);
+        release(u);
+        return c;
+    }
+    Act xb = x;
+    bool own = false;
+    if (x.f32) { xb = to_bf16(x); own = true; }
+    void* wt = pack_conv3_up2(prefix + ".weight", cout, x.C);
+    const float* bias = w32(prefix + ".bias", {cout}, kInitBias);
+    Act y = new_act(x.B, 2 * x.H, 2 * x.W, cout, stream_out);
+    sdod_conv_desc d{};
+    d.X = xb.p; d.Wt = wt; d.B = x.B; d.H = x.H; d.W = x.W; d.Cin = x.C; d.Cout = cout; d.upsample2x = 1;
+    d.epi.C = y.p; d.epi.ldc = cout; d.epi.bias = bias; d.epi.alpha = 1.0f; d.epi.out_mode = stream_out ? SDOD_OUT_F32 : SDOD_OUT_BF16;
+    auto g = std::make_shared<GemmLaunch>();
+    set_splitk_workspace(skw_);
+    const int st_prep = conv3x3_prepare(d, g.get());
+    set_splitk_workspace(SplitKWorkspace{});
+    check(st_prep);
+    note_gemm(g);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, 1,
+                "conv3up2 HW" + std::to_string(x.H * x.W) + " Cin" + std::to_string(x.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn));
+    if (own) release(xb);
+    return y;
+}
+
 Act NetBase::to_bf16(const Act& x) {
     if (!x.f32) throw std::runtime_error("to_bf16: already bf16");
     Act y = new_act(x.B, x.H, x.W, x.C, false);

@@ -129,6 +129,10 @@ protected:
               bool stream_out = false, float* out_f32 = nullptr);
     // out = conv3x3(x) + conv1x1(x_skip) + biases, one launch (skip weights K-concatenated); fp32 stream output
     Act conv3_skip(const Act& x, const std::string& prefix, const std::string& skip_prefix, const Act& x_skip, int cout);
+    // conv3x3(nearest_upsample_2x(x)) in sub-pixel form: four 2x2 convolutions over x with pre-summed weights, output [B, 2H, 2W, cout]
+    // written in place through a 5-D tensor map (no upsampled tensor, 4/9 of the multiply-adds).  x fp32 is cast to bf16 first.
+    Act conv3_up2(const Act& x, const std::string& prefix, int cout, bool stream_out = false);
+    void* pack_conv3_up2(const std::string& wname, int Cout, int Cin);
     Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride, bool stream_out = false);
     Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out = false);
     Act to_bf16(const Act& x);

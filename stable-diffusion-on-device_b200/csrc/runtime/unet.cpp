@@ -294,10 +294,8 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
                 sub = 2;
             }
             if (level > 0 && i == 2) {
-                Act u = upsample(r);
+                Act c = conv3_up2(r, p + "." + std::to_string(sub) + ".conv", r.C, true);     // Upsample: nearest 2x + conv3x3, sub-pixel form
                 release(r);
-                Act c = conv3(u, p + "." + std::to_string(sub) + ".conv", u.C, nullptr, 0, nullptr, true);
-                release(u);
                 r = c;
             }
             h = r;

@@ -132,10 +132,9 @@ std::unique_ptr<Plan> VaeDecoder::build(int B) {
             h = r;
         }
         if (level != 0) {
-            Act u = upsample(h);
+            Act c = conv3_up2(h, "decoder.up." + std::to_string(level) + ".upsample.conv", h.C);     // nearest 2x + conv3x3, sub-pixel form
             release(h);
-            h = conv3(u, "decoder.up." + std::to_string(level) + ".upsample.conv", u.C, nullptr, 0, nullptr);
-            release(u);
+            h = c;
         }
     }
     Act hn = gn(h, "decoder.norm_out", 1e-6f, true);

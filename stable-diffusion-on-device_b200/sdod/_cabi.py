@@ -38,7 +38,7 @@ class GemmDesc(ctypes.Structure):
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [("X", c_vp), ("Wt", c_vp), ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("block_n", c_int), ("epi", Epilogue), ("X2", c_vp), ("ldx2", c_ll), ("Cin2", c_int)]
+                ("block_n", c_int), ("epi", Epilogue), ("X2", c_vp), ("ldx2", c_ll), ("Cin2", c_int), ("upsample2x", c_int)]
 
 
 _SIGS = {
@@ -75,6 +75,7 @@ _SIGS = {
     "sdod_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_vp, c_sz]),
     "sdod_silu_bf16": (c_int, [c_vp, c_vp, c_vp, c_sz]),
     "sdod_pack_conv3x3_weight": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),
+    "sdod_pack_conv3x3_up2_weight": (c_int, [c_vp, c_vp, c_vp, c_int, c_int]),
     # include/sdod_model.h
     "sdod_weights_create": (c_int, [ctypes.POINTER(c_vp)]),
     "sdod_weights_set_f32": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_int, ctypes.POINTER(c_ll)]),

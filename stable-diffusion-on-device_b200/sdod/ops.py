@@ -314,6 +314,25 @@ def _(x, wt, bias=None, residual=None, row_bias=None, act=0, block_n=0, x2=None)
     return x.new_empty(x.shape[:3] + (wt.shape[0],))
 
 
+def conv3x3_up2(x, w_oihw, bias=None, out_f32=False, block_n=0):
+    """conv3x3(nearest_upsample_2x(x)) without the upsampled tensor (sub-pixel form, 4/9 of the multiply-adds).
+    x [B,H,W,Cin] bf16 NHWC, w_oihw [Cout,Cin,3,3] fp32 -> [B,2H,2W,Cout] bf16 (or fp32)."""
+    _need_cuda(x, w_oihw, bias)
+    assert x.dtype == torch.bfloat16 and x.dim() == 4
+    x = x.contiguous()
+    w = w_oihw.detach().to(torch.float32).contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    wt = torch.empty(4, Cout, 4 * Cin, dtype=torch.bfloat16, device=x.device)
+    C.check(C.lib().sdod_pack_conv3x3_up2_weight(_stream(), _p(w), _p(wt), Cout, Cin), "sdod_pack_conv3x3_up2_weight")
+    out = torch.empty(B, 2 * H, 2 * W, Cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    d = C.ConvDesc()
+    d.X, d.Wt, d.B, d.H, d.W, d.Cin, d.Cout, d.block_n, d.upsample2x = _p(x), _p(wt), B, H, W, Cin, Cout, block_n, 1
+    d.epi = _epilogue(out.view(B * 4 * H * W, Cout), _f32(bias), None, 0, None, 1.0, 0)
+    C.check(C.lib().sdod_conv3x3_bf16(_stream(), d), "sdod_conv3x3_bf16")
+    return out
+
+
 def pack_conv3x3_weight(w_oihw, kpad=None):
     """[Cout,Cin,3,3] fp32 -> [Cout, 9*Cin (padded to kpad)] bf16 with k = (ky*3+kx)*Cin + c."""
     _need_cuda(w_oihw)

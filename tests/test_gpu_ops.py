@@ -361,6 +361,22 @@ def test_conv3x3_cta_pair_epilogues():
     assert rel_err(torch.ops.sdod.conv3x3(x, wt, bias, None, None, C.ACT_SILU), F.silu(base)) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 1280, 1280), (2, 32, 640, 640), (2, 8, 1280, 1280), (1, 64, 256, 256), (8, 32, 640, 640), (2, 4, 128, 64), (3, 2, 64, 40)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_conv3x3_after_nearest_upsample_subpixel_form(B, H, Cin, Cout, f32):
+    """UNet / VAE Upsample blocks: conv3x3(nearest 2x(x)) as four 2x2 parity convolutions with pre-summed weights, written in place."""
+    torch.manual_seed(H + Cin)
+    x = bf(torch.randn(B, H, H, Cin)).to(DEV)
+    w = (torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    b = torch.randn(Cout, device=DEV)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    want = F.conv2d(up, w.to(torch.bfloat16).float(), b, padding=1).permute(0, 2, 3, 1)
+    got = ops.conv3x3_up2(x, w, b, out_f32=f32)
+    assert got.shape == (B, 2 * H, 2 * H, Cout) and got.dtype == (torch.float32 if f32 else torch.bfloat16)
+    # (the product rounds the SUMS of up to four taps to bf16 once, the reference rounds each tap: 2e-2 covers the difference)
+    assert rel_err(got, want) < TOL_BF16
+
+
 def test_conv3x3_fused_temb_and_residual():
     torch.manual_seed(21)
     B, H, W, Cin, Cout = 2, 32, 32, 320, 640
