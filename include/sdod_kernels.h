@@ -196,6 +196,9 @@ typedef struct sdod_conv_desc {
      * the four output parities (y%2, x%2) is a 2x2 convolution over X with pre-summed weights — 4/9 of the multiply-adds.  Wt is then
      * [4 parities][Cout][4*Cin] as packed by sdod_pack_conv3x3_up2_weight; epi.C is [B, 2H, 2W, Cout]; no residual / row_bias / X2. */
     int upsample2x;
+    /* 0 / 1: stride 1.  2: stride-2 convolution with padding 1 (the UNet's Downsample blocks): H, W are the INPUT size (even), the output
+     * is [B, H/2, W/2, Cout]; the A tiles are TMA boxes with element strides {1, 2, 2, 1} on the input — no im2col buffer. */
+    int stride;
 } sdod_conv_desc;
 SDOD_API int sdod_conv3x3_bf16(sdod_stream_t stream, const sdod_conv_desc* d);
 /* OIHW fp32 [Cout,Cin,3,3] -> bf16 [4][Cout][4*Cin] for sdod_conv_desc.upsample2x: parity p = 2*py+px, k = (2a+b)*Cin + c, weight = sum of the

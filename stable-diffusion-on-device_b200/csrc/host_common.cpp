@@ -47,7 +47,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }
 
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(kNoDevice, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
     cuuint64_t gdim[5];
@@ -57,7 +57,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bx[i] = box[i];
-        es[i] = 1;
+        es[i] = elem_strides ? elem_strides[i] : 1;
         if (i + 1 < rank) gstr[i] = strides_bytes[i];
     }
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(kInvalidArgument, "TMA base must be 16-byte aligned");

@@ -28,8 +28,10 @@ int check_launch(const char* what);                  // cudaGetLastError()
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
 // General form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 0 / 32 / 64 / 128.
+// elem_strides (optional, rank entries): traversal stride per dimension; box[i] is then the extent of the traversed bounding box
+// (ceil(box[i] / elem_strides[i]) elements are moved) — how a stride-2 convolution reads every second pixel.
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides = nullptr);
 
 int device_sm_count();
 bool pdl_enabled();   // SDOD_PDL=0 in the environment turns programmatic dependent launch off (A/B measurements)

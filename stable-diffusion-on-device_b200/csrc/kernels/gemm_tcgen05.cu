@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                         const int cb = kb - tap * mp.cin_blocks;
                         // 3x3 taps, or (sub-pixel form of upsample + conv) the 2x2 source taps of output parity bz = 2*py + px
                         const int ky = mp.up2 ? (tap >> 1) + (bz >> 1) : tap / 3, kx = mp.up2 ? (tap & 1) + (bz & 1) : tap - ky * 3;
-                        tma_load_4d_pair(sA + s * kABytes, &tmA, fb, cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+                        tma_load_4d_pair(sA + s * kABytes, &tmA, fb, cb * kBlockK, mp.cstride * x0 + kx - 1, mp.cstride * y0 + ky - 1, b0);
                     } else {
                         tma_load_3d_pair(sA + s * kABytes, &tmA, fb, kb * kBlockK, m0, bz);
                     }
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     const int tap = kb / mp.cin_blocks;
                     const int cb = kb - tap * mp.cin_blocks;
                     const int ky = mp.up2 ? (tap >> 1) + (bz >> 1) : tap / 3, kx = mp.up2 ? (tap & 1) + (bz & 1) : tap - ky * 3;
-                    tma_load_4d(sA + s * kABytes, &tmA, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+                    tma_load_4d(sA + s * kABytes, &tmA, &full_bar[s], cb * kBlockK, mp.cstride * x0 + kx - 1, mp.cstride * y0 + ky - 1, b0);
                 } else {
                     tma_load_3d(sA + s * kABytes, &tmA, &full_bar[s], kb * kBlockK, m0, bz);
                 }
@@ -1691,13 +1691,17 @@ static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool t
     if (!d.X || !d.Wt) return fail(kInvalidArgument, "conv3x3: NULL operand");
     if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.Cin <= 0 || d.Cout <= 0) return fail(kInvalidArgument, "conv3x3: non-positive extent");
     if (d.Cin % kBlockK != 0) return fail(kInvalidArgument, "conv3x3: Cin must be a multiple of 64 (use im2col + gemm otherwise)");
-    const int bw = d.W < 128 ? d.W : 128;
-    if (128 % bw != 0 || d.W % bw != 0) return fail(kInvalidArgument, "conv3x3: W must be a power of two (or a multiple of 128)");
+    const int cstride = d.stride == 2 ? 2 : 1;
+    if (d.stride != 0 && d.stride != 1 && d.stride != 2) return fail(kInvalidArgument, "conv3x3: stride must be 1 or 2");
+    if (cstride == 2 && (d.H % 2 != 0 || d.W % 2 != 0 || d.upsample2x || d.X2)) return fail(kUnsupported, "conv3x3 (stride 2): even H, W; no upsample / second operand");
+    const int Ho = d.H / cstride, Wo = d.W / cstride;            // tiles are laid out on the OUTPUT grid
+    const int bw = Wo < 128 ? Wo : 128;
+    if (128 % bw != 0 || Wo % bw != 0) return fail(kInvalidArgument, "conv3x3: W must be a power of two (or a multiple of 128)");
     int bh = 128 / bw;
-    if (bh > d.H) bh = d.H;
-    if (d.H % bh != 0 || 128 % (bw * bh) != 0) return fail(kInvalidArgument, "conv3x3: H*W must tile into 128-pixel boxes");
+    if (bh > Ho) bh = Ho;
+    if (Ho % bh != 0 || 128 % (bw * bh) != 0) return fail(kInvalidArgument, "conv3x3: H*W must tile into 128-pixel boxes");
     const int bb = 128 / (bw * bh);
-    const int M = d.B * d.H * d.W;
+    const int M = d.B * Ho * Wo;
     SDOD_TRY(validate_epilogue(d.epi, d.Cout));
     if (d.epi.ln_out) return fail(kUnsupported, "conv3x3: no fused LayerNorm epilogue");
     const int Cin2 = d.X2 ? d.Cin2 : 0;
@@ -1726,8 +1730,9 @@ static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool t
         uint64_t dims[4] = {static_cast<uint64_t>(d.Cin), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
         uint64_t strides[3] = {static_cast<uint64_t>(d.Cin) * 2, static_cast<uint64_t>(d.W) * d.Cin * 2,
                                static_cast<uint64_t>(d.H) * d.W * d.Cin * 2};
-        uint32_t box[4] = {kBlockK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
-        SDOD_TRY(encode_tmap_bf16(&tmA, d.X, 4, dims, strides, box, true));
+        uint32_t box[4] = {kBlockK, static_cast<uint32_t>(cstride * bw), static_cast<uint32_t>(cstride * bh), static_cast<uint32_t>(bb)};
+        const uint32_t estr[4] = {1, static_cast<uint32_t>(cstride), static_cast<uint32_t>(cstride), 1};
+        SDOD_TRY(encode_tmap(&tmA, d.X, 2, 4, dims, strides, box, 128, cstride == 2 ? estr : nullptr));
     }
     const int K = taps * d.Cin + Cin2;
     {
@@ -1739,7 +1744,7 @@ static int conv3x3_prepare_impl(const sdod_conv_desc& d, GemmLaunch* out, bool t
     out->pair = pair ? 1 : 0;
     MainloopParams mp{};
     mp.M = M; mp.N = d.Cout; mp.k_blocks = K / kBlockK; mp.conv = 1; mp.cin_blocks = d.Cin / kBlockK;
-    mp.H = d.H; mp.W = d.W; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = up2 ? 1 : 0; mp.up2 = up2 ? 1 : 0;
+    mp.H = Ho; mp.W = Wo; mp.cstride = cstride; mp.bw = bw; mp.bh = bh; mp.bb = bb; mp.w_batched = up2 ? 1 : 0; mp.up2 = up2 ? 1 : 0;
     mp.k_rot = k_rotation(mp.k_blocks);
     choose_split(&mp, bn, (M + kBlockM - 1) / kBlockM, (d.Cout + bn - 1) / bn, up2 ? 4 : 1);      // (batch != 1: grid.z is taken by the parities)
     if (sk_grid) { mp.split = 1; mp.kb_per_split = mp.k_blocks; mp.streamk = 1; mp.ws = g_splitk.ws; mp.counters = g_splitk.counters; }

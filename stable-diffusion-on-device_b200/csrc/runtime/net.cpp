@@ -557,6 +557,31 @@ Act NetBase::conv3_up2(const Act& x, const std::string& prefix, int cout, bool s
     return y;
 }
 
+Act NetBase::conv3_s2(const Act& x, const std::string& prefix, int cout, bool stream_out) {
+    static const int env = [] { const char* e = std::getenv("SDOD_CONV_S2"); return e ? std::atoi(e) : 1; }();      // 0: im2col + GEMM (A/B)
+    if (!env || x.C % 64 != 0 || x.H % 2 != 0 || x.W % 2 != 0) return conv3_im2col(x, prefix, cout, 2, stream_out);
+    Act xb = x;
+    bool own = false;
+    if (x.f32) { xb = to_bf16(x); own = true; }
+    void* wt = pack_conv3(prefix + ".weight", cout, x.C);
+    const float* bias = w32(prefix + ".bias", {cout}, kInitBias);
+    Act y = new_act(x.B, x.H / 2, x.W / 2, cout, stream_out);
+    sdod_conv_desc d{};
+    d.X = xb.p; d.Wt = wt; d.B = x.B; d.H = x.H; d.W = x.W; d.Cin = x.C; d.Cout = cout; d.stride = 2;
+    d.epi.C = y.p; d.epi.ldc = cout; d.epi.bias = bias; d.epi.alpha = 1.0f; d.epi.out_mode = stream_out ? SDOD_OUT_F32 : SDOD_OUT_BF16;
+    auto g = std::make_shared<GemmLaunch>();
+    set_splitk_workspace(skw_);
+    const int st_prep = conv3x3_prepare(d, g.get());
+    set_splitk_workspace(SplitKWorkspace{});
+    check(st_prep);
+    note_gemm(g);
+    plan_->push([g](cudaStream_t st) { return gemm_launch(*g, st); }, (g->mp.split > 1 && !g->mp.split_cluster) ? 2 : 1,
+                "conv3s2 HW" + std::to_string(y.H * y.W) + " Cin" + std::to_string(x.C) + " Cout" + std::to_string(cout) + " bn" + std::to_string(g->bn) +
+                    (g->mp.streamk ? " sk" + std::to_string(g->sk_grid) : " split" + std::to_string(g->mp.split)));
+    if (own) release(xb);
+    return y;
+}
+
 Act NetBase::to_bf16(const Act& x) {
     if (!x.f32) throw std::runtime_error("to_bf16: already bf16");
     Act y = new_act(x.B, x.H, x.W, x.C, false);

@@ -133,6 +133,8 @@ protected:
     // written in place through a 5-D tensor map (no upsampled tensor, 4/9 of the multiply-adds).  x fp32 is cast to bf16 first.
     Act conv3_up2(const Act& x, const std::string& prefix, int cout, bool stream_out = false);
     void* pack_conv3_up2(const std::string& wname, int Cout, int Cin);
+    // stride-2 conv3x3, padding 1 (UNet Downsample): implicit GEMM on TMA boxes with element strides 2 — no im2col buffer.  x fp32 is cast first.
+    Act conv3_s2(const Act& x, const std::string& prefix, int cout, bool stream_out = false);
     Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride, bool stream_out = false);
     Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out = false);
     Act to_bf16(const Act& x);

@@ -264,7 +264,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
         }
         if (level != 3) {
             const std::string p = "input_blocks." + std::to_string(k++);
-            h = conv3_im2col(h, p + ".0.op", h.C, 2, true);
+            h = conv3_s2(h, p + ".0.op", h.C, true);          // Downsample: stride-2 conv as an implicit GEMM on strided TMA boxes
             hs.push_back(h);
         }
     }

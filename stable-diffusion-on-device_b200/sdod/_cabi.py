@@ -38,7 +38,7 @@ class GemmDesc(ctypes.Structure):
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [("X", c_vp), ("Wt", c_vp), ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("block_n", c_int), ("epi", Epilogue), ("X2", c_vp), ("ldx2", c_ll), ("Cin2", c_int), ("upsample2x", c_int)]
+                ("block_n", c_int), ("epi", Epilogue), ("X2", c_vp), ("ldx2", c_ll), ("Cin2", c_int), ("upsample2x", c_int), ("stride", c_int)]
 
 
 _SIGS = {

@@ -314,6 +314,22 @@ def _(x, wt, bias=None, residual=None, row_bias=None, act=0, block_n=0, x2=None)
     return x.new_empty(x.shape[:3] + (wt.shape[0],))
 
 
+def conv3x3_s2(x, wt, bias=None, out_f32=False, block_n=0):
+    """Stride-2 conv3x3 with padding 1 (UNet Downsample) as an implicit GEMM on TMA boxes with element strides 2.
+    x [B,H,W,Cin] bf16 NHWC (H, W even), wt [Cout, 9*Cin] bf16 as pack_conv3x3_weight lays it out -> [B,H/2,W/2,Cout]."""
+    _need_cuda(x, wt, bias)
+    assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and x.dim() == 4
+    x, wt = x.contiguous(), wt.contiguous()
+    B, H, W, Cin = x.shape
+    Cout = wt.shape[0]
+    out = torch.empty(B, H // 2, W // 2, Cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    d = C.ConvDesc()
+    d.X, d.Wt, d.B, d.H, d.W, d.Cin, d.Cout, d.block_n, d.stride = _p(x), _p(wt), B, H, W, Cin, Cout, block_n, 2
+    d.epi = _epilogue(out.view(-1, Cout), _f32(bias), None, 0, None, 1.0, 0)
+    C.check(C.lib().sdod_conv3x3_bf16(_stream(), d), "sdod_conv3x3_bf16")
+    return out
+
+
 def conv3x3_up2(x, w_oihw, bias=None, out_f32=False, block_n=0):
     """conv3x3(nearest_upsample_2x(x)) without the upsampled tensor (sub-pixel form, 4/9 of the multiply-adds).
     x [B,H,W,Cin] bf16 NHWC, w_oihw [Cout,Cin,3,3] fp32 -> [B,2H,2W,Cout] bf16 (or fp32)."""

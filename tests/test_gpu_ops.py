@@ -377,6 +377,20 @@ def test_conv3x3_after_nearest_upsample_subpixel_form(B, H, Cin, Cout, f32):
     assert rel_err(got, want) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 64, 320, 320), (2, 32, 640, 640), (2, 16, 1280, 1280), (8, 64, 320, 320), (1, 8, 64, 96), (3, 4, 128, 64)])
+def test_conv3x3_stride2_on_strided_tma_boxes(B, H, Cin, Cout):
+    """UNet Downsample: stride 2, padding 1, no im2col buffer."""
+    torch.manual_seed(H + Cout)
+    x = bf(torch.randn(B, H, H, Cin)).to(DEV)
+    w = bf(torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).to(DEV)
+    b = torch.randn(Cout, device=DEV)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    got = ops.conv3x3_s2(x, ops.pack_conv3x3_weight(w), b, out_f32=True)
+    assert got.shape == (B, H // 2, H // 2, Cout) and rel_err(got, want) < TOL_BF16
+    got16 = ops.conv3x3_s2(x, ops.pack_conv3x3_weight(w), b)
+    assert rel_err(got16, want) < TOL_BF16
+
+
 def test_conv3x3_fused_temb_and_residual():
     torch.manual_seed(21)
     B, H, W, Cin, Cout = 2, 32, 32, 320, 640
