@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 32 * EW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], (PERSIST && mp.epi_groups == 2) ? 16 * EW : 32 * EW); }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
@@ -580,16 +580,29 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     } else {
         // -------------------------------------------------------------------- epilogue
         int res_uses = 0;                              // residual-barrier phases consumed so far (stream-K head segments load no residual)
+        // Two epilogue groups (persistent variant, mp.epi_groups == 2): the 16 epilogue warps split into two groups of 8 that take ALTERNATE tiles —
+        // group g always drains TMEM accumulator g and stages in half g of the epilogue region — so one group's TMEM-load / math / store latencies
+        // overlap the other group's instead of all 16 warps walking one tile in lockstep (ncu, GEGLU projection at batch 8: issue slots 48 %,
+        // tensor pipe 26 %, L2 24 %: nothing saturated, the per-tile epilogue chain was the critical path).
+        const bool two = PERSIST && mp.epi_groups == 2;
+        const int half_raw = (warp - 2) >> 2;          // which of the quarter's NPART warps
+        const int grp = two ? (half_raw >> 1) : 0;
+        const int half = two ? (half_raw & 1) : half_raw;
+        const int npart = two ? NPART / 2 : NPART;
+        const int gthreads = two ? 16 * EW : 32 * EW;  // threads of this group
+        const int gbar = 5 + grp;                      // the group's named barrier (5 | 6); per-quarter barriers: 1..4 (group 0), 7..10 (group 1)
+        auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(gthreads) : "memory"); };
         SDOD_TILE_LOOP {
+        if (two && (wk.iter & 1) != grp) continue;     // the other group's tile
         SDOD_TILE_COORDS
         const int ab = PERSIST ? (iter & 1) : 0;
         float* s_bias = s_bias_base + ab * BN;         // double-buffered: a fast warp may already stage the next tile's bias
         // Bias tile: staged while the mainloop runs.  A persistent CTA stages tile i+1's bias during tile i's epilogue (the global
         // load is issued here and parked in a register; it lands in the other buffer at the end of the iteration), so no tile starts
         // with an exposed L2 round trip.
-        const int te = static_cast<int>(threadIdx.x) - 64;
+        const int te = static_cast<int>(threadIdx.x) - 64 - grp * gthreads;
         float bias_next = 0.f;
-        const bool stage_next = PERSIST && !wk.sk && mp.tma_epi && t + static_cast<int>(gridDim.x) < wk.t_end && te < BN;
+        const bool stage_next = PERSIST && !two && !wk.sk && mp.tma_epi && t + static_cast<int>(gridDim.x) < wk.t_end && te < BN;
         // stream-K role of this segment: a head segment (starts inside the tile) only publishes its partial; the segment that starts the tile
         // folds the partials of the CTAs that follow it (their shares begin inside this tile) and runs the epilogue
         const bool sk_publish = PERSIST && wk.sk && wk.seg_lo > 0;
@@ -600,9 +613,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                    WorkWalk::share_begin(mp, blockIdx.x + sk_parts + 1) < tile_end) ++sk_parts;
         }
         if (mp.tma_epi) {
-            if (!PERSIST || iter == 0 || wk.sk)
-                for (int i = te; i < BN; i += 32 * EW) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
-            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");   // (persistent: also orders the previous tile's staging reads/stores)
+            if (!PERSIST || iter == 0 || wk.sk || two)
+                for (int i = te; i < BN; i += gthreads) s_bias[i] = (ep.bias && n0 + i < mp.N) ? ep.bias[n0 + i] : 0.f;
+            group_sync();                                                // (persistent: also orders the previous tile's staging reads/stores)
             if (stage_next) {
                 const int n_next = ((t + static_cast<int>(gridDim.x)) % mp.n_tiles) * BN + te;
                 bias_next = (ep.bias && n_next < mp.N) ? __ldg(ep.bias + n_next) : 0.f;
@@ -613,11 +626,10 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         if (threadIdx.x == 64 && iter == 0) tstamp(mp, 5);                 // accumulator complete
         const uint32_t res_parity = PERSIST ? (res_uses & 1) : 0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which of the quarter's NPART warps
         // this warp's columns, in 16-column units: [j_lo, j_hi) of the BN-wide tile, [g_lo, g_hi) of a GEGLU half tile
-        const int j_lo = 16 * (((BN / 16) * half) / NPART), j_hi = 16 * (((BN / 16) * (half + 1)) / NPART);
-        const int g_lo = 16 * (((BN / 32) * half) / NPART), g_hi = 16 * (((BN / 32) * (half + 1)) / NPART);
-        auto quarter_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(32 * NPART) : "memory"); };
+        const int j_lo = 16 * (((BN / 16) * half) / npart), j_hi = 16 * (((BN / 16) * (half + 1)) / npart);
+        const int g_lo = 16 * (((BN / 32) * half) / npart), g_hi = 16 * (((BN / 32) * (half + 1)) / npart);
+        auto quarter_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(q + 1 + 6 * grp), "r"(32 * npart) : "memory"); };
         const int row = q * 32 + lane;
         const int m = m0 + row;
         const uint32_t taddr = tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -632,7 +644,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     } while (!seen);
                 }
             }
-            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");
+            group_sync();
         }
         // 16 accumulator columns [j, j+16) of this thread's row: TMEM, plus (stream-K) the published partials of the later K ranges
         auto acc_ld16 = [&](int j, uint32_t (&acc)[16]) {
@@ -667,7 +679,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                                           __uint_as_float(acc[4 * q4 + 3]));
             }
             __threadfence();
-            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");
+            group_sync();
             if (threadIdx.x == 64) {
                 const unsigned int one = 1u;
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mp.counters + blockIdx.x), "r"(one) : "memory");
@@ -712,8 +724,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     const uint64_t a23 = fma_f32x2(pack_f32x2(__uint_as_float(a[4 * q4 + 2]), __uint_as_float(a[4 * q4 + 3])), alpha2, pack_f32x2(ba.z, ba.w));
                     const uint64_t g01 = fma_f32x2(pack_f32x2(__uint_as_float(g[4 * q4]), __uint_as_float(g[4 * q4 + 1])), alpha2, pack_f32x2(bg.x, bg.y));
                     const uint64_t g23 = fma_f32x2(pack_f32x2(__uint_as_float(g[4 * q4 + 2]), __uint_as_float(g[4 * q4 + 3])), alpha2, pack_f32x2(bg.z, bg.w));
-                    unpack_f32x2(mul_f32x2(a01, gelu_f32x2(g01)), v[4 * q4], v[4 * q4 + 1]);
-                    unpack_f32x2(mul_f32x2(a23, gelu_f32x2(g23)), v[4 * q4 + 2], v[4 * q4 + 3]);
+                    unpack_f32x2(mul_f32x2(a01, mp.geglu_tanh ? gelu_tanh_f32x2(g01) : gelu_f32x2(g01)), v[4 * q4], v[4 * q4 + 1]);
+                    unpack_f32x2(mul_f32x2(a23, mp.geglu_tanh ? gelu_tanh_f32x2(g23) : gelu_f32x2(g23)), v[4 * q4 + 2], v[4 * q4 + 3]);
                 }
                 uint8_t* rowp = qbase + (j >> 5) * 4096 + lane * 64;
                 const int u0 = (j & 31) >> 3;
@@ -731,8 +743,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 for (int bx = 0; bx < NBG; ++bx)
                     if (n_tile * HALF + bx * 32 < mp.N / 2) tma_store_3d(&tmC, qbase + bx * 4096, n_tile * HALF + bx * 32, m0 + q * 32, bz);
                 bulk_commit();
-                if (dbuf) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
-                else bulk_wait_read_all();
+                if (dbuf && !two) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
+                else bulk_wait_read_all();                     // (two groups: this group re-stages the same half on its next tile)
             }
         } else if (ep.act == SDOD_ACT_GEGLU && !(ep.out_mode == SDOD_OUT_BF16 && mp.N % 8 == 0 && ep.ldc % 4 == 0)) {
             constexpr int HALF = BN / 2;
@@ -799,8 +811,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     else tma_store_3d(&tmC2, qbase + bx * BOXB, tok, d0, bh);
                 }
                 bulk_commit();
-                if (dbuf) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
-                else bulk_wait_read_all();
+                if (dbuf && !two) bulk_wait_read_but_last();   // the buffer staged next was stored a whole tile ago
+                else bulk_wait_read_all();                     // (two groups: this group re-stages the same half on its next tile)
             }
         } else if (mp.ln_fuse) {
             // fp32 TMA epilogue + LayerNorm of the finished rows (SpatialTransformer norm1/2/3 folded into the GEMM that produces
@@ -1028,7 +1040,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                         if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
                 }
                 bulk_commit();
-                if (dbuf) bulk_wait_read_but_last();
+                if (dbuf && !two) bulk_wait_read_but_last();
                 else bulk_wait_read_all();             // smem may be released once the stores have read it
             }
         } else if (ep.out_mode == SDOD_OUT_BF16 || ep.out_mode == SDOD_OUT_F32) {
@@ -1201,7 +1213,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         if (threadIdx.x == 64 && iter == 0) tstamp(mp, 6);                 // epilogue of the first tile done (stores issued and read)
         if (mp.tma_epi == 2 && !(PERSIST && sk_publish)) ++res_uses;
         if (PERSIST && sk_parts) {                                         // every thread has folded the partials: re-arm their flags
-            asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory");
+            group_sync();
             if (threadIdx.x == 64)
                 for (int c = 1; c <= sk_parts; ++c) mp.counters[blockIdx.x + c] = 0u;
         }
@@ -1304,6 +1316,8 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     dim3 grid(g.n_tiles, g.m_tiles, mp.split > 1 ? mp.split : g.batch);
     if (g.pair) grid = dim3((g.m_tiles + 1) & ~1, g.n_tiles, grid.z);
     const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
+    if (grid.y > 65535u || grid.z > 65535u)
+        return fail(kUnsupported, "gemm / conv: " + std::to_string(g.m_tiles) + " row tiles exceed one launch (65,535): split the batch");
     if constexpr (BN == 128 || BN == 160) {
         if (g.persist) {
             const int sms = device_sm_count();
@@ -1505,6 +1519,10 @@ static void choose_persist(GemmLaunch* out) {
     // measured (tools/hot_kernels.py, B200 r1): K=320 GEGLU 111.6 -> 92.2 us, QKV 87.0 -> 82.9 us; K=1280 (20 blocks) 46.1 -> 58.3 us,
     // where two co-resident CTAs with their own rings hide the loads better than one 4-stage ring
     out->persist = (mp.tiles_total >= 3 * sms && mp.k_blocks <= 10) ? 1 : 0;
+    // two epilogue groups on alternate tiles wherever the staging region holds two tiles (bf16 / GEGLU / head-layout outputs, no residual to
+    // pre-load): SDOD_EPI_GROUPS=1 restores the single group of 16 warps (A/B measurements)
+    static const int groups_env = [] { const char* e = std::getenv("SDOD_EPI_GROUPS"); return e ? std::atoi(e) : 2; }();
+    mp.epi_groups = (out->persist && groups_env == 2 && (mp.tma_epi == 3 || (mp.tma_epi == 1 && mp.c_bytes == 2))) ? 2 : 1;
 }
 
 static int k_rotation(int k_blocks) {
@@ -1655,6 +1673,12 @@ static int gemm_prepare_impl(const sdod_gemm_desc& d, GemmLaunch* out, bool try_
     if (sk_grid) { mp.streamk = 1; mp.ws = g_splitk.ws; mp.counters = g_splitk.counters; }
     out->sk_grid = sk_grid;
     mp.split_cluster = split_cluster_mode(mp, pair, d.epi.act);
+    {
+        // Off by default: measured on B200 (r2) the tanh form takes the isolated 64x64 GEGLU projection at batch 32 from 373.8 to 353.2 us but the
+        // whole batch-32 pass does not move (40.38 vs 40.33 ms) — not worth leaving the exact erf form for.  SDOD_GEGLU_TANH=1 enables it (A/B).
+        static const int env = [] { const char* e = std::getenv("SDOD_GEGLU_TANH"); return e ? std::atoi(e) : 0; }();
+        mp.geglu_tanh = env;
+    }
     out->mp = mp; out->ep = d.epi; out->bn = bn;
     out->mp.tlog = g_tlog;
     SDOD_TRY(setup_second_operand(out, d.A2, d.lda2, K2, d.M, d.K / kBlockK));

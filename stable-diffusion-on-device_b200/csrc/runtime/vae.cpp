@@ -7,6 +7,8 @@
 // O accumulator (128x512 fp32) would fill TMEM on its own and it is 1.4 % of the decoder FLOPs.
 #include "vae.h"
 
+#include <algorithm>
+
 #include <cmath>
 #include <stdexcept>
 
@@ -154,14 +156,22 @@ std::unique_ptr<Plan> VaeDecoder::build(int B) {
 
 int VaeDecoder::decode(cudaStream_t s, const float* z, uint8_t* image_u8, float* image_f32, int B, bool use_graph) {
     if (B < 1 || B > max_batch_) return fail(kInvalidArgument, "vae decode: batch exceeds max_batch");
+    // Large batches are decoded in chunks: at 512x512 one image is 2,048 row tiles of the last level's convolutions, and a launch addresses at
+    // most 65,535 row tiles (gridDim.y) — 32 images per launch would be 65,536.  16 images per chunk keeps every level multi-wave anyway.
+    int chunk_max = 1;
+    while (2LL * chunk_max * 64 * hw_ * hw_ / 128 <= 65535 && 2 * chunk_max <= max_batch_) chunk_max *= 2;     // largest power of two that fits
     try {
-        auto it = plans_.find(B);
-        if (it == plans_.end()) it = plans_.emplace(B, build(B)).first;
-        if (z != z_in_) SDOD_TRY(check_cuda(cudaMemcpyAsync(z_in_, z, static_cast<size_t>(B) * hw_ * hw_ * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s), "copy z"));
-        SDOD_TRY(it->second->run(s, use_graph));
-        const size_t n = static_cast<size_t>(B) * 8 * hw_ * 8 * hw_ * 3;
-        if (image_u8) SDOD_TRY(check_cuda(cudaMemcpyAsync(image_u8, u8_out_, n, cudaMemcpyDefault, s), "copy image u8"));
-        if (image_f32) SDOD_TRY(check_cuda(cudaMemcpyAsync(image_f32, img_out_, n * sizeof(float), cudaMemcpyDefault, s), "copy image f32"));
+        const size_t lat1 = static_cast<size_t>(hw_) * hw_ * 4, img1 = static_cast<size_t>(8) * hw_ * 8 * hw_ * 3;
+        for (int b0 = 0; b0 < B; b0 += chunk_max) {
+            const int nb = std::min(chunk_max, B - b0);
+            auto it = plans_.find(nb);
+            if (it == plans_.end()) it = plans_.emplace(nb, build(nb)).first;
+            const float* zc = z + b0 * lat1;
+            if (zc != z_in_) SDOD_TRY(check_cuda(cudaMemcpyAsync(z_in_, zc, nb * lat1 * sizeof(float), cudaMemcpyDeviceToDevice, s), "copy z"));
+            SDOD_TRY(it->second->run(s, use_graph));
+            if (image_u8) SDOD_TRY(check_cuda(cudaMemcpyAsync(image_u8 + b0 * img1, u8_out_, nb * img1, cudaMemcpyDefault, s), "copy image u8"));
+            if (image_f32) SDOD_TRY(check_cuda(cudaMemcpyAsync(image_f32 + b0 * img1, img_out_, nb * img1 * sizeof(float), cudaMemcpyDefault, s), "copy image f32"));
+        }
         return kOk;
     } catch (const std::exception& e) {
         return fail(kCudaError, std::string("vae decode: ") + e.what());

@@ -129,3 +129,15 @@ def test_random_init_models_run():
     vae = M.VaeDecoder(None, seed=7, latent_hw=8, max_batch=1)
     u8, img = vae(torch.randn(1, 4, 8, 8))
     assert u8.shape == (1, 64, 64, 3) and img.min() >= 0 and img.max() <= 1
+
+
+def test_vae_decode_more_images_than_one_launch_can_address():
+    """32 images at 512x512 are 65,536 row tiles in the last level — one more than gridDim.y allows: the decoder splits the batch itself
+    (found by the 4-GPU C5 sweep, where a rank decodes 32 images per call)."""
+    vae = M.VaeDecoder(None, seed=1, latent_hw=64, max_batch=32)
+    z = torch.randn(32, 4, 64, 64, generator=torch.Generator().manual_seed(9)).to(DEV)
+    u8, _ = vae(z)
+    ref = M.VaeDecoder(None, seed=1, latent_hw=64, max_batch=16)
+    a, _ = ref(z[:16])
+    b, _ = ref(z[16:])
+    assert torch.equal(u8, torch.cat([a, b], 0))
