@@ -317,6 +317,18 @@ def test_gemm_persistent_scheduler_epilogues():
         assert got.shape == want.shape and rel_err(got, want) < TOL_BF16
 
 
+def test_gemm_persistent_single_epilogue_group_in_subprocess():
+    """The persistent GEMM's two epilogue groups (alternate tiles) are the default; SDOD_EPI_GROUPS=1 (all 16 epilogue warps on one tile, the
+    round-1 form) is read once per process, so it is checked in a child process."""
+    import subprocess
+    import sys
+    root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "persistent_scheduler or geglu_packed or qkv_projection"], env=dict(os.environ, SDOD_EPI_GROUPS="1"), capture_output=True,
+                       text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_gemm_batched():
     torch.manual_seed(13)
     a, w = bf(torch.randn(6, 200, 128)).to(DEV), bf(torch.randn(6, 328, 128) / 11).to(DEV)
