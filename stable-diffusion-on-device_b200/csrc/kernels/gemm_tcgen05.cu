@@ -525,7 +525,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                     tma_load_3d_pair(sB + s * Cfg::kBBytes, &tmW, fb, kb * kBlockK, n0 + static_cast<int>(rank) * (BN / 2), mp.w_batched ? bz : 0);
                     continue;
                 }
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                // weight-stationary walk: after this CTA's first tile the B half of every stage already holds the right K block of its one N tile
+                const bool load_b = !(PERSIST && mp.b_resident && wk.iter > 0);
+                mbar_arrive_expect_tx(&full_bar[s], load_b ? Cfg::kStageBytes : kABytes);
                 if (kb >= mp.kb_a2) {
                     tma_load_3d(sA + s * kABytes, &tmA2, &full_bar[s], (kb - mp.kb_a2) * kBlockK, m0, bz);
                 } else if (mp.conv) {
@@ -536,7 +538,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 } else {
                     tma_load_3d(sA + s * kABytes, &tmA, &full_bar[s], kb * kBlockK, m0, bz);
                 }
-                tma_load_3d(sB + s * Cfg::kBBytes, &tmW, &full_bar[s], kb * kBlockK, n0, mp.w_batched ? bz : 0);
+                if (load_b) tma_load_3d(sB + s * Cfg::kBBytes, &tmW, &full_bar[s], kb * kBlockK, n0, mp.w_batched ? bz : 0);
             }
             }   // tile loop
         }
@@ -1321,7 +1323,9 @@ static int launch_gemm(cudaStream_t stream, const GemmLaunch& g) {
     if constexpr (BN == 128 || BN == 160) {
         if (g.persist) {
             const int sms = device_sm_count();
-            SDOD_TRY((launch_gemm_cfg<BN, true, false, true>(stream, g, dim3(mp.streamk ? g.sk_grid : (mp.tiles_total < sms ? mp.tiles_total : sms)))));
+            int pgrid = mp.streamk ? g.sk_grid : (mp.tiles_total < sms ? mp.tiles_total : sms);
+            if (mp.b_resident) pgrid = (sms / g.n_tiles) * g.n_tiles;      // a multiple of the N tile count: tile t + k*grid keeps t's N tile
+            SDOD_TRY((launch_gemm_cfg<BN, true, false, true>(stream, g, dim3(pgrid))));
             count_launch();
             return check_launch("gemm_tcgen05_kernel (persistent)");
         }
@@ -1521,6 +1525,16 @@ static void choose_persist(GemmLaunch* out) {
     out->persist = (mp.tiles_total >= 3 * sms && mp.k_blocks <= 10) ? 1 : 0;
     // two epilogue groups on alternate tiles wherever the staging region holds two tiles (bf16 / GEGLU / head-layout outputs, no residual to
     // pre-load): SDOD_EPI_GROUPS=1 restores the single group of 16 warps (A/B measurements)
+    // weight-stationary walk (see MainloopParams::b_resident): with the ring exactly one tile deep the weight half never has to be re-fetched, which
+    // halves the L2 -> SM operand bytes of a K = 320 layer.  Opt-in (SDOD_B_RESIDENT=1): measured on B200 (r2) it is SLOWER — GEGLU projection at
+    // batch 32 383.9 vs 369.7 us, batch 8 106.5 vs 103.5 us — so operand traffic is not what bounds these layers (and 140 of 148 SMs are used).
+    static const int bres_env = [] { const char* e = std::getenv("SDOD_B_RESIDENT"); return e ? std::atoi(e) : 0; }();
+    mp.b_resident = 0;
+    if (out->persist && bres_env && out->batch == 1 && !mp.w_batched && !mp.k_rot && mp.kb_a2 >= mp.k_blocks && out->n_tiles <= sms &&
+        mp.tiles_total >= (sms / out->n_tiles) * out->n_tiles) {
+        const int stages = out->bn == 128 ? GemmCfg<128, true, false, true>::kStages : GemmCfg<160, true, false, true>::kStages;
+        if (mp.k_blocks == stages) mp.b_resident = 1;
+    }
     static const int groups_env = [] { const char* e = std::getenv("SDOD_EPI_GROUPS"); return e ? std::atoi(e) : 2; }();
     mp.epi_groups = (out->persist && groups_env == 2 && (mp.tma_epi == 3 || (mp.tma_epi == 1 && mp.c_bytes == 2))) ? 2 : 1;
 }

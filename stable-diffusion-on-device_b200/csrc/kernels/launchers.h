@@ -32,6 +32,8 @@ struct MainloopParams {
     unsigned long long* tlog; // profiling hook (tools/gemm_timeline.py): per-CTA globaltimer stamps of the kernel's phases, 16 slots per CTA; NULL = off
     const char* pf_ptr;       // L2 prefetch of the NEXT layer's weights (constant data, issued before griddepcontrol.wait); NULL = none
     long long pf_bytes;
+    int b_resident;    // persistent variant, k_blocks == ring stages and grid % n_tiles == 0: a CTA keeps one N tile for its whole walk and stage s always
+                       //    holds K block s, so the weight tile is loaded once and only the A rows are streamed (half the L2 -> SM operand bytes)
     int epi_groups;    // persistent variant: 2 = two epilogue warp groups on alternate tiles / TMEM accumulators (see the kernel); else one group of 16 warps
     int geglu_tanh;    // GEGLU TMA epilogue: gate GELU in tanh form (1 MUFU + 5 packed ops instead of 2 MUFU + 14; see common.cuh)
     int cstride;       // conv stride (1 | 2): tile pixel (x, y) reads input (cstride*x + kx - 1, cstride*y + ky - 1); H, W, bw, bh are OUTPUT extents
