@@ -42,6 +42,8 @@ template <> SDOD_DEVICE void ld8<float>(const float* p, float* f) {
 
 // One warp normalises R consecutive rows at once: all R x NV 32-byte loads are issued before the first reduction, so a warp
 // keeps R rows in flight (with one row per warp the kernel ran at ~2.3 TB/s, bound by load latency and CTA turnover).
+// (Round 2: a <= 64-register form with half the rows per warp and four CTAs per SM was slower at batch 32 — 77.5 vs 75.2 us at 131,072 x 320,
+// 57.7 vs 45.0 us at 32,768 x 640 — rows in flight per warp matter more than resident warps; dropped.)
 // MINB: resident CTAs per SM the register budget must allow.  Round 2: at large row counts the <2,4> form (113 registers, 2 CTAs per SM) ran at
 // 39 % of DRAM bandwidth — the CTA is a load phase, a reduce phase and a store phase with nothing overlapping them but the other resident CTA —
 // so big launches use two rows per warp and four CTAs per SM (profiles/r02_kernels_ncu_full.txt, r02_layer_norm.txt).
