@@ -44,12 +44,9 @@ template <> SDOD_DEVICE void ld8<float>(const float* p, float* f) {
 // keeps R rows in flight (with one row per warp the kernel ran at ~2.3 TB/s, bound by load latency and CTA turnover).
 // (Round 2: a <= 64-register form with half the rows per warp and four CTAs per SM was slower at batch 32 — 77.5 vs 75.2 us at 131,072 x 320,
 // 57.7 vs 45.0 us at 32,768 x 640 — rows in flight per warp matter more than resident warps; dropped.)
-// MINB: resident CTAs per SM the register budget must allow.  Round 2: at large row counts the <2,4> form (113 registers, 2 CTAs per SM) ran at
-// 39 % of DRAM bandwidth — the CTA is a load phase, a reduce phase and a store phase with nothing overlapping them but the other resident CTA —
-// so big launches use two rows per warp and four CTAs per SM (profiles/r02_kernels_ncu_full.txt, r02_layer_norm.txt).
-template <typename T, int NV, int R, int MINB = 1>
-__global__ void __launch_bounds__(256, MINB) layer_norm_kernel(const T* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
-                                                               const float* __restrict__ b, int rows, int width, float eps) {
+template <typename T, int NV, int R>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int rows, int width, float eps) {
     griddep_wait();
     griddep_launch();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -322,21 +319,7 @@ SDOD_API int sdod_layer_norm(sdod_stream_t stream, const void* x, int in_dtype, 
         else                                                                                                                                     \
             launch_pdl(layer_norm_kernel<bf16, NV, R>, dim3(grid), dim3(256), 0, ST(stream), static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);  \
     } while (0)
-    static const int ln_env = [] { const char* e = std::getenv("SDOD_LN_VARIANT"); return e ? std::atoi(e) : 1; }();     // 0: round-1 shapes (A/B)
-    if (ln_env && rows >= 32768 && nv <= 3) {
-        // many rows: two (one) rows per warp at <= 64 registers, four CTAs per SM
-#define SDOD_LN4(NV, R)                                                                                                                          \
-    do {                                                                                                                                         \
-        const unsigned grid = static_cast<unsigned>((rows + 8 * R - 1) / (8 * R));                                                               \
-        if (in_dtype == SDOD_F32)                                                                                                                \
-            launch_pdl(layer_norm_kernel<float, NV, R, 4>, dim3(grid), dim3(256), 0, ST(stream), static_cast<const float*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps); \
-        else                                                                                                                                     \
-            launch_pdl(layer_norm_kernel<bf16, NV, R, 4>, dim3(grid), dim3(256), 0, ST(stream), static_cast<const bf16*>(x), static_cast<bf16*>(y), weight, bias, rows, width, eps);  \
-    } while (0)
-        if (nv <= 2) SDOD_LN4(2, 2);
-        else SDOD_LN4(3, 1);
-#undef SDOD_LN4
-    } else if (nv <= 2) SDOD_LN(2, 4);
+    if (nv <= 2) SDOD_LN(2, 4);
     else if (nv <= 3) SDOD_LN(3, 2);
     else if (nv <= 5) SDOD_LN(5, 2);
     else SDOD_LN(8, 1);
