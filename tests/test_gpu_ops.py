@@ -179,6 +179,20 @@ def test_layer_norm():
         assert rel_err(torch.ops.sdod.layer_norm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5), want) < TOL_BF16
 
 
+@pytest.mark.parametrize("rows,width", [(131072, 320), (32768 + 13, 640), (16384, 1280), (20000, 2048), (16392, 96)])
+@pytest.mark.parametrize("f32", [True, False])
+def test_layer_norm_tma_pipelined_kernel_for_many_rows(rows, width, f32):
+    """>= 16,384 rows go through the persistent kernel that streams row blocks with TMA bulk copies (ragged last block included)."""
+    torch.manual_seed(rows % 97 + width)
+    x = torch.randn(rows, width, device=DEV) * 2 + 1
+    x = x if f32 else x.to(torch.bfloat16)
+    w, b = torch.randn(width, device=DEV), torch.randn(width, device=DEV)
+    want = F.layer_norm(x.float(), (width,), w, b, 1e-5)
+    got = torch.ops.sdod.layer_norm(x, w, b, 1e-5)
+    assert got.dtype == torch.bfloat16 and rel_err(got, want) < TOL_BF16
+    assert torch.equal(got, torch.ops.sdod.layer_norm(x, w, b, 1e-5))
+
+
 # ------------------------------------------------------------------------------------------ sampler
 @pytest.mark.parametrize("guidance", [7.5, 1.0])
 def test_cfg_dpm_sampler_bit_exact_20_steps(guidance):
