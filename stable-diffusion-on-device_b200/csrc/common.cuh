@@ -293,7 +293,15 @@ SDOD_DEVICE float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
-SDOD_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (5 instructions).  The IEEE division of the first version (x / (1 + __expf(-x))) expands to MUFU.RCP + FCHK +
+// a Newton step + a slow-path branch: ncu showed the in-network GroupNorm at batch 32 instruction-bound (issue slots 59 %, DRAM 14 %,
+// profiles/r02_gn_group_b32_source_top.txt).  ~2 ulp of fp32; saturates correctly (x -> -inf gives -0, x -> +inf gives x).
+SDOD_DEVICE float silu_f(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 SDOD_DEVICE float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }     // CLIP's QuickGELU: x * sigmoid(1.702 x)
 // exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): a handful of FMAs + one MUFU exp + one rcp
 // instead of erff's long polynomial — the GEGLU epilogue evaluates it on 21 M elements per 64x64 transformer block.

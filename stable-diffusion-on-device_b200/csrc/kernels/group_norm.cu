@@ -537,15 +537,20 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
         const float w0 = weight ? weight[c] : 1.f, w1 = weight ? weight[c + 1] : 1.f;
         const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
         const float A0 = rstd * w0, A1 = rstd * w1, B0 = -mean * A0 + b0, B1 = -mean * A1 + b1;
-        TO* ycol = y + static_cast<long long>(n) * HW * C + c;
-        bf16* rcol = raw ? raw + static_cast<long long>(n) * HW * C + c : nullptr;
-        for (int p = p0 + r0; p < p1; p += rpb) {
-            const float2 v = slab[(p - p0) * upr + u];
-            if (rcol) *reinterpret_cast<uint32_t*>(rcol + static_cast<long long>(p) * C) = pack_bf16x2(v.x, v.y);
+        // pointers advance by a fixed step (no 64-bit multiply per row); two rows per trip for instruction-level parallelism
+        const long long step = static_cast<long long>(rpb) * C;
+        TO* yp = y + (static_cast<long long>(n) * HW + p0 + r0) * C + c;
+        bf16* rp = raw ? raw + (static_cast<long long>(n) * HW + p0 + r0) * C + c : nullptr;
+        const float2* sp = slab + r0 * upr + u;
+        const int sstep = rpb * upr;
+#pragma unroll 2
+        for (int p = p0 + r0; p < p1; p += rpb, yp += step, sp += sstep) {
+            const float2 v = *sp;
+            if (rp) { *reinterpret_cast<uint32_t*>(rp) = pack_bf16x2(v.x, v.y); rp += step; }
             float o0 = fmaf(v.x, A0, B0), o1 = fmaf(v.y, A1, B1);
             if (fuse_silu) { o0 = silu_f(o0); o1 = silu_f(o1); }
-            if (sizeof(TO) == 4) *reinterpret_cast<float2*>(ycol + static_cast<long long>(p) * C) = make_float2(o0, o1);
-            else *reinterpret_cast<uint32_t*>(ycol + static_cast<long long>(p) * C) = pack_bf16x2(o0, o1);
+            if (sizeof(TO) == 4) *reinterpret_cast<float2*>(yp) = make_float2(o0, o1);
+            else *reinterpret_cast<uint32_t*>(yp) = pack_bf16x2(o0, o1);
         }
     }
     if (cs > 1) cluster_sync_all();                         // peers may still be reading this CTA's totals
