@@ -57,7 +57,10 @@ struct GemmCfg {
     static constexpr int kBiasBytes = 2 * BN * 4 < 1024 ? 1024 : 2 * BN * 4;      // two bias tiles (double-buffered when persistent)
     static constexpr int kPersistRaw = (232448 - 1024 - 256 - kBiasBytes - kEpiBytes) / kStageBytes;
     static constexpr int kStages = PERSIST ? (kPersistRaw > 8 ? 8 : kPersistRaw) : (DEEP ? (kDeepRaw > 8 ? 8 : kDeepRaw) : kShallow);
-    static constexpr int kTmemCols = PERSIST ? (2 * BN <= 256 ? 256 : 512) : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
+    // persistent: as many accumulators as the 512 TMEM columns hold (4 x 128 or 3 x 160) — the MMA thread runs up to kAccs - 1 tiles ahead of the
+    // epilogue groups (with two buffers it waited 30 % of its time for a drained accumulator, profiles/r02_geglu_source_top.txt)
+    static constexpr int kAccs = PERSIST ? (512 / BN > 4 ? 4 : 512 / BN) : 1;
+    static constexpr int kTmemCols = PERSIST ? 512 : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
     static_assert(PERSIST || kStages * kStageBytes >= 512 * (BN + 4), "the idle ring doubles as the epilogue staging area");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
@@ -419,9 +422,11 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     uint8_t* stage = PERSIST ? sB + STAGES * Cfg::kBBytes : smem;     // epilogue staging: own region, or the idle ring
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;             // [2] accumulator ready (one per TMEM buffer)
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2] accumulator drained by the epilogue (persistent only)
-    uint64_t* res_bar = tmem_empty_bar + 2;                   // [4] residual tiles landed (TMA epilogue), one per lane quarter
+    uint64_t* tmem_full_bar = empty_bar + STAGES;             // [4] accumulator ready (one per TMEM buffer)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 4;             // [4] accumulator drained by the epilogue (persistent only)
+    uint64_t* res_bar = tmem_empty_bar + 4;                   // [4] residual tiles landed (TMA epilogue), one per lane quarter
+    static_assert((2 * STAGES + 12) * 8 + 4 <= 256, "barrier block");
+    const int naccs = PERSIST ? min(Cfg::kAccs, mp.tmem_accs > 0 ? mp.tmem_accs : Cfg::kAccs) : 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
     float* s_bias_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2][BN] bias tiles
 
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], (PERSIST && mp.epi_groups == 2) ? 16 * EW : 32 * EW); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], (PERSIST && mp.epi_groups == 2) ? 16 * EW : 32 * EW); }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
@@ -549,10 +554,10 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             int g = 0;
             SDOD_TILE_LOOP {
             const int iter = wk.iter;
-            const int ab = PERSIST ? (iter & 1) : 0;                 // TMEM accumulator buffer of this tile
+            const int ab = PERSIST ? (iter % naccs) : 0;             // TMEM accumulator buffer of this tile
             const uint32_t tmem_acc = tmem_base + ab * BN;
-            if (PERSIST && iter >= 2) {                               // the epilogue of tile iter-2 has drained this buffer
-                mbar_wait(&tmem_empty_bar[ab], ((iter >> 1) - 1) & 1);
+            if (PERSIST && iter >= naccs) {                           // the epilogue of tile iter - naccs has drained this buffer
+                mbar_wait(&tmem_empty_bar[ab], ((iter / naccs) - 1) & 1);
                 tc_fence_after();
             }
             for (int kb = wk.seg_lo; kb < wk.seg_hi; ++kb, ++g) {
@@ -597,7 +602,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         SDOD_TILE_LOOP {
         if (two && (wk.iter & 1) != grp) continue;     // the other group's tile
         SDOD_TILE_COORDS
-        const int ab = PERSIST ? (iter & 1) : 0;
+        const int ab = PERSIST ? (iter & 1) : 0;       // bias / staging buffer
+        const int acc = PERSIST ? (iter % naccs) : 0;  // TMEM accumulator
         float* s_bias = s_bias_base + ab * BN;         // double-buffered: a fast warp may already stage the next tile's bias
         // Bias tile: staged while the mainloop runs.  A persistent CTA stages tile i+1's bias during tile i's epilogue (the global
         // load is issued here and parked in a register; it lands in the other buffer at the end of the iteration), so no tile starts
@@ -623,7 +629,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 bias_next = (ep.bias && n_next < mp.N) ? __ldg(ep.bias + n_next) : 0.f;
             }
         }
-        mbar_wait(&tmem_full_bar[ab], PERSIST ? ((iter >> 1) & 1) : 0);
+        mbar_wait(&tmem_full_bar[acc], PERSIST ? ((iter / naccs) & 1) : 0);
         tc_fence_after();
         if (threadIdx.x == 64 && iter == 0) tstamp(mp, 5);                 // accumulator complete
         const uint32_t res_parity = PERSIST ? (res_uses & 1) : 0;
@@ -634,7 +640,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         auto quarter_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(q + 1 + 6 * grp), "r"(32 * npart) : "memory"); };
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        const uint32_t taddr = tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         if (PERSIST && sk_parts) {
             // the CTAs whose shares begin inside this tile published their partials at the very start of their walks; the check is a formality
             if (threadIdx.x == 64) {
@@ -1221,7 +1227,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }
         tc_fence_before();
         if (stage_next) s_bias_base[(ab ^ 1) * BN + te] = bias_next;
-        if (PERSIST) mbar_arrive(&tmem_empty_bar[ab]);     // every TMEM read of this buffer has completed (tcgen05.wait::ld above)
+        if (PERSIST) mbar_arrive(&tmem_empty_bar[acc]);     // every TMEM read of this buffer has completed (tcgen05.wait::ld above)
         }   // tile loop
         if (PERSIST) bulk_wait_read_all();                 // (storing threads) shared memory stays valid until the last store has read it
     }
@@ -1536,6 +1542,8 @@ static void choose_persist(GemmLaunch* out) {
         if (mp.k_blocks == stages) mp.b_resident = 1;
     }
     static const int groups_env = [] { const char* e = std::getenv("SDOD_EPI_GROUPS"); return e ? std::atoi(e) : 2; }();
+    static const int accs_env = [] { const char* e = std::getenv("SDOD_TMEM_ACCS"); return e ? std::atoi(e) : 0; }();
+    mp.tmem_accs = accs_env;
     mp.epi_groups = (out->persist && groups_env == 2 && (mp.tma_epi == 3 || (mp.tma_epi == 1 && mp.c_bytes == 2))) ? 2 : 1;
 }
 
