@@ -35,7 +35,9 @@ constexpr int kBKV = 64;    // keys per tile: one thread holds a whole S row (64
 template <int DH, int MODE = 1>
 struct AttCfg {
     static constexpr bool PT = MODE >= 1;
-    static constexpr bool kOnes = MODE == 2;                  // ones row at V^T row DH
+    static constexpr bool kOnes = MODE >= 2;                  // ones row at V^T row DH
+    // MODE 3 / 4 / 5: 2 / 1 / 3 of every 8 exponential pairs run on the FMA pipe (ex2_poly2) instead of MUFU — bit i of the mask = pair i & 7
+    static constexpr unsigned kPolyMask = MODE == 3 ? 0x88u : (MODE == 4 ? 0x80u : (MODE == 5 ? 0xA4u : 0u));
     static constexpr int kVBoxRows = kOnes ? DH : ((DH + 15) / 16) * 16;
     static constexpr int kNK = (DH + 63) / 64;            // 64-wide d chunks of Q / K
     static constexpr int kKSteps = (DH + 15) / 16;        // UMMA K steps for S = Q K^T
@@ -62,7 +64,8 @@ SDOD_DEVICE float ex2(float x) {
 // P double-buffered in smem).  The O rescale is lazy: a row keeps its old reference max until the true max has grown by
 // more than 2^8, so most tiles skip the TMEM round trip and never wait for the previous PV.
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel err 7.7e-5 — well inside bf16 P).
-// Kept for the record: swapping 3 of every 8 MUFU exponentials for this did not pay off in round 1 (see the softmax loop).
+// Round 1 (P through shared memory, shared-memory-bound) lost 20 % with 3 of every 8 exponentials moved here; with P in TMEM the d = 40 kernel is
+// MUFU-bound (XU pipe 70 %) and moving ONE pair in eight (packed form below) gains 5.5 %; more than that and the issue slots bind instead.
 SDOD_DEVICE float ex2_poly(float x) {
     x = fmaxf(x, -120.0f);
     const float t = x + 12582912.0f;                 // 1.5 * 2^23: round to nearest integer in the low mantissa bits
@@ -71,6 +74,22 @@ SDOD_DEVICE float ex2_poly(float x) {
     p = fmaf(p, f, 0.6932762265205383f);
     p = fmaf(p, f, 0.9999289512634277f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Two exponentials at once in packed fp32 (FADD2 / FFMA2): ~11 issue slots per pair and no MUFU slot.
+SDOD_DEVICE void ex2_poly2(float x0, float x1, float& p0, float& p1) {
+    const uint64_t x = pack_f32x2(fmaxf(x0, -120.0f), fmaxf(x1, -120.0f));
+    const uint64_t t = add_f32x2(x, pack_f32x2(12582912.0f, 12582912.0f));
+    const uint64_t r = add_f32x2(t, pack_f32x2(-12582912.0f, -12582912.0f));
+    const uint64_t f = fma_f32x2(r, pack_f32x2(-1.0f, -1.0f), x);
+    uint64_t p = fma_f32x2(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f, pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+    p = fma_f32x2(p, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+    p = fma_f32x2(p, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(p, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 // PT = true: P never touches shared memory.  Each softmax thread writes its 32 probabilities (bf16 pairs, 16 columns) over the first half of
@@ -257,7 +276,13 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                 for (int i = 0; i < 16; ++i) {
                     float x0, x1;
                     unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), scale2, negm2), x0, x1);
-                    pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
+                    if ((Cfg::kPolyMask >> (i & 7)) & 1u) {
+                        float p0, p1;
+                        ex2_poly2(x0, x1, p0, p1);
+                        pk[i] = pack_bf16x2(p0, p1);
+                    } else {
+                        pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
+                    }
                 }
             } else
 #pragma unroll
@@ -371,8 +396,10 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
 static int attention_mode(int DH) {
     // SDOD_ATTN_MODE = 0 | 1 | 2 overrides the default (A/B measurements); MODE 2 exists for head dims with a spare V^T row group only
     static const int env = [] { const char* e = std::getenv("SDOD_ATTN_MODE"); return e ? std::atoi(e) : -1; }();
-    const int best = DH == 40 ? 2 : 1;
-    return env < 0 ? best : (env > best ? best : env);
+    // d = 40: MODE 4 = MODE 2 with one exponential pair in eight on the FMA pipe (B200 r2, B8 x 8 heads x 4096^2: 370.7 us as MODE 2, 350.2 as MODE 4,
+    // 354.3 with two pairs in eight (MODE 3), 372.8 with three (MODE 5); B2: 118.8 -> 108.5 us)
+    const int best = DH == 40 ? 4 : 1;
+    return env < 0 ? best : (env > (DH == 40 ? 5 : 1) ? best : env);
 }
 
 template <int DH>
@@ -400,7 +427,7 @@ static int prepare_attention(AttnLaunch* out, const void* Qh, const void* Kh, co
     {
         uint64_t dims[3] = {static_cast<uint64_t>(kv_pad), static_cast<uint64_t>(Cfg::kDV), static_cast<uint64_t>(BH)};
         uint64_t strides[2] = {static_cast<uint64_t>(kv_pad) * 2, static_cast<uint64_t>(Cfg::kDV) * kv_pad * 2};
-        uint32_t box[3] = {64, static_cast<uint32_t>(attention_mode(DH) == 2 ? DH : Cfg::kDV), 1};
+        uint32_t box[3] = {64, static_cast<uint32_t>(attention_mode(DH) >= 2 ? DH : Cfg::kDV), 1};
         SDOD_TRY(encode_tmap_bf16(&tmV, Vt, 3, dims, strides, box, true));
     }
     out->O = O; out->heads = heads; out->Nq = Nq; out->Nkv = Nkv; out->head_dim = DH; out->BH = BH; out->causal = 0;
@@ -429,6 +456,9 @@ static int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
     const int mode = attention_mode(DH);
     if constexpr (DH == 40) {
         if (mode == 2) return launch_attention_v<DH, 2>(a, stream);
+        if (mode == 3) return launch_attention_v<DH, 3>(a, stream);
+        if (mode == 4) return launch_attention_v<DH, 4>(a, stream);
+        if (mode == 5) return launch_attention_v<DH, 5>(a, stream);
     }
     return mode ? launch_attention_v<DH, 1>(a, stream) : launch_attention_v<DH, 0>(a, stream);
 }
