@@ -44,13 +44,14 @@ struct AttCfg {
     static constexpr int kDV = ((DH + 15) / 16) * 16;     // N of the PV MMA (rows of the V^T tile)
     static constexpr int kStages = DH > 80 ? 3 : 4;
     static constexpr int kQBytes = kNK * kBQ * 128;
+    static constexpr int kQBufs = DH <= 80 ? 2 : 1;       // two Q buffers: a CTA that walks several query tiles (qpc > 1) loads tile i+1 while it works on tile i
     static constexpr int kKBytes = kNK * kBKV * 128;
     static constexpr int kVBytes = kVBoxRows * 128;       // one 64-key chunk: the TMA box, kVBoxRows rows of 128 B
     static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;
     static constexpr int kStageBytes = kKBytes + kVChunk;
     static constexpr int kPBytes = kBQ * 128;             // one P buffer: 128 rows x 64 keys bf16
     static constexpr int kTmemCols = (128 + 2 * kDV) <= 256 ? 256 : 512;   // S double buffer + two O accumulators
-    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + (PT ? 0 : 2 * kPBytes) + 1024 + 256 + 3 * 256 * 4;   // + row-max / row-sum exchange
+    static constexpr int kSmemBytes = kQBufs * kQBytes + kStages * kStageBytes + (PT ? 0 : 2 * kPBytes) + 1024 + 256 + 4096;   // + row-max / row-sum exchange
 };
 
 SDOD_DEVICE float ex2(float x) {
@@ -102,7 +103,7 @@ template <int DH, int MODE>
 __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O,
-                                                                 int heads, int Nq, int Nkv, float scale_log2, int causal) {
+                                                                 int heads, int Nq, int Nkv, float scale_log2, int causal, int qpc) {
     using Cfg = AttCfg<DH, MODE>;
     constexpr bool PT = Cfg::PT;
     constexpr int STAGES = Cfg::kStages;
@@ -110,11 +111,11 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned shared-space pointer
     uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + Cfg::kQBytes;
+    uint8_t* sKV = sQ + (qpc > 1 ? 2 : 1) * Cfg::kQBytes;        // (the second Q buffer exists only in multi-tile launches: same footprint as before otherwise)
     uint8_t* sP = sKV + STAGES * Cfg::kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PT ? 0 : 2 * Cfg::kPBytes));
-    uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                 // [STAGES]
+    uint64_t* q_full = bars;                      // [2]
+    uint64_t* kv_full = bars + 2;                 // [STAGES]
     uint64_t* kv_empty = kv_full + STAGES;        // [STAGES]
     uint64_t* s_full = kv_empty + STAGES;         // [2]
     uint64_t* s_free = s_full + 2;                // [2]
@@ -122,20 +123,31 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     uint64_t* p_free = p_full + 2;                // [2]
     uint64_t* o_ready = p_free + 2;
     uint64_t* o_final = o_ready + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
-    float* xch = reinterpret_cast<float*>(bars + 32);          // [2 tile parities][2 halves][128 rows] partner exchange
+    uint64_t* q_free = o_final + 1;               // [2] every S MMA that reads Q buffer i has retired
+    uint64_t* o_free = q_free + 2;                // the epilogue has read both O accumulators (multi-tile CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+    static_assert(2 + 2 * STAGES + 8 + 2 + 2 + 1 < 32, "barrier block");
+    float* xch = reinterpret_cast<float*>(bars + 32);          // [2 query-tile parities][max | sum][2 halves][128 rows] partner exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q_tile = blockIdx.x, bh = blockIdx.y;
-    const int q0 = q_tile * kBQ;
-    // causal (the CLIP text encoder): key k is visible to query q iff k <= q, so this query tile needs the key tiles up to its last row only
-    const int n_tiles = causal ? (min(Nkv, q0 + kBQ) + kBKV - 1) / kBKV : (Nkv + kBKV - 1) / kBKV;
+    // A CTA walks qpc consecutive query tiles of one (batch, head).  qpc > 1 is the cross-attention form (host: all keys fit the K/V ring, not
+    // causal): K / V are loaded once and stay resident, Q is double-buffered, and the flat tile counter G = it * n_tiles + j drives the S / P
+    // buffers and their barrier phases, so tile i+1's Q load and QK^T overlap tile i's softmax tail and epilogue.  With 77 keys a CTA's life was
+    // one long latency chain (setup, TMEM allocation, three TMA round trips, two tiles, epilogue: 5.4 us per 128 queries at 2 CTAs/SM).
+    const int bh = blockIdx.y;
+    const int qt0 = blockIdx.x * qpc;
+    const int n_qt = (Nq + kBQ - 1) / kBQ;
+    const int n_it = min(qpc, n_qt - qt0);
+    // causal (the CLIP text encoder): key k is visible to query q iff k <= q, so a query tile needs the key tiles up to its last row only
+    const int n_tiles = causal ? (min(Nkv, qt0 * kBQ + kBQ) + kBKV - 1) / kBKV : (Nkv + kBKV - 1) / kBKV;
+    const bool kv_resident = qpc > 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(q_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&q_full[b], 1); mbar_init(&q_free[b], 1); }
+        mbar_init(o_free, 256);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 256); mbar_init(&p_full[b], 256); mbar_init(&p_free[b], 1); }
         mbar_init(o_ready, 1);
@@ -164,17 +176,23 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
-            mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
-            for (int c = 0; c < Cfg::kNK; ++c) tma_load_3d(sQ + c * (kBQ * 128), &tmQ, q_full, c * 64, q0, bh);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % STAGES;
-                const uint32_t ph = (j / STAGES) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], Cfg::kKBytes + Cfg::kVBytes);
-                uint8_t* sK = sKV + st * Cfg::kStageBytes;
-                uint8_t* sV = sK + Cfg::kKBytes;
-                for (int c = 0; c < Cfg::kNK; ++c) tma_load_3d(sK + c * (kBKV * 128), &tmK, &kv_full[st], c * 64, j * kBKV, bh);
-                tma_load_3d(sV, &tmV, &kv_full[st], j * kBKV, 0, bh);
+            for (int it = 0; it < n_it; ++it) {
+                const int qb = Cfg::kQBufs == 2 ? (it & 1) : 0;
+                if (it >= 2) mbar_wait(&q_free[qb], ((it >> 1) - 1) & 1);      // (qpc > 1 implies two Q buffers)
+                mbar_arrive_expect_tx(&q_full[qb], Cfg::kQBytes);
+                for (int c = 0; c < Cfg::kNK; ++c)
+                    tma_load_3d(sQ + qb * Cfg::kQBytes + c * (kBQ * 128), &tmQ, &q_full[qb], c * 64, (qt0 + it) * kBQ, bh);
+                if (it > 0) continue;                                          // K / V resident for the whole walk
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int st = j % STAGES;
+                    const uint32_t ph = (j / STAGES) & 1;
+                    mbar_wait(&kv_empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[st], Cfg::kKBytes + Cfg::kVBytes);
+                    uint8_t* sK = sKV + st * Cfg::kStageBytes;
+                    uint8_t* sV = sK + Cfg::kKBytes;
+                    for (int c = 0; c < Cfg::kNK; ++c) tma_load_3d(sK + c * (kBKV * 128), &tmK, &kv_full[st], c * 64, j * kBKV, bh);
+                    tma_load_3d(sV, &tmV, &kv_full[st], j * kBKV, 0, bh);
+                }
             }
         }
     } else if (warp == 1) {
@@ -182,41 +200,90 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, kBKV);
             constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, Cfg::kDV);
-            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-            mbar_wait(q_full, 0);
-            for (int j = 0; j <= n_tiles; ++j) {
-                if (j < n_tiles) {                                   // S_j = Q K_j^T -> S buffer j&1
-                    const int st = j % STAGES;
-                    mbar_wait(&kv_full[st], (j / STAGES) & 1);
-                    if (!PT && j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
-                    tc_fence_after();
-                    const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
+            const uint32_t p_addr = smem_u32(sP);
+            if (qpc == 1) {
+                // one query tile per CTA (self-attention): the round-2 loop, kept apart.  Routing self-attention through the general loop below cost
+                // 15 % (B8 d=40: 350 -> 401 us; 471 us with two integer divisions per tile); taking the next tile's K / V wait before the P wait
+                // changed nothing (365.5 vs 365.6 us with the switch compiled in) — the kernel is sensitive to code generation, not to that chain
+                const uint32_t q_addr = smem_u32(sQ);
+                mbar_wait(&q_full[0], 0);
+                for (int j = 0; j <= n_tiles; ++j) {
+                    if (j < n_tiles) {                                   // S_j = Q K_j^T -> S buffer j&1
+                        const int st = j % STAGES;
+                        mbar_wait(&kv_full[st], (j / STAGES) & 1);
+                        if (!PT && j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
+                        tc_fence_after();
+                        const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
 #pragma unroll
-                    for (int k = 0; k < Cfg::kKSteps; ++k) {
-                        const uint32_t qoff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
-                        const uint32_t koff = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
-                        tc_mma_bf16(tmem_base + (j & 1) * 64, make_kmajor_sw128_desc(q_addr + qoff), make_kmajor_sw128_desc(k_addr + koff), idesc_s, k != 0);
+                        for (int k = 0; k < Cfg::kKSteps; ++k) {
+                            const uint32_t qoff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                            const uint32_t koff = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
+                            tc_mma_bf16(tmem_base + (j & 1) * 64, make_kmajor_sw128_desc(q_addr + qoff), make_kmajor_sw128_desc(k_addr + koff), idesc_s, k != 0);
+                        }
+                        tc_commit(&s_full[j & 1]);
                     }
-                    tc_commit(&s_full[j & 1]);
+                    if (j >= 1) {                                        // O += P_i V_i for the previous tile
+                        const int i = j - 1, st = i % STAGES;
+                        mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
+                        const uint32_t pb = p_addr + (i & 1) * Cfg::kPBytes;
+#pragma unroll
+                        for (int k = 0; k < kBKV / 16; ++k) {  // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
+                            if (PT) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
+                                                   make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | (k & 1)) != 0);
+                            else tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
+                                             (i | (k & 1)) != 0);
+                        }
+                        tc_commit(&kv_empty[st]);
+                        tc_commit(o_ready);
+                    }
                 }
-                if (j >= 1) {                                        // O += P_i V_i for the previous tile
-                    const int i = j - 1, st = i % STAGES;
-                    mbar_wait(&p_full[i & 1], (i >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
-                    const uint32_t pb = p_addr + (i & 1) * Cfg::kPBytes;
-#pragma unroll
-                    for (int k = 0; k < kBKV / 16; ++k) {  // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
-                        if (PT) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
-                                               make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | (k & 1)) != 0);
-                        else tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
-                                         (i | (k & 1)) != 0);
+                tc_commit(o_final);                                      // every PV has retired
+            } else {
+                const int total = n_it * n_tiles;
+                int it = 0, j = 0, itp = 0, i = 0;                       // (query tile, key tile) of S_G and of PV_{G-1}: walked, not divided
+                for (int G = 0; G <= total; ++G) {                       // flat tile counter over the CTA's query tiles
+                    if (G < total) {                                     // S_G = Q K_j^T -> S buffer G&1
+                        const int st = j % STAGES;
+                        const int qb = Cfg::kQBufs == 2 ? (it & 1) : 0;
+                        if (j == 0) mbar_wait(&q_full[qb], (Cfg::kQBufs == 2 ? (it >> 1) : it) & 1);
+                        if (it == 0) mbar_wait(&kv_full[st], (j / STAGES) & 1);
+                        if (!PT && G >= 2) mbar_wait(&s_free[G & 1], ((G >> 1) - 1) & 1);
+                        tc_fence_after();
+                        const uint32_t q_addr = smem_u32(sQ + qb * Cfg::kQBytes);
+                        const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
+    #pragma unroll
+                        for (int k = 0; k < Cfg::kKSteps; ++k) {
+                            const uint32_t qoff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                            const uint32_t koff = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
+                            tc_mma_bf16(tmem_base + (G & 1) * 64, make_kmajor_sw128_desc(q_addr + qoff), make_kmajor_sw128_desc(k_addr + koff), idesc_s, k != 0);
+                        }
+                        tc_commit(&s_full[G & 1]);
+                        if (j == n_tiles - 1) tc_commit(&q_free[qb]);    // the last QK^T of this query tile: its Q buffer may be refilled
+                        if (++j == n_tiles) { j = 0; ++it; }
                     }
-                    tc_commit(&kv_empty[st]);
-                    tc_commit(o_ready);
+                    if (G >= 1) {                                        // O += P_i V_i for the previous tile
+                        const int Gp = G - 1, st = i % STAGES;
+                        mbar_wait(&p_full[Gp & 1], (Gp >> 1) & 1);
+                        if (i == 0 && itp > 0) mbar_wait(o_free, (itp - 1) & 1);   // the previous query tile's epilogue has read the accumulators
+                        tc_fence_after();
+                        const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
+                        const uint32_t pb = p_addr + (Gp & 1) * Cfg::kPBytes;
+    #pragma unroll
+                        for (int k = 0; k < kBKV / 16; ++k) {  // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
+                            if (PT) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + (Gp & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
+                                                   make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | (k & 1)) != 0);
+                            else tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
+                                             (i | (k & 1)) != 0);
+                        }
+                        if (!kv_resident) tc_commit(&kv_empty[st]);
+                        tc_commit(o_ready);
+                        if (i == n_tiles - 1) tc_commit(o_final);        // every PV of this query tile has retired
+                        if (++i == n_tiles) { i = 0; ++itp; }
+                    }
                 }
             }
-            tc_commit(o_final);                                      // every PV has retired
         }
     } else {
         // ---------------------------------------------------------------- softmax / lazy correction / epilogue
@@ -229,11 +296,14 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
         const int row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t tmem_mine = tmem_O + lane_off + half * Cfg::kDV;
-        float m_run = -1.0e30f, l_run = 0.f;          // finite "minus infinity": a half with no valid key yet keeps p = 0, alpha = 1
         const int sw = row & 7;
         const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+        for (int it = 0; it < n_it; ++it) {
+        const int q0 = (qt0 + it) * kBQ;
+        float m_run = -1.0e30f, l_run = 0.f;          // finite "minus infinity": a half with no valid key yet keeps p = 0, alpha = 1
         for (int j = 0; j < n_tiles; ++j) {
-            const int b = j & 1, u = j >> 1;
+            const int G = it * n_tiles + j;           // flat tile counter: S / P buffer and barrier phases
+            const int b = G & 1, u = G >> 1;
             const int kv_valid = min(kBKV, Nkv - j * kBKV) - half * 32;      // valid keys among this thread's 32
             mbar_wait(&s_full[b], u & 1);
             tc_fence_after();
@@ -318,7 +388,7 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             if (j > 0 && __any_sync(0xffffffffu, need)) {            // rare: this warp's accumulator must be rescaled
                 // PV_{j-1} must have completed.  s_full(j) above proves PV_{j-2} has, so o_ready is either in phase j-1 (pending) or
                 // already past it: the parity test is unambiguous even though this wait is not taken every tile.
-                mbar_wait(o_ready, (j - 1) & 1);
+                mbar_wait(o_ready, (G - 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < Cfg::kDV / 16; ++c) {
@@ -331,22 +401,23 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                 }
             }
             if (PT) tmem_st_wait();              // P (and a rescaled O) have landed in TMEM
-            else if (j > 0) tmem_st_wait();
+            else if (j > 0) tmem_st_wait();   // (MODE 0: only a rescale stores to TMEM)
             tc_fence_before();
             if (!PT) fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the UMMA async proxy
             mbar_arrive(&p_full[b]);
         }
         // epilogue: merge the two halves of each row
-        xch[half * 128 + row] = m_run;
-        xch[(2 + half) * 128 + row] = l_run;
+        float* xc = xch + (it & 1) * 512;            // double-buffered across query tiles: the partner may still be reading the previous one
+        xc[half * 128 + row] = m_run;
+        xc[(2 + half) * 128 + row] = l_run;
         asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-        const float m_o = xch[(half ^ 1) * 128 + row];
-        float l_o = xch[(2 + (half ^ 1)) * 128 + row];
+        const float m_o = xc[(half ^ 1) * 128 + row];
+        float l_o = xc[(2 + (half ^ 1)) * 128 + row];
         const float m_all = fmaxf(m_run, m_o);
         const float f_me = ex2(m_run - m_all), f_ot = ex2(m_o - m_all);
         // All PVs retired: a barrier of its own, committed once after the last PV.  (o_ready flips every tile and is no longer waited in
         // lockstep, so its parity cannot tell "all done" from "two behind" here.)
-        mbar_wait(o_final, 0);
+        mbar_wait(o_final, it & 1);
         tc_fence_after();
         if (Cfg::kOnes) {                                   // the row sums are column DH of the two accumulators
             uint32_t a[8], b[8];
@@ -385,6 +456,8 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             }
         }
         tc_fence_before();
+        if (it + 1 < n_it) mbar_arrive(o_free);      // both accumulators read: the next query tile's PV may overwrite them
+        }   // query tiles
     }
     __syncthreads();
     if (warp == 2) {
@@ -444,9 +517,21 @@ static int launch_attention_v(const AttnLaunch& a, cudaStream_t stream) {
                             "cudaFuncSetAttribute(attention)"));
         configured = true;
     }
-    dim3 grid((a.Nq + kBQ - 1) / kBQ, a.BH);
-    SDOD_TRY(check_cuda(launch_pdl(attention_kernel<DH, MODE>, grid, dim3(kAttThreads), Cfg::kSmemBytes, stream, a.tmQ, a.tmK, a.tmV,
-                                   static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv, a.scale_log2, a.causal), "launch attention_kernel"));
+    // Query tiles per CTA: cross-attention shapes (every key tile fits the K/V ring, so K / V stay resident) walk several query tiles per CTA
+    // as long as the grid still holds >= 4 CTAs per resident slot.  SDOD_ATTN_QPC overrides (1 = one tile per CTA as in round 1).
+    const int n_qt = (a.Nq + kBQ - 1) / kBQ, n_kt = (a.Nkv + kBKV - 1) / kBKV;
+    int qpc = 1;
+    if (Cfg::kQBufs == 2 && !a.causal && n_kt <= Cfg::kStages && n_qt > 1) {
+        static const int env = [] { const char* e = std::getenv("SDOD_ATTN_QPC"); return e ? std::atoi(e) : 0; }();
+        const long long slots = static_cast<long long>(device_sm_count()) * (DH <= 40 ? 2 : 1);
+        for (int c = 8; c >= 2 && qpc == 1; c >>= 1)
+            if (static_cast<long long>(a.BH) * ((n_qt + c - 1) / c) >= 4 * slots) qpc = c;
+        if (env >= 1) qpc = env > n_qt ? n_qt : env;
+    }
+    dim3 grid((n_qt + qpc - 1) / qpc, a.BH);
+    const size_t smem = Cfg::kSmemBytes - (qpc > 1 ? 0 : (Cfg::kQBufs - 1) * Cfg::kQBytes);
+    SDOD_TRY(check_cuda(launch_pdl(attention_kernel<DH, MODE>, grid, dim3(kAttThreads), smem, stream, a.tmQ, a.tmK, a.tmV,
+                                   static_cast<bf16*>(a.O), a.heads, a.Nq, a.Nkv, a.scale_log2, a.causal, qpc), "launch attention_kernel"));
     count_launch();
     return check_launch("attention_kernel");
 }

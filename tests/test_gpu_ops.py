@@ -485,6 +485,32 @@ def test_fused_attention(B, heads, dh, Nq, Nkv):
     assert rel_err(got, want) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,heads,dh,Nq", [(16, 8, 40, 4096), (32, 8, 80, 1024), (3, 8, 40, 1000)])
+def test_cross_attention_several_query_tiles_per_cta(B, heads, dh, Nq):
+    """Cross-attention grids with >= 4 CTAs per resident slot walk several query tiles per CTA (K / V resident, Q double-buffered, flat S / P
+    phase counter); the third case is below that threshold (one tile per CTA) with a ragged last query tile."""
+    torch.manual_seed(Nq + dh)
+    Cc, Nkv = heads * dh, 77
+    q, k, v = (bf(torch.randn(B, n, Cc) * s).to(DEV) for n, s in ((Nq, 1.5), (Nkv, 1.5), (Nkv, 1.0)))
+    got = torch.ops.sdod.attention(ops.pack_heads(q, heads, dh), ops.pack_heads(k, heads, dh), ops.pack_heads(v, heads, dh, True),
+                                   B, heads, dh, Nkv, dh ** -0.5)
+    want = _attn_ref(q, k, v, heads)
+    assert rel_err(got, want) < TOL_BF16
+    per_image = [rel_err(got[i], want[i]) for i in range(B)]           # no query tile may be skipped or written twice
+    assert max(per_image) < TOL_BF16, per_image
+
+
+def test_cross_attention_forced_ragged_tile_walk_in_subprocess():
+    """SDOD_ATTN_QPC=3 (read once per process): 3 query tiles per CTA does not divide the tile counts, so the last CTA of each head walks fewer."""
+    import subprocess
+    import sys
+    root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "test_fused_attention or several_query_tiles"], env=dict(os.environ, SDOD_ATTN_QPC="3"), capture_output=True,
+                       text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_attention_peaked_softmax_rescale_path():
     """Row maxima that keep growing along the key axis force the in-TMEM O rescale on every tile."""
     torch.manual_seed(77)

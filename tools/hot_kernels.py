@@ -69,3 +69,15 @@ if which in ("attn", "all"):
     fl = 4.0 * B * HEADS * TOK * TOK * DH
     ex = B * HEADS * TOK * TOK
     print("attn   B%d h%d N%d d%d: %.1f us  %.0f TFLOP/s  %.2f Texp/s" % (B, HEADS, TOK, DH, us, fl / us * 1e-6, ex / us * 1e-6))
+if which in ("xattn", "all"):
+    # cross-attention against the 77 CLIP tokens at the three UNet levels (d = 40 / 80 / 160)
+    for tok, heads_dh in ((4096, 40), (1024, 80), (256, 160)):
+        nkv = 77
+        dpad, vt_rows, kv_pad = ops.head_geometry(heads_dh, nkv)
+        q = torch.randn(B, tok, HEADS * heads_dh, device="cuda").to(torch.bfloat16)
+        k = torch.randn(B, nkv, HEADS * heads_dh, device="cuda").to(torch.bfloat16)
+        v = torch.randn(B, nkv, HEADS * heads_dh, device="cuda").to(torch.bfloat16)
+        qh, kh, vt = ops.pack_heads(q, HEADS, heads_dh), ops.pack_heads(k, HEADS, heads_dh), ops.pack_heads(v, HEADS, heads_dh, transpose=True)
+        us = timeit(lambda: torch.ops.sdod.attention(qh, kh, vt, B, HEADS, heads_dh, nkv, heads_dh ** -0.5))
+        by = qh.numel() * 2 + B * tok * HEADS * heads_dh * 2
+        print("xattn  B%d h%d Nq%d Nkv%d d%d: %.1f us  %.0f GB/s (Q read + O write)" % (B, HEADS, tok, nkv, heads_dh, us, by / us * 1e-3))
