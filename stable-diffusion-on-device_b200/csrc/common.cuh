@@ -141,6 +141,27 @@ SDOD_DEVICE void cluster_sync_unaligned() {     // same barrier, callable from d
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
+// Split cluster barrier without memory ordering (UCGABAR only).  barrier.cluster.arrive.release compiles to MEMBAR.ALL.GPU + ERRBAR: a warp
+// then waits for every global store it has in flight, which the short GroupNorm kernels cannot afford twice per launch.
+SDOD_DEVICE void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+SDOD_DEVICE void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+// Two / three floats into CTA `rank`'s shared memory at the address `local_dst` has here, completion (8 / 12 bytes) counted on that CTA's
+// mbarrier `local_bar`: the data and the transaction count travel together (STAS), so an all-gather of per-CTA statistics needs no fence,
+// no release/acquire cluster barrier and no exit barrier — the receiver waits on its own mbarrier and reads its own shared memory.
+SDOD_DEVICE void st_async_f32x2(const void* local_dst, const void* local_bar, uint32_t rank, float a, float b) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_dst)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(ra), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(rb) : "memory");
+}
+SDOD_DEVICE void st_async_f32x4(const void* local_dst, const void* local_bar, uint32_t rank, float a, float b, float c, float d) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_dst)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(ra), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(rb) : "memory");
+}
 SDOD_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 // fp32 load from the shared memory of CTA `rank` of this cluster, at the address `local_ptr` has in this CTA (distributed shared memory)
 SDOD_DEVICE float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {

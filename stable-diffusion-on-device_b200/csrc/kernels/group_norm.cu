@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(kGnClusterThreads) gn_nchw_cluster_kernel(cons
     __shared__ __align__(8) uint64_t bars[kGnMaxChunks];
     __shared__ float red_s[NT / 32], red_ss[NT / 32];
     __shared__ float cta_stats[4];   // n, mean, M2
+    __shared__ __align__(16) float peer_stats[16][4];   // [rank]{n, mean, M2, -}: pushed by every CTA of the cluster (st.async)
+    __shared__ __align__(8) uint64_t xbar;
     __shared__ float pivot_sh;
     __shared__ float sc_sh[kGnMaxCpgSmem], sh_sh[kGnMaxCpgSmem];
 
@@ -114,9 +116,11 @@ __global__ void __launch_bounds__(kGnClusterThreads) gn_nchw_cluster_kernel(cons
 
     if (threadIdx.x == 0) {
         for (int c = 0; c < nch; ++c) mbar_init(&bars[c], 1);
+        mbar_init(&xbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
+    cluster_arrive_relaxed();             // "my mbarriers exist": waited for just before the statistics push
     griddep_wait();                       // PDL: x may be the previous kernel's output
     if (threadIdx.x == 0) {
         for (int c = 0; c < nch; ++c) {
@@ -160,11 +164,17 @@ __global__ void __launch_bounds__(kGnClusterThreads) gn_nchw_cluster_kernel(cons
         cta_stats[1] = K + S / cnt;
         cta_stats[2] = fmaxf(SS - S * S / cnt, 0.f);
     }
-    // ---- cluster merge over DSMEM (fixed rank order => identical result in every CTA)
-    cluster_sync_all();
+    // ---- cluster merge: every CTA pushes (n, mean, M2) into every CTA's peer_stats[rank] (st.async + mbarrier transaction bytes: no
+    // cluster-scope fence, no exit barrier), then merges in fixed rank order => identical result in every CTA
+    cluster_wait();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&xbar, cs * 16u);
+        for (uint32_t r = 0; r < cs; ++r) st_async_f32x4(&peer_stats[rank][0], &xbar, r, cta_stats[0], cta_stats[1], cta_stats[2], 0.f);
+    }
+    mbar_wait(&xbar, 0);
     float cn = 0.f, cmean = 0.f, cm2 = 0.f;
     for (uint32_t r = 0; r < cs; ++r) {
-        float nb = ld_dsmem_f32(&cta_stats[0], r), mb = ld_dsmem_f32(&cta_stats[1], r), qb = ld_dsmem_f32(&cta_stats[2], r);
+        float nb = peer_stats[r][0], mb = peer_stats[r][1], qb = peer_stats[r][2];
         if (r == 0) { cn = nb; cmean = mb; cm2 = qb; }
         else welford_merge(cn, cmean, cm2, nb, mb, qb);
     }
@@ -234,7 +244,6 @@ __global__ void __launch_bounds__(kGnClusterThreads) gn_nchw_cluster_kernel(cons
         bulk_commit();
         bulk_wait_read_all();             // shared memory may go away once the stores have read it
     }
-    cluster_sync_all();                   // peers have finished reading my cta_stats (DSMEM) before any CTA of the cluster exits
 }
 
 // Any shape: one CTA per (n,g), exact two-pass statistics straight from global memory.
@@ -469,6 +478,8 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
     extern __shared__ float2 slab[];            // [rows_per_cta][upr]
     __shared__ float red[2][16];
     __shared__ float cta_tot[2];
+    __shared__ __align__(16) float peer_tot[8][2];          // [rank]{sum, sum of squares}: every CTA of the cluster pushes its totals here (st.async)
+    __shared__ __align__(8) uint64_t xbar;                  // ... and credits their bytes to this mbarrier
     const int C = Ca + Cb, cpg = C / G, upr = cpg / 2;
     const int g = blockIdx.x / cs, rank = blockIdx.x - g * cs, n = blockIdx.y;
     const int rpb = blockDim.x / upr;                       // rows per pass
@@ -478,6 +489,10 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
     const bool from_b = c >= Ca;
     const int ldx = from_b ? Cb : Ca;
     const int p0 = rank * rows_per_cta, p1 = min(HW, p0 + rows_per_cta);
+    if (cs > 1) {
+        if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
+        cluster_arrive_relaxed();                           // "my mbarrier exists": waited for just before the push, after the whole load phase
+    }
     griddep_wait();
     griddep_launch();
     const TI* xcol = from_b ? xb + static_cast<long long>(n) * HW * Cb + (c - Ca) : xa + static_cast<long long>(n) * HW * Ca + c;
@@ -522,9 +537,16 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
     }
     float ts, tss;
     if (cs > 1) {
-        cluster_sync_all();                                 // (also a block barrier) every CTA's totals are visible cluster-wide
+        // all-gather of the cs CTA totals by push: no cluster-scope fence (the release form of the cluster barrier is a MEMBAR.ALL.GPU per warp,
+        // ~9 % of this kernel's stall samples at batch 32 together with the exit barrier it needed; profiles/r02_gn_group_b32_source_top.txt)
+        cluster_wait();                                     // every peer's mbarrier is initialised
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&xbar, static_cast<uint32_t>(cs) * 8u);
+            for (int r = 0; r < cs; ++r) st_async_f32x2(&peer_tot[rank][0], &xbar, r, cta_tot[0], cta_tot[1]);
+        }
+        mbar_wait(&xbar, 0);
         ts = 0.f; tss = 0.f;
-        for (int r = 0; r < cs; ++r) { ts += ld_dsmem_f32(&cta_tot[0], r); tss += ld_dsmem_f32(&cta_tot[1], r); }
+        for (int r = 0; r < cs; ++r) { ts += peer_tot[r][0]; tss += peer_tot[r][1]; }      // fixed rank order: identical in every CTA
     } else {
         __syncthreads();
         ts = cta_tot[0]; tss = cta_tot[1];
@@ -553,7 +575,7 @@ __global__ void __launch_bounds__(512) gn_nhwc_group_kernel(const TI* __restrict
             else *reinterpret_cast<uint32_t*>(yp) = pack_bf16x2(o0, o1);
         }
     }
-    if (cs > 1) cluster_sync_all();                         // peers may still be reading this CTA's totals
+    // (no exit barrier: nobody reads this CTA's shared memory remotely, and every push INTO it had landed before its mbarrier wait returned)
 }
 
 // Single-launch cooperative NHWC GroupNorm for L2-resident tensors (the batch-2 UNet step), register-resident:
