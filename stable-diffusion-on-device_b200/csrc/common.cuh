@@ -148,6 +148,12 @@ SDOD_DEVICE void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" :
 // Two / three floats into CTA `rank`'s shared memory at the address `local_dst` has here, completion (8 / 12 bytes) counted on that CTA's
 // mbarrier `local_bar`: the data and the transaction count travel together (STAS), so an all-gather of per-CTA statistics needs no fence,
 // no release/acquire cluster barrier and no exit barrier — the receiver waits on its own mbarrier and reads its own shared memory.
+SDOD_DEVICE void st_async_f32(const void* local_dst, const void* local_bar, uint32_t rank, float a) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_dst)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(a)), "r"(rb) : "memory");
+}
 SDOD_DEVICE void st_async_f32x2(const void* local_dst, const void* local_bar, uint32_t rank, float a, float b) {
     uint32_t ra, rb;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_dst)), "r"(rank));

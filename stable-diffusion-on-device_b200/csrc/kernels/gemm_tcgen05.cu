@@ -425,9 +425,10 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     uint64_t* tmem_full_bar = empty_bar + STAGES;             // [4] accumulator ready (one per TMEM buffer)
     uint64_t* tmem_empty_bar = tmem_full_bar + 4;             // [4] accumulator drained by the epilogue (persistent only)
     uint64_t* res_bar = tmem_empty_bar + 4;                   // [4] residual tiles landed (TMA epilogue), one per lane quarter
-    static_assert((2 * STAGES + 12) * 8 + 4 <= 256, "barrier block");
+    static_assert((2 * STAGES + 14) * 8 + 4 <= 256, "barrier block");
     const int naccs = PERSIST ? min(Cfg::kAccs, mp.tmem_accs > 0 ? mp.tmem_accs : Cfg::kAccs) : 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+    uint64_t* ln_bar = res_bar + 4;                           // [2] LayerNorm epilogue: the cluster's row sums / squared deviations have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_bar + 2);
     float* s_bias_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2][BN] bias tiles
 
     const int warp = threadIdx.x >> 5;
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }
         for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], (PERSIST && mp.epi_groups == 2) ? 16 * EW : 32 * EW); }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&ln_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();      // the peer's barriers exist before any TMA / commit of ours can signal them
+    if (!PAIR && !PERSIST && mp.ln_fuse) cluster_arrive_relaxed();   // "my ln_bar exists": waited for right before the first row-sum push
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     // PDL: everything above overlapped the previous kernel's tail; its outputs are visible from here.  CTA-pair kernels stay out of
@@ -835,7 +838,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             float* s_gamma = reinterpret_cast<float*>(stage + 4 * NB * 6144);
             float* s_beta = s_gamma + BN;
             float* s_halfsum = s_beta + BN;                                 // [NPART][128] partial row moments of the column parts
-            float* ln_part = s_halfsum + NPART * kBlockM;                   // [2][128] this CTA's row sum / row sum of squared deviations
+            // [2][8][128]: row sums / squared deviations of every CTA of the cluster, PUSHED here by their owners (st.async, bytes counted on
+            // ln_bar): no release/acquire cluster barrier (a MEMBAR.ALL.GPU per warp each) and no exit barrier
+            float* ln_peer = s_halfsum + NPART * kBlockM;
             if (mp.tma_epi == 2 && half == 0 && lane == 0) {
                 mbar_arrive_expect_tx(&res_bar[q], NB * 4096);
                 for (int bx = 0; bx < NB; ++bx) tma_load_3d(qbase + bx * 4096, &tmR, &res_bar[q], n0 + bx * 32, m0 + q * 32, bz);
@@ -877,8 +882,13 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 }
             }
             auto epi_sync = [&]() { asm volatile("bar.sync 5, %0;" ::"n"(32 * EW) : "memory"); };
-            const uint32_t n_cta = cluster_nctarank();
+            const uint32_t n_cta = cluster_nctarank(), my_cta = cluster_ctarank();
             const float inv_n = 1.0f / static_cast<float>(mp.N);
+            asm volatile("barrier.cluster.wait;" ::: "memory");      // every CTA of the cluster has initialised its ln_bar
+            if (threadIdx.x == 64) {
+                mbar_arrive_expect_tx(&ln_bar[0], n_cta * kBlockM * 4u);
+                mbar_arrive_expect_tx(&ln_bar[1], n_cta * kBlockM * 4u);
+            }
             // ---- mean
             s_halfsum[half * kBlockM + row] = part;
             epi_sync();
@@ -886,11 +896,11 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 float t = 0.f;
 #pragma unroll
                 for (int h = 0; h < NPART; ++h) t += s_halfsum[h * kBlockM + row];
-                ln_part[row] = t;
+                for (uint32_t r = 0; r < n_cta; ++r) st_async_f32(ln_peer + my_cta * kBlockM + row, &ln_bar[0], r, t);
             }
-            cluster_sync_unaligned();
+            mbar_wait(&ln_bar[0], 0);
             float mean = 0.f;
-            for (uint32_t r = 0; r < n_cta; ++r) mean += ld_dsmem_f32(ln_part + row, r);
+            for (uint32_t r = 0; r < n_cta; ++r) mean += ln_peer[r * kBlockM + row];      // fixed order: identical in every CTA
             mean *= inv_n;
             // ---- variance (second pass over the staged row)
             part = 0.f;
@@ -912,11 +922,11 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 float t = 0.f;
 #pragma unroll
                 for (int h = 0; h < NPART; ++h) t += s_halfsum[h * kBlockM + row];
-                ln_part[kBlockM + row] = t;
+                for (uint32_t r = 0; r < n_cta; ++r) st_async_f32(ln_peer + (8 + my_cta) * kBlockM + row, &ln_bar[1], r, t);
             }
-            cluster_sync_unaligned();
+            mbar_wait(&ln_bar[1], 0);
             float var = 0.f;
-            for (uint32_t r = 0; r < n_cta; ++r) var += ld_dsmem_f32(ln_part + kBlockM + row, r);
+            for (uint32_t r = 0; r < n_cta; ++r) var += ln_peer[(8 + r) * kBlockM + row];
             const float rstd = rsqrtf(var * inv_n + ep.ln_eps);
             // ---- normalised bf16 rows into the second set of boxes (64-B swizzled 32x32 bf16)
 #pragma unroll 1
@@ -1231,10 +1241,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         }   // tile loop
         if (PERSIST) bulk_wait_read_all();                 // (storing threads) shared memory stays valid until the last store has read it
     }
-    if (!PAIR && !PERSIST && mp.ln_fuse && warp < 2) {      // the producer / MMA warps take part in the epilogue's two cluster barriers
-        cluster_sync_unaligned();
-        cluster_sync_unaligned();
-    }
+    if (!PAIR && !PERSIST && mp.ln_fuse && warp < 2) asm volatile("barrier.cluster.wait;" ::: "memory");   // (completes the split barrier of the setup)
     if (!PAIR && !PERSIST && mp.split_cluster) {
         // Split-K inside one launch: the `split` CTAs of this output tile are one thread-block cluster (1,1,split).  Each has published its
         // fp32 partial tile to the L2-resident scratch above; after the cluster barrier (release/acquire at cluster scope) every CTA folds
@@ -1260,7 +1267,8 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     }
     __syncthreads();
     if (threadIdx.x == 0) tstamp(mp, 8);                                   // all roles done
-    if (PAIR || (!PERSIST && mp.ln_fuse)) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while a peer may still touch it
+    if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the peer may still touch it
+    // (LayerNorm epilogue: no exit barrier — peers only ever WRITE into this CTA, and all of those writes had landed before its ln_bar waits returned)
     if (warp == 2) {
         tc_fence_after();
         if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
