@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool pair_relaxed = PAIR && mp.pair_relaxed;
     if (threadIdx.x == 0) tstamp(mp, 0);                                   // CTA started
     // Tile coordinates come from SDOD_TILE_COORDS inside each role's tile loop (one trip unless PERSIST).  Pair grids put M on
     // x: the two CTAs of a cluster (dims 2x1x1, as cta_group::2 kernels must be launched) are consecutive M tiles.
@@ -474,7 +475,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();      // the peer's barriers exist before any TMA / commit of ours can signal them
+    // the peer's barriers exist before any TMA / commit of ours can signal them.  Execution barrier only (fence.mbarrier_init above publishes the
+    // barriers): the release/acquire form costs a MEMBAR.ALL.GPU per warp
+    if (PAIR) { if (pair_relaxed) { cluster_arrive_relaxed(); cluster_wait(); } else cluster_sync_all(); }
     if (!PAIR && !PERSIST && mp.ln_fuse) cluster_arrive_relaxed();   // "my ln_bar exists": waited for right before the first row-sum push
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
@@ -1267,7 +1270,9 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     }
     __syncthreads();
     if (threadIdx.x == 0) tstamp(mp, 8);                                   // all roles done
-    if (PAIR) cluster_sync_all();      // neither CTA's shared / tensor memory goes away while the peer may still touch it
+    // neither CTA's shared / tensor memory goes away while the peer may still touch it (execution barrier: every cross-CTA access was already
+    // ordered by the mbarriers the MMAs commit to)
+    if (PAIR) { if (pair_relaxed) { cluster_arrive_relaxed(); cluster_wait(); } else cluster_sync_all(); }
     // (LayerNorm epilogue: no exit barrier — peers only ever WRITE into this CTA, and all of those writes had landed before its ln_bar waits returned)
     if (warp == 2) {
         tc_fence_after();
@@ -1529,6 +1534,8 @@ static void choose_persist(GemmLaunch* out) {
     MainloopParams& mp = out->mp;
     mp.n_tiles = out->n_tiles; mp.m_tiles = out->m_tiles;
     mp.tiles_total = out->n_tiles * out->m_tiles * out->batch;
+    static const int pair_relaxed_env = [] { const char* e = std::getenv("SDOD_PAIR_RELAXED"); return e ? std::atoi(e) : 1; }();
+    mp.pair_relaxed = pair_relaxed_env;
     out->persist = 0;
     if (mp.streamk) { out->persist = 1; return; }     // stream-K runs on the persistent variant, grid = out->sk_grid
     if (!env || out->pair || mp.split > 1 || !mp.tma_epi || (out->bn != 128 && out->bn != 160)) return;
