@@ -35,22 +35,28 @@ constexpr int kBKV = 64;    // keys per tile: one thread holds a whole S row (64
 template <int DH, int MODE = 1>
 struct AttCfg {
     static constexpr bool PT = MODE >= 1;
-    static constexpr bool kOnes = MODE >= 2;                  // ones row at V^T row DH
+    static constexpr bool kOnes = MODE >= 2 && MODE <= 5;     // ones row at V^T row DH
+    // MODE 6 (d = 80): ONE S buffer + a separate P region.  S double buffer + two 80-column accumulators = 288 TMEM columns round up to 512, i.e.
+    // one CTA (8 softmax warps) per SM; S is consumed at the START of a tile's softmax (one tcgen05.ld into registers), so a single buffer released
+    // right after that load (s_free) still lets S_{j+1} run under tile j's exponentials — 64 (S) + 32 (P) + 160 (O) = 256 columns, two CTAs per SM.
+    static constexpr bool SB = MODE == 6;
     // MODE 3 / 4 / 5: 2 / 1 / 3 of every 8 exponential pairs run on the FMA pipe (ex2_poly2) instead of MUFU — bit i of the mask = pair i & 7
     static constexpr unsigned kPolyMask = MODE == 3 ? 0x88u : (MODE == 4 ? 0x80u : (MODE == 5 ? 0xA4u : 0u));
     static constexpr int kVBoxRows = kOnes ? DH : ((DH + 15) / 16) * 16;
     static constexpr int kNK = (DH + 63) / 64;            // 64-wide d chunks of Q / K
     static constexpr int kKSteps = (DH + 15) / 16;        // UMMA K steps for S = Q K^T
     static constexpr int kDV = ((DH + 15) / 16) * 16;     // N of the PV MMA (rows of the V^T tile)
-    static constexpr int kStages = DH > 80 ? 3 : 4;
+    static constexpr int kStages = SB ? 2 : (DH > 80 ? 3 : 4);    // (SB: two CTAs share the SM's shared memory)
     static constexpr int kQBytes = kNK * kBQ * 128;
-    static constexpr int kQBufs = DH <= 80 ? 2 : 1;       // two Q buffers: a CTA that walks several query tiles (qpc > 1) loads tile i+1 while it works on tile i
+    static constexpr int kQBufs = (DH <= 80 && !SB) ? 2 : 1;       // two Q buffers: a CTA that walks several query tiles (qpc > 1) loads tile i+1 while it works on tile i
     static constexpr int kKBytes = kNK * kBKV * 128;
     static constexpr int kVBytes = kVBoxRows * 128;       // one 64-key chunk: the TMA box, kVBoxRows rows of 128 B
     static constexpr int kVChunk = ((kDV * 128 + 1023) / 1024) * 1024;
     static constexpr int kStageBytes = kKBytes + kVChunk;
     static constexpr int kPBytes = kBQ * 128;             // one P buffer: 128 rows x 64 keys bf16
-    static constexpr int kTmemCols = (128 + 2 * kDV) <= 256 ? 256 : 512;   // S double buffer + two O accumulators
+    static constexpr int kSCols = SB ? 96 : 128;          // S double buffer (P written over it) | one S buffer + the P region
+    static constexpr int kTmemCols = (kSCols + 2 * kDV) <= 256 ? 256 : 512;   // + two O accumulators
+    static constexpr int kCtasPerSm = (DH <= 40 || SB) ? 2 : 1;
     static constexpr int kSmemBytes = kQBufs * kQBytes + kStages * kStageBytes + (PT ? 0 : 2 * kPBytes) + 1024 + 256 + 4096;   // + row-max / row-sum exchange
 };
 
@@ -100,12 +106,13 @@ SDOD_DEVICE void ex2_poly2(float x0, float x1, float& p0, float& p1) {
 // S_{j+2} overwrites the buffer that holds P_j: it is issued after PV_j and tcgen05.mma instructions execute in issue order, so the separate
 // "S buffer drained" barrier goes away too (p_full(j) already says every thread has read S_j).
 template <int DH, int MODE>
-__global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(kAttThreads, AttCfg<DH, MODE>::kCtasPerSm) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O,
                                                                  int heads, int Nq, int Nkv, float scale_log2, int causal, int qpc) {
     using Cfg = AttCfg<DH, MODE>;
     constexpr bool PT = Cfg::PT;
+    constexpr bool SB = Cfg::SB;
     constexpr int STAGES = Cfg::kStages;
     static_assert(!Cfg::kOnes || (DH % 8 == 0 && Cfg::kDV >= DH + 8), "the ones row needs a spare 8-row group in the V^T tile");
     extern __shared__ uint8_t smem_raw[];
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_O = tmem_base + Cfg::kSCols;
     griddep_wait();                    // PDL: the setup above overlapped the projection GEMM's tail
     griddep_launch();
 
@@ -212,25 +219,28 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
                         const int st = j % STAGES;
                         mbar_wait(&kv_full[st], (j / STAGES) & 1);
                         if (!PT && j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
+                        if (SB && j >= 1) mbar_wait(&s_free[0], (j - 1) & 1);      // every softmax thread holds S_{j-1} in registers
                         tc_fence_after();
                         const uint32_t k_addr = smem_u32(sKV + st * Cfg::kStageBytes);
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k) {
                             const uint32_t qoff = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
                             const uint32_t koff = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
-                            tc_mma_bf16(tmem_base + (j & 1) * 64, make_kmajor_sw128_desc(q_addr + qoff), make_kmajor_sw128_desc(k_addr + koff), idesc_s, k != 0);
+                            tc_mma_bf16(tmem_base + (SB ? 0 : (j & 1) * 64), make_kmajor_sw128_desc(q_addr + qoff), make_kmajor_sw128_desc(k_addr + koff), idesc_s, k != 0);
                         }
-                        tc_commit(&s_full[j & 1]);
+                        tc_commit(&s_full[SB ? 0 : (j & 1)]);
                     }
                     if (j >= 1) {                                        // O += P_i V_i for the previous tile
                         const int i = j - 1, st = i % STAGES;
-                        mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+                        mbar_wait(&p_full[SB ? 0 : (i & 1)], (SB ? i : (i >> 1)) & 1);
                         tc_fence_after();
                         const uint32_t v_addr = smem_u32(sKV + st * Cfg::kStageBytes) + Cfg::kKBytes;
                         const uint32_t pb = p_addr + (i & 1) * Cfg::kPBytes;
 #pragma unroll
                         for (int k = 0; k < kBKV / 16; ++k) {  // keys [0,32) -> O_0, keys [32,64) -> O_1 (one accumulator per softmax thread of a row)
-                            if (PT) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
+                            if (SB) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + 64 + (k >> 1) * 16 + (k & 1) * 8,
+                                                   make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | (k & 1)) != 0);
+                            else if (PT) tc_mma_bf16_ts(tmem_O + (k >> 1) * Cfg::kDV, tmem_base + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
                                                    make_kmajor_sw128_desc(v_addr + k * 32), idesc_o, (i | (k & 1)) != 0);
                             else tc_mma_bf16(tmem_O + (k >> 1) * Cfg::kDV, make_kmajor_sw128_desc(pb + k * 32), make_kmajor_sw128_desc(v_addr + k * 32), idesc_o,
                                              (i | (k & 1)) != 0);
@@ -303,16 +313,16 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
         float m_run = -1.0e30f, l_run = 0.f;          // finite "minus infinity": a half with no valid key yet keeps p = 0, alpha = 1
         for (int j = 0; j < n_tiles; ++j) {
             const int G = it * n_tiles + j;           // flat tile counter: S / P buffer and barrier phases
-            const int b = G & 1, u = G >> 1;
+            const int b = SB ? 0 : (G & 1), u = SB ? G : (G >> 1);
             const int kv_valid = min(kBKV, Nkv - j * kBKV) - half * 32;      // valid keys among this thread's 32
             mbar_wait(&s_full[b], u & 1);
             tc_fence_after();
             uint32_t sv[32];
             tmem_ld32(tmem_base + lane_off + b * 64 + half * 32, sv);
             tmem_ld_wait();
-            if (!PT) {
+            if (!PT || SB) {
                 tc_fence_before();
-                mbar_arrive(&s_free[b]);             // S buffer b may be overwritten by S_{j+2}
+                mbar_arrive(&s_free[b]);             // S buffer b may be overwritten by S_{j+2} (SB: by S_{j+1})
             }
             if (kv_valid < 32) {
 #pragma unroll
@@ -376,7 +386,11 @@ __global__ void __launch_bounds__(kAttThreads, DH <= 40 ? 2 : 1) attention_kerne
             // P buffer b is free: the MMA thread issues S_j after PV_{j-2}, and a tcgen05.commit covers every MMA issued before it, so
             // having seen s_full for tile j already implies PV_{j-2} has consumed this buffer.  (A satisfied mbarrier wait still costs
             // ~200 clk here — clock64 phase timing, profiles/r01_attention_notes.txt — so the loop keeps exactly one per tile.)
-            if (PT) {
+            if (SB) {
+                // the one P region is free once PV_{j-1} has retired (it was issued as soon as the slowest warp handed over P_{j-1})
+                if (j > 0) { mbar_wait(o_ready, (G - 1) & 1); tc_fence_after(); }
+                tmem_st16(tmem_base + lane_off + 64 + half * 16, pk);
+            } else if (PT) {
                 // keys (2i, 2i+1) of this thread's 32 -> column i of its own S half: lane = query row, 32-bit column = two consecutive K elements
                 tmem_st16(tmem_base + lane_off + b * 64 + half * 32, pk);
             } else {
@@ -521,7 +535,7 @@ static int launch_attention_v(const AttnLaunch& a, cudaStream_t stream) {
     // as long as the grid still holds >= 4 CTAs per resident slot.  SDOD_ATTN_QPC overrides (1 = one tile per CTA as in round 1).
     const int n_qt = (a.Nq + kBQ - 1) / kBQ, n_kt = (a.Nkv + kBKV - 1) / kBKV;
     int qpc = 1;
-    if (Cfg::kQBufs == 2 && !a.causal && n_kt <= Cfg::kStages && n_qt > 1) {
+    if (Cfg::kQBufs == 2 && !Cfg::SB && !a.causal && n_kt <= Cfg::kStages && n_qt > 1) {
         static const int env = [] { const char* e = std::getenv("SDOD_ATTN_QPC"); return e ? std::atoi(e) : 0; }();
         const long long slots = static_cast<long long>(device_sm_count()) * (DH <= 40 ? 2 : 1);
         for (int c = 8; c >= 2 && qpc == 1; c >>= 1)
@@ -544,6 +558,15 @@ static int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
         if (mode == 3) return launch_attention_v<DH, 3>(a, stream);
         if (mode == 4) return launch_attention_v<DH, 4>(a, stream);
         if (mode == 5) return launch_attention_v<DH, 5>(a, stream);
+    }
+    if constexpr (DH == 80) {
+        // self-attention (more key tiles than the ring holds): the single-S-buffer layout that fits two CTAs per SM; cross-attention keeps MODE 1
+        // and walks several query tiles per CTA instead
+        static const int sb = [] { const char* e = std::getenv("SDOD_ATTN_SB"); return e ? std::atoi(e) : 1; }();
+        // (multi-wave grids only: B32 x 8 heads x 1024^2 222.9 -> 197.4 us; a single-wave grid has one CTA per SM either way and loses to the
+        // shallower K/V ring and the extra waits: batch 2 20.8 -> 29.0 us)
+        const long long ctas = static_cast<long long>(a.BH) * ((a.Nq + kBQ - 1) / kBQ);
+        if (mode && sb && (a.Nkv + kBKV - 1) / kBKV > AttCfg<DH, 1>::kStages && ctas > device_sm_count()) return launch_attention_v<DH, 6>(a, stream);
     }
     return mode ? launch_attention_v<DH, 1>(a, stream) : launch_attention_v<DH, 0>(a, stream);
 }

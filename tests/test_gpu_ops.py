@@ -500,6 +500,17 @@ def test_cross_attention_several_query_tiles_per_cta(B, heads, dh, Nq):
     assert max(per_image) < TOL_BF16, per_image
 
 
+def test_self_attention_d80_two_ctas_per_sm_layout():
+    """Multi-wave d = 80 self-attention takes the single-S-buffer TMEM layout (64 S + 32 P + 160 O columns, two CTAs per SM)."""
+    torch.manual_seed(80)
+    B, heads, dh, N = 6, 8, 80, 1024          # 48 heads x 8 query tiles = 384 CTAs > 148 SMs
+    q, k, v = (bf(torch.randn(B, N, heads * dh) * s).to(DEV) for s in (1.5, 1.5, 1.0))
+    k[:, N // 2:] *= 3.0                        # growing row maxima: the lazy rescale path runs too
+    got = torch.ops.sdod.attention(ops.pack_heads(q, heads, dh), ops.pack_heads(k, heads, dh), ops.pack_heads(v, heads, dh, True),
+                                   B, heads, dh, N, dh ** -0.5)
+    assert rel_err(got, _attn_ref(q, k, v, heads)) < TOL_BF16
+
+
 def test_cross_attention_forced_ragged_tile_walk_in_subprocess():
     """SDOD_ATTN_QPC=3 (read once per process): 3 query tiles per CTA does not divide the tile counts, so the last CTA of each head walks fewer."""
     import subprocess
