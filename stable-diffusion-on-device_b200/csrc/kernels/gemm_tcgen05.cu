@@ -703,6 +703,32 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
             // the partials in fixed order (deterministic) and applies the epilogue.
             const long long tile_id = static_cast<long long>(m_tile) * (PAIR ? gridDim.y : gridDim.x) + n_tile;
             float* mine = mp.ws + (tile_id * mp.split + zs) * (BN * kBlockM);
+            if (!PAIR && !PERSIST && mp.split_cluster == 2) {
+                // In-cluster reduction over distributed shared memory: the `split` CTAs of this tile are one (1,1,split) cluster.  Warp task u
+                // (16 rows x 16 columns; u = chunk * 8 + row / 16) is folded by CTA u % split, so every CTA PUSHES each of its task partials into
+                // the owner's idle operand ring with st.async (bytes counted on the owner's mbarrier): no scratch round trip through L2, no
+                // release/acquire barrier (MEMBAR.ALL.GPU behind 80 KB of stores), no second launch.  The one cluster barrier below carries no
+                // data: it says that every CTA's MMAs have retired, i.e. every ring may be overwritten.
+                asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory");
+                asm volatile("barrier.cluster.wait;" ::: "memory");
+                constexpr int kTasks = (BN / 16) * 8;
+                const int T = (kTasks + mp.split - 1) / mp.split;
+                if (threadIdx.x == 64) mbar_arrive_expect_tx(&ln_bar[0], static_cast<uint32_t>((kTasks - zs + mp.split - 1) / mp.split) * mp.split * 1024u);
+                float* rx = reinterpret_cast<float*>(sA);                        // [split][T][16 rows][16 columns]
+#pragma unroll 1
+                for (int j = j_lo; j < j_hi; j += 16) {
+                    uint32_t acc[16];
+                    tmem_ld16(taddr + j, acc);
+                    tmem_ld_wait();
+                    const int u = (j >> 4) * 8 + (row >> 4);
+                    const int t = u / mp.split, owner = u - t * mp.split;
+                    float* dst = rx + ((zs * T + t) * 16 + (row & 15)) * 16;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        st_async_f32x4(dst + 4 * q4, &ln_bar[0], owner, __uint_as_float(acc[4 * q4]), __uint_as_float(acc[4 * q4 + 1]),
+                                       __uint_as_float(acc[4 * q4 + 2]), __uint_as_float(acc[4 * q4 + 3]));
+                }
+            } else
 #pragma unroll 1
             for (int j = j_lo; j < j_hi && m0 < mp.M; j += 16) {    // (m0 >= M: padding CTA of an odd pair grid)
                 uint32_t acc[16];
@@ -1250,6 +1276,30 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
         // fp32 partial tile to the L2-resident scratch above; after the cluster barrier (release/acquire at cluster scope) every CTA folds
         // 1/split of the tile — warp tasks of 16 rows x 16 columns, dealt round-robin over the CTAs and their 8 epilogue warps — in fixed
         // z order (deterministic, independent of arrival order) and runs the shared epilogue on it.
+        if (mp.split_cluster == 2) {
+            if (warp < 2) {                                                // (the epilogue warps took part right after their accumulator wait)
+                asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory");
+                asm volatile("barrier.cluster.wait;" ::: "memory");
+            } else {
+                mbar_wait(&ln_bar[0], 0);                                  // every partial of the tasks this CTA folds has landed in its ring
+                constexpr int kTasks = (BN / 16) * 8;
+                const int T = (kTasks + mp.split - 1) / mp.split;
+                const float* rx = reinterpret_cast<const float*>(sA);
+                const int n_tile = static_cast<int>(blockIdx.x), m_tile = static_cast<int>(blockIdx.y);
+                const int row_in = lane >> 1, half = lane & 1;
+                for (int u = zs + mp.split * (warp - 2); u < kTasks; u += mp.split * 8) {
+                    const int chunk = u >> 3, row = (u & 7) * 16 + row_in, t = u / mp.split;
+                    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                    for (int z = 0; z < mp.split; ++z) {                   // fixed z order: deterministic
+                        const float4* src = reinterpret_cast<const float4*>(rx + ((z * T + t) * 16 + row_in) * 16 + half * 8);
+                        const float4 a = src[0], b = src[1];
+                        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+                    }
+                    float acc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    epilogue_plain8(ep, mp, 0, m_tile * kBlockM + row, n_tile * BN + chunk * 16 + half * 8, acc);
+                }
+            }
+        } else {
         asm volatile("barrier.cluster.arrive.release;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
         if (threadIdx.x == 64) tstamp(mp, 7);                              // split-K: all partials published
@@ -1266,6 +1316,7 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                 fold_partials8(reinterpret_cast<const float4*>(base + (chunk * kBlockM + row) * 16 + half * 8), mp.split, zstride4, acc);
                 epilogue_plain8(ep, mp, 0, m_tile * kBlockM + row, n_tile * BN + chunk * 16 + half * 8, acc);
             }
+        }
         }
     }
     __syncthreads();
@@ -1620,12 +1671,15 @@ static int streamk_grid(int bn, long long tiles, int k_blocks, int batch, bool p
     return grid;
 }
 
-// In-kernel reduction over a (1,1,split) cluster (one launch instead of two) with SDOD_SPLITK_CLUSTER=1.  Off by default: measured on B200 (r2) the
-// batch-2 step is 0.2 ms faster with the separate reduce kernel (5.28 vs 5.49 ms) — its 80 x tiles CTAs fold the partials with far more loads
-// in flight than the 8 epilogue warps of each cluster CTA, and 8-CTA clusters wait for 8 simultaneously free SMs of one GPC.
+// In-kernel reduction over a (1,1,split) cluster (one launch instead of two) with SDOD_SPLITK_CLUSTER=1 (partials through the L2 scratch, release/
+// acquire cluster barrier) or =2 (partials pushed into the owner CTA's idle ring over distributed shared memory, st.async on mbarriers: no scratch
+// round trip, no fence).  Off by default: measured on B200 (r2) the batch-2 step is slower either way — 4.92 ms (=1) and 4.94 ms (=2) against 4.80 ms
+// with the separate reduce kernel, at 299 instead of 340 launches.  The exchange mechanism is not what costs: a (1,1,split) cluster can only start
+// when `split` SMs of one GPC are free at once, so these launches lose the programmatic overlap with their predecessor's tail that the plain
+// launches (and the reduce kernel's 80 x tiles small CTAs) get.
 static int split_cluster_mode(const MainloopParams& mp, bool pair, int act) {
     static const int env = [] { const char* e = std::getenv("SDOD_SPLITK_CLUSTER"); return e ? std::atoi(e) : 0; }();
-    return (env && mp.split > 1 && mp.split <= 8 && !pair && act != SDOD_ACT_GEGLU) ? 1 : 0;
+    return (env && mp.split > 1 && mp.split <= 8 && !pair && act != SDOD_ACT_GEGLU) ? (env == 2 ? 2 : 1) : 0;
 }
 
 // Second A operand (K-concatenated): bf16 [M, K2] rows of ld2 elements, loaded as plain {64, 128} boxes after tmA's K blocks.

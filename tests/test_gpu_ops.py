@@ -778,8 +778,11 @@ def test_optional_scheduling_variants_in_subprocess():
     their env switches are read once per process, so their parity tests run in a child process with the switches on."""
     import subprocess
     import sys
-    env = dict(os.environ, SDOD_STREAMK="1", SDOD_SPLITK_CLUSTER="1")
     root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-x", "-q", "-m", "gpu", "-k",
-                        "stream_k or split_k or second_operand or fused_skip"], env=env, capture_output=True, text=True, timeout=900, cwd=root)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    # SDOD_SPLITK_CLUSTER: 1 = partials through the L2 scratch + a release/acquire cluster barrier, 2 = partials pushed into the owner CTA's idle
+    # operand ring over distributed shared memory (st.async on mbarriers)
+    for mode in ("1", "2"):
+        env = dict(os.environ, SDOD_STREAMK="1", SDOD_SPLITK_CLUSTER=mode)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-x", "-q", "-m", "gpu", "-k",
+                            "stream_k or split_k or second_operand or fused_skip"], env=env, capture_output=True, text=True, timeout=900, cwd=root)
+        assert r.returncode == 0, "SDOD_SPLITK_CLUSTER=" + mode + "\n" + r.stdout[-3000:] + r.stderr[-2000:]
