@@ -482,10 +482,12 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     // PDL: everything above overlapped the previous kernel's tail; its outputs are visible from here.  CTA-pair kernels stay out of
-    // it (ordinary launch, no early trigger): a cta_group::2 TMEM allocation racing the neighbour kernel's allocation on the same
-    // SM pair deadlocked the step (B200, r1).
+    // it by default (ordinary launch, no early trigger): a cta_group::2 TMEM allocation racing the neighbour kernel's allocation on the
+    // same SM pair deadlocked the step in round 1.  With the allocation now ahead of the trigger that no longer reproduces
+    // (SDOD_PAIR_PDL=1: a batch-2 step with every eligible layer forced onto pairs replays cleanly), but it gains nothing measurable
+    // where pairs are used (batch-32 pass 39.85 vs 39.96 ms), so the switch stays off.
     if (threadIdx.x == 0) tstamp(mp, 1);                                   // barriers + TMEM ready
-    if (!PAIR) {
+    if (!PAIR || mp.pair_pdl) {
         griddep_wait();
         griddep_launch();
     }
@@ -1369,7 +1371,15 @@ static int launch_gemm_cfg(cudaStream_t stream, const GemmLaunch& g, dim3 grid) 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // two consecutive M tiles
-    cfg.attrs = attr; cfg.numAttrs = 1;      // no programmatic serialization for pairs (see the kernel)
+    cudaLaunchAttribute attr_pdl[2];
+    if (g.mp.pair_pdl && pdl_enabled()) {    // experiment switch SDOD_PAIR_PDL=1 (default: no programmatic serialization for pairs, see the kernel)
+        attr_pdl[0] = attr[0];
+        attr_pdl[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr_pdl[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr_pdl; cfg.numAttrs = 2;
+    } else {
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, DEEP, PAIR, PERSIST>, g.tmA, g.tmW, g.tmC, g.tmR, g.tmC2, g.tmA2, g.mp, g.ep);
     if (e != cudaSuccess) {
         int nc = -1;
@@ -1441,6 +1451,7 @@ static bool use_pair(int bn, int m_tiles, int n_tiles, bool conv) {
     static const int env = [] { const char* e = std::getenv("SDOD_GEMM_PAIR"); return e ? std::atoi(e) : 1; }();
     if (!env || bn < 128 || m_tiles < 2) return false;
     if (env == 2) return (m_tiles % 2 == 0) || m_tiles >= 9;
+    if (env == 3) return conv && (m_tiles % 2 == 0);                     // (experiment: single-wave convs as pairs too)
     return conv && (m_tiles % 2 == 0) && static_cast<long long>(m_tiles) * n_tiles > 148;
 }
 
@@ -1587,6 +1598,8 @@ static void choose_persist(GemmLaunch* out) {
     mp.tiles_total = out->n_tiles * out->m_tiles * out->batch;
     static const int pair_relaxed_env = [] { const char* e = std::getenv("SDOD_PAIR_RELAXED"); return e ? std::atoi(e) : 1; }();
     mp.pair_relaxed = pair_relaxed_env;
+    static const int pair_pdl_env = [] { const char* e = std::getenv("SDOD_PAIR_PDL"); return e ? std::atoi(e) : 0; }();
+    mp.pair_pdl = pair_pdl_env;
     out->persist = 0;
     if (mp.streamk) { out->persist = 1; return; }     // stream-K runs on the persistent variant, grid = out->sk_grid
     if (!env || out->pair || mp.split > 1 || !mp.tma_epi || (out->bn != 128 && out->bn != 160)) return;

@@ -35,6 +35,7 @@ struct MainloopParams {
     int b_resident;    // persistent variant, k_blocks == ring stages and grid % n_tiles == 0: a CTA keeps one N tile for its whole walk and stage s always
                        //    holds K block s, so the weight tile is loaded once and only the A rows are streamed (half the L2 -> SM operand bytes)
     int epi_groups;    // persistent variant: 2 = two epilogue warp groups on alternate tiles / TMEM accumulators (see the kernel); else one group of 16 warps
+    int pair_pdl;      // CTA-pair variant: take part in programmatic dependent launch (experiment switch, default 0)
     int pair_relaxed;  // CTA-pair variant: setup / exit cluster barriers without release/acquire memory ordering (0 = the round-1 form, A/B switch)
     int tmem_accs;     // persistent variant: TMEM accumulators in rotation (0 = all that fit: 4 x 128 / 3 x 160 columns; 2 = the round-2 double buffer)
     int geglu_tanh;    // GEGLU TMA epilogue: gate GELU in tanh form (1 MUFU + 5 packed ops instead of 2 MUFU + 14; see common.cuh)
