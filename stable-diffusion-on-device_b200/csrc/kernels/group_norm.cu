@@ -857,7 +857,8 @@ static int group_kernel_geometry(int N, int Ca, int Cb, int HW, int G, int in_dt
     while (cs < 8 && (slab / cs > (static_cast<size_t>(slab_kb) << 10) || HW % cs != 0)) cs *= 2;      // <= 100 KB: two CTAs per SM
     // small batch: spread each group over more CTAs (two 512-thread CTAs per SM) while a thread still walks >= 8 rows
     const int rpb = std::max(1, 512 / (cpg / 2));
-    while (cs < 8 && static_cast<long long>(N) * G * cs < 256 && HW / (cs * 2) >= 8 * rpb && HW % (cs * 2) == 0) cs *= 2;
+    static const long long spread = [] { const char* e = std::getenv("SDOD_GN_GROUP_SPREAD"); return e ? std::atoll(e) : 256LL; }();   // A/B knob
+    while (cs < 8 && static_cast<long long>(N) * G * cs < spread && HW / (cs * 2) >= 8 * rpb && HW % (cs * 2) == 0) cs *= 2;
     if (HW % cs != 0 || slab / cs > (static_cast<size_t>(200) << 10)) return 0;
     // Tensors beyond L2 whose groups only fit as one 100-200 KB CTA per SM (the VAE's 128x128 x 512-channel level at batch 8) stay on the
     // stats + apply pair: measured 30.7 vs 31.8 ms for the batch-8 decoder (B200 r2).
