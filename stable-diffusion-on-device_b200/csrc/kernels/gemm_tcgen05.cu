@@ -1608,6 +1608,11 @@ static void choose_persist(GemmLaunch* out) {
     // measured (tools/hot_kernels.py, B200 r1): K=320 GEGLU 111.6 -> 92.2 us, QKV 87.0 -> 82.9 us; K=1280 (20 blocks) 46.1 -> 58.3 us,
     // where two co-resident CTAs with their own rings hide the loads better than one 4-stage ring
     out->persist = (mp.tiles_total >= 3 * sms && mp.k_blocks <= 10) ? 1 : 0;
+    // fp32 output with an fp32 residual (the transformer blocks' to_out / proj_out at K = 320): the staging region holds ONE fp32 tile, so a persistent
+    // CTA runs residual load -> add -> store strictly in sequence per tile, while two co-resident one-tile CTAs overlap theirs
+    // (B200 r2, M131072 N320 K320: 98.7 us persistent, 90.4 us not; K = 640: 60.3 vs 61.0 us, left persistent)
+    static const int res_env = [] { const char* e = std::getenv("SDOD_PERSIST_RES"); return e ? std::atoi(e) : 0; }();
+    if (!res_env && mp.tma_epi == 2 && mp.k_blocks <= 5) out->persist = 0;
     // two epilogue groups on alternate tiles wherever the staging region holds two tiles (bf16 / GEGLU / head-layout outputs, no residual to
     // pre-load): SDOD_EPI_GROUPS=1 restores the single group of 16 warps (A/B measurements)
     // weight-stationary walk (see MainloopParams::b_resident): with the ring exactly one tile deep the weight half never has to be re-fetched, which
