@@ -142,7 +142,7 @@ typedef struct sdod_epilogue {
     const float* row_bias;   /* [M/rows_per_group, ld_row_bias] fp32 or NULL (timestep-embedding add) */
     int rows_per_group;
     long long ld_row_bias;   /* row stride of row_bias in elements; 0 = N                           */
-    const void* residual;    /* bf16 [M,N] row-major or NULL, added last                           */
+    const void* residual;    /* bf16 [M,N] row-major or NULL, added last; may alias C (x += f(x)): an fp32 in-place residual leaves through a TMA reduce-add store */
     long long ldr;
     long long strideR;
     float alpha;

@@ -1086,7 +1086,12 @@ __global__ void __launch_bounds__(PERSIST ? kGemmThreadsPersist : kGemmThreads, 
                         if (n0 + bx * 32 < mp.N) tma_store_5d(&tmC, qbase + bx * bstr, n0 + bx * 32, bz & 1, xq, bz >> 1, biq);
                 } else {
                     for (int bx = 0; bx < NB; ++bx)
-                        if (n0 + bx * 32 < mp.N) tma_store_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
+                        if (n0 + bx * 32 < mp.N) {
+                            // tma_epi 4: the fp32 residual IS the output tensor (x += f(x), in place): the add happens in the TMA reduction at L2,
+                            // the SM neither loads the residual nor re-reads it from shared memory
+                            if (mp.tma_epi == 4) tma_reduce_add_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
+                            else tma_store_3d(&tmC, qbase + bx * bstr, n0 + bx * 32, m0 + q * 32, bz);
+                        }
                 }
                 bulk_commit();
                 if (dbuf && !two) bulk_wait_read_but_last();
@@ -1795,6 +1800,13 @@ static int gemm_prepare_impl(const sdod_gemm_desc& d, GemmLaunch* out, bool try_
     SDOD_TRY(setup_tma_epilogue(out, d.epi, d.M, d.N, d.batch));
     SDOD_TRY(setup_heads_epilogue(out, d.epi, d.M, d.N, d.batch));
     SDOD_TRY(setup_ln_epilogue(out, d.epi, d.M, d.N, d.batch, pair));
+    {
+        // in-place residual (fp32 stream: x += f(x)) without the LayerNorm epilogue: TMA reduce-add store instead of residual load + add
+        static const int env = [] { const char* e = std::getenv("SDOD_TMA_REDUCE"); return e ? std::atoi(e) : 1; }();
+        if (env && out->mp.tma_epi == 2 && !out->mp.ln_fuse && out->mp.c_bytes == 4 && d.epi.residual == d.epi.C && d.epi.ldr == d.epi.ldc &&
+            (d.batch == 1 || d.epi.strideR == d.epi.strideC))
+            out->mp.tma_epi = 4;
+    }
     out->m_tiles = (d.M + kBlockM - 1) / kBlockM;
     out->n_tiles = (d.N + bn - 1) / bn;
     out->batch = d.batch;

@@ -441,7 +441,8 @@ int NetBase::gemm_into(const sdod_gemm_desc& d, bool may_fail) {
 Act NetBase::linear(const Act& x, const void* w_bf16, int N, const LinearOpts& o) {
     const int n_out = o.act == SDOD_ACT_GEGLU ? N / 2 : N;
     if (x.f32) throw std::runtime_error("linear: GEMM operand must be bf16");
-    Act y = new_act(x.B, x.H, x.W, n_out, o.out_f32);
+    const bool in_place = o.in_place && o.residual && o.out_f32 && o.residual->f32 && o.residual->C == n_out && o.residual->M() == x.M();
+    Act y = in_place ? *o.residual : new_act(x.B, x.H, x.W, n_out, o.out_f32);
     sdod_gemm_desc d{};
     d.A = x.p; d.lda = x.C; d.strideA = 0;
     d.W = w_bf16; d.ldw = x.C; d.strideW = 0;

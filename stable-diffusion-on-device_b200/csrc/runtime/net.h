@@ -117,6 +117,7 @@ protected:
         float alpha = 1.0f;
         int block_n = 0;
         bool out_f32 = false;    // write the fp32 residual stream
+        bool in_place = false;   // fp32 stream with a residual: write the result over the residual (x += f(x)); the returned Act IS *residual
         // LayerNorm of the output rows (fp32 stream outputs only): *ln_out receives bf16 LN(y) * ln_w + ln_b — fused into the GEMM's
         // epilogue where the shape allows (gemm_tcgen05.cu, ln_fuse), else a separate layer_norm launch
         Act* ln_out = nullptr;

@@ -158,11 +158,12 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     o1.bias = w32(tb + ".attn1.to_out.0.bias", {C}, kInitBias);
     o1.residual = &h;
     o1.out_f32 = true;
+    o1.in_place = true;       // h += to_out(attention): the block's fp32 token stream is updated in place (TMA reduce-add store where no LayerNorm rides along)
     Act n2;
     o1.ln_out = &n2; o1.ln_w = w32(tb + ".norm2.weight", {C}, kInitOnes); o1.ln_b = w32(tb + ".norm2.bias", {C}, kInitZeros);
     Act h2 = linear(a1, pack_linear(tb + ".attn1.to_out.0.weight", C, C), C, o1);
     release(a1);
-    release(h);
+    if (h2.p != h.p) release(h);
 
     // ---- cross-attention against the cached prompt K / V^T
     {
@@ -180,11 +181,12 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     o2.bias = w32(tb + ".attn2.to_out.0.bias", {C}, kInitBias);
     o2.residual = &h2;
     o2.out_f32 = true;
+    o2.in_place = true;
     Act n3;
     o2.ln_out = &n3; o2.ln_w = w32(tb + ".norm3.weight", {C}, kInitOnes); o2.ln_b = w32(tb + ".norm3.bias", {C}, kInitZeros);
     Act h3 = linear(a2, pack_linear(tb + ".attn2.to_out.0.weight", C, C), C, o2);
     release(a2);
-    release(h2);
+    if (h3.p != h2.p) release(h2);
 
     // ---- GEGLU feed-forward (gate fused in the projection's epilogue)
     std::vector<int> rowmap(8 * C);
@@ -204,7 +206,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     release(n3);
     LinearOpts o3;
     o3.bias = w32(tb + ".ff.net.2.bias", {C}, kInitBias);
-    o3.residual = &h3;
+    o3.residual = &h3;        // (bf16 output: h4 is proj_out's GEMM operand, so this one cannot update the fp32 stream in place)
     Act h4 = linear(gg, pack_linear(tb + ".ff.net.2.weight", C, 4 * C), C, o3);
     release(gg);
     release(h3);

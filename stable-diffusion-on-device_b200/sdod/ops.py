@@ -253,6 +253,24 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+def linear_accumulate_(x: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    """In place on the fp32 stream: x += alpha * a @ w^T + bias (x fp32 [M,N] contiguous, a [M,K] / w [N,K] bf16).  The residual IS the
+    output tensor, so eligible shapes take the TMA reduce-add epilogue (no residual load in the kernel); others add and store as usual."""
+    _need_cuda(x, a, w, bias)
+    assert x.dtype == torch.float32 and x.is_contiguous() and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert x.shape == (M, N)
+    d = C.GemmDesc()
+    d.A, d.lda, d.strideA = _p(a), K, M * K
+    d.W, d.ldw, d.strideW = _p(w), K, 0
+    d.M, d.N, d.K, d.batch, d.block_n = M, N, K, 1, 0
+    d.epi = _epilogue(x, _f32(bias), None, 0, x, alpha, C.ACT_NONE)
+    C.check(C.lib().sdod_gemm_bf16(_stream(), d), "sdod_gemm_bf16 (in place)")
+    return x
+
+
 @linear.register_fake
 def _(a, w, bias=None, residual=None, act=0, alpha=1.0, out_f32=False, row_bias=None, rows_per_group=0, block_n=0, a2=None):
     n = w.shape[-2] // 2 if act == C.ACT_GEGLU else w.shape[-2]

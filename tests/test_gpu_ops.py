@@ -343,6 +343,22 @@ def test_gemm_persistent_single_epilogue_group_in_subprocess():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (65536, 640, 640), (8192, 1280, 1280), (1000, 320, 640)])
+def test_gemm_in_place_residual_reduce_add(M, N, K):
+    """x += a @ w^T + bias with the residual aliasing the output (the transformer blocks' to_out projections on the fp32 stream): eligible shapes
+    leave through a TMA reduce-add store; twice in a row, so a store that overwrote instead of adding would show."""
+    torch.manual_seed(M + N)
+    a, w = bf(torch.randn(M, K)).to(DEV), bf(torch.randn(N, K) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, device=DEV)
+    x0 = torch.randn(M, N, device=DEV)
+    x = x0.clone()
+    y = a.float() @ w.float().t() + bias
+    assert ops.linear_accumulate_(x, a, w, bias) is x
+    assert rel_err(x, x0 + y) < TOL_F32
+    ops.linear_accumulate_(x, a, w, bias)
+    assert rel_err(x, x0 + 2 * y) < TOL_F32
+
+
 def test_gemm_batched():
     torch.manual_seed(13)
     a, w = bf(torch.randn(6, 200, 128)).to(DEV), bf(torch.randn(6, 328, 128) / 11).to(DEV)
