@@ -614,12 +614,13 @@ Act NetBase::conv3_im2col(const Act& x, const std::string& prefix, int cout, int
     return y;
 }
 
-Act NetBase::conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out) {
+Act NetBase::conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out, bool in_place) {
     void* w = pack_linear(prefix + ".weight", cout, x.C);
     LinearOpts o;
     o.bias = w32(prefix + ".bias", {cout}, kInitBias);
     o.residual = residual;
     o.out_f32 = stream_out;
+    o.in_place = in_place;
     return linear(x, w, cout, o);
 }
 

@@ -137,7 +137,7 @@ protected:
     // stride-2 conv3x3, padding 1 (UNet Downsample): implicit GEMM on TMA boxes with element strides 2 — no im2col buffer.  x fp32 is cast first.
     Act conv3_s2(const Act& x, const std::string& prefix, int cout, bool stream_out = false);
     Act conv3_im2col(const Act& x, const std::string& prefix, int cout, int stride, bool stream_out = false);
-    Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out = false);
+    Act conv1x1(const Act& x, const std::string& prefix, int cout, const Act* residual, bool stream_out = false, bool in_place = false);
     Act to_bf16(const Act& x);
     Act upsample(const Act& x);
     Act concat(const Act& a, const Act& b);

@@ -211,7 +211,7 @@ Act UNet::spatial_transformer(const Act& x, const std::string& prefix, int level
     release(gg);
     release(h3);
 
-    Act out = conv1x1(h4, prefix + ".proj_out", C, &x, true);
+    Act out = conv1x1(h4, prefix + ".proj_out", C, &x, true, true);     // x += proj_out(h4): in place (x is this block's private ResBlock output)
     release(h4);
     return out;
 }
@@ -258,7 +258,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
             // h stays alive: it is in hs (skip connection)
             if (level < 3) {
                 Act t = spatial_transformer(r, p + ".1", level);
-                release(r);
+                if (t.p != r.p) release(r);
                 r = t;
             }
             h = r;
@@ -273,7 +273,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
     {
         Act r = res_block(h, nullptr, "middle_block.0", h.C, emb_index++);
         Act t = spatial_transformer(r, "middle_block.1", 3);
-        release(r);
+        if (t.p != r.p) release(r);
         Act r2 = res_block(t, nullptr, "middle_block.2", t.C, emb_index++);
         release(t);
         h = r2;     // previous h is hs.back(): released when popped
@@ -291,7 +291,7 @@ std::unique_ptr<Plan> UNet::build_forward(int B) {
             int sub = 1;
             if (level < 3) {
                 Act t = spatial_transformer(r, p + ".1", level);
-                release(r);
+                if (t.p != r.p) release(r);
                 r = t;
                 sub = 2;
             }
